@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""Benchmark of the MatchNeRF per-ray hot path on B200 (contract: see the task statement / DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--samples S]
+
+A step = one pass of the hot path over one batch of synthetic input: the full forward of ONE target view per rank
+(GMFlow encoder on the 3 source views incl. K-attn, then K-gather + K-mlp-composite over all 512x640 rays, 64 depth
+samples -- BASELINE.json configs[1]) followed, for N > 1, by the single all-gather of the rendered tiles.
+``value`` = rays/s over the whole job with inputs resident in HBM; ``e2e`` = the same through ``MatchNeRF.forward``
+with the batch in pinned HOST memory (H2D of the images/cameras and D2H of rgb/depth/opacity inside the timed
+region).  ``--impl reference`` times the CPU oracle port of the reference path on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+H_IMG, W_IMG = 512, 640
+FLOP_PER_SAMPLE = {64: 262432, 128: 266528}     # decoder, 2*MAC, unpadded
+GATHER_BYTES_PER_SAMPLE = 12520                 # 3 views x 4 taps x 512 ch x 2 B + colours + 22 floats out
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=float(d["hbm_gbs"]), tensor=float(d["bf16_tflops"]), tensor_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tensor=1590.0, tensor_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+
+
+def make_opts(S: int, device: str):
+    from matchnerf_b200.utils import AttrDict
+    return AttrDict(dict(
+        device=device, n_src_views=3,
+        encoder=dict(attn_splits_list=[2], cos_n_group=[2, 8], num_transformer_layers=6, feature_upsampler="network",
+                     upsample_factor=2, wo_self_attn=False, feature_sample_local_radius=0, feature_sample_local_dilation=1),
+        decoder=dict(net_width=128, net_depth=6, skip=[4], posenc=dict(L_3D=10, L_view=0), raytrans_posenc=False,
+                     density_maskfill=False, raytrans_act="ReLU"),
+        nerf=dict(legacy_coord=True, wo_render_interval=True, view_dep=True, depth=dict(param="metric"), sample_intvs=S,
+                  sample_stratified=True, rand_rays_test=20480, rand_rays_train=1024)))
+
+
+def synthetic_batch(seed: int):
+    from oracle import synth
+    g = torch.Generator().manual_seed(seed)
+    images = torch.rand(1, 4, 3, H_IMG, W_IMG, generator=g)
+    extr, intr, nf = synth.synthetic_cameras(H_IMG, W_IMG)
+    return dict(images=images, extrinsics=extr, intrinsics=intr, near_fars=nf)
+
+
+# ================================================================================================ reference arm
+def run_reference(args):
+    """CPU oracle port of the reference path (oracle/ validated against the unmodified reference, tests/golden/REPORT.txt).
+    Step = render of a bounded sample of rays of the same 512x640x3-view workload; the encoder is timed once and amortised
+    over the image, so value = HW / (t_encoder + t_sample * HW / rays_sample)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import encoder_oracle as EO
+    from oracle import render_oracle as RO
+    from oracle import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    S = args.samples
+    batch = synthetic_batch(100)
+    enc_sd, dec_sd = synth.synthetic_encoder(1), synth.synthetic_decoder(0)
+    imgs = batch["images"][0, :3]
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        feats = EO.encode_views(enc_sd, imgs)
+        t_enc = time.perf_counter() - t0
+        fl = RO.to_channels_last([f[None] for f in feats])
+        img_l = imgs.permute(0, 2, 3, 1).contiguous()
+        extr, intr, nf = batch["extrinsics"], batch["intrinsics"], batch["near_fars"]
+        n_sample = args.ref_rays
+
+        def step(i):
+            first = (i * 7919 * 640) % (H_IMG * W_IMG - n_sample)
+            idx = torch.arange(first, first + n_sample)
+            RO.render_rays(dec_sd, fl, img_l, extr[0, :3, :3], intr[0, :3], nf[0, :3], extr[0, 3, :3], intr[0, 3], nf[0, 3], idx, S)
+
+        for i in range(args.warmup):
+            step(i)
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            step(args.warmup + i)
+        t_s = (time.perf_counter() - t0) / args.steps
+    hw = H_IMG * W_IMG
+    t_img = t_enc + t_s * hw / n_sample
+    value = hw / t_img
+    sample = (f"{n_sample} contiguous rays x {S} samples per step on the CPU oracle port (fp32 torch, {torch.get_num_threads()} threads); "
+              f"encoder timed once ({t_enc:.2f} s) and amortised over the {hw}-ray image")
+    line = dict(impl="reference", metric="rays/sec (DTU 3-view 512x640, %d depth samples, encoder + render)" % S, value=value,
+                unit="rays/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=t_s * 1e3,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=f"DTU 3-view 512x640 full-image forward, S={S}, random-init weights", views=3, samples=S,
+                            image=[H_IMG, W_IMG]),
+                cpu_baseline=dict(value=value, unit="rays/s", cores=torch.get_num_threads(), kind="port", sample=sample),
+                e2e=dict(value=value, unit="rays/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+# ================================================================================================ our arm
+def run_ours(args):
+    import torch.distributed as dist
+
+    from matchnerf_b200 import capi
+    from matchnerf_b200.matchnerf import MatchNeRF
+    from matchnerf_b200.sharding import gather_tiles
+    from matchnerf_b200.utils import AttrDict
+    from oracle import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    S = args.samples
+    opt = make_opts(S, str(dev))
+    model = MatchNeRF(opt).eval()
+    model.feat_enc.load_state_dict(synth.synthetic_encoder(1))
+    model.nerf_dec.load_state_dict(synth.synthetic_decoder(0))
+    model.to(dev)
+    ctx = capi.get_context(dev)
+    hw = H_IMG * W_IMG
+
+    host = synthetic_batch(100 + rank)                      # each rank renders its own target view (image-parallel round)
+    host = {k: v.pin_memory() for k, v in host.items()}
+    resident = {k: v.to(dev) for k, v in host.items()}
+    out_host = torch.empty((hw, 5), dtype=torch.float32).pin_memory()
+    counts = [hw] * world
+
+    def step_resident():
+        with torch.no_grad():
+            out = model(AttrDict(resident), mode="test")
+            tile = torch.cat([out.rgb[0], out.depth[0], out.opacity[0]], dim=1)
+            if world > 1:
+                tile = gather_tiles(tile, counts)            # the single NCCL all-gather of rendered tiles
+        return tile
+
+    def step_e2e():
+        with torch.no_grad():
+            b = AttrDict({k: v.to(dev, non_blocking=True) for k, v in host.items()})
+            out = model(b, mode="test")
+            tile = torch.cat([out.rgb[0], out.depth[0], out.opacity[0]], dim=1)
+            out_host.copy_(tile, non_blocking=True)
+            if world > 1:
+                gather_tiles(tile, counts)
+        return tile
+
+    def timed(fn, steps, warmup, sample_clocks=False):
+        for _ in range(warmup):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        clocks = sampler.stop() if sampler else None
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps, clocks
+
+    ms_step, clocks = timed(step_resident, args.steps, max(args.warmup, 3), sample_clocks=True)
+    ms_e2e, _ = timed(step_e2e, args.steps, 1)
+    value = world * hw / (ms_step * 1e-3)
+    e2e_value = world * hw / (ms_e2e * 1e-3)
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = out_host.numel() * out_host.element_size()
+
+    # ---- per-kernel timing (CUDA events on the launching stream) for the roofline of the dominant kernel
+    roofline, kernels, launches = None, {}, None
+    if rank == 0:
+        pk = peaks()
+        with torch.no_grad():
+            b = AttrDict(resident)
+            feats = model.get_img_feat(b["images"][:, :3])
+            tgt, ref = model.extract_poses(b)
+            scene = model._packed_scenes(ref, b["images"][:, :3], feats)[0]
+            sc = scene.c_scene(tgt["extrinsics"][0], tgt["intrinsics"][0], tgt["near_fars"][0])
+            cfg = model.nerf_dec.decoder_cfg(opt)
+            chunk = model.render_chunk
+            impl = 2 if _tc_decoder_ok(ctx, sc, cfg) else 1
+
+            def k_gather():
+                return ctx.gather_cossim(sc, S, first_ray=0, n_rays=chunk, want_f32=(impl == 1), want_f16=(impl == 2))
+
+            c32, c16 = k_gather()
+
+            def k_decoder():
+                return ctx.decoder_composite(sc, cfg, cond_f32=c32, cond_f16=c16, first_ray=0, n_rays=chunk, impl=impl)
+
+            def k_encoder():
+                return model.get_img_feat(b["images"][:, :3])
+
+            def ev_time(fn, reps=5):
+                fn()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / reps
+
+            t_g, t_d, t_e = ev_time(k_gather), ev_time(k_decoder), ev_time(k_encoder, 3)
+        n_chunks = (hw + chunk - 1) // chunk
+        n_samp = chunk * S
+        gather_gbs = n_samp * GATHER_BYTES_PER_SAMPLE / (t_g * 1e-3) / 1e9
+        dec_tfs = n_samp * FLOP_PER_SAMPLE.get(S, 262432) / (t_d * 1e-3) / 1e12
+        kernels = dict(
+            gather_cossim=dict(ms_per_launch=t_g, rays_per_launch=chunk, launches_per_step=n_chunks, algorithmic_GBps=gather_gbs,
+                               frac_of_hbm_peak=gather_gbs / pk["hbm"]),
+            decoder_composite=dict(ms_per_launch=t_d, rays_per_launch=chunk, launches_per_step=n_chunks, impl=("tcgen05" if impl == 2 else "fp32"),
+                                   algorithmic_TFLOPs=dec_tfs, frac_of_tensor_peak=dec_tfs / pk["tensor"]),
+            encoder=dict(ms_per_call=t_e, note="torch conv/linear + 12 K-attn launches"))
+        if t_g * n_chunks >= t_d * n_chunks:
+            roofline = dict(kernel="gather_cossim_kernel", bound="hbm", achieved=gather_gbs, peak=pk["hbm"], unit="GB/s",
+                            frac=gather_gbs / pk["hbm"], traffic=None, peak_source=pk["source"])
+        else:
+            roofline = dict(kernel="decoder_%s_kernel" % ("tc" if impl == 2 else "ref"), bound="tensor", achieved=dec_tfs, peak=pk["tensor"],
+                            unit="TFLOP/s", frac=dec_tfs / pk["tensor"], traffic=None, peak_source=pk["source"])
+        launches = args.steps * (n_chunks * 2 + 12 + 3)      # per step: gather+decoder per chunk, 12 K-attn, 3 pack kernels
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = cpu_baseline_sample(S)
+
+    if rank == 0:
+        line = dict(metric="rays/sec (DTU 3-view 512x640, %d depth samples, encoder + render)" % S, value=value, unit="rays/s",
+                    n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_step, higher_is_better=True,
+                    scaling="weak", vs_baseline=None, dtype="f16 operands / f32 accumulate (decoder), f16 feature maps, f32 elsewhere",
+                    data="synthetic",
+                    config=dict(workload=f"DTU 3-view 512x640 full-image forward (BASELINE configs[1]), S={S}, random-init weights, "
+                                         "one target view per rank",
+                                views=3, samples=S, image=[H_IMG, W_IMG], rays_per_step=world * hw,
+                                parallelism=("single GPU" if world == 1 else f"image-parallel x{world} + 1 NCCL all-gather of rendered tiles"),
+                                l2="per-step working set (conditioning workspace %.1f GB, activations) exceeds the 126 MB L2; no explicit flush"
+                                   % (hw * S * 64 / 1e9)),
+                    clocks=clocks,
+                    e2e=dict(value=e2e_value, unit="rays/s", ms_per_step=ms_e2e, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
+                    gpu_launches=launches, roofline=roofline, kernels=kernels, cpu_baseline=cpu_baseline)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _tc_decoder_ok(ctx, sc, cfg) -> bool:
+    try:
+        c16 = torch.zeros((cfg.n_samples, 32), dtype=torch.float16, device=ctx.device)
+        ctx.decoder_composite(sc, cfg, cond_f16=c16, first_ray=0, n_rays=1, impl=2)
+        torch.cuda.synchronize()
+        return True
+    except RuntimeError:
+        return False
+
+
+def cpu_baseline_sample(S: int, n_rays: int = 2048):
+    """The oracle port timed on this box's host cores on a bounded sample of the same workload."""
+    from oracle import render_oracle as RO
+    from oracle import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    feats, imgs, _ = synth.synthetic_scene(H_IMG, W_IMG, seed=1234)
+    extr, intr, nf = synth.synthetic_cameras(H_IMG, W_IMG)
+    dec = synth.synthetic_decoder(0)
+    fl = RO.to_channels_last(feats)
+    il = imgs[0].permute(0, 2, 3, 1).contiguous()
+    idx = torch.arange(200 * W_IMG, 200 * W_IMG + n_rays)
+    with torch.no_grad():
+        RO.render_rays(dec, fl, il, extr[0, :3, :3], intr[0, :3], nf[0, :3], extr[0, 3, :3], intr[0, 3], nf[0, 3], idx[:256], S)
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            RO.render_rays(dec, fl, il, extr[0, :3, :3], intr[0, :3], nf[0, :3], extr[0, 3, :3], intr[0, 3], nf[0, 3], idx, S)
+        dt = (time.perf_counter() - t0) / reps
+    return dict(value=n_rays / dt, unit="rays/s", cores=torch.get_num_threads(), kind="port",
+                sample=f"render only: {n_rays} contiguous rays x {S} samples x 3 views, random feature maps, oracle port (fp32 torch CPU), "
+                       f"{reps} reps after warm-up")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--samples", type=int, default=64)
+    ap.add_argument("--ref-rays", type=int, default=2048)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,168 @@
+/*
+ * matchnerf_b200.h -- C ABI of the B200-native MatchNeRF per-ray hot path.
+ *
+ * The reference (donydchen/matchnerf) is pure Python/PyTorch and has NO FFI of its own;
+ * this header is the new seam placed directly under the Python methods that make up its hot
+ * path.  Each entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - All data pointers are DEVICE pointers unless the name ends in _host.  The caller owns
+ *     every buffer (inputs, outputs, workspaces); nothing on the per-ray path allocates,
+ *     synchronises the host, or throws.  Work is enqueued on `stream` (a cudaStream_t passed
+ *     as void*; NULL = legacy default stream).
+ *   - Every function returns 0 on success and a negative mnf_status on failure;
+ *     mnf_last_error() returns a thread-local, human-readable reason.
+ *   - A mnf_ctx is bound to one (process, device) pair and holds the packed decoder
+ *     weights.  It is re-entrant across streams once loaded.
+ *   - Shapes: V source views (must be 3), S samples per ray, R rays, N = R*S samples
+ *     stored ray-major.  The decoder architecture is the one every shipped reference config
+ *     uses (configs/base.yaml:29-39): width 128, depth 6, skip [4], L_3D 10, L_view 0,
+ *     cos_n_group [2, 8]; other values are rejected with MNF_EUNSUPPORTED.
+ */
+#ifndef MATCHNERF_B200_H_
+#define MATCHNERF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MNF_ABI_VERSION 1
+
+typedef enum mnf_status {
+  MNF_OK = 0,
+  MNF_EINVAL = -1,       /* bad argument (null pointer, size mismatch, misaligned buffer) */
+  MNF_EUNSUPPORTED = -2, /* configuration outside the supported architecture */
+  MNF_ECUDA = -3,        /* CUDA runtime error; see mnf_last_error() */
+  MNF_ESTATE = -4,       /* e.g. decoder weights not loaded */
+  MNF_ENOMEM = -5        /* caller workspace too small */
+} mnf_status;
+
+typedef struct mnf_ctx mnf_ctx;
+
+/* Number of conditioning channels per sample: sum(cos_n_group)=10 + 3 views * RGB = 9 + 3 masks.
+ * (models/rfdecoder/cond_nerf.py:18, :59) */
+#define MNF_COND_DIM 22
+/* cond rows are also produced as fp16 padded to 32 columns: the K extent of the gate MMA. */
+#define MNF_COND_PAD 32
+/* channels per source view per scale (two 128-channel halves, models/matchnerf.py:192-205) */
+#define MNF_FEAT_CH 256
+
+/* Decoder options that vary between the shipped configs (configs/*.yaml `decoder:` / `nerf:`). */
+typedef struct mnf_decoder_cfg {
+  int32_t n_samples;        /* nerf.sample_intvs (S); 2..256 */
+  int32_t raytrans_act;     /* decoder.raytrans_act: 0 = ReLU, 1 = ELU */
+  int32_t raytrans_posenc;  /* decoder.raytrans_posenc: add the sinusoid table to raw_alpha */
+  int32_t density_maskfill; /* decoder.density_maskfill: sigma = 0 where no view sees the sample */
+} mnf_decoder_cfg;
+
+/* One encoded scene: 3 source views, their packed feature maps and cameras, plus the target camera.
+ * Cameras are plain host values inside the struct (it is passed by pointer and read on the host). */
+typedef struct mnf_scene {
+  int32_t n_views;          /* must be 3 */
+  int32_t H, W;             /* full-resolution size of source images and target view */
+  int32_t h0, w0;           /* coarse feature map size (1/8 scale in the shipped configs) */
+  int32_t h1, w1;           /* fine feature map size (1/4 scale) */
+  const void* feat0;        /* device, packed by mnf_pack_features: [V][h0][w0][256] fp16 */
+  const void* feat1;        /* device, packed by mnf_pack_features: [V][h1][w1][256] fp16 */
+  const void* images;       /* device, packed by mnf_pack_images:   [V][H][W][4]   fp32 (RGB + pad) */
+  float src_w2c[3][12];     /* world->camera [3x4] row-major per source view (batch.extrinsics[:, :3, :3, :]) */
+  float src_K[3][9];        /* intrinsics per source view */
+  float src_near_far[3][2];
+  float tgt_c2w[12];        /* camera->world [3x4] of the target = float64 inverse of its w2c (misc/camera.py:231-240) */
+  float tgt_Kinv[9];        /* inverse target intrinsics (misc/camera.py:221) */
+  float tgt_near_far[2];
+} mnf_scene;
+
+/* Which rays to render: either an explicit pixel-id list or a contiguous row-major range. */
+typedef struct mnf_rays {
+  int64_t n_rays;           /* R */
+  const int64_t* ray_idx;   /* device [R] pixel ids (y*W + x), or NULL to use first_ray + i */
+  int64_t first_ray;        /* used when ray_idx == NULL (render_by_slices: models/matchnerf.py:153) */
+  const float* jitter;      /* device [R][S] stratified offsets u in [0,1) (train mode), or NULL (models/matchnerf.py:168-172) */
+} mnf_rays;
+
+/* ---- library / context ------------------------------------------------------------------ */
+int32_t mnf_abi_version(void);
+const char* mnf_last_error(void);
+int32_t mnf_ctx_create(int32_t device, mnf_ctx** out);
+int32_t mnf_ctx_destroy(mnf_ctx* ctx);
+
+/* Load the `nerf_dec` parameters (reference state_dict order, fp32, contiguous, HOST memory):
+ *   pts_linears.{0..5}.{weight,bias}, pts_bias.{weight,bias}, views_linears.0.{weight,bias},
+ *   alpha_linear.0.{weight,bias}, ray_attention.{w_qs,w_ks,w_vs,fc}.weight,
+ *   ray_attention.layer_norm.{weight,bias}, out_alpha_linear.{0,2}.{weight,bias},
+ *   feature_linear.{weight,bias}, rgb_linear.{weight,bias}            (130,324 floats)
+ * Replaces: CondNeRF.define_network / load_state_dict (models/rfdecoder/cond_nerf.py:15-50).
+ * Not a hot-path call: allocates device buffers inside the ctx and synchronises. */
+int32_t mnf_decoder_load_host(mnf_ctx* ctx, const float* params_host, int64_t n_floats);
+/* Number of floats mnf_decoder_load_host expects. */
+int64_t mnf_decoder_param_count(void);
+
+/* ---- layout packing (once per encoded scene) -------------------------------------------- */
+/* fp32 NCHW feature maps [V][256][h][w] (the layout get_img_feat returns, models/matchnerf.py:183-207)
+ * -> fp16 channels-last [V][h][w][256] with the two 128-channel halves interleaved in groups of 4
+ * (see DESIGN.md "feature map layout").  out must hold V*h*w*256 halves. */
+int32_t mnf_pack_features(mnf_ctx* ctx, const float* feat_nchw, int32_t V, int32_t h, int32_t w,
+                          void* out_packed, void* stream);
+/* fp32 [V][3][H][W] images in [0,1] -> fp32 [V][H][W][4].  out must hold V*H*W*4 floats. */
+int32_t mnf_pack_images(mnf_ctx* ctx, const float* images_nchw, int32_t V, int32_t H, int32_t W,
+                        void* out_packed, void* stream);
+
+/* ---- K-gather: epipolar projection + bilinear gather + grouped cosine similarity ---------- */
+/* Replaces MatchNeRF.query_cond_info (models/matchnerf.py:209-293) incl. camera.get_coord_ref_ndc
+ * (misc/camera.py:351-379), sample_depth (:163-181) and ray casting (misc/camera.py:255-286) for
+ * the requested rays.  Writes, for each of the N = R*S samples, the 22 conditioning values in the
+ * order CondNeRF.forward concatenates them (feat_info[10], color_info[9], mask_info[3]).
+ *   cond_f32: [N][22] fp32 or NULL;  cond_f16: [N][32] fp16 (cols 22..31 zero) or NULL. */
+int32_t mnf_gather_cossim_fwd(mnf_ctx* ctx, const mnf_scene* scene, const mnf_rays* rays, int32_t n_samples,
+                              float* cond_f32, void* cond_f16, void* stream);
+
+/* ---- K-mlp-composite: conditional MLP + ray transformer + alpha compositing -------------- */
+/* Replaces CondNeRF.forward (models/rfdecoder/cond_nerf.py:52-100), MultiHeadAttention.forward
+ * (models/rfdecoder/ray_transformer.py:49-79), NeRF.composite (models/rfdecoder/nerf.py:101-124) and
+ * the view-0 NDC / ray-direction preparation in MatchNeRF.render (models/matchnerf.py:120-134).
+ *   cond_f16 [N][32] fp16 as written by mnf_gather_cossim_fwd (used by the tensor-core kernel),
+ *   cond_f32 [N][22] fp32 (used by the fp32 kernel); pass whichever the chosen impl needs (or both).
+ *   out_rgb [R][3], out_depth [R], out_opacity [R] fp32.
+ *   aux_rgb_sigma: optional [N][4] fp32 per-sample (r,g,b,sigma) for tests, or NULL.
+ *   impl: 0 = auto (tensor-core kernel when the config allows), 1 = fp32 CUDA-core kernel,
+ *         2 = tcgen05 kernel (error if unsupported for this config). */
+int32_t mnf_decoder_composite_fwd(mnf_ctx* ctx, const mnf_scene* scene, const mnf_rays* rays,
+                                  const mnf_decoder_cfg* cfg, const float* cond_f32, const void* cond_f16,
+                                  int32_t setbg_opaque, float* out_rgb, float* out_depth, float* out_opacity,
+                                  float* aux_rgb_sigma, int32_t impl, void* stream);
+
+/* ---- fused per-slice render: MatchNeRF.render (models/matchnerf.py:88-143) ---------------- */
+/* Bytes of caller-provided workspace mnf_render_rays_fwd needs for R rays of S samples. */
+int64_t mnf_render_workspace_bytes(int64_t n_rays, int32_t n_samples);
+int32_t mnf_render_rays_fwd(mnf_ctx* ctx, const mnf_scene* scene, const mnf_rays* rays,
+                            const mnf_decoder_cfg* cfg, int32_t setbg_opaque,
+                            float* out_rgb, float* out_depth, float* out_opacity,
+                            void* workspace, int64_t workspace_bytes, int32_t impl, void* stream);
+
+/* ---- K-attn: GMFlow split-window single-head attention ----------------------------------- */
+/* Replaces single_head_split_window_attention / single_head_full_attention
+ * (models/gmflow/transformer.py:46-105 / :8-16) including the roll, the window partition and the
+ * shifted-window mask (:19-43), none of which are materialised.
+ *   q, k, v, out: [B][h*w][128] fp32, token order row-major over (h, w).
+ *   num_splits: windows per axis (1 = full attention); with_shift: Swin shift of half a window.
+ *   impl: 0 = auto, 1 = fp32 CUDA-core kernel, 2 = tcgen05 kernel. */
+int32_t mnf_window_attn_fwd(mnf_ctx* ctx, const float* q, const float* k, const float* v, float* out,
+                            int32_t B, int32_t h, int32_t w, int32_t C, int32_t num_splits, int32_t with_shift,
+                            int32_t impl, void* stream);
+
+/* ---- self tests of the tcgen05 building blocks (used by tests/ on the GPU box) ------------- */
+/* D[128][N] = A[128][K] * B[N][K]^T with fp16 operands, fp32 accumulate, one CTA.
+ * mode 0: A and B from shared memory (SWIZZLE_128B K-major descriptors);
+ * mode 1: A staged in tensor memory (tcgen05.st), B from shared memory.
+ * a_f16 [128][K], b_f16 [N][K] device fp16; d_f32 [128][N] device fp32.  K % 64 == 0, N % 16 == 0, N <= 256. */
+int32_t mnf_selftest_umma(const void* a_f16, const void* b_f16, float* d_f32, int32_t N, int32_t K,
+                          int32_t mode, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MATCHNERF_B200_H_ */

@@ -1,0 +1,15 @@
+"""matchnerf_b200: B200-native (sm_100a) implementation of MatchNeRF's per-ray hot path.
+
+The product is ``libmatchnerf_b200.so`` (hand-written CUDA behind the C ABI in ``include/matchnerf_b200.h``);
+this package is the Python host side mirroring the reference's model interface.
+"""
+from .utils import AttrDict  # noqa: F401
+
+__all__ = ["AttrDict", "models_dict", "MatchNeRF"]
+
+
+def __getattr__(name):
+    if name in ("models_dict", "MatchNeRF"):
+        from . import matchnerf as _m
+        return getattr(_m, name)
+    raise AttributeError(name)

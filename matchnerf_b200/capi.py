@@ -1,0 +1,304 @@
+"""ctypes binding of libmatchnerf_b200.so (the C ABI in include/matchnerf_b200.h).
+
+PyTorch is used here only as the owner of device memory and streams: every call passes raw device
+pointers plus the current CUDA stream.  There is no fallback: if the shared library is missing or a
+call fails, a ``RuntimeError`` carrying ``mnf_last_error()`` is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmatchnerf_b200.so")
+
+COND_DIM = 22
+COND_PAD = 32
+FEAT_CH = 256
+
+# reference ``nerf_dec`` state_dict order (models/rfdecoder/cond_nerf.py:15-50); must match csrc/decoder_weights.cuh
+DECODER_PARAM_ORDER = (
+    [f"pts_linears.{i}.{n}" for i in range(6) for n in ("weight", "bias")]
+    + ["pts_bias.weight", "pts_bias.bias", "views_linears.0.weight", "views_linears.0.bias",
+       "alpha_linear.0.weight", "alpha_linear.0.bias",
+       "ray_attention.w_qs.weight", "ray_attention.w_ks.weight", "ray_attention.w_vs.weight", "ray_attention.fc.weight",
+       "ray_attention.layer_norm.weight", "ray_attention.layer_norm.bias",
+       "out_alpha_linear.0.weight", "out_alpha_linear.0.bias", "out_alpha_linear.2.weight", "out_alpha_linear.2.bias",
+       "feature_linear.weight", "feature_linear.bias", "rgb_linear.weight", "rgb_linear.bias"]
+)
+
+
+class DecoderCfg(C.Structure):
+    _fields_ = [("n_samples", C.c_int32), ("raytrans_act", C.c_int32), ("raytrans_posenc", C.c_int32),
+                ("density_maskfill", C.c_int32)]
+
+
+class Scene(C.Structure):
+    _fields_ = [("n_views", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("h0", C.c_int32), ("w0", C.c_int32), ("h1", C.c_int32), ("w1", C.c_int32),
+                ("feat0", C.c_void_p), ("feat1", C.c_void_p), ("images", C.c_void_p),
+                ("src_w2c", (C.c_float * 12) * 3), ("src_K", (C.c_float * 9) * 3), ("src_near_far", (C.c_float * 2) * 3),
+                ("tgt_c2w", C.c_float * 12), ("tgt_Kinv", C.c_float * 9), ("tgt_near_far", C.c_float * 2)]
+
+
+class Rays(C.Structure):
+    _fields_ = [("n_rays", C.c_int64), ("ray_idx", C.c_void_p), ("first_ray", C.c_int64), ("jitter", C.c_void_p)]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (built by ``matchnerf_b200.build``); fail loudly if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m matchnerf_b200.build` "
+                           "(there is no CPU or PyTorch fallback for the hot path)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, fp = C.c_void_p, C.c_int32, C.c_int64, C.c_void_p
+    lib.mnf_abi_version.restype = i32
+    lib.mnf_last_error.restype = C.c_char_p
+    lib.mnf_decoder_param_count.restype = i64
+    lib.mnf_ctx_create.argtypes = [i32, C.POINTER(vp)]
+    lib.mnf_ctx_destroy.argtypes = [vp]
+    lib.mnf_decoder_load_host.argtypes = [vp, fp, i64]
+    lib.mnf_pack_features.argtypes = [vp, fp, i32, i32, i32, vp, vp]
+    lib.mnf_pack_images.argtypes = [vp, fp, i32, i32, i32, vp, vp]
+    lib.mnf_gather_cossim_fwd.argtypes = [vp, C.POINTER(Scene), C.POINTER(Rays), i32, fp, vp, vp]
+    lib.mnf_decoder_composite_fwd.argtypes = [vp, C.POINTER(Scene), C.POINTER(Rays), C.POINTER(DecoderCfg), fp, vp, i32,
+                                              fp, fp, fp, fp, i32, vp]
+    lib.mnf_render_workspace_bytes.argtypes = [i64, i32]
+    lib.mnf_render_workspace_bytes.restype = i64
+    lib.mnf_render_rays_fwd.argtypes = [vp, C.POINTER(Scene), C.POINTER(Rays), C.POINTER(DecoderCfg), i32, fp, fp, fp,
+                                        vp, i64, i32, vp]
+    lib.mnf_window_attn_fwd.argtypes = [vp, fp, fp, fp, fp, i32, i32, i32, i32, i32, i32, i32, vp]
+    lib.mnf_selftest_umma.argtypes = [vp, vp, fp, i32, i32, i32, vp]
+    for name in ("mnf_ctx_create", "mnf_ctx_destroy", "mnf_decoder_load_host", "mnf_pack_features", "mnf_pack_images",
+                 "mnf_gather_cossim_fwd", "mnf_decoder_composite_fwd", "mnf_render_rays_fwd", "mnf_window_attn_fwd",
+                 "mnf_selftest_umma"):
+        getattr(lib, name).restype = i32
+    if lib.mnf_abi_version() != 1:
+        raise RuntimeError(f"libmatchnerf_b200.so ABI {lib.mnf_abi_version()} != 1")
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().mnf_last_error().decode(errors="replace")
+        raise RuntimeError(f"{what} failed with status {rc}: {msg}")
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _dev_f32(t: torch.Tensor, device: torch.device, name: str) -> torch.Tensor:
+    if t.device != device:
+        raise ValueError(f"{name} is on {t.device}, the context is bound to {device}")
+    if t.dtype != torch.float32:
+        raise ValueError(f"{name} must be float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def flatten_decoder_state(sd: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """``nerf_dec`` state_dict -> the flat fp32 host blob mnf_decoder_load_host expects."""
+    missing = [k for k in DECODER_PARAM_ORDER if k not in sd]
+    if missing:
+        raise KeyError(f"decoder state_dict lacks {missing}")
+    return torch.cat([sd[k].detach().to("cpu", torch.float32).reshape(-1) for k in DECODER_PARAM_ORDER]).contiguous()
+
+
+class PackedScene:
+    """Device-resident packed feature maps / images of one encoded source-view triplet plus its cameras."""
+
+    def __init__(self, feat0, feat1, images, H, W, h0, w0, h1, w1, src_w2c, src_K, src_nf):
+        self.feat0, self.feat1, self.images = feat0, feat1, images
+        self.H, self.W, self.h0, self.w0, self.h1, self.w1 = H, W, h0, w0, h1, w1
+        self.src_w2c, self.src_K, self.src_nf = src_w2c, src_K, src_nf   # CPU float32 [3,3,4], [3,3,3], [3,2]
+
+    def c_scene(self, tgt_w2c: torch.Tensor, tgt_K: torch.Tensor, tgt_nf: torch.Tensor) -> Scene:
+        """Fill the C struct for one target camera (w2c [3,4], K [3,3], near_far [2]; any device)."""
+        sc = Scene()
+        sc.n_views, sc.H, sc.W = 3, self.H, self.W
+        sc.h0, sc.w0, sc.h1, sc.w1 = self.h0, self.w0, self.h1, self.w1
+        sc.feat0, sc.feat1, sc.images = self.feat0.data_ptr(), self.feat1.data_ptr(), self.images.data_ptr()
+        w2c, K, nf = self.src_w2c.tolist(), self.src_K.tolist(), self.src_nf.tolist()
+        for v in range(3):
+            sc.src_w2c[v][:] = [x for row in w2c[v] for x in row]
+            sc.src_K[v][:] = [x for row in K[v] for x in row]
+            sc.src_near_far[v][:] = nf[v]
+        # float64 inverse of the target pose, cast to fp32 (misc/camera.py:231-240); fp32 inverse of K (camera.py:221)
+        sq = torch.eye(4, dtype=torch.float64)
+        sq[:3, :] = tgt_w2c.detach().to("cpu", torch.float64)
+        c2w = torch.linalg.inv(sq)[:3, :].to(torch.float32)
+        kinv = torch.linalg.inv(tgt_K.detach().to("cpu", torch.float32))
+        sc.tgt_c2w[:] = c2w.reshape(-1).tolist()
+        sc.tgt_Kinv[:] = kinv.reshape(-1).tolist()
+        sc.tgt_near_far[:] = tgt_nf.detach().to("cpu", torch.float32).tolist()
+        return sc
+
+
+class Context:
+    """One mnf_ctx: bound to a CUDA device, owns the packed decoder weights."""
+
+    def __init__(self, device=None):
+        self.lib = load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("matchnerf_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        h = C.c_void_p()
+        _check(self.lib.mnf_ctx_create(self.device.index, C.byref(h)), "mnf_ctx_create")
+        self._h = h
+        self.decoder_loaded = False
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.mnf_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- weights
+    def load_decoder(self, state_dict: Dict[str, torch.Tensor]) -> None:
+        blob = flatten_decoder_state(state_dict)
+        if blob.numel() != self.lib.mnf_decoder_param_count():
+            raise ValueError(f"decoder has {blob.numel()} parameters, library expects {self.lib.mnf_decoder_param_count()}")
+        with torch.cuda.device(self.device):
+            _check(self.lib.mnf_decoder_load_host(self._h, blob.data_ptr(), blob.numel()), "mnf_decoder_load_host")
+        self.decoder_loaded = True
+
+    # ---- packing
+    def pack_scene(self, feats: Sequence[torch.Tensor], images: torch.Tensor, src_w2c: torch.Tensor, src_K: torch.Tensor,
+                   src_nf: torch.Tensor) -> PackedScene:
+        """feats: [feat_coarse [V,256,h0,w0], feat_fine [V,256,h1,w1]] fp32 NCHW on device (get_img_feat layout
+        without the batch dim); images [V,3,H,W] fp32 in [0,1]; cameras [V,3,4], [V,3,3], [V,2]."""
+        f0 = _dev_f32(feats[0], self.device, "feat0")
+        f1 = _dev_f32(feats[1], self.device, "feat1")
+        im = _dev_f32(images, self.device, "images")
+        V, ch, h0, w0 = f0.shape
+        _, _, h1, w1 = f1.shape
+        _, _, H, W = im.shape
+        if V != 3 or ch != FEAT_CH or f1.shape[1] != FEAT_CH or im.shape[1] != 3:
+            raise ValueError("expected 3 views x 256 channels feature maps and RGB images")
+        p0 = torch.empty((V, h0, w0, FEAT_CH), dtype=torch.float16, device=self.device)
+        p1 = torch.empty((V, h1, w1, FEAT_CH), dtype=torch.float16, device=self.device)
+        pi = torch.empty((V, H, W, 4), dtype=torch.float32, device=self.device)
+        st = _stream(self.device)
+        _check(self.lib.mnf_pack_features(self._h, f0.data_ptr(), V, h0, w0, p0.data_ptr(), st), "mnf_pack_features")
+        _check(self.lib.mnf_pack_features(self._h, f1.data_ptr(), V, h1, w1, p1.data_ptr(), st), "mnf_pack_features")
+        _check(self.lib.mnf_pack_images(self._h, im.data_ptr(), V, H, W, pi.data_ptr(), st), "mnf_pack_images")
+        return PackedScene(p0, p1, pi, H, W, h0, w0, h1, w1,
+                           src_w2c.detach().to("cpu", torch.float32)[:, :3, :4].contiguous(),
+                           src_K.detach().to("cpu", torch.float32).contiguous(),
+                           src_nf.detach().to("cpu", torch.float32).contiguous())
+
+    # ---- rays helper
+    def _rays(self, n_rays: int, ray_idx: Optional[torch.Tensor], first_ray: int, jitter: Optional[torch.Tensor], S: int):
+        r = Rays()
+        keep = []
+        if ray_idx is not None:
+            ri = ray_idx.to(self.device, torch.int64).contiguous()
+            keep.append(ri)
+            n_rays = ri.numel()
+            r.ray_idx = ri.data_ptr()
+        else:
+            r.ray_idx = None
+        if jitter is not None:
+            jt = _dev_f32(jitter, self.device, "jitter").reshape(n_rays, S)
+            keep.append(jt)
+            r.jitter = jt.data_ptr()
+        else:
+            r.jitter = None
+        r.n_rays, r.first_ray = n_rays, first_ray
+        return r, n_rays, keep
+
+    # ---- kernels
+    def gather_cossim(self, scene: Scene, S: int, ray_idx=None, first_ray=0, n_rays=0, jitter=None, want_f32=True,
+                      want_f16=False):
+        rays, R, keep = self._rays(n_rays, ray_idx, first_ray, jitter, S)
+        c32 = torch.empty((R * S, COND_DIM), dtype=torch.float32, device=self.device) if want_f32 else None
+        c16 = torch.empty((R * S, COND_PAD), dtype=torch.float16, device=self.device) if want_f16 else None
+        _check(self.lib.mnf_gather_cossim_fwd(self._h, C.byref(scene), C.byref(rays), S, _ptr(c32), _ptr(c16),
+                                              _stream(self.device)), "mnf_gather_cossim_fwd")
+        return c32, c16
+
+    def decoder_composite(self, scene: Scene, cfg: DecoderCfg, cond_f32=None, cond_f16=None, ray_idx=None, first_ray=0,
+                          n_rays=0, jitter=None, setbg_opaque=False, impl=0, want_aux=False):
+        S = cfg.n_samples
+        rays, R, keep = self._rays(n_rays, ray_idx, first_ray, jitter, S)
+        rgb = torch.empty((R, 3), dtype=torch.float32, device=self.device)
+        depth = torch.empty((R,), dtype=torch.float32, device=self.device)
+        opac = torch.empty((R,), dtype=torch.float32, device=self.device)
+        aux = torch.empty((R * S, 4), dtype=torch.float32, device=self.device) if want_aux else None
+        _check(self.lib.mnf_decoder_composite_fwd(self._h, C.byref(scene), C.byref(rays), C.byref(cfg), _ptr(cond_f32),
+                                                  _ptr(cond_f16), int(setbg_opaque), rgb.data_ptr(), depth.data_ptr(),
+                                                  opac.data_ptr(), _ptr(aux), impl, _stream(self.device)),
+               "mnf_decoder_composite_fwd")
+        return rgb, depth, opac, aux
+
+    def render_rays(self, scene: Scene, cfg: DecoderCfg, ray_idx=None, first_ray=0, n_rays=0, jitter=None,
+                    setbg_opaque=False, impl=0, out=None, workspace=None):
+        """MatchNeRF.render for one slice.  Returns (rgb [R,3], depth [R], opacity [R])."""
+        S = cfg.n_samples
+        rays, R, keep = self._rays(n_rays, ray_idx, first_ray, jitter, S)
+        if out is None:
+            out = (torch.empty((R, 3), dtype=torch.float32, device=self.device),
+                   torch.empty((R,), dtype=torch.float32, device=self.device),
+                   torch.empty((R,), dtype=torch.float32, device=self.device))
+        need = self.lib.mnf_render_workspace_bytes(R, S)
+        if workspace is None or workspace.numel() < need:
+            workspace = torch.empty((max(need, 256),), dtype=torch.uint8, device=self.device)
+        _check(self.lib.mnf_render_rays_fwd(self._h, C.byref(scene), C.byref(rays), C.byref(cfg), int(setbg_opaque),
+                                            out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), workspace.data_ptr(),
+                                            workspace.numel(), impl, _stream(self.device)), "mnf_render_rays_fwd")
+        return out
+
+    def window_attn(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, h: int, w: int, num_splits: int,
+                    with_shift: bool, impl: int = 0) -> torch.Tensor:
+        q = _dev_f32(q, self.device, "q")
+        k = _dev_f32(k, self.device, "k")
+        v = _dev_f32(v, self.device, "v")
+        B, L, Cc = q.shape
+        if L != h * w:
+            raise ValueError("q.shape[1] != h*w")
+        out = torch.empty_like(q)
+        _check(self.lib.mnf_window_attn_fwd(self._h, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, h, w, Cc,
+                                            num_splits, int(with_shift), impl, _stream(self.device)), "mnf_window_attn_fwd")
+        return out
+
+    def selftest_umma(self, a: torch.Tensor, b: torch.Tensor, mode: int) -> torch.Tensor:
+        a = a.to(self.device, torch.float16).contiguous()
+        b = b.to(self.device, torch.float16).contiguous()
+        assert a.shape[0] == 128 and a.shape[1] == b.shape[1]
+        d = torch.empty((128, b.shape[0]), dtype=torch.float32, device=self.device)
+        _check(self.lib.mnf_selftest_umma(a.data_ptr(), b.data_ptr(), d.data_ptr(), b.shape[0], a.shape[1], mode,
+                                          _stream(self.device)), "mnf_selftest_umma")
+        return d
+
+
+_contexts: Dict[int, Context] = {}
+
+
+def get_context(device=None) -> Context:
+    """Process-wide context per device."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if idx not in _contexts:
+        _contexts[idx] = Context(torch.device("cuda", idx))
+    return _contexts[idx]

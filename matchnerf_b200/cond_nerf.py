@@ -1,0 +1,108 @@
+"""Host-side mirror of the reference radiance-field decoder module (``models/rfdecoder/cond_nerf.py``).
+
+It is a parameter container with the reference's module tree / state_dict keys (so ``nerf_dec`` checkpoints
+load with ``strict=True``) plus the glue that hands the weights to the CUDA library.  The arithmetic lives
+in ``csrc/decoder_*.cu`` behind ``mnf_decoder_composite_fwd`` / ``mnf_render_rays_fwd``.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import capi
+from .utils import get_opt
+
+
+class _RayAttentionParams(nn.Module):
+    """Parameters of the 4-head ray transformer (models/rfdecoder/ray_transformer.py:29-47)."""
+
+    def __init__(self, n_head=4, d_model=16, d_k=4, d_v=4):
+        super().__init__()
+        self.w_qs = nn.Linear(d_model, n_head * d_k, bias=False)
+        self.w_ks = nn.Linear(d_model, n_head * d_k, bias=False)
+        self.w_vs = nn.Linear(d_model, n_head * d_v, bias=False)
+        self.fc = nn.Linear(n_head * d_v, d_model, bias=False)
+        self.layer_norm = nn.LayerNorm(d_model, eps=1e-6)
+
+
+class CondNeRF(nn.Module):
+    """Parameter tree of models/rfdecoder/cond_nerf.py:15-50 (view-dependent branch)."""
+
+    def __init__(self, opt):
+        super().__init__()
+        W = int(get_opt(opt, "decoder.net_width", 128))
+        D = int(get_opt(opt, "decoder.net_depth", 6))
+        skips = list(get_opt(opt, "decoder.skip", [4]))
+        L3 = int(get_opt(opt, "decoder.posenc.L_3D", 10))
+        Lv = int(get_opt(opt, "decoder.posenc.L_view", 0))
+        groups = get_opt(opt, "encoder.cos_n_group", [2, 8])
+        groups = [groups] if isinstance(groups, int) else list(groups)
+        n_views = int(get_opt(opt, "n_src_views", 3))
+        if (W, D, skips, L3, Lv, groups, n_views) != (128, 6, [4], 10, 0, [2, 8], 3) or not get_opt(opt, "nerf.view_dep", True):
+            raise NotImplementedError(
+                "matchnerf_b200 builds the decoder architecture every shipped reference config uses "
+                "(net_width 128, net_depth 6, skip [4], L_3D 10, L_view 0, cos_n_group [2, 8], 3 views, view_dep); "
+                f"got width={W} depth={D} skip={skips} L_3D={L3} L_view={Lv} groups={groups} views={n_views}")
+        in3d = 3 + 6 * L3
+        in_feat = sum(groups) + n_views * 4
+        act = getattr(nn, str(get_opt(opt, "decoder.raytrans_act", "ReLU")))
+        self.pts_linears = nn.ModuleList([nn.Linear(in3d, W)] + [nn.Linear(W + in3d if i in skips else W, W) for i in range(D - 1)])
+        self.pts_bias = nn.Linear(in_feat, W)
+        self.views_linears = nn.ModuleList([nn.Linear(3 + W, W // 2)])
+        self.alpha_linear = nn.Sequential(nn.Linear(W, 16), act())
+        self.ray_attention = _RayAttentionParams()
+        self.out_alpha_linear = nn.Sequential(nn.Linear(16, 16), act(), nn.Linear(16, 1), nn.ReLU())
+        self.feature_linear = nn.Linear(W, W)
+        self.rgb_linear = nn.Linear(W // 2, 3)
+        for grp in (self.pts_linears, self.views_linears, self.feature_linear, self.alpha_linear, self.rgb_linear):
+            for m in grp.modules():                       # cond_nerf.py:46-50, :102-106
+                if isinstance(m, nn.Linear):
+                    nn.init.kaiming_normal_(m.weight)
+                    nn.init.zeros_(m.bias)
+        self._loaded_version = None
+
+    # ---- weights -> library
+    def _version(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def sync_to_library(self, ctx: Optional["capi.Context"] = None) -> "capi.Context":
+        """(Re)upload the weights into the library context when they changed (load_state_dict, optimiser step)."""
+        dev = next(self.parameters()).device
+        ctx = ctx or capi.get_context(dev)
+        ver = self._version()
+        if self._loaded_version != (id(ctx), ver) or not ctx.decoder_loaded:
+            ctx.load_decoder(self.state_dict())
+            self._loaded_version = (id(ctx), ver)
+        return ctx
+
+    def decoder_cfg(self, opt) -> "capi.DecoderCfg":
+        cfg = capi.DecoderCfg()
+        cfg.n_samples = int(get_opt(opt, "nerf.sample_intvs", 128))
+        cfg.raytrans_act = {"ReLU": 0, "ELU": 1}[str(get_opt(opt, "decoder.raytrans_act", "ReLU"))]
+        cfg.raytrans_posenc = int(bool(get_opt(opt, "decoder.raytrans_posenc", False)))
+        cfg.density_maskfill = int(bool(get_opt(opt, "decoder.density_maskfill", False)))
+        return cfg
+
+    def forward(self, *args, **kwargs):
+        raise NotImplementedError(
+            "matchnerf_b200: the decoder runs fused with ray casting and compositing inside "
+            "MatchNeRF.render (mnf_render_rays_fwd); a standalone CondNeRF.forward on explicit sample tensors is not built")
+
+    @staticmethod
+    def composite(opt, ray, rgb_samples, density_samples, depth_samples, setbg_opaque):
+        """Alpha compositing on explicit sample tensors (models/rfdecoder/nerf.py:101-124).  Compatibility helper for
+        callers of the unfused API; MatchNeRF.render composites inside the CUDA kernel."""
+        if not get_opt(opt, "nerf.wo_render_interval", True):
+            raise NotImplementedError("only wo_render_interval=True (all shipped configs) is built")
+        sigma = density_samples
+        alpha = 1.0 - torch.exp(-sigma)
+        trans = torch.exp(-(torch.cumsum(sigma, dim=2) - sigma))
+        prob = (trans * alpha)[..., None]
+        depth = (depth_samples * prob).sum(dim=2)
+        rgb = (rgb_samples * prob).sum(dim=2)
+        opacity = prob.sum(dim=2)
+        if setbg_opaque:
+            rgb = rgb + (1.0 - opacity)
+        return rgb, depth, opacity, prob

@@ -1,0 +1,124 @@
+// Shared declarations for the matchnerf_b200 CUDA kernels (sm_100a only).
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/matchnerf_b200.h"
+
+namespace mnf {
+
+constexpr int kViews = 3;
+constexpr int kWidth = 128;       // decoder.net_width
+constexpr int kDepth = 6;         // decoder.net_depth
+constexpr int kSkip = 4;          // decoder.skip = [4]
+constexpr int kL3D = 10;          // decoder.posenc.L_3D
+constexpr int kEnc = 3 + 6 * kL3D;  // 63
+constexpr int kCond = MNF_COND_DIM; // 22
+constexpr int kCondPad = MNF_COND_PAD;
+constexpr int kFeatCh = MNF_FEAT_CH;
+constexpr int kG0 = 2;            // encoder.cos_n_group[0]
+constexpr int kG1 = 8;            // encoder.cos_n_group[1]
+constexpr int kMaxSamples = 256;
+
+// error plumbing (api.cu)
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+#define MNF_CUDA_TRY(expr)                                  \
+  do {                                                      \
+    cudaError_t _e = (expr);                                \
+    if (_e != cudaSuccess) return ::mnf::cuda_fail(_e, #expr); \
+  } while (0)
+
+// Camera block handed to kernels by value (constant bank): everything the per-ray geometry needs.
+struct DevCams {
+  float w2c[kViews][12];
+  float K[kViews][9];
+  float nf[kViews][2];
+  float inv_w1, inv_h1;      // unused placeholders kept for alignment
+  float c2w[12];             // target camera->world
+  float Kinv[9];             // target inverse intrinsics
+  float tnear, tfar;
+  int W, H;
+};
+
+struct DevRays {
+  const int64_t* ray_idx;
+  int64_t first_ray;
+  const float* jitter;
+  int64_t n_rays;
+};
+
+// ---- per-ray geometry ---------------------------------------------------------------------
+// misc/camera.py:255-278 (legacy): pixel centre at integer coords; ray = c2w*[K^-1 (x,y,1), 1] - centre.
+__device__ __forceinline__ void cast_ray(const DevCams& c, int64_t pix, float o[3], float d[3]) {
+  const float x = (float)(pix % c.W);
+  const float y = (float)(pix / c.W);
+  float cam[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    cam[i] = __fadd_rn(__fadd_rn(__fmul_rn(x, c.Kinv[i * 3 + 0]), __fmul_rn(y, c.Kinv[i * 3 + 1])), c.Kinv[i * 3 + 2]);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float t = c.c2w[i * 4 + 3];
+    float p = __fmul_rn(cam[0], c.c2w[i * 4 + 0]);
+    p = __fadd_rn(p, __fmul_rn(cam[1], c.c2w[i * 4 + 1]));
+    p = __fadd_rn(p, __fmul_rn(cam[2], c.c2w[i * 4 + 2]));
+    p = __fadd_rn(p, t);
+    o[i] = t;
+    d[i] = __fsub_rn(p, t);
+  }
+}
+
+// models/matchnerf.py:163-181 (legacy): t_i = near + (i + u)/(S-1) * (far - near)
+__device__ __forceinline__ float sample_depth(const DevCams& c, int i, int S, float u) {
+  return __fadd_rn(__fmul_rn(__fdiv_rn(__fadd_rn((float)i, u), (float)(S - 1)), __fsub_rn(c.tfar, c.tnear)), c.tnear);
+}
+
+// misc/camera.py:351-379: world point -> (u, v, z) normalised by (W-1, H-1, near..far) in source view v.
+__device__ __forceinline__ void project_ndc(const DevCams& c, int v, const float p[3], float& u, float& vv, float& z) {
+  const float* E = c.w2c[v];
+  const float* K = c.K[v];
+  float cam[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float a = __fmul_rn(p[0], E[i * 4 + 0]);
+    a = __fadd_rn(a, __fmul_rn(p[1], E[i * 4 + 1]));
+    a = __fadd_rn(a, __fmul_rn(p[2], E[i * 4 + 2]));
+    cam[i] = __fadd_rn(a, E[i * 4 + 3]);
+  }
+  float q[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float a = __fmul_rn(cam[0], K[i * 3 + 0]);
+    a = __fadd_rn(a, __fmul_rn(cam[1], K[i * 3 + 1]));
+    q[i] = __fadd_rn(a, __fmul_rn(cam[2], K[i * 3 + 2]));
+  }
+  u = __fdiv_rn(__fdiv_rn(q[0], q[2]), (float)(c.W - 1));
+  vv = __fdiv_rn(__fdiv_rn(q[1], q[2]), (float)(c.H - 1));
+  z = __fdiv_rn(__fsub_rn(q[2], c.nf[v][0]), __fsub_rn(c.nf[v][1], c.nf[v][0]));
+}
+
+// grid_sample(align_corners=True, padding_mode='border') coordinate: g = uv*2-1; i = ((g+1)/2)*(n-1), clipped.
+__device__ __forceinline__ float grid_unnormalize(float g, int n) {
+  float i = __fmul_rn(__fmul_rn(__fadd_rn(g, 1.0f), 0.5f), (float)(n - 1));
+  return fminf(fmaxf(i, 0.0f), (float)(n - 1));
+}
+
+// kernel launchers (defined in the .cu files; called from api.cu)
+int launch_pack_features(const float* nchw, int V, int h, int w, __half* out, cudaStream_t s);
+int launch_pack_images(const float* nchw, int V, int H, int W, float* out, cudaStream_t s);
+int launch_gather(const DevCams& cams, const DevRays& rays, int S, const __half* f0, int h0, int w0,
+                  const __half* f1, int h1, int w1, const float* images, float* cond_f32, __half* cond_f16,
+                  cudaStream_t s);
+
+struct DecoderWeightsF32;  // decoder_ref.cu
+int launch_decoder_ref(const DevCams& cams, const DevRays& rays, const mnf_decoder_cfg& cfg,
+                       const DecoderWeightsF32& w, const float* cond_f32, int setbg_opaque, float* out_rgb,
+                       float* out_depth, float* out_opacity, float* aux, cudaStream_t s);
+
+int launch_window_attn_ref(const float* q, const float* k, const float* v, float* out, int B, int h, int w, int C,
+                           int num_splits, int with_shift, cudaStream_t s);
+
+}  // namespace mnf

@@ -1,0 +1,65 @@
+// Layout packing kernels: reference NCHW fp32 tensors -> the channels-last layouts the gather kernel reads.
+//
+// Feature map layout ("interleaved halves"): a source view's 256 channels are two 128-channel halves,
+// one per image pair the view takes part in (models/matchnerf.py:192-205).  A texel is stored as 256
+// fp16 = 512 B so that one warp reads it with a single 16 B load per lane; lane l holds original channels
+//   half0[4l .. 4l+3], half1[4l .. 4l+3]
+// i.e. packed position p = 8*l + j  <->  channel (j < 4 ? 0 : 128) + 4*l + (j & 3).
+// Every lane therefore owns the same channel indices of both halves of every view, which makes all three
+// pair products (v0h0.v1h0, v0h1.v2h0, v1h1.v2h1) lane-local, and a cosine group of 128/G channels is a
+// contiguous run of 32/G lanes.
+#include "mnf_common.cuh"
+
+namespace mnf {
+
+__global__ void pack_features_kernel(const float* __restrict__ in, __half* __restrict__ out, int hw) {
+  // grid: (ceil(hw/32), V); block 256 threads.  Tile = 32 pixels x 256 channels through shared memory.
+  __shared__ float tile[kFeatCh][33];
+  const int v = blockIdx.y;
+  const int p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 rows of 32
+  const float* src = in + (size_t)v * kFeatCh * hw;
+  for (int c = ty; c < kFeatCh; c += 8) {
+    const int p = p0 + tx;
+    tile[c][tx] = p < hw ? src[(size_t)c * hw + p] : 0.f;
+  }
+  __syncthreads();
+  // each thread emits 16 B (8 packed channels) for one (pixel, lane) pair; 32 pixels x 32 lanes = 1024 items
+  for (int item = threadIdx.x; item < 32 * 32; item += blockDim.x) {
+    const int pix = item >> 5, lane = item & 31;
+    const int p = p0 + pix;
+    if (p >= hw) continue;
+    __align__(16) __half vals[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = (j < 4 ? 0 : 128) + 4 * lane + (j & 3);
+      vals[j] = __float2half_rn(tile[c][pix]);
+    }
+    *reinterpret_cast<uint4*>(out + ((size_t)v * hw + p) * kFeatCh + lane * 8) = *reinterpret_cast<const uint4*>(vals);
+  }
+}
+
+__global__ void pack_images_kernel(const float* __restrict__ in, float4* __restrict__ out, int hw, int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int v = i / hw, p = i - v * hw;
+  const float* src = in + (size_t)v * 3 * hw + p;
+  out[i] = make_float4(src[0], src[hw], src[2 * (size_t)hw], 0.f);
+}
+
+int launch_pack_features(const float* nchw, int V, int h, int w, __half* out, cudaStream_t s) {
+  const int hw = h * w;
+  dim3 grid((hw + 31) / 32, V);
+  pack_features_kernel<<<grid, 256, 0, s>>>(nchw, out, hw);
+  MNF_CUDA_TRY(cudaGetLastError());
+  return MNF_OK;
+}
+
+int launch_pack_images(const float* nchw, int V, int H, int W, float* out, cudaStream_t s) {
+  const int hw = H * W, total = V * hw;
+  pack_images_kernel<<<(total + 255) / 256, 256, 0, s>>>(nchw, reinterpret_cast<float4*>(out), hw, total);
+  MNF_CUDA_TRY(cudaGetLastError());
+  return MNF_OK;
+}
+
+}  // namespace mnf

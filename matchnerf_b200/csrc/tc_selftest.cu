@@ -1,0 +1,123 @@
+// Self-test of the tcgen05 building blocks the decoder / attention kernels are made of.
+// D[128][N] = A[128][K] * B[N][K]^T, fp16 operands, fp32 accumulation in tensor memory, one CTA of 128 threads.
+//   mode 0 (SS): A and B in shared memory, SWIZZLE_128B K-major tiles of 64 columns, written with plain stores.
+//   mode 1 (TS): A written to tensor memory with tcgen05.st (two fp16 per column), B in shared memory.
+// tests/test_gpu_tc.py compares the result with a float64 product of the same fp16 inputs.
+#include <cuda_fp16.h>
+
+#include "mnf_common.cuh"
+#include "tcgen05.cuh"
+
+namespace mnf {
+
+namespace {
+constexpr int kTmemCols = 512;
+}
+
+__global__ void __launch_bounds__(128, 1)
+umma_selftest_kernel(const __half* __restrict__ A, const __half* __restrict__ B, float* __restrict__ D, const int N,
+                     const int K, const int mode) {
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  // SWIZZLE_128B tiles need a 1024 B aligned base; do not rely on the toolchain for it
+  unsigned char* smem = smem_dyn + ((1024u - (tc::smem_u32(smem_dyn) & 1023u)) & 1023u);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int kblocks = K / 64;
+  // smem carve-up: A tiles [kblocks][128 x 128 B] (mode 0 only), then B tiles [kblocks][N x 128 B]; all 1024 B multiples
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + (mode == 0 ? (size_t)kblocks * 128 * 128 : 0);
+
+  if (tid == 0) {
+    tc::mbar_init(&bar, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc<kTmemCols>(&tmem_base_slot);
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  tc::tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_slot;
+  const uint32_t d_tmem = tmem;            // columns [0, N)
+  const uint32_t a_tmem = tmem + 256;      // columns [256, 256 + K/2) in TS mode
+
+  // ---- stage B (and A in SS mode) into the swizzled layout, 16 B chunks
+  for (int i = tid; i < N * (K / 8); i += blockDim.x) {
+    const int row = i / (K / 8), ch = i - row * (K / 8);
+    const int kb = ch / 8, c8 = ch & 7;
+    const uint4 val = *reinterpret_cast<const uint4*>(B + (size_t)row * K + ch * 8);
+    *reinterpret_cast<uint4*>(sB + (size_t)kb * N * 128 + tc::sw128_offset(row, c8 * 8)) = val;
+  }
+  if (mode == 0) {
+    for (int i = tid; i < 128 * (K / 8); i += blockDim.x) {
+      const int row = i / (K / 8), ch = i - row * (K / 8);
+      const int kb = ch / 8, c8 = ch & 7;
+      const uint4 val = *reinterpret_cast<const uint4*>(A + (size_t)row * K + ch * 8);
+      *reinterpret_cast<uint4*>(sA + (size_t)kb * 128 * 128 + tc::sw128_offset(row, c8 * 8)) = val;
+    }
+  } else {
+    // thread = row; 16 columns (32 halves) per tcgen05.st
+    const uint32_t lane_base = (uint32_t)(warp * 32);
+    for (int c0 = 0; c0 < K / 2; c0 += 16) {
+      uint32_t r[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) r[j] = *reinterpret_cast<const uint32_t*>(A + (size_t)tid * K + (c0 + j) * 2);
+      tc::tmem_st16(tc::tmem_addr(a_tmem, lane_base, c0), r);
+    }
+    tc::tmem_wait_st();
+  }
+  tc::fence_proxy_async_smem();
+  tc::tc_fence_before_sync();
+  __syncthreads();
+
+  if (tid == 0) {
+    tc::tc_fence_after_sync();
+    const uint32_t idesc = tc::umma_idesc_f16(128, N);
+    for (int kb = 0; kb < kblocks; ++kb) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {  // 4 x K=16 per 64-wide block; +32 B per step inside the swizzle atom
+        const uint64_t bdesc = tc::umma_desc_sw128(tc::smem_u32(sB + (size_t)kb * N * 128) + ks * 32);
+        const uint32_t acc = (kb | ks) ? 1u : 0u;
+        if (mode == 0) {
+          const uint64_t adesc = tc::umma_desc_sw128(tc::smem_u32(sA + (size_t)kb * 128 * 128) + ks * 32);
+          tc::umma_ss(d_tmem, adesc, bdesc, idesc, acc);
+        } else {
+          tc::umma_ts(d_tmem, a_tmem + (kb * 64 + ks * 16) / 2, bdesc, idesc, acc);
+        }
+      }
+    }
+    tc::umma_commit(&bar);
+  }
+  tc::mbar_wait(&bar, 0);
+  tc::tc_fence_after_sync();
+
+  // ---- read the accumulator back: thread = row, 32 columns per load
+  const uint32_t lane_base = (uint32_t)(warp * 32);
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    uint32_t r[32];
+    tc::tmem_ld32(tc::tmem_addr(d_tmem, lane_base, c0), r);
+    tc::tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (c0 + j < N) D[(size_t)tid * N + c0 + j] = __uint_as_float(r[j]);
+  }
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<kTmemCols>(tmem);
+}
+
+}  // namespace mnf
+
+extern "C" int32_t mnf_selftest_umma(const void* a_f16, const void* b_f16, float* d_f32, int32_t N, int32_t K, int32_t mode,
+                                     void* stream) {
+  using namespace mnf;
+  if (!a_f16 || !b_f16 || !d_f32 || K % 64 != 0 || K <= 0 || K > 256 || N % 16 != 0 || N < 16 || N > 256 || (mode != 0 && mode != 1)) {
+    set_error("mnf_selftest_umma: bad arguments (N=%d K=%d mode=%d)", N, K, mode);
+    return MNF_EINVAL;
+  }
+  const size_t smem = (size_t)(K / 64) * (128 + N) * 128 + 1024;
+  MNF_CUDA_TRY(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(reinterpret_cast<const __half*>(a_f16),
+                                                              reinterpret_cast<const __half*>(b_f16), d_f32, N, K, mode);
+  MNF_CUDA_TRY(cudaGetLastError());
+  return MNF_OK;
+}

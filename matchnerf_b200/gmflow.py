@@ -1,0 +1,234 @@
+"""Host-side mirror of the reference feature encoder (``models/gmflow``): same module tree and
+parameter names, so ``feat_enc`` checkpoints (and GMFlow pre-training weights) load unchanged.
+
+What runs where
+  * split-window attention (models/gmflow/transformer.py:46-105, :8-16): this repo's CUDA kernel through the
+    C ABI (``mnf_window_attn_fwd``) -- no roll, no window copies, no L x L score tensor;
+  * the CNN backbone, linear projections, LayerNorm, FFN and the up-sampler: PyTorch library calls
+    (cuDNN / cuBLAS), as SURVEY.md 8(f) schedules them after the per-ray path.
+There is no CPU execution path for the attention: off-GPU the forward raises.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import capi
+
+
+# ----------------------------------------------------------------------------------------------
+# CNN backbone (models/gmflow/backbone.py) -- parameter names: conv1, layer{1,2,3}.{0,1}.{conv1,conv2,
+# downsample.0}, conv2
+# ----------------------------------------------------------------------------------------------
+class ResidualBlock(nn.Module):
+    """Two 3x3 convs with instance norm + identity/1x1 shortcut (models/gmflow/backbone.py:6-36)."""
+
+    def __init__(self, c_in: int, c_out: int, stride: int):
+        super().__init__()
+        self.conv1 = nn.Conv2d(c_in, c_out, 3, stride, 1, bias=False)
+        self.conv2 = nn.Conv2d(c_out, c_out, 3, 1, 1, bias=False)
+        self.downsample = None
+        if stride != 1 or c_in != c_out:
+            self.downsample = nn.Sequential(nn.Conv2d(c_in, c_out, 1, stride), nn.InstanceNorm2d(c_out))
+
+    def forward(self, x):
+        y = F.relu(F.instance_norm(self.conv1(x)))
+        y = F.relu(F.instance_norm(self.conv2(y)))
+        if self.downsample is not None:
+            x = self.downsample(x)
+        return F.relu(x + y)
+
+
+class CNNEncoder(nn.Module):
+    """1/8-resolution 128-channel features (models/gmflow/backbone.py:39-122, ``num_output_scales = 1``)."""
+
+    def __init__(self, output_dim: int = 128):
+        super().__init__()
+        dims = (64, 96, 128)
+        self.conv1 = nn.Conv2d(3, dims[0], 7, 2, 3, bias=False)
+        self.layer1 = nn.Sequential(ResidualBlock(dims[0], dims[0], 1), ResidualBlock(dims[0], dims[0], 1))
+        self.layer2 = nn.Sequential(ResidualBlock(dims[0], dims[1], 2), ResidualBlock(dims[1], dims[1], 1))
+        self.layer3 = nn.Sequential(ResidualBlock(dims[1], dims[2], 2), ResidualBlock(dims[2], dims[2], 1))
+        self.conv2 = nn.Conv2d(dims[2], output_dim, 1)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+
+    def forward(self, x):
+        x = F.relu(F.instance_norm(self.conv1(x)))
+        x = self.layer3(self.layer2(self.layer1(x)))
+        return self.conv2(x)
+
+
+# ----------------------------------------------------------------------------------------------
+# transformer (models/gmflow/transformer.py) -- names: layers.{i}.{self_attn,cross_attn_ffn}.{q_proj,k_proj,
+# v_proj,merge,norm1[,mlp.0,mlp.2,norm2]}
+# ----------------------------------------------------------------------------------------------
+def window_attention(q, k, v, h: int, w: int, num_splits: int, with_shift: bool, impl: int = 0):
+    """Dispatch to the CUDA kernel behind the C ABI.  q, k, v: [B, h*w, 128] fp32 on a CUDA device."""
+    if not q.is_cuda:
+        raise RuntimeError("matchnerf_b200: split-window attention only exists as a CUDA kernel (no CPU path)")
+    if torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad):
+        raise NotImplementedError("matchnerf_b200: backward of the attention kernel is not built yet; run under torch.no_grad()")
+    return capi.get_context(q.device).window_attn(q, k, v, h, w, num_splits, with_shift, impl)
+
+
+class TransformerLayer(nn.Module):
+    """models/gmflow/transformer.py:108-185."""
+
+    def __init__(self, d_model: int = 128, no_ffn: bool = False, ffn_dim_expansion: int = 4, with_shift: bool = False):
+        super().__init__()
+        self.no_ffn, self.with_shift = no_ffn, with_shift
+        self.q_proj = nn.Linear(d_model, d_model, bias=False)
+        self.k_proj = nn.Linear(d_model, d_model, bias=False)
+        self.v_proj = nn.Linear(d_model, d_model, bias=False)
+        self.merge = nn.Linear(d_model, d_model, bias=False)
+        self.norm1 = nn.LayerNorm(d_model)
+        if not no_ffn:
+            c = 2 * d_model
+            self.mlp = nn.Sequential(nn.Linear(c, c * ffn_dim_expansion, bias=False), nn.GELU(),
+                                     nn.Linear(c * ffn_dim_expansion, d_model, bias=False))
+            self.norm2 = nn.LayerNorm(d_model)
+
+    def forward(self, source, target, height: int, width: int, attn_num_splits: int):
+        shift = self.with_shift and attn_num_splits > 1
+        msg = window_attention(self.q_proj(source), self.k_proj(target), self.v_proj(target), height, width,
+                               attn_num_splits, shift)
+        msg = self.norm1(self.merge(msg))
+        if not self.no_ffn:
+            msg = self.norm2(self.mlp(torch.cat([source, msg], dim=-1)))
+        return source + msg
+
+
+class TransformerBlock(nn.Module):
+    """Self-attention (no FFN) then cross-attention + FFN (models/gmflow/transformer.py:188-247)."""
+
+    def __init__(self, d_model: int = 128, ffn_dim_expansion: int = 4, with_shift: bool = False):
+        super().__init__()
+        self.self_attn = TransformerLayer(d_model, True, ffn_dim_expansion, with_shift)
+        self.cross_attn_ffn = TransformerLayer(d_model, False, ffn_dim_expansion, with_shift)
+
+    def forward(self, source, target, height, width, attn_num_splits, wo_self_attn=False):
+        if not wo_self_attn:
+            source = self.self_attn(source, source, height, width, attn_num_splits)
+        return self.cross_attn_ffn(source, target, height, width, attn_num_splits)
+
+
+class FeatureTransformer(nn.Module):
+    """models/gmflow/transformer.py:250-339."""
+
+    def __init__(self, num_layers: int = 6, d_model: int = 128, ffn_dim_expansion: int = 4):
+        super().__init__()
+        self.d_model = d_model
+        self.layers = nn.ModuleList([TransformerBlock(d_model, ffn_dim_expansion, with_shift=(i % 2 == 1))
+                                     for i in range(num_layers)])
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+
+    def forward(self, feature0, feature1, attn_num_splits: int, wo_self_attn: bool = False):
+        b, c, h, w = feature0.shape
+        x = torch.cat([feature0, feature1], 0).flatten(2).transpose(1, 2).contiguous()      # [2P, hw, C]
+        for layer in self.layers:
+            y = torch.cat([x[b:], x[:b]], 0)          # the other view's tokens from before this block (:331)
+            x = layer(x, y, h, w, attn_num_splits, wo_self_attn)
+        x = x.transpose(1, 2).reshape(2 * b, c, h, w)
+        return x[:b].contiguous(), x[b:].contiguous()
+
+
+def sine_position(hw: int, ww: int, channels: int, device, dtype=torch.float32):
+    """[C, hw, ww] DETR sine embedding, normalised to 2*pi (models/gmflow/position.py:26-47)."""
+    npf = channels // 2
+    ys = torch.arange(1, hw + 1, dtype=torch.float32, device=device) / (hw + 1e-6) * (2 * math.pi)
+    xs = torch.arange(1, ww + 1, dtype=torch.float32, device=device) / (ww + 1e-6) * (2 * math.pi)
+    i = torch.arange(npf, dtype=torch.float32, device=device)
+    dim_t = 10000.0 ** (2 * torch.div(i, 2, rounding_mode="trunc") / npf)
+
+    def interleave(v):
+        a = v[:, None] / dim_t
+        return torch.stack([a[:, 0::2].sin(), a[:, 1::2].cos()], dim=2).flatten(1)
+
+    py, px = interleave(ys), interleave(xs)
+    pos = torch.cat([py[:, None, :].expand(hw, ww, npf), px[None, :, :].expand(hw, ww, npf)], dim=-1)
+    return pos.permute(2, 0, 1).contiguous().to(dtype)
+
+
+# ----------------------------------------------------------------------------------------------
+# up-sampler (models/gmflow/superres.py) -- names: conv_ls.{i}, conv_l2rs.{i}
+# ----------------------------------------------------------------------------------------------
+class UpSampler(nn.Module):
+    def __init__(self, n_feat: int = 128, upsample_factor: int = 2):
+        super().__init__()
+        self.n_blocks = int(math.log2(upsample_factor))
+        self.conv_ls = nn.ModuleList([nn.Conv2d(n_feat, n_feat, 3, 1, 1) for _ in range(self.n_blocks)])
+        self.conv_l2rs = nn.ModuleList([nn.Conv2d(n_feat, n_feat, 3, 1, 1) for _ in range(self.n_blocks + 1)])
+
+    def forward(self, x):
+        right, left = self.conv_l2rs[0](x), x
+        for i in range(self.n_blocks):
+            left = F.leaky_relu(self.conv_ls[i](F.interpolate(left, scale_factor=2.0, mode="nearest")), 0.2)
+            right = F.interpolate(right, scale_factor=2.0, mode="bilinear", align_corners=False) + self.conv_l2rs[i + 1](left)
+        return right
+
+
+# ----------------------------------------------------------------------------------------------
+# GMFlow wrapper (models/gmflow/gmflow.py)
+# ----------------------------------------------------------------------------------------------
+class GMFlow(nn.Module):
+    """Encoder used by MatchNeRF: backbone -> pairwise transformer -> up-sampler.
+
+    ``forward`` keeps the reference's return convention (``aug_feat0s`` / ``aug_feat1s`` lists holding the raw
+    1/8 features then the up-sampled ones, each [B, P, 128, h, w]); models/gmflow/gmflow.py:91-150.
+    """
+
+    def __init__(self, num_scales=1, upsample_factor=2, feature_channels=128, attention_type="swin",
+                 num_transformer_layers=6, ffn_dim_expansion=4, num_head=1, feature_upsampler="network",
+                 device="cuda", **kwargs):
+        super().__init__()
+        if num_scales != 1 or attention_type != "swin" or num_head != 1:
+            raise NotImplementedError("only the configuration MatchNeRF instantiates (1 scale, swin, 1 head) is built")
+        self.feature_channels = feature_channels
+        self.feature_upsampler = feature_upsampler
+        self.backbone = CNNEncoder(feature_channels)
+        self.transformer = FeatureTransformer(num_transformer_layers, feature_channels, ffn_dim_expansion)
+        if feature_upsampler == "network":
+            self.featup_net = UpSampler(feature_channels, upsample_factor)
+
+    @staticmethod
+    def normalize_images(images):
+        mean = torch.tensor([0.485, 0.456, 0.406], device=images.device).view(1, 1, 3, 1, 1)
+        std = torch.tensor([0.229, 0.224, 0.225], device=images.device).view(1, 1, 3, 1, 1)
+        return (images - mean) / std
+
+    def forward(self, imgs, attn_splits_list: Optional[Sequence[int]] = None, keep_raw_feats: bool = False,
+                wo_self_attn: bool = False, **kwargs):
+        B, V, _, H, W = imgs.shape
+        if H == 756 and W == 1008:     # IBRNet setting: pad to a size divisible by 16 (gmflow.py:99-103)
+            imgs = F.interpolate(imgs.reshape(B * V, 3, H, W), size=(768, 1024), mode="bilinear",
+                                 align_corners=True).reshape(B, V, 3, 768, 1024)
+        splits = int((attn_splits_list or [2])[0])
+        base = self.backbone(self.normalize_images(imgs).reshape(B * V, 3, *imgs.shape[-2:]))
+        base = base.reshape(B, V, *base.shape[1:])
+        pairs = [(a, b) for a in range(V - 1) for b in range(a + 1, V)]
+        f0 = torch.stack([base[:, a] for a, _ in pairs], 1).flatten(0, 1)        # [B*P, C, h, w]
+        f1 = torch.stack([base[:, b] for _, b in pairs], 1).flatten(0, 1)
+        h, w = f0.shape[-2:]
+        if h % splits or w % splits:
+            raise ValueError(f"feature map {h}x{w} not divisible by attn_splits {splits}")
+        pos = sine_position(h // splits, w // splits, self.feature_channels, f0.device).repeat(1, splits, splits)
+        f0, f1 = self.transformer(f0 + pos, f1 + pos, splits, wo_self_attn)
+        P = len(pairs)
+        out0, out1 = [], []
+        if keep_raw_feats:
+            out0.append(f0.reshape(B, P, *f0.shape[1:]))
+            out1.append(f1.reshape(B, P, *f1.shape[1:]))
+        if self.feature_upsampler == "network":
+            up = self.featup_net(torch.cat([f0, f1], 0))
+            f0, f1 = up[: B * P], up[B * P:]
+        out0.append(f0.reshape(B, P, *f0.shape[1:]))
+        out1.append(f1.reshape(B, P, *f1.shape[1:]))
+        return {"aug_feat0s": out0, "aug_feat1s": out1}

@@ -1,0 +1,169 @@
+"""Host-side mirror of ``models/matchnerf.py``: same constructor, attributes and method signatures, with the
+per-ray work handed to the CUDA library through the C ABI.
+
+    forward(batch, mode, ...)            models/matchnerf.py:32-73
+    render(opt, tgt_pose, ray_idx, ...)  models/matchnerf.py:88-143   -> mnf_render_rays_fwd
+    render_by_slices(...)                models/matchnerf.py:145-161
+    get_img_feat(imgs, ...)              models/matchnerf.py:183-207  -> GMFlow (K-attn inside)
+    query_cond_info(points, ...)         models/matchnerf.py:209-293  -> (fused; explicit-point variant not built)
+    render_rays(...)                     alias of ``render`` (the name BASELINE.json uses)
+
+PyTorch is the tensor plumbing (device memory, streams, the encoder's conv / linear library calls); there is no
+CPU or pure-PyTorch fallback for the per-ray path.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import capi
+from .cond_nerf import CondNeRF
+from .gmflow import GMFlow
+from .utils import AttrDict, get_opt
+
+
+class MatchNeRF(nn.Module):
+    # rays handed to one kernel launch when rendering a full image.  The reference's ``rand_rays_{mode}`` slice
+    # size is a memory device (models/matchnerf.py:151-152); rays are independent, so results do not depend on it.
+    render_chunk = 81920
+
+    def __init__(self, opts):
+        super().__init__()
+        self.opts = opts
+        self.nerf_setbg_opaque = False
+        self.n_src_views = int(get_opt(opts, "n_src_views", 3))
+        dev = get_opt(opts, "device", "cuda")
+        self.feat_enc = GMFlow(feature_channels=128, num_scales=1, num_head=1, attention_type="swin", ffn_dim_expansion=4,
+                               feature_upsampler=get_opt(opts, "encoder.feature_upsampler", "network"),
+                               upsample_factor=int(get_opt(opts, "encoder.upsample_factor", 2)),
+                               num_transformer_layers=int(get_opt(opts, "encoder.num_transformer_layers", 6)),
+                               device=dev).to(dev)
+        self.nerf_dec = CondNeRF(opts).to(dev)
+        if int(get_opt(opts, "encoder.feature_sample_local_radius", 0)) > 0:
+            raise NotImplementedError("feature_sample_local_radius > 0 is not built (no shipped config uses it)")
+        if not get_opt(opts, "nerf.legacy_coord", True) or get_opt(opts, "nerf.depth.param", "metric") != "metric":
+            raise NotImplementedError("only legacy_coord=True with metric depth (all shipped configs) is built")
+        self._scene_cache = None
+
+    # ------------------------------------------------------------------ helpers
+    @staticmethod
+    def _unwrap(m):
+        return m.module if isinstance(m, nn.DataParallel) else m
+
+    def extract_poses(self, batch):
+        """models/matchnerf.py:75-86."""
+        tgt = dict(extrinsics=batch["extrinsics"][:, -1, :3, :], intrinsics=batch["intrinsics"][:, -1],
+                   near_fars=batch["near_fars"][:, -1])
+        ref = dict(extrinsics=batch["extrinsics"][:, :-1, :3, :], intrinsics=batch["intrinsics"][:, :-1],
+                   near_fars=batch["near_fars"][:, :-1])
+        return tgt, ref
+
+    def get_img_feat(self, imgs, attn_splits_list=None, cur_n_src_views=3) -> List[torch.Tensor]:
+        """[B,V,3,H,W] -> [[B,V,256,H/8,W/8], [B,V,256,H/4,W/4]]: view i holds the features it got as a member of
+        each of its pairs (models/matchnerf.py:183-207)."""
+        if attn_splits_list is None:
+            attn_splits_list = get_opt(self.opts, "encoder.attn_splits_list", [2])
+        V = cur_n_src_views
+        out = self.feat_enc(imgs=imgs[:, :V], attn_splits_list=attn_splits_list, keep_raw_feats=True,
+                            wo_self_attn=bool(get_opt(self.opts, "encoder.wo_self_attn", False)))
+        pairs = [(a, b) for a in range(V - 1) for b in range(a + 1, V)]
+        feats = []
+        for f0, f1 in zip(out["aug_feat0s"], out["aug_feat1s"]):
+            per_view = [[] for _ in range(V)]
+            for p, (i, j) in enumerate(pairs):
+                per_view[i].append(f0[:, p])
+                per_view[j].append(f1[:, p])
+            feats.append(torch.stack([torch.cat(x, dim=1) for x in per_view], dim=1))
+        return feats
+
+    def _packed_scenes(self, ref_poses, ref_images, ref_feats_list):
+        """Pack (once per set of feature maps) the per-batch-item scenes the kernels read."""
+        key = (ref_feats_list[0].data_ptr(), ref_feats_list[1].data_ptr(), ref_images.data_ptr(),
+               ref_feats_list[0]._version, ref_images._version, ref_poses["extrinsics"].data_ptr())
+        if self._scene_cache is not None and self._scene_cache[0] == key:
+            return self._scene_cache[1]
+        ctx = self._unwrap(self.nerf_dec).sync_to_library()
+        scenes = []
+        for b in range(ref_images.shape[0]):
+            scenes.append(ctx.pack_scene([ref_feats_list[0][b], ref_feats_list[1][b]], ref_images[b],
+                                         ref_poses["extrinsics"][b], ref_poses["intrinsics"][b], ref_poses["near_fars"][b]))
+        self._scene_cache = (key, scenes)
+        return scenes
+
+    # ------------------------------------------------------------------ the per-slice pipeline
+    def render(self, opt, tgt_pose=None, ray_idx=None, mode=None, ref_poses=None, ref_images=None, ref_feats_list=None):
+        """models/matchnerf.py:88-143.  Returns AttrDict(rgb [B,R,3], depth [B,R,1], opacity [B,R,1])."""
+        if ray_idx is None:
+            H, W = ref_images.shape[-2:]
+            return self._render(opt, tgt_pose, None, 0, H * W, mode, ref_poses, ref_images, ref_feats_list)
+        return self._render(opt, tgt_pose, ray_idx, 0, ray_idx.numel(), mode, ref_poses, ref_images, ref_feats_list)
+
+    render_rays = render
+
+    def _render(self, opt, tgt_pose, ray_idx, first_ray, n_rays, mode, ref_poses, ref_images, ref_feats_list):
+        """One kernel-side slice: explicit pixel ids (``ray_idx``) or the contiguous range [first_ray, first_ray+n_rays)."""
+        if tgt_pose is None:
+            raise Exception("Must provide tgt_pose.")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("matchnerf_b200: the backward kernels are not built yet; call under torch.no_grad()")
+        dec = self._unwrap(self.nerf_dec)
+        ctx = dec.sync_to_library()
+        cfg = dec.decoder_cfg(opt)
+        S = cfg.n_samples
+        B = ref_images.shape[0]
+        scenes = self._packed_scenes(ref_poses, ref_images, ref_feats_list)
+        stratified = mode == "train" and bool(get_opt(opt, "nerf.sample_stratified", False))
+        outs = []
+        for b in range(B):
+            sc = scenes[b].c_scene(tgt_pose["extrinsics"][b], tgt_pose["intrinsics"][b], tgt_pose["near_fars"][b])
+            jitter = torch.rand(n_rays, S, device=ctx.device) if stratified else None     # matchnerf.py:168-169
+            rgb, depth, opac = ctx.render_rays(sc, cfg, ray_idx=ray_idx, first_ray=first_ray, n_rays=n_rays, jitter=jitter,
+                                               setbg_opaque=self.nerf_setbg_opaque)
+            outs.append((rgb, depth[:, None], opac[:, None]))
+        return AttrDict(rgb=torch.stack([o[0] for o in outs]), depth=torch.stack([o[1] for o in outs]),
+                        opacity=torch.stack([o[2] for o in outs]))
+
+    def render_by_slices(self, opt, tgt_pose, mode=None, ref_poses=None, ref_images=None, ref_feats_list=None):
+        """models/matchnerf.py:145-161: contiguous row-major ray ranges, concatenated."""
+        assert ref_images is not None, "Must provide the reference images for MatchNeRF."
+        H, W = ref_images.shape[-2:]
+        step = max(int(get_opt(opt, f"nerf.rand_rays_{mode}", 0) or 0), int(self.render_chunk))
+        parts = [self._render(opt, tgt_pose, None, c, min(step, H * W - c), mode, ref_poses, ref_images, ref_feats_list)
+                 for c in range(0, H * W, step)]
+        return AttrDict({k: torch.cat([p[k] for p in parts], dim=1) for k in ("rgb", "depth", "opacity")})
+
+    def query_cond_info(self, point_samples, ref_poses, ref_images, ref_feats_list):
+        raise NotImplementedError("matchnerf_b200: the conditioning query runs fused with ray casting inside render(); "
+                                  "the explicit-point variant of models/matchnerf.py:209-293 is not built")
+
+    # ------------------------------------------------------------------ entry point used by Coach
+    def forward(self, batch, mode=None, render_video=False, render_path_mode="interpolate"):
+        """models/matchnerf.py:32-73: encoder once, then random rays (train) or the full image; appends
+        rgb / depth / opacity (and ray_idx in train mode) to ``batch`` and returns it."""
+        if render_video:
+            raise NotImplementedError("matchnerf_b200: video path rendering (models/matchnerf.py:295-325) is not built yet")
+        V = self.n_src_views
+        ref_images = batch["images"][:, :V]
+        ref_feats_list = self.get_img_feat(ref_images, attn_splits_list=get_opt(self.opts, "encoder.attn_splits_list", [2]),
+                                           cur_n_src_views=V)
+        tgt_pose, ref_poses = self.extract_poses(batch)
+        B, _, _, H, W = ref_images.shape
+        n_rand = int(get_opt(self.opts, f"nerf.rand_rays_{mode}", 0) or 0)
+        if n_rand and mode in ("train", "test-optim"):
+            batch["ray_idx"] = torch.randperm(H * W, device=ref_images.device)[: n_rand // B]
+            ret = self.render(self.opts, tgt_pose, ray_idx=batch["ray_idx"], mode=mode, ref_poses=ref_poses,
+                              ref_images=ref_images, ref_feats_list=ref_feats_list)
+        elif n_rand:
+            ret = self.render_by_slices(self.opts, tgt_pose, mode=mode, ref_poses=ref_poses, ref_images=ref_images,
+                                        ref_feats_list=ref_feats_list)
+        else:
+            ret = self.render(self.opts, tgt_pose, mode=mode, ref_poses=ref_poses, ref_images=ref_images,
+                              ref_feats_list=ref_feats_list)
+        for k, v in ret.items():
+            batch[k] = v
+        return batch
+
+
+models_dict = {"matchnerf": MatchNeRF}

@@ -1,0 +1,94 @@
+"""GPU (B200): the reference-facing model interface end to end -- encoder (K-attn inside) + renderer -- against the
+oracle and the reference goldens, plus full-image properties at BASELINE config-2 size."""
+import numpy as np
+import pytest
+import torch
+import yaml
+
+from matchnerf_b200.utils import AttrDict
+from oracle import encoder_oracle as EO
+from oracle import synth
+from tests.helpers import load_npz, oracle_render, psnr, rms
+from tests.test_host_cpu import make_opts
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def build_model(S, **over):
+    from matchnerf_b200.matchnerf import MatchNeRF
+    opt = make_opts(**{"nerf.sample_intvs": S, **over})
+    opt.device = DEV
+    m = MatchNeRF(opt).eval()
+    m.feat_enc.load_state_dict(synth.synthetic_encoder(1), strict=True)
+    m.nerf_dec.load_state_dict(synth.synthetic_decoder(0), strict=True)
+    return m.to(DEV), opt
+
+
+def test_encoder_matches_reference_golden(golden_dir):
+    z = load_npz(golden_dir, "encoder_64x96.npz")
+    m, opt = build_model(16)
+    with torch.no_grad():
+        f8, f4 = m.get_img_feat(torch.from_numpy(z["images"]).to(DEV))
+    scale = float(np.std(z["feat8"]))
+    assert rms(f8[0], z["feat8"]) < 2e-3 * scale, (rms(f8[0], z["feat8"]), scale)     # cuDNN TF32 convs on GPU vs fp32 CPU
+    assert rms(f4[0][:, ::8], z["feat4_ch0mod8"]) < 2e-3 * scale
+
+
+def test_forward_small_image_vs_oracle():
+    """forward(mode='test') on a 64x96 triplet: encoder + full-image render, vs the CPU oracle chain."""
+    H, W, S = 64, 96, 32
+    m, opt = build_model(S)
+    g = torch.Generator().manual_seed(4)
+    images = torch.rand(1, 4, 3, H, W, generator=g)
+    extr, intr, nf = synth.synthetic_cameras(H, W)
+    batch = AttrDict(images=images.to(DEV), extrinsics=extr.to(DEV), intrinsics=intr.to(DEV), near_fars=nf.to(DEV))
+    with torch.no_grad():
+        out = m(batch, mode="test")
+    assert out.rgb.shape == (1, H * W, 3) and out.depth.shape == (1, H * W, 1) and out.opacity.shape == (1, H * W, 1)
+    feats = EO.encode_views(synth.synthetic_encoder(1), images[0, :3])
+    idx = torch.arange(0, H * W, 7)
+    o = oracle_render(synth.synthetic_decoder(0), [f[None] for f in feats], images[:, :3], extr, intr, nf, idx, S)
+    e = (rms(out.rgb[0, idx], o[0]), rms(out.depth[0, idx], o[1]), rms(out.opacity[0, idx], o[2]))
+    assert e[0] < 2e-3 and e[2] < 4e-3, e
+    assert 0.02 < float(out.opacity.mean()) < 0.98
+
+
+def test_train_mode_random_rays_and_slicing_invariance():
+    H, W, S = 64, 96, 16
+    m, opt = build_model(S, **{"nerf.rand_rays_train": 256, "nerf.rand_rays_test": 1000})
+    g = torch.Generator().manual_seed(5)
+    batch = AttrDict(images=torch.rand(1, 4, 3, H, W, generator=g).to(DEV))
+    extr, intr, nf = synth.synthetic_cameras(H, W)
+    batch.update(extrinsics=extr.to(DEV), intrinsics=intr.to(DEV), near_fars=nf.to(DEV))
+    with torch.no_grad():
+        out = m(AttrDict(batch), mode="train")
+        assert out.ray_idx.shape == (256,) and out.rgb.shape == (1, 256, 3)
+        full = m(AttrDict(batch), mode="test")
+        m.render_chunk = 999                         # different slicing must not change any pixel
+        full2 = m(AttrDict(batch), mode="test")
+    assert torch.equal(full.rgb, full2.rgb) and torch.equal(full.depth, full2.depth)
+
+
+def test_full_size_dtu_properties():
+    """BASELINE config 2 size (512x640, S=64): properties that do not need the CPU oracle at full size --
+    opacity in [0,1], rgb in [0,1], background compositing identity rgb_bg = rgb + (1 - opacity),
+    and agreement of a strided subset with the oracle."""
+    H, W, S = 512, 640, 64
+    m, opt = build_model(S)
+    feats, imgs, g = synth.synthetic_scene(H, W, seed=1234)
+    extr, intr, nf = synth.synthetic_cameras(H, W)
+    tgt = dict(extrinsics=extr[:, 3, :3].to(DEV), intrinsics=intr[:, 3].to(DEV), near_fars=nf[:, 3].to(DEV))
+    ref = dict(extrinsics=extr[:, :3, :3].to(DEV), intrinsics=intr[:, :3].to(DEV), near_fars=nf[:, :3].to(DEV))
+    fd = [f.to(DEV) for f in feats]
+    with torch.no_grad():
+        a = m.render_by_slices(opt, tgt, mode="test", ref_poses=ref, ref_images=imgs.to(DEV), ref_feats_list=fd)
+        m.nerf_setbg_opaque = True
+        b = m.render_by_slices(opt, tgt, mode="test", ref_poses=ref, ref_images=imgs.to(DEV), ref_feats_list=fd)
+    assert a.rgb.shape == (1, H * W, 3)
+    assert float(a.opacity.min()) >= 0 and float(a.opacity.max()) <= 1 + 1e-5
+    assert float(a.rgb.min()) >= 0 and float(a.rgb.max()) <= 1 + 1e-5
+    assert rms(b.rgb, a.rgb + (1 - a.opacity)) < 1e-6
+    idx = torch.arange(1000, H * W, 4099)
+    o = oracle_render(synth.synthetic_decoder(0), feats, imgs, extr, intr, nf, idx, S)
+    assert rms(a.rgb[0, idx], o[0]) < 2e-3
