@@ -258,6 +258,7 @@ int32_t mnf_decoder_composite_fwd(mnf_ctx* ctx, const mnf_scene* scene, const mn
   if ((rc = fill_cams(scene, &cams))) return rc;
   if ((rc = fill_rays(scene, rays, &dr))) return rc;
   if ((rc = check_cfg(cfg))) return rc;
+  if (rays->n_rays == 0) return MNF_OK;
   if (!out_rgb || !out_depth || !out_opacity) { set_error("output buffer missing"); return MNF_EINVAL; }
   if (impl == 0) impl = (cond_f16 && decoder_tc_supports(*cfg)) ? 2 : 1;
   if (impl == 2) {
@@ -287,6 +288,7 @@ int32_t mnf_render_rays_fwd(mnf_ctx* ctx, const mnf_scene* scene, const mnf_rays
   if (!ctx || !rays || !cfg) { set_error("NULL argument"); return MNF_EINVAL; }
   int rc;
   if ((rc = check_cfg(cfg))) return rc;
+  if (rays->n_rays == 0) return MNF_OK;
   const int64_t need = mnf_render_workspace_bytes(rays->n_rays, cfg->n_samples);
   if (!workspace || workspace_bytes < need) {
     set_error("workspace too small: %lld < %lld bytes", (long long)workspace_bytes, (long long)need);
