@@ -2,12 +2,12 @@
 //
 // Feature map layout ("interleaved halves"): a source view's 256 channels are two 128-channel halves,
 // one per image pair the view takes part in (models/matchnerf.py:192-205).  A texel is stored as 256
-// fp16 = 512 B so that one warp reads it with a single 16 B load per lane; lane l holds original channels
-//   half0[4l .. 4l+3], half1[4l .. 4l+3]
-// i.e. packed position p = 8*l + j  <->  channel (j < 4 ? 0 : 128) + 4*l + (j & 3).
+// fp16 = 512 B; the gather kernel reads it with 8 lanes x 64 B, and lane l of those 8 holds original channels
+//   half0[16l .. 16l+15], half1[16l .. 16l+15]
+// i.e. packed position p = 32*l + j  <->  channel (j < 16 ? 0 : 128) + 16*l + (j & 15).
 // Every lane therefore owns the same channel indices of both halves of every view, which makes all three
-// pair products (v0h0.v1h0, v0h1.v2h0, v1h1.v2h1) lane-local, and a cosine group of 128/G channels is a
-// contiguous run of 32/G lanes.
+// pair products (v0h0.v1h0, v0h1.v2h0, v1h1.v2h1) lane-local; a fine-scale cosine group (16 channels) is
+// lane-local and a coarse group (64 channels) is a run of 4 lanes.
 #include "mnf_common.cuh"
 
 namespace mnf {
@@ -24,18 +24,20 @@ __global__ void pack_features_kernel(const float* __restrict__ in, __half* __res
     tile[c][tx] = p < hw ? src[(size_t)c * hw + p] : 0.f;
   }
   __syncthreads();
-  // each thread emits 16 B (8 packed channels) for one (pixel, lane) pair; 32 pixels x 32 lanes = 1024 items
+  // each thread emits 16 B (8 packed channels) for one (pixel, 16-byte slot) pair; 32 pixels x 32 slots = 1024 items
   for (int item = threadIdx.x; item < 32 * 32; item += blockDim.x) {
-    const int pix = item >> 5, lane = item & 31;
+    const int pix = item >> 5, slot = item & 31;
     const int p = p0 + pix;
     if (p >= hw) continue;
     __align__(16) __half vals[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = (j < 4 ? 0 : 128) + 4 * lane + (j & 3);
+      const int pp = slot * 8 + j;                 // packed position
+      const int l = pp >> 5, jj = pp & 31;
+      const int c = (jj < 16 ? 0 : 128) + 16 * l + (jj & 15);
       vals[j] = __float2half_rn(tile[c][pix]);
     }
-    *reinterpret_cast<uint4*>(out + ((size_t)v * hw + p) * kFeatCh + lane * 8) = *reinterpret_cast<const uint4*>(vals);
+    *reinterpret_cast<uint4*>(out + ((size_t)v * hw + p) * kFeatCh + slot * 8) = *reinterpret_cast<const uint4*>(vals);
   }
 }
 

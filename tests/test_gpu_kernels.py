@@ -2,7 +2,8 @@
 against the golden vectors of the unmodified reference.
 
 Tolerances (fp32 reference arithmetic; the kernels read fp16 feature maps):
-  * kernel vs oracle evaluated on the SAME fp16-rounded feature maps: fp32 round-off only (<= 2e-5 RMS);
+  * kernel vs oracle evaluated on the SAME fp16-rounded feature maps: fp32 round-off only (<= 2e-5 RMS) for colours,
+    masks and the fp32 decoder; <= 5e-4 RMS for the cosine similarities (the 4 taps are blended in packed fp16);
   * kernel vs reference goldens (fp32 feature maps): the north-star budget, rgb RMS <= 2e-3 (== 0.01 dB at 27 dB
     PSNR) -- measured values are ~1e-4.
 """
@@ -50,9 +51,9 @@ def test_pack_features_layout(ctx):
     imgs = torch.rand(1, 3, 3, 40, 56, generator=g)
     packed, _ = make_scene(ctx, [f[None], torch.randn(1, 3, 256, 10, 14, generator=g)], imgs, *synth.synthetic_cameras(40, 56))
     p = packed.feat0.cpu().float()                                   # [V,h,w,256] packed order
-    lane = torch.arange(32).repeat_interleave(8)
-    j = torch.arange(8).repeat(32)
-    chan = torch.where(j < 4, 0, 128) + 4 * lane + (j & 3)           # DESIGN.md "feature map layout"
+    lane = torch.arange(8).repeat_interleave(32)
+    j = torch.arange(32).repeat(8)
+    chan = torch.where(j < 16, 0, 128) + 16 * lane + (j & 15)        # DESIGN.md "feature map layout"
     assert torch.equal(p, f.half().float().permute(0, 2, 3, 1)[..., chan])
     assert torch.equal(packed.images.cpu()[..., :3].permute(0, 3, 1, 2), imgs[0])
 
@@ -72,7 +73,7 @@ def test_gather_small_golden(ctx, golden_dir, name):
     # masks and colours do not depend on the feature quantisation; sims compared against the quantised-feature oracle
     assert frac_above(c32[:, 19:], cond_q[:, 19:], 0.5) < 2e-3          # a mask flips only for samples on the border
     assert rms(c32[:, 10:19], cond_q[:, 10:19]) < 2e-5
-    assert rms(c32[:, :10], cond_q[:, :10]) < 2e-5, rms(c32[:, :10], cond_q[:, :10])
+    assert rms(c32[:, :10], cond_q[:, :10]) < 5e-4, rms(c32[:, :10], cond_q[:, :10])   # taps blended in packed fp16
     assert rms(c32[:, :10], z["cond"][:, :10]) < 1e-3                   # vs the reference on fp32 features
     assert rms(c16[:, :22].float(), c32) < 5e-4 and float(c16[:, 22:].abs().max()) == 0.0
 
@@ -84,7 +85,7 @@ def test_gather_config1_and_ray_range(ctx):
     sub = ray_idx[:128]
     c32, _ = ctx.gather_cossim(sc, S, ray_idx=sub)
     aux = oracle_render(synth.synthetic_decoder(0), feats, imgs, extr, intr, nf, sub, S, quantize_feats=True, return_aux=True)[3]
-    assert rms(c32, aux["cond"]) < 2e-5
+    assert rms(c32[:, 10:], aux["cond"][:, 10:]) < 2e-5 and rms(c32[:, :10], aux["cond"][:, :10]) < 5e-4
     # contiguous range == explicit ids
     first = 640 * 100 + 17
     a, _ = ctx.gather_cossim(sc, S, first_ray=first, n_rays=96)
@@ -205,11 +206,11 @@ def test_render_edge_cases(ctx):
     # ragged: a single ray, the last pixel; S not a multiple of anything
     rgb1, _, _ = ctx.render_rays(sc, make_cfg(37), first_ray=512 * 640 - 1, n_rays=1, impl=1)
     o = oracle_render(synth.synthetic_decoder(0), feats, imgs, extr, intr, nf, torch.tensor([512 * 640 - 1]), 37, quantize_feats=True)
-    assert rms(rgb1, o[0]) < 2e-5
+    assert rms(rgb1, o[0]) < 3e-4
     # maximum S
     rgb2, _, op2 = ctx.render_rays(sc, make_cfg(256), ray_idx=ray_idx[:8], impl=1)
     o2 = oracle_render(synth.synthetic_decoder(0), feats, imgs, extr, intr, nf, ray_idx[:8], 256, quantize_feats=True)
-    assert rms(rgb2, o2[0]) < 2e-5 and rms(op2, o2[2][:, 0]) < 2e-5
+    assert rms(rgb2, o2[0]) < 3e-4 and rms(op2, o2[2][:, 0]) < 5e-4
     # argument validation surfaces as errors, not crashes
     with pytest.raises(RuntimeError):
         ctx.render_rays(sc, make_cfg(300), ray_idx=ray_idx[:8])
@@ -219,7 +220,7 @@ def test_render_edge_cases(ctx):
     jit = torch.rand(16, 64, generator=torch.Generator().manual_seed(2))
     rgb3, _, _ = ctx.render_rays(sc, make_cfg(64), ray_idx=ray_idx[:16], jitter=jit.to(DEV), impl=1)
     o3 = oracle_render(synth.synthetic_decoder(0), feats, imgs, extr, intr, nf, ray_idx[:16], 64, quantize_feats=True, jitter=jit)
-    assert rms(rgb3, o3[0]) < 2e-5
+    assert rms(rgb3, o3[0]) < 3e-4
 
 
 # ------------------------------------------------------------------------------------------- K-attn
