@@ -65,7 +65,8 @@ __device__ __forceinline__ __half2 h2(uint32_t u) { return *reinterpret_cast<con
 __device__ __forceinline__ void fetch_blend(const __half* __restrict__ fmap, int w, const TapParam& t, int li, __half2 (&acc)[16]) {
   const uint32_t o00 = t.off & 0x3fffffffu;
   const uint32_t dx = (t.off >> 30) & 1u, dy = t.off >> 31;
-  const uint4* p00 = reinterpret_cast<const uint4*>(fmap) + (size_t)o00 * 32 + li * 4;   // 32 uint4 per texel, 4 per lane
+  // 32 uint4 per texel; load j of lane li is uint4 number 8*j + li, so the 8 lanes of a group read 128 contiguous bytes
+  const uint4* p00 = reinterpret_cast<const uint4*>(fmap) + (size_t)o00 * 32 + li;
   const uint4* p01 = p00 + dx * 32;
   const uint4* p10 = p00 + (size_t)dy * w * 32;
   const uint4* p11 = p10 + dx * 32;
@@ -73,7 +74,7 @@ __device__ __forceinline__ void fetch_blend(const __half* __restrict__ fmap, int
   const __half2 w10 = __low2half2(h2(t.w1)), w11 = __high2half2(h2(t.w1));
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const uint4 a = __ldg(p00 + j), b = __ldg(p01 + j), c = __ldg(p10 + j), d = __ldg(p11 + j);
+    const uint4 a = __ldg(p00 + 8 * j), b = __ldg(p01 + 8 * j), c = __ldg(p10 + 8 * j), d = __ldg(p11 + 8 * j);
     const uint32_t* av = &a.x; const uint32_t* bv = &b.x; const uint32_t* cv = &c.x; const uint32_t* dv = &d.x;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -98,7 +99,7 @@ __device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const fl
 }
 
 // 16-channel dot products of this lane for the three view pairs: q[3p] = <A,B>, q[3p+1] = <A,A>, q[3p+2] = <B,B>
-// halves: acc[0..7] = half0 channels, acc[8..15] = half1 channels.  pairs (v0h0,v1h0) (v0h1,v2h0) (v1h1,v2h1)
+// halves: acc[0..7] = half0 channels 16l..16l+15, acc[8..15] = half1 channels 16l..16l+15 (loads j=0,1 / j=2,3).  pairs (v0h0,v1h0) (v0h1,v2h0) (v1h1,v2h1)
 __device__ __forceinline__ void pair_products(const __half2 (&a0)[16], const __half2 (&a1)[16], const __half2 (&a2)[16], float (&q)[9]) {
   float2 s[9];
 #pragma unroll
@@ -205,9 +206,13 @@ gather_cossim_kernel(const __grid_constant__ DevCams cams, const DevRays rays, c
       float3 col = make_float3(0.f, 0.f, 0.f);
       {
         const int v = min(li >> 1, kViews - 1), rowsel = li & 1;
-        const uint32_t offv = __shfl_sync(0xffffffffu, v == 0 ? coff[0] : (v == 1 ? coff[1] : coff[2]), src);
-        const float fx = __shfl_sync(0xffffffffu, v == 0 ? cfx[0] : (v == 1 ? cfx[1] : cfx[2]), src);
-        const float fy = __shfl_sync(0xffffffffu, v == 0 ? cfy[0] : (v == 1 ? cfy[1] : cfy[2]), src);
+        // (the view is chosen by the RECEIVING lane, so all three are shuffled and selected afterwards)
+        const uint32_t o0 = __shfl_sync(0xffffffffu, coff[0], src), o1 = __shfl_sync(0xffffffffu, coff[1], src), o2 = __shfl_sync(0xffffffffu, coff[2], src);
+        const float x0 = __shfl_sync(0xffffffffu, cfx[0], src), x1 = __shfl_sync(0xffffffffu, cfx[1], src), x2 = __shfl_sync(0xffffffffu, cfx[2], src);
+        const float y0 = __shfl_sync(0xffffffffu, cfy[0], src), y1 = __shfl_sync(0xffffffffu, cfy[1], src), y2 = __shfl_sync(0xffffffffu, cfy[2], src);
+        const uint32_t offv = v == 0 ? o0 : (v == 1 ? o1 : o2);
+        const float fx = v == 0 ? x0 : (v == 1 ? x1 : x2);
+        const float fy = v == 0 ? y0 : (v == 1 ? y1 : y2);
         if (li < 2 * kViews) {
           const uint32_t o00 = offv & 0x3fffffffu, dx = (offv >> 30) & 1u, dy = offv >> 31;
           const float4* pr = images + (size_t)v * HW + o00 + (rowsel ? dy * cams.W : 0u);

@@ -2,9 +2,10 @@
 //
 // Feature map layout ("interleaved halves"): a source view's 256 channels are two 128-channel halves,
 // one per image pair the view takes part in (models/matchnerf.py:192-205).  A texel is stored as 256
-// fp16 = 512 B; the gather kernel reads it with 8 lanes x 64 B, and lane l of those 8 holds original channels
-//   half0[16l .. 16l+15], half1[16l .. 16l+15]
-// i.e. packed position p = 32*l + j  <->  channel (j < 16 ? 0 : 128) + 16*l + (j & 15).
+// fp16 = 512 B; the gather kernel reads it with 8 lanes x 4 loads of 16 B, load j of lane l being the 16-byte slot
+// 8*j + l (so one load instruction of a lane group covers 128 contiguous bytes); lane l thereby holds channels
+//   half0[16l .. 16l+15] (loads 0,1) and half1[16l .. 16l+15] (loads 2,3)
+// i.e. packed position p = 64*j + 8*l + e  <->  channel (j < 2 ? 0 : 128) + 16*l + 8*(j & 1) + e.
 // Every lane therefore owns the same channel indices of both halves of every view, which makes all three
 // pair products (v0h0.v1h0, v0h1.v2h0, v1h1.v2h1) lane-local; a fine-scale cosine group (16 channels) is
 // lane-local and a coarse group (64 channels) is a run of 4 lanes.
@@ -32,9 +33,8 @@ __global__ void pack_features_kernel(const float* __restrict__ in, __half* __res
     __align__(16) __half vals[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int pp = slot * 8 + j;                 // packed position
-      const int l = pp >> 5, jj = pp & 31;
-      const int c = (jj < 16 ? 0 : 128) + 16 * l + (jj & 15);
+      const int ld = slot >> 3, l = slot & 7;      // 16-byte slot = 8 * load + lane
+      const int c = (ld < 2 ? 0 : 128) + 16 * l + 8 * (ld & 1) + j;
       vals[j] = __float2half_rn(tile[c][pix]);
     }
     *reinterpret_cast<uint4*>(out + ((size_t)v * hw + p) * kFeatCh + slot * 8) = *reinterpret_cast<const uint4*>(vals);

@@ -51,9 +51,9 @@ def test_pack_features_layout(ctx):
     imgs = torch.rand(1, 3, 3, 40, 56, generator=g)
     packed, _ = make_scene(ctx, [f[None], torch.randn(1, 3, 256, 10, 14, generator=g)], imgs, *synth.synthetic_cameras(40, 56))
     p = packed.feat0.cpu().float()                                   # [V,h,w,256] packed order
-    lane = torch.arange(8).repeat_interleave(32)
-    j = torch.arange(32).repeat(8)
-    chan = torch.where(j < 16, 0, 128) + 16 * lane + (j & 15)        # DESIGN.md "feature map layout"
+    pos = torch.arange(256)
+    ld, lane, e = pos // 64, (pos // 8) % 8, pos % 8
+    chan = torch.where(ld < 2, 0, 128) + 16 * lane + 8 * (ld & 1) + e    # DESIGN.md "feature map layout"
     assert torch.equal(p, f.half().float().permute(0, 2, 3, 1)[..., chan])
     assert torch.equal(packed.images.cpu()[..., :3].permute(0, 3, 1, 2), imgs[0])
 
