@@ -157,8 +157,10 @@ int32_t mnf_window_attn_fwd(mnf_ctx* ctx, const float* q, const float* k, const 
 /* ---- self tests of the tcgen05 building blocks (used by tests/ on the GPU box) ------------- */
 /* D[128][N] = A[128][K] * B[N][K]^T with fp16 operands, fp32 accumulate, one CTA.
  * mode 0: A and B from shared memory (SWIZZLE_128B K-major descriptors);
- * mode 1: A staged in tensor memory (tcgen05.st), B from shared memory.
- * a_f16 [128][K], b_f16 [N][K] device fp16; d_f32 [128][N] device fp32.  K % 64 == 0, N % 16 == 0, N <= 256. */
+ * mode 1: A staged in tensor memory (tcgen05.st), B from shared memory;
+ * mode 2: as mode 1 with B given as [K][N] and consumed as an MN-major operand (N % 64 == 0).
+ * a_f16 [128][K], b_f16 [N][K] ([K][N] in mode 2) device fp16; d_f32 [128][N] device fp32.
+ * K % 64 == 0, K <= 256, N % 16 == 0, N <= 256. */
 int32_t mnf_selftest_umma(const void* a_f16, const void* b_f16, float* d_f32, int32_t N, int32_t K,
                           int32_t mode, void* stream);
 

@@ -285,9 +285,10 @@ class Context:
     def selftest_umma(self, a: torch.Tensor, b: torch.Tensor, mode: int) -> torch.Tensor:
         a = a.to(self.device, torch.float16).contiguous()
         b = b.to(self.device, torch.float16).contiguous()
-        assert a.shape[0] == 128 and a.shape[1] == b.shape[1]
-        d = torch.empty((128, b.shape[0]), dtype=torch.float32, device=self.device)
-        _check(self.lib.mnf_selftest_umma(a.data_ptr(), b.data_ptr(), d.data_ptr(), b.shape[0], a.shape[1], mode,
+        n = b.shape[1] if mode == 2 else b.shape[0]
+        assert a.shape[0] == 128 and a.shape[1] == (b.shape[0] if mode == 2 else b.shape[1])
+        d = torch.empty((128, n), dtype=torch.float32, device=self.device)
+        _check(self.lib.mnf_selftest_umma(a.data_ptr(), b.data_ptr(), d.data_ptr(), n, a.shape[1], mode,
                                           _stream(self.device)), "mnf_selftest_umma")
         return d
 

@@ -50,13 +50,15 @@ constexpr int kPackedBytes = 13 * kChunkBytes + 2 * kHeadChunkBytes;
 
 struct TcParams {             // small fp32 parameters, staged into shared memory once per CTA
   float bias[7][128];         // trunk layers 0..5, [6] = pts_bias.bias
-  float att_q[256], att_k[256], att_v[256], att_fc[256];
+  float wqkv_t[16][48];       // [in][out]: out 0..15 = w_qs * (log2(e)/2), 16..31 = w_ks, 32..47 = w_vs   (transposed)
+  float fc_t[16][16];         // [in][out] ray_attention.fc
+  float oa0_t[16][16];        // [in][out] out_alpha_linear.0
   float ln_w[16], ln_b[16];
-  float oa0_w[256], oa0_b[16], oa2_w[16];
+  float oa0_b[16], oa2_w[16];
   float alpha_b[16];
   float views_dir[64 * 3];    // views_linears.0.weight[:, 128:131]
   float views_b[64];          // views bias + views_w[:, :128] . feature_linear.bias   (feature_linear folded in)
-  float rgb_w[3 * 64];
+  float rgb_w4[64][4];        // [hidden][r, g, b, 0]
   float rgb_b[3];
   float oa2_b;
 };
@@ -85,7 +87,47 @@ __device__ __forceinline__ uint32_t gate_relu(uint32_t t, uint32_t g) {  // relu
   const __half2 r = __hfma2_relu(*reinterpret_cast<const __half2*>(&t), *reinterpret_cast<const __half2*>(&g), __float2half2_rn(0.f));
   return *reinterpret_cast<const uint32_t*>(&r);
 }
-__device__ __forceinline__ float act_fn(int kind, float x) { return kind == 0 ? fmaxf(x, 0.f) : (x > 0.f ? x : expm1f(x)); }
+template <int kAct>
+__device__ __forceinline__ float act_fn(float x) {
+  if constexpr (kAct == 0) return fmaxf(x, 0.f);
+  else return x > 0.f ? x : expm1f(x);
+}
+// packed fp32 math (sm_100: FFMA2 / FADD2)
+__device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(const float2 a, const float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+// y[0..15] (+)= W_t[in][out] . x   with W_t rows of `ld` floats in shared memory (broadcast LDS.128 + FFMA2)
+template <int kOut>
+__device__ __forceinline__ void matvec16_t(const float* __restrict__ wt, int ld, const float (&x)[16], float2 (&y)[kOut / 2]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float2 xi = make_float2(x[i], x[i]);
+    const float4* row = reinterpret_cast<const float4*>(wt + i * ld);
+#pragma unroll
+    for (int o4 = 0; o4 < kOut / 4; ++o4) {
+      const float4 w = row[o4];
+      y[2 * o4] = ffma2(xi, make_float2(w.x, w.y), y[2 * o4]);
+      y[2 * o4 + 1] = ffma2(xi, make_float2(w.z, w.w), y[2 * o4 + 1]);
+    }
+  }
+}
 
 }  // namespace
 
@@ -95,6 +137,7 @@ struct DecoderWeightsTC {
 };
 
 // ------------------------------------------------------------------------------------------------------------------
+template <int kAct>
 __global__ void __launch_bounds__(kThreads, 1)
 decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, const mnf_decoder_cfg cfg,
                   const unsigned char* __restrict__ wpacked, const TcParams* __restrict__ gparams,
@@ -287,8 +330,13 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         tc::tmem_ld32(tb + kColD + c0, r);
         tc::tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          gate[c0 / 2 + j] = pack_h2(__uint_as_float(r[2 * j]) + sm.p.bias[6][c0 + 2 * j], __uint_as_float(r[2 * j + 1]) + sm.p.bias[6][c0 + 2 * j + 1]);
+        for (int j = 0; j < 8; ++j) {
+          const float4 b4 = *reinterpret_cast<const float4*>(&sm.p.bias[6][c0 + 4 * j]);
+          const float2 s0 = fadd2(make_float2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), make_float2(b4.x, b4.y));
+          const float2 s1 = fadd2(make_float2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), make_float2(b4.z, b4.w));
+          gate[c0 / 2 + 2 * j] = pack_h2(s0.x, s0.y);
+          gate[c0 / 2 + 2 * j + 1] = pack_h2(s1.x, s1.y);
+        }
       }
       tc::tc_fence_before_sync();
       tc::mbar_arrive(&sm.a_ready[slot]);
@@ -306,9 +354,12 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
           tc::tmem_wait_ld();
           uint32_t o16[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float2 b2 = *reinterpret_cast<const float2*>(bl + c0 + 2 * j);
-            o16[j] = gate_relu(pack_h2(__uint_as_float(r[2 * j]) + b2.x, __uint_as_float(r[2 * j + 1]) + b2.y), gate[c0 / 2 + j]);
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bl + c0 + 4 * j);
+            const float2 s0 = fadd2(make_float2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), make_float2(b4.x, b4.y));
+            const float2 s1 = fadd2(make_float2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), make_float2(b4.z, b4.w));
+            o16[2 * j] = gate_relu(pack_h2(s0.x, s0.y), gate[c0 / 2 + 2 * j]);
+            o16[2 * j + 1] = gate_relu(pack_h2(s1.x, s1.y), gate[c0 / 2 + 2 * j + 1]);
           }
           tc::tmem_st16(tb + kColH + c0 / 2, o16);
         }
@@ -328,101 +379,170 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         tc::tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          float v = act_fn(cfg.raytrans_act, __uint_as_float(r16[j]) + sm.p.alpha_b[j]);
+          float v = act_fn<kAct>(__uint_as_float(r16[j]) + sm.p.alpha_b[j]);
           if (cfg.raytrans_posenc) {   // cond_nerf.py:118-127
             const float ang = (float)s * exp2f(-(float)(j >> 1) * (13.287712379549449f / 8.f));   // s / 10000^(2*(j/2)/16)
             v += (j & 1) ? cosf(ang) : sinf(ang);
           }
           xr[j] = v;
         }
-        float acc3[3] = {sm.p.rgb_b[0], sm.p.rgb_b[1], sm.p.rgb_b[2]};
+        float2 accrg = make_float2(sm.p.rgb_b[0], sm.p.rgb_b[1]);
+        float accb = sm.p.rgb_b[2];
 #pragma unroll
         for (int c0 = 16; c0 < 80; c0 += 32) {
           uint32_t r[32];
           tc::tmem_ld32(tb + kColD + c0, r);
           tc::tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
+          for (int j = 0; j < 32; j += 4) {
             const int o2 = c0 - 16 + j;
-            const float hv = fmaxf(__uint_as_float(r[j]) + sm.dirvec[slot][ray_local][o2], 0.f);
-            acc3[0] = fmaf(hv, sm.p.rgb_w[o2], acc3[0]);
-            acc3[1] = fmaf(hv, sm.p.rgb_w[64 + o2], acc3[1]);
-            acc3[2] = fmaf(hv, sm.p.rgb_w[128 + o2], acc3[2]);
+            const float4 dv = *reinterpret_cast<const float4*>(&sm.dirvec[slot][ray_local][o2]);
+            const float hv[4] = {fmaxf(__uint_as_float(r[j]) + dv.x, 0.f), fmaxf(__uint_as_float(r[j + 1]) + dv.y, 0.f),
+                                 fmaxf(__uint_as_float(r[j + 2]) + dv.z, 0.f), fmaxf(__uint_as_float(r[j + 3]) + dv.w, 0.f)};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float4 w4 = *reinterpret_cast<const float4*>(sm.p.rgb_w4[o2 + t]);
+              accrg = ffma2(make_float2(hv[t], hv[t]), make_float2(w4.x, w4.y), accrg);
+              accb = fmaf(hv[t], w4.z, accb);
+            }
           }
         }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) rgb[c] = 1.f / (1.f + __expf(-acc3[c]));
+        rgb[0] = 1.f / (1.f + __expf(-accrg.x));
+        rgb[1] = 1.f / (1.f + __expf(-accrg.y));
+        rgb[2] = 1.f / (1.f + __expf(-accb));
       }
 
       // ---------------- ray transformer over the S samples of this ray (ray_transformer.py:49-79)
-      float q[16];
+      // q is pre-scaled by log2(e)/temperature; k, v are laid out [dim][head] so that one float4 holds the 4 heads.
+      const bool row_valid = n_views_seen > 1.f;    // cond_nerf.py:83; the mask disables whole QUERY rows (uniform attention)
+      float2 q2[4][2];                              // [dim][head pair]
+      float kn2[4];                                 // |k_h|^2
+      {
+        float2 y[24];
 #pragma unroll
-      for (int oi = 0; oi < 16; ++oi) {
-        float aq = 0.f, ak = 0.f, av = 0.f;
+        for (int i = 0; i < 24; ++i) y[i] = make_float2(0.f, 0.f);
+        matvec16_t<48>(&sm.p.wqkv_t[0][0], 48, xr, y);
+        const float* yf = reinterpret_cast<const float*>(y);   // [0,16) q, [16,32) k, [32,48) v; index = head*4 + dim
+        float4 kk[4], vv[4];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          aq = fmaf(xr[i], sm.p.att_q[oi * 16 + i], aq);
-          ak = fmaf(xr[i], sm.p.att_k[oi * 16 + i], ak);
-          av = fmaf(xr[i], sm.p.att_v[oi * 16 + i], av);
+        for (int dd = 0; dd < 4; ++dd) {
+          q2[dd][0] = make_float2(yf[0 + dd], yf[4 + dd]);
+          q2[dd][1] = make_float2(yf[8 + dd], yf[12 + dd]);
+          kk[dd] = make_float4(yf[16 + dd], yf[20 + dd], yf[24 + dd], yf[28 + dd]);
+          vv[dd] = make_float4(yf[32 + dd], yf[36 + dd], yf[40 + dd], yf[44 + dd]);
         }
-        q[oi] = aq * (0.5f * kLog2e);          // 1/temperature (sqrt(d_k) = 2), and log2(e) for exp2
-        sm.kbuf[slot][row][oi] = ak;
-        sm.vbuf[slot][row][oi] = av;
+        float4* kdst = reinterpret_cast<float4*>(&sm.kbuf[slot][row][0]);
+        float4* vdst = reinterpret_cast<float4*>(&sm.vbuf[slot][row][0]);
+#pragma unroll
+        for (int dd = 0; dd < 4; ++dd) { kdst[dd] = kk[dd]; vdst[dd] = vv[dd]; }
+        kn2[0] = kk[0].x * kk[0].x + kk[1].x * kk[1].x + kk[2].x * kk[2].x + kk[3].x * kk[3].x;
+        kn2[1] = kk[0].y * kk[0].y + kk[1].y * kk[1].y + kk[2].y * kk[2].y + kk[3].y * kk[3].y;
+        kn2[2] = kk[0].z * kk[0].z + kk[1].z * kk[1].z + kk[2].z * kk[2].z + kk[3].z * kk[3].z;
+        kn2[3] = kk[0].w * kk[0].w + kk[1].w * kk[1].w + kk[2].w * kk[2].w + kk[3].w * kk[3].w;
+      }
+      // per-ray max of |k_h|: bounds every score of this ray from above (Cauchy-Schwarz), so one pass suffices
+      {
+        const int seg = S < 32 ? S : 32;
+#pragma unroll
+        for (int hd = 0; hd < 4; ++hd)
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1)
+            if (off < seg) kn2[hd] = fmaxf(kn2[hd], __shfl_xor_sync(0xffffffffu, kn2[hd], off));
+        if (S > 32 && lane == 0)
+#pragma unroll
+          for (int hd = 0; hd < 4; ++hd) sm.red[slot][quarter][hd] = kn2[hd];
       }
       slot_barrier(slot);
       float sigma;
       {
-        const bool row_valid = n_views_seen > 1.f;    // cond_nerf.py:83; masks whole QUERY rows (uniform attention)
-        const float4* kb = reinterpret_cast<const float4*>(&sm.kbuf[slot][ray_local * S][0]);
-        const float4* vb = reinterpret_cast<const float4*>(&sm.vbuf[slot][ray_local * S][0]);
-        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        if (row_valid) {
-          for (int j = 0; j < S; ++j) {
-#pragma unroll
-            for (int hd = 0; hd < 4; ++hd) {
-              const float4 k4 = kb[j * 4 + hd];
-              const float sc = fmaf(q[hd * 4 + 3], k4.w, fmaf(q[hd * 4 + 2], k4.z, fmaf(q[hd * 4 + 1], k4.y, q[hd * 4] * k4.x)));
-              mx[hd] = fmaxf(mx[hd], sc);
-            }
-          }
-        } else {
-#pragma unroll
-          for (int hd = 0; hd < 4; ++hd) { mx[hd] = 0.f; }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) q[i] = 0.f;
-        }
-        float den[4] = {0.f, 0.f, 0.f, 0.f}, att[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) att[i] = 0.f;
-        for (int j = 0; j < S; ++j) {
+        if (S > 32) {
+          const int w0 = (ray_local * S) >> 5;
 #pragma unroll
           for (int hd = 0; hd < 4; ++hd) {
-            const float4 k4 = kb[j * 4 + hd];
-            const float4 v4 = vb[j * 4 + hd];
-            const float sc = fmaf(q[hd * 4 + 3], k4.w, fmaf(q[hd * 4 + 2], k4.z, fmaf(q[hd * 4 + 1], k4.y, fmaf(q[hd * 4], k4.x, -mx[hd]))));
-            const float pe = exp2f(sc);
-            den[hd] += pe;
-            att[hd * 4 + 0] = fmaf(pe, v4.x, att[hd * 4 + 0]);
-            att[hd * 4 + 1] = fmaf(pe, v4.y, att[hd * 4 + 1]);
-            att[hd * 4 + 2] = fmaf(pe, v4.z, att[hd * 4 + 2]);
-            att[hd * 4 + 3] = fmaf(pe, v4.w, att[hd * 4 + 3]);
+            float m = 0.f;
+            for (int w2 = 0; w2 < S / 32; ++w2) m = fmaxf(m, sm.red[slot][w0 + w2][hd]);
+            kn2[hd] = m;
           }
         }
-#pragma unroll
-        for (int hd = 0; hd < 4; ++hd) {
-          const float inv = 1.f / den[hd];
-#pragma unroll
-          for (int dd = 0; dd < 4; ++dd) att[hd * 4 + dd] *= inv;
+        const float4* kb = reinterpret_cast<const float4*>(&sm.kbuf[slot][ray_local * S][0]);
+        const float4* vb = reinterpret_cast<const float4*>(&sm.vbuf[slot][ray_local * S][0]);
+        float2 negm[2];
+        {
+          float qn[4];
+          qn[0] = q2[0][0].x * q2[0][0].x + q2[1][0].x * q2[1][0].x + q2[2][0].x * q2[2][0].x + q2[3][0].x * q2[3][0].x;
+          qn[1] = q2[0][0].y * q2[0][0].y + q2[1][0].y * q2[1][0].y + q2[2][0].y * q2[2][0].y + q2[3][0].y * q2[3][0].y;
+          qn[2] = q2[0][1].x * q2[0][1].x + q2[1][1].x * q2[1][1].x + q2[2][1].x * q2[2][1].x + q2[3][1].x * q2[3][1].x;
+          qn[3] = q2[0][1].y * q2[0][1].y + q2[1][1].y * q2[1][1].y + q2[2][1].y * q2[2][1].y + q2[3][1].y * q2[3][1].y;
+          negm[0] = make_float2(-sqrtf(qn[0] * kn2[0]), -sqrtf(qn[1] * kn2[1]));
+          negm[1] = make_float2(-sqrtf(qn[2] * kn2[2]), -sqrtf(qn[3] * kn2[3]));
         }
+        if (!row_valid) {
+          negm[0] = negm[1] = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int dd = 0; dd < 4; ++dd) q2[dd][0] = q2[dd][1] = make_float2(0.f, 0.f);
+        }
+        float2 den[2], o2[4][2];
+        auto run = [&]() {
+          den[0] = den[1] = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int dd = 0; dd < 4; ++dd) o2[dd][0] = o2[dd][1] = make_float2(0.f, 0.f);
+#pragma unroll 2
+          for (int j = 0; j < S; ++j) {
+            float2 sc0 = negm[0], sc1 = negm[1];
+#pragma unroll
+            for (int dd = 0; dd < 4; ++dd) {
+              const float4 k4 = kb[j * 4 + dd];
+              sc0 = ffma2(q2[dd][0], make_float2(k4.x, k4.y), sc0);
+              sc1 = ffma2(q2[dd][1], make_float2(k4.z, k4.w), sc1);
+            }
+            const float2 p0 = make_float2(exp2f(sc0.x), exp2f(sc0.y)), p1 = make_float2(exp2f(sc1.x), exp2f(sc1.y));
+            den[0] = fadd2(den[0], p0);
+            den[1] = fadd2(den[1], p1);
+#pragma unroll
+            for (int dd = 0; dd < 4; ++dd) {
+              const float4 v4 = vb[j * 4 + dd];
+              o2[dd][0] = ffma2(p0, make_float2(v4.x, v4.y), o2[dd][0]);
+              o2[dd][1] = ffma2(p1, make_float2(v4.z, v4.w), o2[dd][1]);
+            }
+          }
+        };
+        run();
+        if (fminf(fminf(den[0].x, den[0].y), fminf(den[1].x, den[1].y)) < 1e-30f) {
+          // the norm bound was too loose for this row (all exponentials underflowed): redo with the exact row maxima
+          float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+          for (int j = 0; j < S; ++j) {
+            float2 sc0 = make_float2(0.f, 0.f), sc1 = sc0;
+#pragma unroll
+            for (int dd = 0; dd < 4; ++dd) {
+              const float4 k4 = kb[j * 4 + dd];
+              sc0 = ffma2(q2[dd][0], make_float2(k4.x, k4.y), sc0);
+              sc1 = ffma2(q2[dd][1], make_float2(k4.z, k4.w), sc1);
+            }
+            mx[0] = fmaxf(mx[0], sc0.x); mx[1] = fmaxf(mx[1], sc0.y); mx[2] = fmaxf(mx[2], sc1.x); mx[3] = fmaxf(mx[3], sc1.y);
+          }
+          negm[0] = make_float2(-mx[0], -mx[1]);
+          negm[1] = make_float2(-mx[2], -mx[3]);
+          run();
+        }
+        // att[head*4 + dim] = o / den
+        float att[16];
+        {
+          const float inv[4] = {1.f / den[0].x, 1.f / den[0].y, 1.f / den[1].x, 1.f / den[1].y};
+#pragma unroll
+          for (int dd = 0; dd < 4; ++dd) {
+            att[0 + dd] = o2[dd][0].x * inv[0];
+            att[4 + dd] = o2[dd][0].y * inv[1];
+            att[8 + dd] = o2[dd][1].x * inv[2];
+            att[12 + dd] = o2[dd][1].y * inv[3];
+          }
+        }
+        float2 y2[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y2[i] = make_float2(xr[2 * i], xr[2 * i + 1]);     // residual
+        matvec16_t<16>(&sm.p.fc_t[0][0], 16, att, y2);
         float y[16], mu = 0.f;
 #pragma unroll
-        for (int oi = 0; oi < 16; ++oi) {
-          float a = xr[oi];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) a = fmaf(att[i], sm.p.att_fc[oi * 16 + i], a);
-          y[oi] = a;
-          mu += a;
-        }
+        for (int i = 0; i < 8; ++i) { y[2 * i] = y2[i].x; y[2 * i + 1] = y2[i].y; mu += y2[i].x + y2[i].y; }
         mu *= (1.f / 16.f);
         float var = 0.f;
 #pragma unroll
@@ -430,13 +550,15 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         const float rstd = rsqrtf(var * (1.f / 16.f) + 1e-6f);
 #pragma unroll
         for (int i = 0; i < 16; ++i) y[i] = (y[i] - mu) * rstd * sm.p.ln_w[i] + sm.p.ln_b[i];
+        float2 a2[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a2[i] = make_float2(sm.p.oa0_b[2 * i], sm.p.oa0_b[2 * i + 1]);
+        matvec16_t<16>(&sm.p.oa0_t[0][0], 16, y, a2);
         float acc = sm.p.oa2_b;
 #pragma unroll
-        for (int oi = 0; oi < 16; ++oi) {
-          float a = sm.p.oa0_b[oi];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) a = fmaf(y[i], sm.p.oa0_w[oi * 16 + i], a);
-          acc = fmaf(act_fn(cfg.raytrans_act, a), sm.p.oa2_w[oi], acc);
+        for (int i = 0; i < 8; ++i) {
+          acc = fmaf(act_fn<kAct>(a2[i].x), sm.p.oa2_w[2 * i], acc);
+          acc = fmaf(act_fn<kAct>(a2[i].y), sm.p.oa2_w[2 * i + 1], acc);
         }
         sigma = fmaxf(acc, 0.f);
         if (cfg.density_maskfill && n_views_seen < 1.f) sigma = 0.f;
@@ -562,18 +684,27 @@ int decoder_tc_pack(const float* P, const ParamOffsets& off, DecoderWeightsTC** 
   }
   for (int l = 0; l < kDepth; ++l) memcpy(tp.bias[l], P + off.pts_b[l], 128 * sizeof(float));
   memcpy(tp.bias[6], P + off.gate_b, 128 * sizeof(float));
-  memcpy(tp.att_q, P + off.att_q, sizeof(tp.att_q));
-  memcpy(tp.att_k, P + off.att_k, sizeof(tp.att_k));
-  memcpy(tp.att_v, P + off.att_v, sizeof(tp.att_v));
-  memcpy(tp.att_fc, P + off.att_fc, sizeof(tp.att_fc));
+  const float qscale = 0.5f * 1.4426950408889634f;    // 1/temperature (sqrt(d_k) = 2) and log2(e) for exp2
+  for (int i = 0; i < 16; ++i)
+    for (int o = 0; o < 16; ++o) {
+      tp.wqkv_t[i][o] = P[off.att_q + o * 16 + i] * qscale;
+      tp.wqkv_t[i][16 + o] = P[off.att_k + o * 16 + i];
+      tp.wqkv_t[i][32 + o] = P[off.att_v + o * 16 + i];
+      tp.fc_t[i][o] = P[off.att_fc + o * 16 + i];
+      tp.oa0_t[i][o] = P[off.oa0_w + o * 16 + i];
+    }
   memcpy(tp.ln_w, P + off.ln_w, sizeof(tp.ln_w));
   memcpy(tp.ln_b, P + off.ln_b, sizeof(tp.ln_b));
-  memcpy(tp.oa0_w, P + off.oa0_w, sizeof(tp.oa0_w));
   memcpy(tp.oa0_b, P + off.oa0_b, sizeof(tp.oa0_b));
   memcpy(tp.oa2_w, P + off.oa2_w, sizeof(tp.oa2_w));
   tp.oa2_b = P[off.oa2_b];
   memcpy(tp.alpha_b, P + off.alpha_b, sizeof(tp.alpha_b));
-  memcpy(tp.rgb_w, P + off.rgb_w, sizeof(tp.rgb_w));
+  for (int o = 0; o < 64; ++o) {
+    tp.rgb_w4[o][0] = P[off.rgb_w + 0 * 64 + o];
+    tp.rgb_w4[o][1] = P[off.rgb_w + 1 * 64 + o];
+    tp.rgb_w4[o][2] = P[off.rgb_w + 2 * 64 + o];
+    tp.rgb_w4[o][3] = 0.f;
+  }
   memcpy(tp.rgb_b, P + off.rgb_b, sizeof(tp.rgb_b));
 
   DecoderWeightsTC* w = new DecoderWeightsTC();
@@ -608,14 +739,19 @@ int launch_decoder_tc(const DevCams& cams, const DevRays& rays, const mnf_decode
     int dev = 0;
     MNF_CUDA_TRY(cudaGetDevice(&dev));
     MNF_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    MNF_CUDA_TRY(cudaFuncSetAttribute(decoder_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MNF_CUDA_TRY(cudaFuncSetAttribute(decoder_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MNF_CUDA_TRY(cudaFuncSetAttribute(decoder_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   const int rays_per_tile = kTileM / cfg.n_samples;
   const int64_t n_tiles = (rays.n_rays + rays_per_tile - 1) / rays_per_tile;
   const int64_t n_pairs = (n_tiles + 1) / 2;
   const unsigned grid = (unsigned)(n_pairs < n_sm ? n_pairs : n_sm);
-  decoder_tc_kernel<<<grid, kThreads, smem, s>>>(cams, rays, cfg, w->packed, w->params, cond_f16, setbg_opaque, out_rgb,
-                                                 out_depth, out_opacity, aux);
+  if (cfg.raytrans_act == 0)
+    decoder_tc_kernel<0><<<grid, kThreads, smem, s>>>(cams, rays, cfg, w->packed, w->params, cond_f16, setbg_opaque, out_rgb,
+                                                      out_depth, out_opacity, aux);
+  else
+    decoder_tc_kernel<1><<<grid, kThreads, smem, s>>>(cams, rays, cfg, w->packed, w->params, cond_f16, setbg_opaque, out_rgb,
+                                                      out_depth, out_opacity, aux);
   MNF_CUDA_TRY(cudaGetLastError());
   return MNF_OK;
 }

@@ -2,6 +2,8 @@
 // D[128][N] = A[128][K] * B[N][K]^T, fp16 operands, fp32 accumulation in tensor memory, one CTA of 128 threads.
 //   mode 0 (SS): A and B in shared memory, SWIZZLE_128B K-major tiles of 64 columns, written with plain stores.
 //   mode 1 (TS): A written to tensor memory with tcgen05.st (two fp16 per column), B in shared memory.
+//   mode 2 (TS, MN-major B): as mode 1, but B is given as [K][N] (N contiguous) and used as an MN-major operand --
+//           the layout of the V tile in attention (rows = keys, contiguous value channels).
 // tests/test_gpu_tc.py compares the result with a float64 product of the same fp16 inputs.
 #include <cuda_fp16.h>
 
@@ -41,11 +43,21 @@ umma_selftest_kernel(const __half* __restrict__ A, const __half* __restrict__ B,
   const uint32_t a_tmem = tmem + 256;      // columns [256, 256 + K/2) in TS mode
 
   // ---- stage B (and A in SS mode) into the swizzled layout, 16 B chunks
-  for (int i = tid; i < N * (K / 8); i += blockDim.x) {
-    const int row = i / (K / 8), ch = i - row * (K / 8);
-    const int kb = ch / 8, c8 = ch & 7;
-    const uint4 val = *reinterpret_cast<const uint4*>(B + (size_t)row * K + ch * 8);
-    *reinterpret_cast<uint4*>(sB + (size_t)kb * N * 128 + tc::sw128_offset(row, c8 * 8)) = val;
+  if (mode != 2) {
+    for (int i = tid; i < N * (K / 8); i += blockDim.x) {
+      const int row = i / (K / 8), ch = i - row * (K / 8);
+      const int kb = ch / 8, c8 = ch & 7;
+      const uint4 val = *reinterpret_cast<const uint4*>(B + (size_t)row * K + ch * 8);
+      *reinterpret_cast<uint4*>(sB + (size_t)kb * N * 128 + tc::sw128_offset(row, c8 * 8)) = val;
+    }
+  } else {
+    // B[K][N]: tile nb holds columns [64 nb, 64 nb + 64) of all K rows
+    for (int i = tid; i < K * (N / 8); i += blockDim.x) {
+      const int row = i / (N / 8), ch = i - row * (N / 8);
+      const int nb = ch / 8, c8 = ch & 7;
+      const uint4 val = *reinterpret_cast<const uint4*>(B + (size_t)row * N + ch * 8);
+      *reinterpret_cast<uint4*>(sB + (size_t)nb * K * 128 + tc::sw128_offset(row, c8 * 8)) = val;
+    }
   }
   if (mode == 0) {
     for (int i = tid; i < 128 * (K / 8); i += blockDim.x) {
@@ -71,8 +83,14 @@ umma_selftest_kernel(const __half* __restrict__ A, const __half* __restrict__ B,
 
   if (tid == 0) {
     tc::tc_fence_after_sync();
-    const uint32_t idesc = tc::umma_idesc_f16(128, N);
-    for (int kb = 0; kb < kblocks; ++kb) {
+    const uint32_t idesc = tc::umma_idesc_f16(128, N, mode == 2 ? 1u : 0u);
+    if (mode == 2) {
+      for (int ks = 0; ks < K / 16; ++ks) {
+        const uint64_t bdesc = tc::umma_desc_sw128_mn(tc::smem_u32(sB) + ks * 2048, (uint32_t)K * 128u);
+        tc::umma_ts(d_tmem, a_tmem + ks * 8, bdesc, idesc, ks ? 1u : 0u);
+      }
+    }
+    for (int kb = 0; kb < (mode == 2 ? 0 : kblocks); ++kb) {
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {  // 4 x K=16 per 64-wide block; +32 B per step inside the swizzle atom
         const uint64_t bdesc = tc::umma_desc_sw128(tc::smem_u32(sB + (size_t)kb * N * 128) + ks * 32);
@@ -110,11 +128,11 @@ umma_selftest_kernel(const __half* __restrict__ A, const __half* __restrict__ B,
 extern "C" int32_t mnf_selftest_umma(const void* a_f16, const void* b_f16, float* d_f32, int32_t N, int32_t K, int32_t mode,
                                      void* stream) {
   using namespace mnf;
-  if (!a_f16 || !b_f16 || !d_f32 || K % 64 != 0 || K <= 0 || K > 256 || N % 16 != 0 || N < 16 || N > 256 || (mode != 0 && mode != 1)) {
+  if (!a_f16 || !b_f16 || !d_f32 || K % 64 != 0 || K <= 0 || K > 256 || N % 16 != 0 || N < 16 || N > 256 || (mode < 0 || mode > 2) || (mode == 2 && N % 64 != 0)) {
     set_error("mnf_selftest_umma: bad arguments (N=%d K=%d mode=%d)", N, K, mode);
     return MNF_EINVAL;
   }
-  const size_t smem = (size_t)(K / 64) * (128 + N) * 128 + 1024;
+  const size_t smem = (size_t)(K / 64) * 128 * 128 + (size_t)N * K * 2 + 1024;
   MNF_CUDA_TRY(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(reinterpret_cast<const __half*>(a_f16),
                                                               reinterpret_cast<const __half*>(b_f16), d_f32, N, K, mode);

@@ -114,6 +114,19 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// Same physical tile ([rows][64 fp16], 128 B rows, SWIZZLE_128B) used as an MN-MAJOR operand: rows are the K index
+// (e.g. attention keys), the 64 contiguous elements run along N (e.g. value channels).  One descriptor spans the
+// N extent of the MMA: 64-column blocks are `mn_block_bytes` apart (leading byte offset); 8-row groups along K are
+// 1024 B apart (stride byte offset).  A K=16 step advances the start address by two row groups (2048 B).
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t mn_block_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((mn_block_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // byte offset of element (row, col) [col in 0..63 halves] inside one swizzled [rows][64] tile
 __host__ __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t col) {
   return (row >> 3) * 1024 + (row & 7) * 128 + ((((col >> 3) ^ (row & 7)) & 7) << 4) + (col & 7) * 2;
@@ -122,8 +135,8 @@ __host__ __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t
 // Instruction descriptor for kind::f16: fp16 A/B (K-major), fp32 accumulator, M x N tile.
 //   [4,6) c format (1 = f32)  [7,10) a format (0 = f16)  [10,13) b format  [15] a major  [16] b major (0 = K)
 //   [17,23) N >> 3            [24,29) M >> 4
-__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {
-  return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N, uint32_t b_mn_major = 0) {
+  return (1u << 4) | (b_mn_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 // D[tmem] (+)= A[smem desc] * B[smem desc]^T          (issued by ONE thread)

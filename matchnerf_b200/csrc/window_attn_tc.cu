@@ -1,10 +1,279 @@
-// K-attn, tcgen05 variant (placeholder until the tensor-core kernel lands; reports "unsupported").
+// K-attn, tcgen05 variant: GMFlow split-window single-head attention (head dim 128) as flash attention on the
+// 5th-gen tensor cores.
+//
+// Replaces single_head_split_window_attention / single_head_full_attention
+// (models/gmflow/transformer.py:46-105 / :8-16).  The Swin roll, the window partition and the 9-region shifted-window
+// mask (:19-43) are index arithmetic on token ids; the L x L score matrix only ever exists as 128 x 128 tiles in
+// tensor memory.
+//
+// One CTA (256 threads, 2 CTAs per SM) = one 128-query tile of one window; it walks the window's keys in 128-key tiles:
+//   all threads  gather K / V rows of the tile (fp32 global -> fp16 -> SWIZZLE_128B shared-memory tiles);
+//   thread 0     S = Q K^T          tcgen05.mma  A = Q (smem, K-major)   B = K (smem, K-major)   D = S in tensor memory
+//   warps 0-3    thread = query row: online softmax on S (exp2 domain), P -> fp16 written over the dead S columns,
+//                running output O rescaled in tensor memory when a row maximum moved;
+//   thread 0     O += P V           tcgen05.mma  A = P (tensor memory)    B = V (smem, MN-major: rows = keys)
+// Tensor memory: S / P columns [0,128), O columns [128,256).
+#include <cuda_fp16.h>
+
 #include "mnf_common.cuh"
+#include "tcgen05.cuh"
 
 namespace mnf {
-bool window_attn_tc_supports(int, int, int, int, int) { return false; }
-int launch_window_attn_tc(const float*, const float*, const float*, float*, int, int, int, int, int, int, cudaStream_t) {
-  set_error("tcgen05 attention not built");
-  return MNF_EUNSUPPORTED;
+
+namespace {
+
+constexpr int kC = 128;
+constexpr int kTile = 128;
+constexpr int kBlockBytes = kTile * 128;    // [128 rows][64 fp16]
+constexpr int kColS = 0, kColO = 128;
+constexpr int kAttnThreads = 256;
+
+struct AttnTcSmem {
+  alignas(1024) unsigned char q[2][kBlockBytes];
+  unsigned char k[2][kBlockBytes];
+  unsigned char v[2][kBlockBytes];
+  int qtok[kTile];
+  int ktok[kTile];
+  int kreg[kTile];
+  alignas(8) uint64_t bar_s;
+  uint64_t bar_o;
+  uint32_t tmem_base;
+};
+
+struct WinGeomTc {
+  int h, w, wh, ww, sh, sw, splits;
+};
+
+__device__ __forceinline__ void window_token(const WinGeomTc& g, int wy, int wx, int i, int& tok, int& reg) {
+  const int ly = i / g.ww, lx = i - ly * g.ww;
+  const int ry = wy * g.wh + ly, rx = wx * g.ww + lx;          // rolled frame
+  const int oy = (ry + g.sh) % g.h, ox = (rx + g.sw) % g.w;    // original frame (roll by (-sh, -sw))
+  tok = oy * g.w + ox;
+  const int ay = (ry >= g.h - g.wh) + (ry >= g.h - g.sh);      // transformer.py:25-36
+  const int ax = (rx >= g.w - g.ww) + (rx >= g.w - g.sw);
+  reg = (g.sh | g.sw) ? ay * 3 + ax : 0;
 }
+
+__device__ __forceinline__ uint32_t pack_h2f(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// gather 128 rows x 128 fp32 channels (token ids in tok[], -1 = zero row) into two swizzled [128][64] fp16 blocks
+__device__ __forceinline__ void load_rows_swizzled(const float* __restrict__ src, const int* tok, unsigned char* dst,
+                                                   float scale, int tid) {
+  for (int item = tid; item < kTile * 16; item += kAttnThreads) {
+    const int row = item >> 4, ch = item & 15;          // 16 chunks of 8 channels per row
+    uint4 out = make_uint4(0u, 0u, 0u, 0u);
+    const int t = tok[row];
+    if (t >= 0) {
+      const float4* p = reinterpret_cast<const float4*>(src + (size_t)t * kC + ch * 8);
+      const float4 a = __ldg(p), b = __ldg(p + 1);
+      out.x = pack_h2f(a.x * scale, a.y * scale);
+      out.y = pack_h2f(a.z * scale, a.w * scale);
+      out.z = pack_h2f(b.x * scale, b.y * scale);
+      out.w = pack_h2f(b.z * scale, b.w * scale);
+    }
+    *reinterpret_cast<uint4*>(dst + (ch >> 3) * kBlockBytes + tc::sw128_offset(row, (ch & 7) * 8)) = out;
+  }
+}
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+      "r"(r[31])
+      : "memory");
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(kAttnThreads, 2)
+window_attn_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                      float* __restrict__ out, const WinGeomTc g) {
+  extern __shared__ unsigned char smem_dyn[];
+  AttnTcSmem& sm = *reinterpret_cast<AttnTcSmem*>(smem_dyn + ((1024u - (tc::smem_u32(smem_dyn) & 1023u)) & 1023u));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Lw = g.wh * g.ww;
+  const int win = blockIdx.y % (g.splits * g.splits), b = blockIdx.y / (g.splits * g.splits);
+  const int wy = win / g.splits, wx = win - wy * g.splits;
+  const int q0 = blockIdx.x * kTile;
+  const size_t boff = (size_t)b * g.h * g.w * kC;
+  const bool shifted = (g.sh | g.sw) != 0;
+  const float kLog2e = 1.4426950408889634f;
+
+  if (tid == 0) {
+    tc::mbar_init(&sm.bar_s, 1);
+    tc::mbar_init(&sm.bar_o, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 1) tc::tmem_alloc<256>(&sm.tmem_base);
+  int my_qreg = 0;
+  if (tid < kTile) {
+    int tok = -1, reg = 0;
+    if (q0 + tid < Lw) window_token(g, wy, wx, q0 + tid, tok, reg);
+    sm.qtok[tid] = tok;
+    my_qreg = reg;
+  }
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  tc::tc_fence_after_sync();
+  const uint32_t tmem = sm.tmem_base;
+  // Q, pre-scaled so that scores come out in the exp2 domain: (q . k) / sqrt(C) * log2(e)
+  load_rows_swizzled(q + boff, sm.qtok, &sm.q[0][0], rsqrtf((float)kC) * kLog2e, tid);
+
+  const int row = (warp & 3) * 32 + lane;                      // softmax threads: warps 0-3
+  const uint32_t tb = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  float m_run = -INFINITY, l_run = 0.f;
+  const int n_kt = (Lw + kTile - 1) / kTile;
+  const uint32_t idesc_qk = tc::umma_idesc_f16(128, 128, 0), idesc_pv = tc::umma_idesc_f16(128, 128, 1);
+
+  for (int kt = 0; kt < n_kt; ++kt) {
+    const int k0 = kt * kTile;
+    const int n_valid = min(kTile, Lw - k0);
+    if (tid < kTile) {
+      int tok = -1, reg = 0;
+      if (k0 + tid < Lw) window_token(g, wy, wx, k0 + tid, tok, reg);
+      sm.ktok[tid] = tok;
+      sm.kreg[tid] = reg;
+    }
+    __syncthreads();                                            // ktok visible; previous tile's MMAs were waited for below
+    load_rows_swizzled(k + boff, sm.ktok, &sm.k[0][0], 1.0f, tid);
+    load_rows_swizzled(v + boff, sm.ktok, &sm.v[0][0], 1.0f, tid);
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      tc::tc_fence_after_sync();
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint64_t ad = tc::umma_desc_sw128(tc::smem_u32(&sm.q[ks >> 2][0]) + (ks & 3) * 32);
+        const uint64_t bd = tc::umma_desc_sw128(tc::smem_u32(&sm.k[ks >> 2][0]) + (ks & 3) * 32);
+        tc::umma_ss(tmem + kColS, ad, bd, idesc_qk, ks > 0);
+      }
+      tc::umma_commit(&sm.bar_s);
+    }
+    if (warp < 4) {
+      tc::mbar_wait(&sm.bar_s, kt & 1);
+      tc::tc_fence_after_sync();
+      // sweep 1: row maximum of the masked scores
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c0 = 0; c0 < kTile; c0 += 32) {
+        uint32_t r[32];
+        tc::tmem_ld32(tb + kColS + c0, r);
+        tc::tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float s = __uint_as_float(r[j]);
+          if (shifted && sm.kreg[c0 + j] != my_qreg) s += -100.0f * kLog2e;    // transformer.py:41, :90
+          if (c0 + j >= n_valid) s = -INFINITY;
+          mx = fmaxf(mx, s);
+        }
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float alpha = exp2f(m_run - m_new);                // 0 on the first tile (m_run = -inf)
+      // sweep 2: P = exp2(S - m) -> fp16, written over the S columns already consumed (P col = S col / 2)
+      float sum = 0.f;
+#pragma unroll
+      for (int c0 = 0; c0 < kTile; c0 += 32) {
+        uint32_t r[32];
+        tc::tmem_ld32(tb + kColS + c0, r);
+        tc::tmem_wait_ld();
+        uint32_t p16[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float s0 = __uint_as_float(r[j]), s1 = __uint_as_float(r[j + 1]);
+          if (shifted) {
+            if (sm.kreg[c0 + j] != my_qreg) s0 += -100.0f * kLog2e;
+            if (sm.kreg[c0 + j + 1] != my_qreg) s1 += -100.0f * kLog2e;
+          }
+          const float p0 = c0 + j < n_valid ? exp2f(s0 - m_new) : 0.f;
+          const float p1 = c0 + j + 1 < n_valid ? exp2f(s1 - m_new) : 0.f;
+          sum += p0 + p1;
+          p16[j >> 1] = pack_h2f(p0, p1);
+        }
+        tc::tmem_st16(tb + kColS + c0 / 2, p16);
+      }
+      l_run = l_run * alpha + sum;
+      m_run = m_new;
+      // rescale the running output when some row of this warp moved its maximum (warp-collective TMEM access)
+      if (kt > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll
+        for (int c0 = 0; c0 < kC; c0 += 32) {
+          uint32_t r[32];
+          tc::tmem_ld32(tb + kColO + c0, r);
+          tc::tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * alpha);
+          tmem_st32(tb + kColO + c0, r);
+        }
+      }
+      tc::tmem_wait_st();
+      tc::tc_fence_before_sync();
+    }
+    __syncthreads();
+    if (tid == 0) {
+      tc::tc_fence_after_sync();
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {   // 16 keys per step: A = P columns [8 ks, 8 ks + 8), B = V rows [16 ks, 16 ks + 16)
+        const uint64_t bd = tc::umma_desc_sw128_mn(tc::smem_u32(&sm.v[0][0]) + ks * 2048, kBlockBytes);
+        tc::umma_ts(tmem + kColO, tmem + kColS + ks * 8, bd, idesc_pv, (kt | ks) ? 1u : 0u);
+      }
+      tc::umma_commit(&sm.bar_o);
+    }
+    // K / V shared memory and the S / P columns are reused by the next tile: wait for this tile's MMAs
+    tc::mbar_wait(&sm.bar_o, kt & 1);
+    tc::tc_fence_after_sync();
+  }
+
+  if (warp < 4) {
+    const int tok = sm.qtok[row];
+    const float inv = 1.f / l_run;
+#pragma unroll
+    for (int c0 = 0; c0 < kC; c0 += 32) {
+      uint32_t r[32];
+      tc::tmem_ld32(tb + kColO + c0, r);
+      tc::tmem_wait_ld();
+      if (tok >= 0) {
+        float4* dst = reinterpret_cast<float4*>(out + boff + (size_t)tok * kC + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          dst[j] = make_float4(__uint_as_float(r[4 * j]) * inv, __uint_as_float(r[4 * j + 1]) * inv,
+                               __uint_as_float(r[4 * j + 2]) * inv, __uint_as_float(r[4 * j + 3]) * inv);
+      }
+    }
+  }
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc<256>(tmem);
+}
+
+bool window_attn_tc_supports(int B, int h, int w, int C, int num_splits) {
+  return C == kC && B > 0 && h % num_splits == 0 && w % num_splits == 0;
+}
+
+int launch_window_attn_tc(const float* q, const float* k, const float* v, float* out, int B, int h, int w, int C,
+                          int num_splits, int with_shift, cudaStream_t s) {
+  WinGeomTc g;
+  g.h = h; g.w = w; g.splits = num_splits;
+  g.wh = h / num_splits; g.ww = w / num_splits;
+  g.sh = (with_shift && num_splits > 1) ? g.wh / 2 : 0;
+  g.sw = (with_shift && num_splits > 1) ? g.ww / 2 : 0;
+  const int Lw = g.wh * g.ww;
+  const size_t smem = sizeof(AttnTcSmem) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    MNF_CUDA_TRY(cudaFuncSetAttribute(window_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  dim3 grid((Lw + kTile - 1) / kTile, B * num_splits * num_splits);
+  window_attn_tc_kernel<<<grid, kAttnThreads, smem, s>>>(q, k, v, out, g);
+  MNF_CUDA_TRY(cudaGetLastError());
+  return MNF_OK;
+}
+
 }  // namespace mnf

@@ -44,6 +44,17 @@ def test_umma_selftest(ctx, mode, N, K):
     assert max_abs(d, ref) < 2e-3 * max(1.0, float(ref.abs().max())), (mode, N, K, max_abs(d, ref))
 
 
+@pytest.mark.parametrize("N,K", [(128, 128), (64, 64), (128, 64), (256, 128)])
+def test_umma_selftest_mn_major_b(ctx, N, K):
+    """B consumed as an MN-major operand (the V tile of attention: rows = keys, contiguous channels)."""
+    g = torch.Generator().manual_seed(N + K)
+    a = torch.randn(128, K, generator=g).half()
+    b = torch.randn(K, N, generator=g).half()
+    d = ctx.selftest_umma(a, b, 2).cpu()
+    ref = (a.double() @ b.double()).float()
+    assert max_abs(d, ref) < 2e-3 * max(1.0, float(ref.abs().max())), max_abs(d, ref)
+
+
 # ------------------------------------------------------------------------------------------- K-gather
 def test_pack_features_layout(ctx):
     g = torch.Generator().manual_seed(3)
