@@ -4,17 +4,20 @@
 // (models/rfdecoder/ray_transformer.py:49-79), NeRF.composite (models/rfdecoder/nerf.py:101-124) and the view-0
 // NDC / ray-direction preparation of MatchNeRF.render (models/matchnerf.py:120-134).
 //
-// Structure (one persistent CTA per SM, 320 threads):
+// Structure (one persistent CTA per SM, 640 threads = 5 warpgroups, registers rebalanced with setmaxnreg):
 //   warp 0      weight streamer: the packed fp16 weight chunks (pre-swizzled SWIZZLE_128B K-major tiles) are pulled
 //               through a 6-stage shared-memory ring with cp.async.bulk (TMA unit) + mbarrier complete_tx;
 //   warp 1      MMA issuer: one thread issues tcgen05.mma.kind::f16 with the ACTIVATIONS AS THE A OPERAND IN TENSOR
 //               MEMORY (.ts form) and the weights as the B operand from the ring; accumulators in tensor memory;
-//   warps 2-9   two "slots" of 128 threads; a slot owns one 128-sample tile (thread = sample row = TMEM lane).
-//               A slot thread stages its sample (geometry -> positional encoding -> fp16 A operand via tcgen05.st),
-//               runs every epilogue h = relu((acc + b) * gate) -> fp16 -> tcgen05.st, the 16-wide ray transformer
-//               over the samples of its ray, and the alpha compositing scan.  Ray state never leaves the SM.
-// The two slots run the same layer in lock step so one streamed weight chunk feeds 256 samples; while slot A's
-// accumulator is in its epilogue the tensor pipe works on slot B.
+//   warps 4-11  two TRUNK slots of 128 threads (144 registers); a slot owns one 128-sample tile (thread = sample row
+//               = TMEM lane).  A trunk thread stages its sample (geometry -> positional encoding -> fp16 A operand via
+//               tcgen05.st), runs every epilogue h = relu((acc + b) * gate) -> fp16 -> tcgen05.st and the colour /
+//               alpha heads, then hands 21 floats per sample to its ray group through shared memory;
+//   warps 12-19 two RAY groups of 128 threads (96 registers): the 16-wide 4-head ray transformer over the samples of a
+//               ray, the density head and the alpha-compositing scan.  Ray state never leaves the SM.
+// The two trunk slots run the same layer in lock step so one streamed weight chunk feeds 256 samples; while slot A's
+// accumulator is in its epilogue the tensor pipe works on slot B, and while the trunk warps wait for the tensor pipe
+// the ray groups (decoupled by a double-buffered hand-off) keep the CUDA cores busy with the previous tiles.
 //
 // Tensor-memory map per slot (256 columns): D acc [0,128) | H fp16 act [128,192) | ENC fp16 [192,224) | COND fp16 [224,240)
 //
@@ -39,8 +42,9 @@ constexpr int kHeadN = 80;                        // 16 alpha + 64 colour-hidden
 constexpr int kHeadChunkBytes = kHeadN * 128;
 constexpr int kNumChunks = 15;                    // gate, L0, 4 x 2, 3 (L5), 2 (heads)
 constexpr int kNumPhases = 8;                     // gate, L0..L5, heads
-constexpr int kEpiThreads = 256;
-constexpr int kThreads = 64 + kEpiThreads;
+constexpr int kThreads = 640;                     // 5 warpgroups: control | trunk A | trunk B | ray A | ray B
+// register budgets after setmaxnreg (the kernel launches with 65536 / 640 -> 96 registers per thread)
+constexpr int kRegsCtrl = 32, kRegsTrunk = 144;   // 128*32 + 256*144 + 256*96 = 65536
 constexpr int kColD = 0, kColH = 128, kColEnc = 192, kColCond = 224, kSlotCols = 256;
 constexpr int kMaxRaysPerTile = 8;                // S >= 16
 
@@ -70,14 +74,23 @@ struct TcSmem {
   float vbuf[2][kTileM][16];
   float dirvec[2][kMaxRaysPerTile][64];
   float red[2][4][8];
+  float4 hand[2][2][6][kTileM];                    // trunk -> ray hand-off: [slot][buffer][xr0-3, xr4-7, xr8-11, xr12-15, rgb+depth, nviews][row]
   alignas(8) uint64_t w_full[kNumStages];
   uint64_t w_empty[kNumStages];
   uint64_t a_ready[2];
   uint64_t d_full[2];
+  uint64_t ray_full[2][2];
+  uint64_t ray_empty[2][2];
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void slot_barrier(int slot) { asm volatile("bar.sync %0, 128;" ::"r"(slot + 1) : "memory"); }
+__device__ __forceinline__ void trunk_barrier(int slot) { asm volatile("bar.sync %0, 128;" ::"r"(slot + 1) : "memory"); }
+__device__ __forceinline__ void ray_barrier(int slot) { asm volatile("bar.sync %0, 128;" ::"r"(slot + 3) : "memory"); }
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns) {
+  while (!tc::mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
+template <int kRegs> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+template <int kRegs> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
@@ -162,6 +175,10 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&sm.a_ready[i], kTileM);
       tc::mbar_init(&sm.d_full[i], 1);
+      for (int j = 0; j < 2; ++j) {
+        tc::mbar_init(&sm.ray_full[i][j], kTileM);
+        tc::mbar_init(&sm.ray_empty[i][j], kTileM);
+      }
     }
     tc::fence_mbar_init();
   }
@@ -170,21 +187,24 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
   __syncthreads();
   tc::tc_fence_after_sync();
   const uint32_t tmem = sm.tmem_base;
+  const int wg = warp >> 2;      // warpgroup: 0 control, 1-2 trunk slots, 3-4 ray groups
 
-  if (warp == 0) {
-    // ================================================================== weight streamer
-    if (lane == 0) {
-      uint32_t n = 0;
-      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-        for (int c = 0; c < kNumChunks; ++c, ++n) {
-          const uint32_t st = n % kNumStages, par = (n / kNumStages) & 1;
-          tc::mbar_wait(&sm.w_empty[st], par ^ 1);
-          tc::mbar_arrive_expect_tx(&sm.w_full[st], chunk_bytes(c));
-          tc::bulk_g2s(sm.ring[st], wpacked + chunk_offset(c), chunk_bytes(c), &sm.w_full[st]);
+  if (wg == 0) {
+    reg_dec<kRegsCtrl>();
+    if (warp == 0) {
+      // ================================================================== weight streamer
+      if (lane == 0) {
+        uint32_t n = 0;
+        for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+          for (int c = 0; c < kNumChunks; ++c, ++n) {
+            const uint32_t st = n % kNumStages, par = (n / kNumStages) & 1;
+            mbar_wait_sleep(&sm.w_empty[st], par ^ 1, 200);
+            tc::mbar_arrive_expect_tx(&sm.w_full[st], chunk_bytes(c));
+            tc::bulk_g2s(sm.ring[st], wpacked + chunk_offset(c), chunk_bytes(c), &sm.w_full[st]);
+          }
         }
       }
-    }
-  } else if (warp == 1) {
+    } else if (warp == 1) {
     // ================================================================== MMA issuer
     if (lane == 0) {
       const uint32_t idesc128 = tc::umma_idesc_f16(128, 128), idesc_head = tc::umma_idesc_f16(128, kHeadN);
@@ -194,11 +214,11 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
 #pragma unroll 1
         for (int ph = 0; ph < kNumPhases; ++ph) {
           const int nch = ph <= 1 ? 1 : (ph == 6 ? 3 : 2);
-          for (int j = 0; j < nch; ++j) tc::mbar_wait(&sm.w_full[(n + j) % kNumStages], ((n + j) / kNumStages) & 1);
+          for (int j = 0; j < nch; ++j) mbar_wait_sleep(&sm.w_full[(n + j) % kNumStages], ((n + j) / kNumStages) & 1, 20);
 #pragma unroll 1
           for (int slot = 0; slot < 2; ++slot) {
             if (slot == 1 && !active1) break;
-            tc::mbar_wait(&sm.a_ready[slot], ph & 1);
+            mbar_wait_sleep(&sm.a_ready[slot], ph & 1, 20);
             tc::tc_fence_after_sync();
             const uint32_t tb = tmem + slot * kSlotCols;
             const uint32_t d = tb + kColD;
@@ -222,16 +242,18 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         }
       }
     }
-  } else {
-    // ================================================================== slot threads (epilogue / ray state)
-    const int slot = (warp - 2) >> 2;
+    }
+  } else if (wg <= 2) {
+    // ================================================================== trunk slot: staging, epilogues, heads
+    reg_inc<kRegsTrunk>();
+    const int slot = wg - 1;
     const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;             // sample row inside the tile == TMEM lane
     const uint32_t tb = tmem + slot * kSlotCols + ((uint32_t)(quarter * 32) << 16);
     const int ray_local = row / S, s = row - ray_local * S;
-    const float kLog2e = 1.4426950408889634f;
+    uint32_t it = 0;
 
-    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++it) {
       const int64_t tile = 2 * pair + slot;
       if (tile >= n_tiles) break;
       const int64_t ray = tile * rays_per_tile + ray_local;
@@ -317,12 +339,13 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         tc::tmem_st16(tb + kColCond, cnd);
         tc::tmem_wait_st();
         tc::tc_fence_before_sync();
+        trunk_barrier(slot);          // dirvec visible to the whole slot before the heads epilogue
         tc::mbar_arrive(&sm.a_ready[slot]);
       }
 
       // ---------------- gate = pts_bias(cond) + b, kept as 64 packed-half registers for all six layers
       uint32_t gate[64];
-      tc::mbar_wait(&sm.d_full[slot], 0);
+      mbar_wait_sleep(&sm.d_full[slot], 0, 32);
       tc::tc_fence_after_sync();
 #pragma unroll
       for (int c0 = 0; c0 < 128; c0 += 32) {
@@ -344,7 +367,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
       // ---------------- trunk: h = relu((acc + b_l) * gate) -> fp16 -> tensor memory (next layer's A operand)
 #pragma unroll 1
       for (int l = 0; l < kDepth; ++l) {
-        tc::mbar_wait(&sm.d_full[slot], (l + 1) & 1);
+        mbar_wait_sleep(&sm.d_full[slot], (l + 1) & 1, 32);
         tc::tc_fence_after_sync();
         const float* bl = sm.p.bias[l];
 #pragma unroll
@@ -371,7 +394,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
       // ---------------- heads: raw alpha (16) and the colour hidden layer (64)
       float xr[16];
       float rgb[3];
-      tc::mbar_wait(&sm.d_full[slot], 1);
+      mbar_wait_sleep(&sm.d_full[slot], 1, 32);
       tc::tc_fence_after_sync();
       {
         uint32_t r16[16];
@@ -410,6 +433,49 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         rgb[0] = 1.f / (1.f + __expf(-accrg.x));
         rgb[1] = 1.f / (1.f + __expf(-accrg.y));
         rgb[2] = 1.f / (1.f + __expf(-accb));
+      }
+
+
+      // ---------------- hand the per-sample ray-transformer inputs to the ray group of this slot
+      {
+        const uint32_t buf = it & 1;
+        mbar_wait_sleep(&sm.ray_empty[slot][buf], ((it >> 1) & 1) ^ 1, 64);
+        float4* h = &sm.hand[slot][buf][0][row];
+        h[0 * kTileM] = make_float4(xr[0], xr[1], xr[2], xr[3]);
+        h[1 * kTileM] = make_float4(xr[4], xr[5], xr[6], xr[7]);
+        h[2 * kTileM] = make_float4(xr[8], xr[9], xr[10], xr[11]);
+        h[3 * kTileM] = make_float4(xr[12], xr[13], xr[14], xr[15]);
+        h[4 * kTileM] = make_float4(rgb[0], rgb[1], rgb[2], depth_t);
+        h[5 * kTileM] = make_float4(n_views_seen, 0.f, 0.f, 0.f);
+        tc::mbar_arrive(&sm.ray_full[slot][buf]);       // release semantics: the stores above are visible to the waiter
+      }
+      trunk_barrier(slot);   // dirvec is rewritten by the next tile's staging
+    }
+  } else {
+    // ================================================================== ray group: ray transformer + compositing
+    const int slot = wg - 3;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int ray_local = row / S, s = row - ray_local * S;
+    uint32_t it = 0;
+
+    for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++it) {
+      const int64_t tile = 2 * pair + slot;
+      if (tile >= n_tiles) break;
+      const int64_t ray = tile * rays_per_tile + ray_local;
+      const bool valid = ray < rays.n_rays;
+      const size_t n_glob = valid ? (size_t)ray * S + s : 0;
+      float xr[16], rgb[3], depth_t, n_views_seen;
+      {
+        const uint32_t buf = it & 1;
+        mbar_wait_sleep(&sm.ray_full[slot][buf], (it >> 1) & 1, 64);
+        const float4* h = &sm.hand[slot][buf][0][row];
+        const float4 a0 = h[0 * kTileM], a1 = h[1 * kTileM], a2 = h[2 * kTileM], a3 = h[3 * kTileM], a4 = h[4 * kTileM];
+        n_views_seen = h[5 * kTileM].x;
+        xr[0] = a0.x; xr[1] = a0.y; xr[2] = a0.z; xr[3] = a0.w; xr[4] = a1.x; xr[5] = a1.y; xr[6] = a1.z; xr[7] = a1.w;
+        xr[8] = a2.x; xr[9] = a2.y; xr[10] = a2.z; xr[11] = a2.w; xr[12] = a3.x; xr[13] = a3.y; xr[14] = a3.z; xr[15] = a3.w;
+        rgb[0] = a4.x; rgb[1] = a4.y; rgb[2] = a4.z; depth_t = a4.w;
+        tc::mbar_arrive(&sm.ray_empty[slot][buf]);
       }
 
       // ---------------- ray transformer over the S samples of this ray (ray_transformer.py:49-79)
@@ -452,7 +518,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
 #pragma unroll
           for (int hd = 0; hd < 4; ++hd) sm.red[slot][quarter][hd] = kn2[hd];
       }
-      slot_barrier(slot);
+      ray_barrier(slot);
       float sigma;
       {
         if (S > 32) {
@@ -581,7 +647,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         const int wq = quarter;                     // warp index inside the slot == row / 32
         if (S > 32) {
           if (lane == 31) sm.red[slot][wq][5] = incl;
-          slot_barrier(slot);
+          ray_barrier(slot);
           const int w0 = (ray_local * S) >> 5;      // first warp of this ray
           float base = 0.f;
           for (int w2 = w0; w2 < wq; ++w2) base += sm.red[slot][w2][5];
@@ -599,7 +665,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
           if (lane == 0)
 #pragma unroll
             for (int i = 0; i < 5; ++i) sm.red[slot][wq][i] = part[i];
-          slot_barrier(slot);
+          ray_barrier(slot);
           if (s == 0) {
 #pragma unroll
             for (int i = 0; i < 5; ++i) {
@@ -617,7 +683,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
           out_depth[ray] = part[3];
           out_opacity[ray] = part[4];
         }
-        slot_barrier(slot);   // kbuf / vbuf / red / dirvec are rewritten by the next tile
+        ray_barrier(slot);   // kbuf / vbuf / red / dirvec are rewritten by the next tile
       }
     }
   }

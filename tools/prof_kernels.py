@@ -59,6 +59,31 @@ def main():
                                                                                       n_rays=args.rays, impl=impl))
             except RuntimeError as e:
                 print(f"decoder impl={impl}: {e}")
+    if "encoder" in which:
+        from matchnerf_b200.matchnerf import MatchNeRF
+        sys.path.insert(0, ROOT)
+        from bench import make_opts
+        opt = make_opts(S, str(dev))
+        model = MatchNeRF(opt).eval()
+        model.feat_enc.load_state_dict(synth.synthetic_encoder(1))
+        model.to(dev)
+        enc = model.feat_enc
+        images = imgs.to(dev)
+        with torch.no_grad():
+            timeit("encoder total (get_img_feat)", lambda: model.get_img_feat(images))
+            x = enc.normalize_images(images).reshape(3, 3, H, W)
+            timeit("  backbone (3 views)", lambda: enc.backbone(x))
+            base = enc.backbone(x)
+            f0 = torch.stack([base[0], base[0], base[1]])
+            f1 = torch.stack([base[1], base[2], base[2]])
+            timeit("  transformer (3 pairs, 6 blocks)", lambda: enc.transformer(f0, f1, 2))
+            t0, t1 = enc.transformer(f0, f1, 2)
+            timeit("  upsampler", lambda: enc.featup_net(torch.cat([t0, t1], 0)))
+            layer = enc.transformer.layers[0].cross_attn_ffn
+            xx = torch.cat([f0, f1], 0).flatten(2).transpose(1, 2).contiguous()
+            timeit("    one cross_attn_ffn layer", lambda: layer(xx, xx, 64, 80, 2))
+            timeit("    its q/k/v/merge projections + norms only", lambda: (layer.norm1(layer.merge(layer.q_proj(xx))), layer.k_proj(xx), layer.v_proj(xx)))
+            timeit("    its FFN only", lambda: layer.norm2(layer.mlp(torch.cat([xx, xx], dim=-1))))
     if "attn" in which:
         g = torch.Generator().manual_seed(0)
         q, k, v = (torch.randn(6, 64 * 80, 128, generator=g).to(dev) for _ in range(3))
