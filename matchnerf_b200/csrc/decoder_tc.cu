@@ -9,11 +9,11 @@
 //               through a 6-stage shared-memory ring with cp.async.bulk (TMA unit) + mbarrier complete_tx;
 //   warp 1      MMA issuer: one thread issues tcgen05.mma.kind::f16 with the ACTIVATIONS AS THE A OPERAND IN TENSOR
 //               MEMORY (.ts form) and the weights as the B operand from the ring; accumulators in tensor memory;
-//   warps 4-11  two TRUNK slots of 128 threads (144 registers); a slot owns one 128-sample tile (thread = sample row
+//   warps 4-11  two TRUNK slots of 128 threads (136 registers); a slot owns one 128-sample tile (thread = sample row
 //               = TMEM lane).  A trunk thread stages its sample (geometry -> positional encoding -> fp16 A operand via
 //               tcgen05.st), runs every epilogue h = relu((acc + b) * gate) -> fp16 -> tcgen05.st and the colour /
 //               alpha heads, then hands 21 floats per sample to its ray group through shared memory;
-//   warps 12-19 two RAY groups of 128 threads (96 registers): the 16-wide 4-head ray transformer over the samples of a
+//   warps 12-19 two RAY groups of 128 threads (88 registers): the 16-wide 4-head ray transformer over the samples of a
 //               ray, the density head and the alpha-compositing scan.  Ray state never leaves the SM.
 // The two trunk slots run the same layer in lock step so one streamed weight chunk feeds 256 samples; while slot A's
 // accumulator is in its epilogue the tensor pipe works on slot B, and while the trunk warps wait for the tensor pipe
@@ -43,8 +43,9 @@ constexpr int kHeadChunkBytes = kHeadN * 128;
 constexpr int kNumChunks = 15;                    // gate, L0, 4 x 2, 3 (L5), 2 (heads)
 constexpr int kNumPhases = 8;                     // gate, L0..L5, heads
 constexpr int kThreads = 640;                     // 5 warpgroups: control | trunk A | trunk B | ray A | ray B
-// register budgets after setmaxnreg (the kernel launches with 65536 / 640 -> 96 registers per thread)
-constexpr int kRegsCtrl = 32, kRegsTrunk = 144;   // 128*32 + 256*144 + 256*96 = 65536
+// register budgets after setmaxnreg.  The kernel launches with 640 x 96 = 61440 registers and the rebalancing must fit
+// inside that per-CTA pool: 128*32 + 256*136 + 256*88 = 61440.
+constexpr int kRegsCtrl = 32, kRegsTrunk = 136, kRegsRay = 88;
 constexpr int kColD = 0, kColH = 128, kColEnc = 192, kColCond = 224, kSlotCols = 256;
 constexpr int kMaxRaysPerTile = 8;                // S >= 16
 
@@ -86,9 +87,7 @@ struct TcSmem {
 
 __device__ __forceinline__ void trunk_barrier(int slot) { asm volatile("bar.sync %0, 128;" ::"r"(slot + 1) : "memory"); }
 __device__ __forceinline__ void ray_barrier(int slot) { asm volatile("bar.sync %0, 128;" ::"r"(slot + 3) : "memory"); }
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns) {
-  while (!tc::mbar_try_wait(bar, parity)) __nanosleep(ns);
-}
+using tc::mbar_wait_sleep;
 template <int kRegs> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 template <int kRegs> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 
@@ -453,6 +452,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
     }
   } else {
     // ================================================================== ray group: ray transformer + compositing
+    reg_dec<kRegsRay>();
     const int slot = wg - 3;
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;

@@ -32,8 +32,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Every wait is bounded: a protocol bug must surface as a trapped kernel (an error the host sees), never as a hung GPU.
+constexpr uint32_t kWaitTrapSpins = 1u << 26;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if (++spins > kWaitTrapSpins) __trap();
+  }
+}
+// same, yielding the issue slot between polls (for warps whose wake-up latency is not critical)
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (++spins > (kWaitTrapSpins >> 4)) __trap();
   }
 }
 
