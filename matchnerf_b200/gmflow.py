@@ -178,6 +178,25 @@ class UpSampler(nn.Module):
 # ----------------------------------------------------------------------------------------------
 # GMFlow wrapper (models/gmflow/gmflow.py)
 # ----------------------------------------------------------------------------------------------
+class _matmul_precision:
+    """Scoped cuBLAS/cuDNN math mode for the encoder's library calls.  "tf32" lets the 128/256/1024-wide linear layers
+    (48 + 145 GFLOP of fp32 SGEMM per DTU triplet) run on the tensor cores with 10-bit-mantissa operands and
+    fp32 accumulation -- the same operand precision the decoder kernel uses; "fp32" keeps PyTorch's default."""
+
+    def __init__(self, mode: str):
+        self.mode = mode
+
+    def __enter__(self):
+        self.prev = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+        if self.mode == "tf32":
+            torch.backends.cuda.matmul.allow_tf32 = True
+            torch.backends.cudnn.allow_tf32 = True
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = self.prev
+        return False
+
+
 class GMFlow(nn.Module):
     """Encoder used by MatchNeRF: backbone -> pairwise transformer -> up-sampler.
 
@@ -204,8 +223,14 @@ class GMFlow(nn.Module):
         std = torch.tensor([0.229, 0.224, 0.225], device=images.device).view(1, 1, 3, 1, 1)
         return (images - mean) / std
 
+    matmul_precision = "tf32"      # "tf32" | "fp32" for the cuBLAS / cuDNN calls of the encoder
+
     def forward(self, imgs, attn_splits_list: Optional[Sequence[int]] = None, keep_raw_feats: bool = False,
                 wo_self_attn: bool = False, **kwargs):
+        with _matmul_precision(self.matmul_precision):
+            return self._forward(imgs, attn_splits_list, keep_raw_feats, wo_self_attn)
+
+    def _forward(self, imgs, attn_splits_list, keep_raw_feats, wo_self_attn):
         B, V, _, H, W = imgs.shape
         if H == 756 and W == 1008:     # IBRNet setting: pad to a size divisible by 16 (gmflow.py:99-103)
             imgs = F.interpolate(imgs.reshape(B * V, 3, H, W), size=(768, 1024), mode="bilinear",
