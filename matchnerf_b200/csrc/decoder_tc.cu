@@ -125,18 +125,51 @@ __device__ __forceinline__ float2 fadd2(const float2 a, const float2 b) {
       : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
   return d;
 }
-// y[0..15] (+)= W_t[in][out] . x   with W_t rows of `ld` floats in shared memory (broadcast LDS.128 + FFMA2)
+// Packed pairs of fp32 kept in ONE 64-bit register for their whole life, so that FFMA2 / FADD2 need no re-packing
+// moves (ncu of v3: 25 MOVs per 32 FFMA2 in the attention loop when pairs were rebuilt from scalar registers).
+typedef unsigned long long pk2;
+__device__ __forceinline__ pk2 pk(float lo, float hi) {
+  pk2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float pk_lo(pk2 v) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+  return lo;
+}
+__device__ __forceinline__ float pk_hi(pk2 v) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+  return hi;
+}
+__device__ __forceinline__ pk2 pk_fma(pk2 a, pk2 b, pk2 c) {
+  pk2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ pk2 pk_add(pk2 a, pk2 b) {
+  pk2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float ex2_fast(float x) {   // MUFU.EX2 without the denormal-range fix-up of exp2f()
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// y[0..kOut) (+)= W_t[in][out] . x   with W_t rows of `ld` floats in shared memory (broadcast LDS.128 + FFMA2)
 template <int kOut>
-__device__ __forceinline__ void matvec16_t(const float* __restrict__ wt, int ld, const float (&x)[16], float2 (&y)[kOut / 2]) {
+__device__ __forceinline__ void matvec16_t(const float* __restrict__ wt, int ld, const float (&x)[16], pk2 (&y)[kOut / 2]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    const float2 xi = make_float2(x[i], x[i]);
-    const float4* row = reinterpret_cast<const float4*>(wt + i * ld);
+    const pk2 xi = pk(x[i], x[i]);
+    const ulonglong2* row = reinterpret_cast<const ulonglong2*>(wt + i * ld);
 #pragma unroll
     for (int o4 = 0; o4 < kOut / 4; ++o4) {
-      const float4 w = row[o4];
-      y[2 * o4] = ffma2(xi, make_float2(w.x, w.y), y[2 * o4]);
-      y[2 * o4 + 1] = ffma2(xi, make_float2(w.z, w.w), y[2 * o4 + 1]);
+      const ulonglong2 w = row[o4];
+      y[2 * o4] = pk_fma(xi, w.x, y[2 * o4]);
+      y[2 * o4 + 1] = pk_fma(xi, w.y, y[2 * o4 + 1]);
     }
   }
 }
@@ -353,11 +386,11 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         tc::tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 b4 = *reinterpret_cast<const float4*>(&sm.p.bias[6][c0 + 4 * j]);
-          const float2 s0 = fadd2(make_float2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), make_float2(b4.x, b4.y));
-          const float2 s1 = fadd2(make_float2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), make_float2(b4.z, b4.w));
-          gate[c0 / 2 + 2 * j] = pack_h2(s0.x, s0.y);
-          gate[c0 / 2 + 2 * j + 1] = pack_h2(s1.x, s1.y);
+          const ulonglong2 b4 = *reinterpret_cast<const ulonglong2*>(&sm.p.bias[6][c0 + 4 * j]);
+          const pk2 s0 = pk_add(pk(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), b4.x);
+          const pk2 s1 = pk_add(pk(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), b4.y);
+          gate[c0 / 2 + 2 * j] = pack_h2(pk_lo(s0), pk_hi(s0));
+          gate[c0 / 2 + 2 * j + 1] = pack_h2(pk_lo(s1), pk_hi(s1));
         }
       }
       tc::tc_fence_before_sync();
@@ -377,11 +410,11 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
           uint32_t o16[16];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 b4 = *reinterpret_cast<const float4*>(bl + c0 + 4 * j);
-            const float2 s0 = fadd2(make_float2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), make_float2(b4.x, b4.y));
-            const float2 s1 = fadd2(make_float2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), make_float2(b4.z, b4.w));
-            o16[2 * j] = gate_relu(pack_h2(s0.x, s0.y), gate[c0 / 2 + 2 * j]);
-            o16[2 * j + 1] = gate_relu(pack_h2(s1.x, s1.y), gate[c0 / 2 + 2 * j + 1]);
+            const ulonglong2 b4 = *reinterpret_cast<const ulonglong2*>(bl + c0 + 4 * j);
+            const pk2 s0 = pk_add(pk(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), b4.x);
+            const pk2 s1 = pk_add(pk(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), b4.y);
+            o16[2 * j] = gate_relu(pack_h2(pk_lo(s0), pk_hi(s0)), gate[c0 / 2 + 2 * j]);
+            o16[2 * j + 1] = gate_relu(pack_h2(pk_lo(s1), pk_hi(s1)), gate[c0 / 2 + 2 * j + 1]);
           }
           tc::tmem_st16(tb + kColH + c0 / 2, o16);
         }
@@ -408,8 +441,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
           }
           xr[j] = v;
         }
-        float2 accrg = make_float2(sm.p.rgb_b[0], sm.p.rgb_b[1]);
-        float accb = sm.p.rgb_b[2];
+        pk2 accrg = pk(sm.p.rgb_b[0], sm.p.rgb_b[1]), accb = pk(sm.p.rgb_b[2], 0.f);
 #pragma unroll
         for (int c0 = 16; c0 < 80; c0 += 32) {
           uint32_t r[32];
@@ -423,17 +455,17 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
                                  fmaxf(__uint_as_float(r[j + 2]) + dv.z, 0.f), fmaxf(__uint_as_float(r[j + 3]) + dv.w, 0.f)};
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-              const float4 w4 = *reinterpret_cast<const float4*>(sm.p.rgb_w4[o2 + t]);
-              accrg = ffma2(make_float2(hv[t], hv[t]), make_float2(w4.x, w4.y), accrg);
-              accb = fmaf(hv[t], w4.z, accb);
+              const ulonglong2 w4 = *reinterpret_cast<const ulonglong2*>(sm.p.rgb_w4[o2 + t]);
+              const pk2 hh = pk(hv[t], hv[t]);
+              accrg = pk_fma(hh, w4.x, accrg);
+              accb = pk_fma(hh, w4.y, accb);
             }
           }
         }
-        rgb[0] = 1.f / (1.f + __expf(-accrg.x));
-        rgb[1] = 1.f / (1.f + __expf(-accrg.y));
-        rgb[2] = 1.f / (1.f + __expf(-accb));
+        rgb[0] = 1.f / (1.f + __expf(-pk_lo(accrg)));
+        rgb[1] = 1.f / (1.f + __expf(-pk_hi(accrg)));
+        rgb[2] = 1.f / (1.f + __expf(-pk_lo(accb)));
       }
-
 
       // ---------------- hand the per-sample ray-transformer inputs to the ray group of this slot
       {
@@ -479,136 +511,95 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
       }
 
       // ---------------- ray transformer over the S samples of this ray (ray_transformer.py:49-79)
-      // q is pre-scaled by log2(e)/temperature; k, v are laid out [dim][head] so that one float4 holds the 4 heads.
+      // q is pre-scaled by log2(e)/temperature; k, v are laid out [dim][head], so one 16-byte load holds the 4 heads of
+      // a dim as two packed pairs (heads 0,1 | heads 2,3) and every multiply-add below is a packed FFMA2.
       const bool row_valid = n_views_seen > 1.f;    // cond_nerf.py:83; the mask disables whole QUERY rows (uniform attention)
-      float2 q2[4][2];                              // [dim][head pair]
-      float kn2[4];                                 // |k_h|^2
+      pk2 q2[4][2];                                 // [dim][head pair]
       {
-        float2 y[24];
+        pk2 y[24];
 #pragma unroll
-        for (int i = 0; i < 24; ++i) y[i] = make_float2(0.f, 0.f);
+        for (int i = 0; i < 24; ++i) y[i] = 0ull;
         matvec16_t<48>(&sm.p.wqkv_t[0][0], 48, xr, y);
-        const float* yf = reinterpret_cast<const float*>(y);   // [0,16) q, [16,32) k, [32,48) v; index = head*4 + dim
-        float4 kk[4], vv[4];
+        float yf[48];                               // [0,16) q, [16,32) k, [32,48) v; index = head*4 + dim
+#pragma unroll
+        for (int i = 0; i < 24; ++i) { yf[2 * i] = pk_lo(y[i]); yf[2 * i + 1] = pk_hi(y[i]); }
+        ulonglong2* kdst = reinterpret_cast<ulonglong2*>(&sm.kbuf[slot][row][0]);
+        ulonglong2* vdst = reinterpret_cast<ulonglong2*>(&sm.vbuf[slot][row][0]);
 #pragma unroll
         for (int dd = 0; dd < 4; ++dd) {
-          q2[dd][0] = make_float2(yf[0 + dd], yf[4 + dd]);
-          q2[dd][1] = make_float2(yf[8 + dd], yf[12 + dd]);
-          kk[dd] = make_float4(yf[16 + dd], yf[20 + dd], yf[24 + dd], yf[28 + dd]);
-          vv[dd] = make_float4(yf[32 + dd], yf[36 + dd], yf[40 + dd], yf[44 + dd]);
+          q2[dd][0] = pk(yf[0 + dd], yf[4 + dd]);
+          q2[dd][1] = pk(yf[8 + dd], yf[12 + dd]);
+          kdst[dd] = make_ulonglong2(pk(yf[16 + dd], yf[20 + dd]), pk(yf[24 + dd], yf[28 + dd]));
+          vdst[dd] = make_ulonglong2(pk(yf[32 + dd], yf[36 + dd]), pk(yf[40 + dd], yf[44 + dd]));
         }
-        float4* kdst = reinterpret_cast<float4*>(&sm.kbuf[slot][row][0]);
-        float4* vdst = reinterpret_cast<float4*>(&sm.vbuf[slot][row][0]);
-#pragma unroll
-        for (int dd = 0; dd < 4; ++dd) { kdst[dd] = kk[dd]; vdst[dd] = vv[dd]; }
-        kn2[0] = kk[0].x * kk[0].x + kk[1].x * kk[1].x + kk[2].x * kk[2].x + kk[3].x * kk[3].x;
-        kn2[1] = kk[0].y * kk[0].y + kk[1].y * kk[1].y + kk[2].y * kk[2].y + kk[3].y * kk[3].y;
-        kn2[2] = kk[0].z * kk[0].z + kk[1].z * kk[1].z + kk[2].z * kk[2].z + kk[3].z * kk[3].z;
-        kn2[3] = kk[0].w * kk[0].w + kk[1].w * kk[1].w + kk[2].w * kk[2].w + kk[3].w * kk[3].w;
-      }
-      // per-ray max of |k_h|: bounds every score of this ray from above (Cauchy-Schwarz), so one pass suffices
-      {
-        const int seg = S < 32 ? S : 32;
-#pragma unroll
-        for (int hd = 0; hd < 4; ++hd)
-#pragma unroll
-          for (int off = 16; off >= 1; off >>= 1)
-            if (off < seg) kn2[hd] = fmaxf(kn2[hd], __shfl_xor_sync(0xffffffffu, kn2[hd], off));
-        if (S > 32 && lane == 0)
-#pragma unroll
-          for (int hd = 0; hd < 4; ++hd) sm.red[slot][quarter][hd] = kn2[hd];
       }
       ray_barrier(slot);
       float sigma;
       {
-        if (S > 32) {
-          const int w0 = (ray_local * S) >> 5;
-#pragma unroll
-          for (int hd = 0; hd < 4; ++hd) {
-            float m = 0.f;
-            for (int w2 = 0; w2 < S / 32; ++w2) m = fmaxf(m, sm.red[slot][w0 + w2][hd]);
-            kn2[hd] = m;
-          }
-        }
-        const float4* kb = reinterpret_cast<const float4*>(&sm.kbuf[slot][ray_local * S][0]);
-        const float4* vb = reinterpret_cast<const float4*>(&sm.vbuf[slot][ray_local * S][0]);
-        float2 negm[2];
-        {
-          float qn[4];
-          qn[0] = q2[0][0].x * q2[0][0].x + q2[1][0].x * q2[1][0].x + q2[2][0].x * q2[2][0].x + q2[3][0].x * q2[3][0].x;
-          qn[1] = q2[0][0].y * q2[0][0].y + q2[1][0].y * q2[1][0].y + q2[2][0].y * q2[2][0].y + q2[3][0].y * q2[3][0].y;
-          qn[2] = q2[0][1].x * q2[0][1].x + q2[1][1].x * q2[1][1].x + q2[2][1].x * q2[2][1].x + q2[3][1].x * q2[3][1].x;
-          qn[3] = q2[0][1].y * q2[0][1].y + q2[1][1].y * q2[1][1].y + q2[2][1].y * q2[2][1].y + q2[3][1].y * q2[3][1].y;
-          negm[0] = make_float2(-sqrtf(qn[0] * kn2[0]), -sqrtf(qn[1] * kn2[1]));
-          negm[1] = make_float2(-sqrtf(qn[2] * kn2[2]), -sqrtf(qn[3] * kn2[3]));
-        }
+        // Exact two-pass softmax (row maxima first).  A norm bound |q||k|max instead of the first pass was measured to
+        // underflow for 87 % of the rows on real encoder features (scores reach several hundred in the exp2 domain).
+        const ulonglong2* kb = reinterpret_cast<const ulonglong2*>(&sm.kbuf[slot][ray_local * S][0]);
+        const ulonglong2* vb = reinterpret_cast<const ulonglong2*>(&sm.vbuf[slot][ray_local * S][0]);
         if (!row_valid) {
-          negm[0] = negm[1] = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int dd = 0; dd < 4; ++dd) q2[dd][0] = q2[dd][1] = make_float2(0.f, 0.f);
+          for (int dd = 0; dd < 4; ++dd) q2[dd][0] = q2[dd][1] = 0ull;   // masked query row: all scores equal -> uniform attention
         }
-        float2 den[2], o2[4][2];
-        auto run = [&]() {
-          den[0] = den[1] = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int dd = 0; dd < 4; ++dd) o2[dd][0] = o2[dd][1] = make_float2(0.f, 0.f);
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 2
-          for (int j = 0; j < S; ++j) {
-            float2 sc0 = negm[0], sc1 = negm[1];
+        for (int j = 0; j < S; ++j) {
+          pk2 sc0 = 0ull, sc1 = 0ull;
 #pragma unroll
-            for (int dd = 0; dd < 4; ++dd) {
-              const float4 k4 = kb[j * 4 + dd];
-              sc0 = ffma2(q2[dd][0], make_float2(k4.x, k4.y), sc0);
-              sc1 = ffma2(q2[dd][1], make_float2(k4.z, k4.w), sc1);
-            }
-            const float2 p0 = make_float2(exp2f(sc0.x), exp2f(sc0.y)), p1 = make_float2(exp2f(sc1.x), exp2f(sc1.y));
-            den[0] = fadd2(den[0], p0);
-            den[1] = fadd2(den[1], p1);
-#pragma unroll
-            for (int dd = 0; dd < 4; ++dd) {
-              const float4 v4 = vb[j * 4 + dd];
-              o2[dd][0] = ffma2(p0, make_float2(v4.x, v4.y), o2[dd][0]);
-              o2[dd][1] = ffma2(p1, make_float2(v4.z, v4.w), o2[dd][1]);
-            }
+          for (int dd = 0; dd < 4; ++dd) {
+            const ulonglong2 k4 = kb[j * 4 + dd];
+            sc0 = pk_fma(q2[dd][0], k4.x, sc0);
+            sc1 = pk_fma(q2[dd][1], k4.y, sc1);
           }
-        };
-        run();
-        if (fminf(fminf(den[0].x, den[0].y), fminf(den[1].x, den[1].y)) < 1e-30f) {
-          // the norm bound was too loose for this row (all exponentials underflowed): redo with the exact row maxima
-          float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-          for (int j = 0; j < S; ++j) {
-            float2 sc0 = make_float2(0.f, 0.f), sc1 = sc0;
+          mx[0] = fmaxf(mx[0], pk_lo(sc0)); mx[1] = fmaxf(mx[1], pk_hi(sc0));
+          mx[2] = fmaxf(mx[2], pk_lo(sc1)); mx[3] = fmaxf(mx[3], pk_hi(sc1));
+        }
+        const pk2 negm[2] = {pk(-mx[0], -mx[1]), pk(-mx[2], -mx[3])};
+        pk2 den[2] = {0ull, 0ull}, o2[4][2];
 #pragma unroll
-            for (int dd = 0; dd < 4; ++dd) {
-              const float4 k4 = kb[j * 4 + dd];
-              sc0 = ffma2(q2[dd][0], make_float2(k4.x, k4.y), sc0);
-              sc1 = ffma2(q2[dd][1], make_float2(k4.z, k4.w), sc1);
-            }
-            mx[0] = fmaxf(mx[0], sc0.x); mx[1] = fmaxf(mx[1], sc0.y); mx[2] = fmaxf(mx[2], sc1.x); mx[3] = fmaxf(mx[3], sc1.y);
+        for (int dd = 0; dd < 4; ++dd) o2[dd][0] = o2[dd][1] = 0ull;
+#pragma unroll 2
+        for (int j = 0; j < S; ++j) {
+          pk2 sc0 = negm[0], sc1 = negm[1];
+#pragma unroll
+          for (int dd = 0; dd < 4; ++dd) {
+            const ulonglong2 k4 = kb[j * 4 + dd];
+            sc0 = pk_fma(q2[dd][0], k4.x, sc0);
+            sc1 = pk_fma(q2[dd][1], k4.y, sc1);
           }
-          negm[0] = make_float2(-mx[0], -mx[1]);
-          negm[1] = make_float2(-mx[2], -mx[3]);
-          run();
+          const pk2 p0 = pk(ex2_fast(pk_lo(sc0)), ex2_fast(pk_hi(sc0)));
+          const pk2 p1 = pk(ex2_fast(pk_lo(sc1)), ex2_fast(pk_hi(sc1)));
+          den[0] = pk_add(den[0], p0);
+          den[1] = pk_add(den[1], p1);
+#pragma unroll
+          for (int dd = 0; dd < 4; ++dd) {
+            const ulonglong2 v4 = vb[j * 4 + dd];
+            o2[dd][0] = pk_fma(p0, v4.x, o2[dd][0]);
+            o2[dd][1] = pk_fma(p1, v4.y, o2[dd][1]);
+          }
         }
         // att[head*4 + dim] = o / den
         float att[16];
         {
-          const float inv[4] = {1.f / den[0].x, 1.f / den[0].y, 1.f / den[1].x, 1.f / den[1].y};
+          const float inv[4] = {1.f / pk_lo(den[0]), 1.f / pk_hi(den[0]), 1.f / pk_lo(den[1]), 1.f / pk_hi(den[1])};
 #pragma unroll
           for (int dd = 0; dd < 4; ++dd) {
-            att[0 + dd] = o2[dd][0].x * inv[0];
-            att[4 + dd] = o2[dd][0].y * inv[1];
-            att[8 + dd] = o2[dd][1].x * inv[2];
-            att[12 + dd] = o2[dd][1].y * inv[3];
+            att[0 + dd] = pk_lo(o2[dd][0]) * inv[0];
+            att[4 + dd] = pk_hi(o2[dd][0]) * inv[1];
+            att[8 + dd] = pk_lo(o2[dd][1]) * inv[2];
+            att[12 + dd] = pk_hi(o2[dd][1]) * inv[3];
           }
         }
-        float2 y2[8];
+        pk2 y2[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) y2[i] = make_float2(xr[2 * i], xr[2 * i + 1]);     // residual
+        for (int i = 0; i < 8; ++i) y2[i] = pk(xr[2 * i], xr[2 * i + 1]);     // residual
         matvec16_t<16>(&sm.p.fc_t[0][0], 16, att, y2);
         float y[16], mu = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { y[2 * i] = y2[i].x; y[2 * i + 1] = y2[i].y; mu += y2[i].x + y2[i].y; }
+        for (int i = 0; i < 8; ++i) { y[2 * i] = pk_lo(y2[i]); y[2 * i + 1] = pk_hi(y2[i]); mu += y[2 * i] + y[2 * i + 1]; }
         mu *= (1.f / 16.f);
         float var = 0.f;
 #pragma unroll
@@ -616,15 +607,15 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         const float rstd = rsqrtf(var * (1.f / 16.f) + 1e-6f);
 #pragma unroll
         for (int i = 0; i < 16; ++i) y[i] = (y[i] - mu) * rstd * sm.p.ln_w[i] + sm.p.ln_b[i];
-        float2 a2[8];
+        pk2 a2[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) a2[i] = make_float2(sm.p.oa0_b[2 * i], sm.p.oa0_b[2 * i + 1]);
+        for (int i = 0; i < 8; ++i) a2[i] = pk(sm.p.oa0_b[2 * i], sm.p.oa0_b[2 * i + 1]);
         matvec16_t<16>(&sm.p.oa0_t[0][0], 16, y, a2);
         float acc = sm.p.oa2_b;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          acc = fmaf(act_fn<kAct>(a2[i].x), sm.p.oa2_w[2 * i], acc);
-          acc = fmaf(act_fn<kAct>(a2[i].y), sm.p.oa2_w[2 * i + 1], acc);
+          acc = fmaf(act_fn<kAct>(pk_lo(a2[i])), sm.p.oa2_w[2 * i], acc);
+          acc = fmaf(act_fn<kAct>(pk_hi(a2[i])), sm.p.oa2_w[2 * i + 1], acc);
         }
         sigma = fmaxf(acc, 0.f);
         if (cfg.density_maskfill && n_views_seen < 1.f) sigma = 0.f;

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--which", default="gather,decoder,attn")
     ap.add_argument("--impl", type=int, default=0)
+    ap.add_argument("--random-feats", action="store_true", help="N(0,1) feature maps instead of real encoder output")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     ctx = capi.get_context(dev)
@@ -29,6 +30,18 @@ def main():
     feats, imgs, _ = synth.synthetic_scene(H, W, seed=1234)
     extr, intr, nf = synth.synthetic_cameras(H, W)
     ctx.load_decoder(synth.synthetic_decoder(0))
+    if not args.random_feats:
+        # feature maps produced by the encoder (synthetic weights) on random images: the decoder's data-dependent paths
+        # (activation magnitudes, attention score ranges) then match what bench.py runs
+        from matchnerf_b200.matchnerf import MatchNeRF
+        from bench import make_opts
+        m = MatchNeRF(make_opts(S, str(dev))).eval()
+        m.feat_enc.load_state_dict(synth.synthetic_encoder(1))
+        m.to(dev)
+        with torch.no_grad():
+            f = m.get_img_feat(imgs.to(dev))
+        feats = [f[0].cpu(), f[1].cpu()]
+        del m
     packed = ctx.pack_scene([feats[0][0].to(dev), feats[1][0].to(dev)], imgs[0].to(dev), extr[0, :3], intr[0, :3], nf[0, :3])
     sc = packed.c_scene(extr[0, 3, :3], intr[0, 3], nf[0, 3])
     cfg = capi.DecoderCfg()
