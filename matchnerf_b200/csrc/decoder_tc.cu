@@ -53,7 +53,8 @@ __host__ __device__ constexpr int chunk_bytes(int c) { return c < 13 ? kChunkByt
 __host__ __device__ constexpr int chunk_offset(int c) { return c <= 13 ? c * kChunkBytes : 13 * kChunkBytes + (c - 13) * kHeadChunkBytes; }
 constexpr int kPackedBytes = 13 * kChunkBytes + 2 * kHeadChunkBytes;
 
-struct TcParams {             // small fp32 parameters, staged into shared memory once per CTA
+struct TcParams {             // small fp32 parameters, passed BY VALUE as a __grid_constant__ kernel parameter (10.6 KB): they
+                              // live in the constant bank, so matvec weights are FFMA operands and cost no load instruction
   float bias[7][128];         // trunk layers 0..5, [6] = pts_bias.bias
   float wqkv_t[16][48];       // [in][out]: out 0..15 = w_qs * (log2(e)/2), 16..31 = w_ks, 32..47 = w_vs   (transposed)
   float fc_t[16][16];         // [in][out] ray_attention.fc
@@ -70,7 +71,7 @@ struct TcParams {             // small fp32 parameters, staged into shared memor
 
 struct TcSmem {
   alignas(1024) unsigned char ring[kNumStages][kChunkBytes];
-  TcParams p;
+  float qbuf[2][kTileM][16];                       // scaled queries in, normalised head outputs out
   float kbuf[2][kTileM][16];
   float vbuf[2][kTileM][16];
   float dirvec[2][kMaxRaysPerTile][64];
@@ -178,14 +179,14 @@ __device__ __forceinline__ void matvec16_t(const float* __restrict__ wt, int ld,
 
 struct DecoderWeightsTC {
   unsigned char* packed = nullptr;   // device: kPackedBytes of pre-swizzled fp16 chunks
-  TcParams* params = nullptr;        // device
+  TcParams params;                   // host copy, handed to the kernel by value
 };
 
 // ------------------------------------------------------------------------------------------------------------------
 template <int kAct>
 __global__ void __launch_bounds__(kThreads, 1)
 decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, const mnf_decoder_cfg cfg,
-                  const unsigned char* __restrict__ wpacked, const TcParams* __restrict__ gparams,
+                  const unsigned char* __restrict__ wpacked, const __grid_constant__ TcParams P,
                   const __half* __restrict__ cond, const int setbg_opaque, float* __restrict__ out_rgb,
                   float* __restrict__ out_depth, float* __restrict__ out_opacity, float* __restrict__ aux) {
   extern __shared__ unsigned char smem_dyn[];
@@ -197,8 +198,6 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
   const int64_t n_pairs = (n_tiles + 1) / 2;
 
   // ---- one-time setup
-  for (int i = tid; i < (int)(sizeof(TcParams) / 4); i += blockDim.x)
-    reinterpret_cast<float*>(&sm.p)[i] = reinterpret_cast<const float*>(gparams)[i];
   if (tid == 0) {
     for (int i = 0; i < kNumStages; ++i) {
       tc::mbar_init(&sm.w_full[i], 1);
@@ -316,8 +315,8 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         }
         // direction term of the colour head, one vector per ray (the ray's threads split its 64 outputs)
         for (int o2 = s; o2 < 64; o2 += S)
-          sm.dirvec[slot][ray_local][o2] = sm.p.views_dir[o2 * 3] * dir[0] + sm.p.views_dir[o2 * 3 + 1] * dir[1] +
-                                           sm.p.views_dir[o2 * 3 + 2] * dir[2] + sm.p.views_b[o2];
+          sm.dirvec[slot][ray_local][o2] = P.views_dir[o2 * 3] * dir[0] + P.views_dir[o2 * 3 + 1] * dir[1] +
+                                           P.views_dir[o2 * 3 + 2] * dir[2] + P.views_b[o2];
         // encoding order (cond_nerf.py:108-116, :56-57): x, sin(2^k x) k-major, cos(2^k x) k-major, zero pad
         float sn[3], cs[3];
 #pragma unroll
@@ -386,7 +385,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         tc::tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const ulonglong2 b4 = *reinterpret_cast<const ulonglong2*>(&sm.p.bias[6][c0 + 4 * j]);
+          const ulonglong2 b4 = *reinterpret_cast<const ulonglong2*>(&P.bias[6][c0 + 4 * j]);
           const pk2 s0 = pk_add(pk(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), b4.x);
           const pk2 s1 = pk_add(pk(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), b4.y);
           gate[c0 / 2 + 2 * j] = pack_h2(pk_lo(s0), pk_hi(s0));
@@ -401,7 +400,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
       for (int l = 0; l < kDepth; ++l) {
         mbar_wait_sleep(&sm.d_full[slot], (l + 1) & 1, 32);
         tc::tc_fence_after_sync();
-        const float* bl = sm.p.bias[l];
+        const float* bl = P.bias[l];
 #pragma unroll
         for (int c0 = 0; c0 < 128; c0 += 32) {
           uint32_t r[32];
@@ -434,14 +433,14 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         tc::tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          float v = act_fn<kAct>(__uint_as_float(r16[j]) + sm.p.alpha_b[j]);
+          float v = act_fn<kAct>(__uint_as_float(r16[j]) + P.alpha_b[j]);
           if (cfg.raytrans_posenc) {   // cond_nerf.py:118-127
             const float ang = (float)s * exp2f(-(float)(j >> 1) * (13.287712379549449f / 8.f));   // s / 10000^(2*(j/2)/16)
             v += (j & 1) ? cosf(ang) : sinf(ang);
           }
           xr[j] = v;
         }
-        pk2 accrg = pk(sm.p.rgb_b[0], sm.p.rgb_b[1]), accb = pk(sm.p.rgb_b[2], 0.f);
+        pk2 accrg = pk(P.rgb_b[0], P.rgb_b[1]), accb = pk(P.rgb_b[2], 0.f);
 #pragma unroll
         for (int c0 = 16; c0 < 80; c0 += 32) {
           uint32_t r[32];
@@ -455,7 +454,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
                                  fmaxf(__uint_as_float(r[j + 2]) + dv.z, 0.f), fmaxf(__uint_as_float(r[j + 3]) + dv.w, 0.f)};
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-              const ulonglong2 w4 = *reinterpret_cast<const ulonglong2*>(sm.p.rgb_w4[o2 + t]);
+              const ulonglong2 w4 = *reinterpret_cast<const ulonglong2*>(P.rgb_w4[o2 + t]);
               const pk2 hh = pk(hv[t], hv[t]);
               accrg = pk_fma(hh, w4.x, accrg);
               accb = pk_fma(hh, w4.y, accb);
@@ -511,112 +510,127 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
       }
 
       // ---------------- ray transformer over the S samples of this ray (ray_transformer.py:49-79)
-      // q is pre-scaled by log2(e)/temperature; k, v are laid out [dim][head], so one 16-byte load holds the 4 heads of
-      // a dim as two packed pairs (heads 0,1 | heads 2,3) and every multiply-add below is a packed FFMA2.
+      // q is pre-scaled by log2(e)/temperature; q, k, v rows are laid out [dim][head], so an 8-byte load holds one dim of
+      // a head pair and every multiply-add below is a packed FFMA2.
       const bool row_valid = n_views_seen > 1.f;    // cond_nerf.py:83; the mask disables whole QUERY rows (uniform attention)
-      pk2 q2[4][2];                                 // [dim][head pair]
       {
-        pk2 y[24];
+        float y[48];                                // [0,16) q, [16,32) k, [32,48) v; index = head*4 + dim
 #pragma unroll
-        for (int i = 0; i < 24; ++i) y[i] = 0ull;
-        matvec16_t<48>(&sm.p.wqkv_t[0][0], 48, xr, y);
-        float yf[48];                               // [0,16) q, [16,32) k, [32,48) v; index = head*4 + dim
+        for (int o = 0; o < 48; ++o) y[o] = 0.f;
 #pragma unroll
-        for (int i = 0; i < 24; ++i) { yf[2 * i] = pk_lo(y[i]); yf[2 * i + 1] = pk_hi(y[i]); }
+        for (int i = 0; i < 16; ++i)
+#pragma unroll
+          for (int o = 0; o < 48; ++o) y[o] = fmaf(xr[i], P.wqkv_t[i][o], y[o]);     // weights are constant-bank operands
+        ulonglong2* qdst = reinterpret_cast<ulonglong2*>(&sm.qbuf[slot][row][0]);
         ulonglong2* kdst = reinterpret_cast<ulonglong2*>(&sm.kbuf[slot][row][0]);
         ulonglong2* vdst = reinterpret_cast<ulonglong2*>(&sm.vbuf[slot][row][0]);
+        const float qm = row_valid ? 1.f : 0.f;     // masked query row: all scores equal -> uniform attention
 #pragma unroll
         for (int dd = 0; dd < 4; ++dd) {
-          q2[dd][0] = pk(yf[0 + dd], yf[4 + dd]);
-          q2[dd][1] = pk(yf[8 + dd], yf[12 + dd]);
-          kdst[dd] = make_ulonglong2(pk(yf[16 + dd], yf[20 + dd]), pk(yf[24 + dd], yf[28 + dd]));
-          vdst[dd] = make_ulonglong2(pk(yf[32 + dd], yf[36 + dd]), pk(yf[40 + dd], yf[44 + dd]));
+          qdst[dd] = make_ulonglong2(pk(qm * y[0 + dd], qm * y[4 + dd]), pk(qm * y[8 + dd], qm * y[12 + dd]));
+          kdst[dd] = make_ulonglong2(pk(y[16 + dd], y[20 + dd]), pk(y[24 + dd], y[28 + dd]));
+          vdst[dd] = make_ulonglong2(pk(y[32 + dd], y[36 + dd]), pk(y[40 + dd], y[44 + dd]));
         }
       }
       ray_barrier(slot);
       float sigma;
       {
-        // Exact two-pass softmax (row maxima first).  A norm bound |q||k|max instead of the first pass was measured to
-        // underflow for 87 % of the rows on real encoder features (scores reach several hundred in the exp2 domain).
-        const ulonglong2* kb = reinterpret_cast<const ulonglong2*>(&sm.kbuf[slot][ray_local * S][0]);
-        const ulonglong2* vb = reinterpret_cast<const ulonglong2*>(&sm.vbuf[slot][ray_local * S][0]);
-        if (!row_valid) {
+        // Exact two-pass softmax (row maxima first; a norm bound instead of the first pass underflows for 87 % of the
+        // rows on real encoder features).  Work split inside a warp: lane = (pair of adjacent query rows, pair of heads),
+        // so every 8-byte shared-memory load feeds two rows -- broadcast 16-byte loads with lane = row had made the
+        // kernel shared-memory-bandwidth bound (ncu v4: L1/TEX 78 %).
+        const int hp = lane >> 4;                                   // head pair of this lane
+        const int ra = (quarter << 5) + ((lane & 15) << 1);         // first of its two rows (same ray: S is even)
+        const pk2* qa = reinterpret_cast<const pk2*>(&sm.qbuf[slot][ra][0]) + hp;
+        const pk2* kp = reinterpret_cast<const pk2*>(&sm.kbuf[slot][(ra / S) * S][0]) + hp;
+        const pk2* vp = reinterpret_cast<const pk2*>(&sm.vbuf[slot][(ra / S) * S][0]) + hp;
+        pk2 q_a[4], q_b[4];
 #pragma unroll
-          for (int dd = 0; dd < 4; ++dd) q2[dd][0] = q2[dd][1] = 0ull;   // masked query row: all scores equal -> uniform attention
-        }
+        for (int dd = 0; dd < 4; ++dd) { q_a[dd] = qa[dd * 2]; q_b[dd] = qa[8 + dd * 2]; }
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 2
         for (int j = 0; j < S; ++j) {
-          pk2 sc0 = 0ull, sc1 = 0ull;
+          pk2 sa = 0ull, sb = 0ull;
 #pragma unroll
           for (int dd = 0; dd < 4; ++dd) {
-            const ulonglong2 k4 = kb[j * 4 + dd];
-            sc0 = pk_fma(q2[dd][0], k4.x, sc0);
-            sc1 = pk_fma(q2[dd][1], k4.y, sc1);
+            const pk2 k2 = kp[j * 8 + dd * 2];
+            sa = pk_fma(q_a[dd], k2, sa);
+            sb = pk_fma(q_b[dd], k2, sb);
           }
-          mx[0] = fmaxf(mx[0], pk_lo(sc0)); mx[1] = fmaxf(mx[1], pk_hi(sc0));
-          mx[2] = fmaxf(mx[2], pk_lo(sc1)); mx[3] = fmaxf(mx[3], pk_hi(sc1));
+          mx[0] = fmaxf(mx[0], pk_lo(sa)); mx[1] = fmaxf(mx[1], pk_hi(sa));
+          mx[2] = fmaxf(mx[2], pk_lo(sb)); mx[3] = fmaxf(mx[3], pk_hi(sb));
         }
-        const pk2 negm[2] = {pk(-mx[0], -mx[1]), pk(-mx[2], -mx[3])};
-        pk2 den[2] = {0ull, 0ull}, o2[4][2];
+        const pk2 nma = pk(-mx[0], -mx[1]), nmb = pk(-mx[2], -mx[3]);
+        pk2 den_a = 0ull, den_b = 0ull, o_a[4], o_b[4];
 #pragma unroll
-        for (int dd = 0; dd < 4; ++dd) o2[dd][0] = o2[dd][1] = 0ull;
+        for (int dd = 0; dd < 4; ++dd) o_a[dd] = o_b[dd] = 0ull;
 #pragma unroll 2
         for (int j = 0; j < S; ++j) {
-          pk2 sc0 = negm[0], sc1 = negm[1];
+          pk2 sa = nma, sb = nmb;
 #pragma unroll
           for (int dd = 0; dd < 4; ++dd) {
-            const ulonglong2 k4 = kb[j * 4 + dd];
-            sc0 = pk_fma(q2[dd][0], k4.x, sc0);
-            sc1 = pk_fma(q2[dd][1], k4.y, sc1);
+            const pk2 k2 = kp[j * 8 + dd * 2];
+            sa = pk_fma(q_a[dd], k2, sa);
+            sb = pk_fma(q_b[dd], k2, sb);
           }
-          const pk2 p0 = pk(ex2_fast(pk_lo(sc0)), ex2_fast(pk_hi(sc0)));
-          const pk2 p1 = pk(ex2_fast(pk_lo(sc1)), ex2_fast(pk_hi(sc1)));
-          den[0] = pk_add(den[0], p0);
-          den[1] = pk_add(den[1], p1);
+          const pk2 pa = pk(ex2_fast(pk_lo(sa)), ex2_fast(pk_hi(sa)));
+          const pk2 pb = pk(ex2_fast(pk_lo(sb)), ex2_fast(pk_hi(sb)));
+          den_a = pk_add(den_a, pa);
+          den_b = pk_add(den_b, pb);
 #pragma unroll
           for (int dd = 0; dd < 4; ++dd) {
-            const ulonglong2 v4 = vb[j * 4 + dd];
-            o2[dd][0] = pk_fma(p0, v4.x, o2[dd][0]);
-            o2[dd][1] = pk_fma(p1, v4.y, o2[dd][1]);
+            const pk2 v2 = vp[j * 8 + dd * 2];
+            o_a[dd] = pk_fma(pa, v2, o_a[dd]);
+            o_b[dd] = pk_fma(pb, v2, o_b[dd]);
           }
         }
-        // att[head*4 + dim] = o / den
-        float att[16];
+        // normalised head outputs back through shared memory in [head*4 + dim] order (all within this warp)
+        __syncwarp();
         {
-          const float inv[4] = {1.f / pk_lo(den[0]), 1.f / pk_hi(den[0]), 1.f / pk_lo(den[1]), 1.f / pk_hi(den[1])};
+          const float ia0 = 1.f / pk_lo(den_a), ia1 = 1.f / pk_hi(den_a), ib0 = 1.f / pk_lo(den_b), ib1 = 1.f / pk_hi(den_b);
+          float* da = &sm.qbuf[slot][ra][hp * 8];
+          float* db = &sm.qbuf[slot][ra + 1][hp * 8];
+          *reinterpret_cast<float4*>(da) = make_float4(pk_lo(o_a[0]) * ia0, pk_lo(o_a[1]) * ia0, pk_lo(o_a[2]) * ia0, pk_lo(o_a[3]) * ia0);
+          *reinterpret_cast<float4*>(da + 4) = make_float4(pk_hi(o_a[0]) * ia1, pk_hi(o_a[1]) * ia1, pk_hi(o_a[2]) * ia1, pk_hi(o_a[3]) * ia1);
+          *reinterpret_cast<float4*>(db) = make_float4(pk_lo(o_b[0]) * ib0, pk_lo(o_b[1]) * ib0, pk_lo(o_b[2]) * ib0, pk_lo(o_b[3]) * ib0);
+          *reinterpret_cast<float4*>(db + 4) = make_float4(pk_hi(o_b[0]) * ib1, pk_hi(o_b[1]) * ib1, pk_hi(o_b[2]) * ib1, pk_hi(o_b[3]) * ib1);
+        }
+        __syncwarp();
+        float att[16];                                              // att[head*4 + dim] of this thread's own row
+        {
+          const float4* src = reinterpret_cast<const float4*>(&sm.qbuf[slot][row][0]);
 #pragma unroll
-          for (int dd = 0; dd < 4; ++dd) {
-            att[0 + dd] = pk_lo(o2[dd][0]) * inv[0];
-            att[4 + dd] = pk_hi(o2[dd][0]) * inv[1];
-            att[8 + dd] = pk_lo(o2[dd][1]) * inv[2];
-            att[12 + dd] = pk_hi(o2[dd][1]) * inv[3];
+          for (int i = 0; i < 4; ++i) {
+            const float4 t4 = src[i];
+            att[4 * i] = t4.x; att[4 * i + 1] = t4.y; att[4 * i + 2] = t4.z; att[4 * i + 3] = t4.w;
           }
         }
-        pk2 y2[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) y2[i] = pk(xr[2 * i], xr[2 * i + 1]);     // residual
-        matvec16_t<16>(&sm.p.fc_t[0][0], 16, att, y2);
         float y[16], mu = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { y[2 * i] = pk_lo(y2[i]); y[2 * i + 1] = pk_hi(y2[i]); mu += y[2 * i] + y[2 * i + 1]; }
+        for (int o = 0; o < 16; ++o) y[o] = xr[o];                  // residual
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+#pragma unroll
+          for (int o = 0; o < 16; ++o) y[o] = fmaf(att[i], P.fc_t[i][o], y[o]);
+#pragma unroll
+        for (int o = 0; o < 16; ++o) mu += y[o];
         mu *= (1.f / 16.f);
         float var = 0.f;
 #pragma unroll
         for (int i = 0; i < 16; ++i) var += (y[i] - mu) * (y[i] - mu);
         const float rstd = rsqrtf(var * (1.f / 16.f) + 1e-6f);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) y[i] = (y[i] - mu) * rstd * sm.p.ln_w[i] + sm.p.ln_b[i];
-        pk2 a2[8];
+        for (int i = 0; i < 16; ++i) y[i] = (y[i] - mu) * rstd * P.ln_w[i] + P.ln_b[i];
+        float a1[16];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) a2[i] = pk(sm.p.oa0_b[2 * i], sm.p.oa0_b[2 * i + 1]);
-        matvec16_t<16>(&sm.p.oa0_t[0][0], 16, y, a2);
-        float acc = sm.p.oa2_b;
+        for (int o = 0; o < 16; ++o) a1[o] = P.oa0_b[o];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          acc = fmaf(act_fn<kAct>(pk_lo(a2[i])), sm.p.oa2_w[2 * i], acc);
-          acc = fmaf(act_fn<kAct>(pk_hi(a2[i])), sm.p.oa2_w[2 * i + 1], acc);
-        }
+        for (int i = 0; i < 16; ++i)
+#pragma unroll
+          for (int o = 0; o < 16; ++o) a1[o] = fmaf(y[i], P.oa0_t[i][o], a1[o]);
+        float acc = P.oa2_b;
+#pragma unroll
+        for (int o = 0; o < 16; ++o) acc = fmaf(act_fn<kAct>(a1[o]), P.oa2_w[o], acc);
         sigma = fmaxf(acc, 0.f);
         if (cfg.density_maskfill && n_views_seen < 1.f) sigma = 0.f;
         if (!valid) sigma = 0.f;
@@ -767,8 +781,7 @@ int decoder_tc_pack(const float* P, const ParamOffsets& off, DecoderWeightsTC** 
   DecoderWeightsTC* w = new DecoderWeightsTC();
   MNF_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&w->packed), kPackedBytes));
   MNF_CUDA_TRY(cudaMemcpy(w->packed, buf.data(), kPackedBytes, cudaMemcpyHostToDevice));
-  MNF_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&w->params), sizeof(TcParams)));
-  MNF_CUDA_TRY(cudaMemcpy(w->params, &tp, sizeof(TcParams), cudaMemcpyHostToDevice));
+  w->params = tp;
   *out = w;
   return MNF_OK;
 }
@@ -776,7 +789,6 @@ int decoder_tc_pack(const float* P, const ParamOffsets& off, DecoderWeightsTC** 
 void decoder_tc_free(DecoderWeightsTC* w) {
   if (!w) return;
   cudaFree(w->packed);
-  cudaFree(w->params);
   delete w;
 }
 

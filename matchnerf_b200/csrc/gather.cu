@@ -14,6 +14,8 @@
 // The packed feature layout (pack.cu) makes the three pair products lane-local, a fine-scale cosine group (16 ch)
 // lane-local and a coarse group (64 ch) a run of 4 lanes (2 xor-shuffles).  The 4 rays of a quad are adjacent pixels:
 // their taps mostly coincide, so the 4 groups of one load instruction hit the same L1 lines.
+#include <cstdlib>
+
 #include "mnf_common.cuh"
 
 namespace mnf {
@@ -131,7 +133,8 @@ __device__ __forceinline__ float mean_cosine(const float (&q)[9]) {
 
 }  // namespace
 
-__global__ void __launch_bounds__(256, 2)
+template <int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks)
 gather_cossim_kernel(const __grid_constant__ DevCams cams, const DevRays rays, const int S,
                      const __half* __restrict__ f0, const int h0, const int w0,
                      const __half* __restrict__ f1, const int h1, const int w1,
@@ -271,8 +274,13 @@ int launch_gather(const DevCams& cams, const DevRays& rays, int S, const __half*
   const int warps = 8;
   const int64_t quads = (rays.n_rays + kQuad - 1) / kQuad;
   const int64_t blocks = (quads + warps - 1) / warps;
-  gather_cossim_kernel<<<(unsigned)blocks, warps * 32, 0, s>>>(cams, rays, S, f0, h0, w0, f1, h1, w1,
-                                                              reinterpret_cast<const float4*>(images), cond_f32, cond_f16);
+  static const int occ = [] { const char* e = getenv("MNF_GATHER_OCC"); return e ? atoi(e) : 2; }();   // A/B knob: CTAs per SM
+  if (occ == 3)
+    gather_cossim_kernel<3><<<(unsigned)blocks, warps * 32, 0, s>>>(cams, rays, S, f0, h0, w0, f1, h1, w1,
+                                                                   reinterpret_cast<const float4*>(images), cond_f32, cond_f16);
+  else
+    gather_cossim_kernel<2><<<(unsigned)blocks, warps * 32, 0, s>>>(cams, rays, S, f0, h0, w0, f1, h1, w1,
+                                                                   reinterpret_cast<const float4*>(images), cond_f32, cond_f16);
   MNF_CUDA_TRY(cudaGetLastError());
   return MNF_OK;
 }
