@@ -86,6 +86,22 @@ struct TcSmem {
   uint32_t tmem_base;
 };
 
+// ---- optional timeline trace (debug aid; mnf_debug_decoder_trace): CTA 0 records clock64() at protocol points
+__device__ unsigned long long* g_trace_buf = nullptr;
+__device__ unsigned int g_trace_cap = 0;
+__device__ unsigned int g_trace_cnt = 0;
+// role: 0 mma, 1 trunk, 2 ray.  Only one lane per role group records.
+__device__ __forceinline__ void trace(int role, int slot, int ev, unsigned it) {
+  if (g_trace_buf != nullptr && blockIdx.x == 0) {
+    const unsigned i = atomicAdd(&g_trace_cnt, 1u);
+    if (i < g_trace_cap)
+      g_trace_buf[i] = ((unsigned long long)clock64() << 24) | ((unsigned long long)(role & 15) << 20) | ((unsigned long long)(slot & 15) << 16) |
+                       ((unsigned long long)(ev & 255) << 8) | (it & 255);
+  }
+}
+#define TRACE_TRUNK(ev) do { if (quarter == 0 && lane == 0) trace(1, slot, ev, it); } while (0)
+#define TRACE_RAY(ev) do { if (quarter == 0 && lane == 0) trace(2, slot, ev, it); } while (0)
+
 __device__ __forceinline__ void trunk_barrier(int slot) { asm volatile("bar.sync %0, 128;" ::"r"(slot + 1) : "memory"); }
 __device__ __forceinline__ void ray_barrier(int slot) { asm volatile("bar.sync %0, 128;" ::"r"(slot + 3) : "memory"); }
 using tc::mbar_wait_sleep;
@@ -250,6 +266,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
           for (int slot = 0; slot < 2; ++slot) {
             if (slot == 1 && !active1) break;
             mbar_wait_sleep(&sm.a_ready[slot], ph & 1, 20);
+            trace(0, slot, 10 + ph, (unsigned)(n & 255));
             tc::tc_fence_after_sync();
             const uint32_t tb = tmem + slot * kSlotCols;
             const uint32_t d = tb + kColD;
@@ -267,6 +284,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
               for (int ks = 0; ks < 8; ++ks) tc::umma_ts(d, tb + kColH + ks * 8, bdesc(ks >> 2, ks & 3), idesc_head, ks > 0);
             }
             tc::umma_commit(&sm.d_full[slot]);
+            trace(0, slot, 30 + ph, (unsigned)(n & 255));
           }
           for (int j = 0; j < nch; ++j) tc::umma_commit(&sm.w_empty[(n + j) % kNumStages]);
           n += nch;
@@ -291,6 +309,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
       const bool valid = ray < rays.n_rays;
       const size_t n_glob = valid ? (size_t)ray * S + s : 0;
 
+      TRACE_TRUNK(0);
       // ---------------- stage this sample: geometry -> positional encoding -> fp16 A operands in tensor memory
       float depth_t = 0.f, n_views_seen = 0.f;
       {
@@ -376,7 +395,9 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
 
       // ---------------- gate = pts_bias(cond) + b, kept as 64 packed-half registers for all six layers
       uint32_t gate[64];
+      TRACE_TRUNK(1);
       mbar_wait_sleep(&sm.d_full[slot], 0, 32);
+      TRACE_TRUNK(2);
       tc::tc_fence_after_sync();
 #pragma unroll
       for (int c0 = 0; c0 < 128; c0 += 32) {
@@ -398,7 +419,9 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
       // ---------------- trunk: h = relu((acc + b_l) * gate) -> fp16 -> tensor memory (next layer's A operand)
 #pragma unroll 1
       for (int l = 0; l < kDepth; ++l) {
+        TRACE_TRUNK(10 + l);
         mbar_wait_sleep(&sm.d_full[slot], (l + 1) & 1, 32);
+        TRACE_TRUNK(20 + l);
         tc::tc_fence_after_sync();
         const float* bl = P.bias[l];
 #pragma unroll
@@ -425,7 +448,9 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
       // ---------------- heads: raw alpha (16) and the colour hidden layer (64)
       float xr[16];
       float rgb[3];
+      TRACE_TRUNK(3);
       mbar_wait_sleep(&sm.d_full[slot], 1, 32);
+      TRACE_TRUNK(4);
       tc::tc_fence_after_sync();
       {
         uint32_t r16[16];
@@ -469,7 +494,9 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
       // ---------------- hand the per-sample ray-transformer inputs to the ray group of this slot
       {
         const uint32_t buf = it & 1;
+        TRACE_TRUNK(5);
         mbar_wait_sleep(&sm.ray_empty[slot][buf], ((it >> 1) & 1) ^ 1, 64);
+        TRACE_TRUNK(6);
         float4* h = &sm.hand[slot][buf][0][row];
         h[0 * kTileM] = make_float4(xr[0], xr[1], xr[2], xr[3]);
         h[1 * kTileM] = make_float4(xr[4], xr[5], xr[6], xr[7]);
@@ -480,6 +507,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         tc::mbar_arrive(&sm.ray_full[slot][buf]);       // release semantics: the stores above are visible to the waiter
       }
       trunk_barrier(slot);   // dirvec is rewritten by the next tile's staging
+      TRACE_TRUNK(7);
     }
   } else {
     // ================================================================== ray group: ray transformer + compositing
@@ -499,7 +527,9 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
       float xr[16], rgb[3], depth_t, n_views_seen;
       {
         const uint32_t buf = it & 1;
+        TRACE_RAY(0);
         mbar_wait_sleep(&sm.ray_full[slot][buf], (it >> 1) & 1, 64);
+        TRACE_RAY(1);
         const float4* h = &sm.hand[slot][buf][0][row];
         const float4 a0 = h[0 * kTileM], a1 = h[1 * kTileM], a2 = h[2 * kTileM], a3 = h[3 * kTileM], a4 = h[4 * kTileM];
         n_views_seen = h[5 * kTileM].x;
@@ -532,7 +562,9 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
           vdst[dd] = make_ulonglong2(pk(y[32 + dd], y[36 + dd]), pk(y[40 + dd], y[44 + dd]));
         }
       }
+      TRACE_RAY(2);
       ray_barrier(slot);
+      TRACE_RAY(3);
       float sigma;
       {
         // Exact two-pass softmax (row maxima first; a norm bound instead of the first pass underflows for 87 % of the
@@ -560,6 +592,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
           mx[0] = fmaxf(mx[0], pk_lo(sa)); mx[1] = fmaxf(mx[1], pk_hi(sa));
           mx[2] = fmaxf(mx[2], pk_lo(sb)); mx[3] = fmaxf(mx[3], pk_hi(sb));
         }
+        TRACE_RAY(4);
         const pk2 nma = pk(-mx[0], -mx[1]), nmb = pk(-mx[2], -mx[3]);
         pk2 den_a = 0ull, den_b = 0ull, o_a[4], o_b[4];
 #pragma unroll
@@ -584,6 +617,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
             o_b[dd] = pk_fma(pb, v2, o_b[dd]);
           }
         }
+        TRACE_RAY(5);
         // normalised head outputs back through shared memory in [head*4 + dim] order (all within this warp)
         __syncwarp();
         {
@@ -635,6 +669,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         if (cfg.density_maskfill && n_views_seen < 1.f) sigma = 0.f;
         if (!valid) sigma = 0.f;
       }
+      TRACE_RAY(6);
       if (aux && valid) {
         float4* a4 = reinterpret_cast<float4*>(aux) + n_glob;
         *a4 = make_float4(rgb[0], rgb[1], rgb[2], sigma);
@@ -689,6 +724,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
           out_opacity[ray] = part[4];
         }
         ray_barrier(slot);   // kbuf / vbuf / red / dirvec are rewritten by the next tile
+        TRACE_RAY(7);
       }
     }
   }
@@ -826,3 +862,16 @@ int launch_decoder_tc(const DevCams& cams, const DevRays& rays, const mnf_decode
 }
 
 }  // namespace mnf
+
+// Debug aid (not part of the reference-facing ABI): arm / disarm the decoder timeline trace.  buf = device array of
+// `cap` u64 records ([clock:40 | role:4 | slot:4 | event:8 | iteration:8]); buf = NULL disarms.  Synchronises.
+extern "C" int32_t mnf_debug_decoder_trace(void* buf, int32_t cap) {
+  using namespace mnf;
+  unsigned long long* p = reinterpret_cast<unsigned long long*>(buf);
+  unsigned int c = buf ? (unsigned)cap : 0u, z = 0u;
+  MNF_CUDA_TRY(cudaMemcpyToSymbol(g_trace_buf, &p, sizeof(p)));
+  MNF_CUDA_TRY(cudaMemcpyToSymbol(g_trace_cap, &c, sizeof(c)));
+  MNF_CUDA_TRY(cudaMemcpyToSymbol(g_trace_cnt, &z, sizeof(z)));
+  MNF_CUDA_TRY(cudaDeviceSynchronize());
+  return MNF_OK;
+}
