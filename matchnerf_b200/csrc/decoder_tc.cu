@@ -89,18 +89,20 @@ struct TcSmem {
 // ---- optional timeline trace (debug aid; mnf_debug_decoder_trace): CTA 0 records clock64() at protocol points
 __device__ unsigned long long* g_trace_buf = nullptr;
 __device__ unsigned int g_trace_cap = 0;
-__device__ unsigned int g_trace_cnt = 0;
-// role: 0 mma, 1 trunk, 2 ray.  Only one lane per role group records.
-__device__ __forceinline__ void trace(int role, int slot, int ev, unsigned it) {
+__device__ unsigned int g_trace_unused = 0;
+// role: 0 mma, 1 trunk, 2 ray.  One lane per role group records into its own sixth of the buffer (no atomics, so the
+// probe costs a clock read and one store).
+__device__ __forceinline__ void trace(int role, int slot, int ev, unsigned it, unsigned& n) {
   if (g_trace_buf != nullptr && blockIdx.x == 0) {
-    const unsigned i = atomicAdd(&g_trace_cnt, 1u);
-    if (i < g_trace_cap)
-      g_trace_buf[i] = ((unsigned long long)clock64() << 24) | ((unsigned long long)(role & 15) << 20) | ((unsigned long long)(slot & 15) << 16) |
-                       ((unsigned long long)(ev & 255) << 8) | (it & 255);
+    const unsigned per = g_trace_cap / 6u;
+    if (n < per)
+      g_trace_buf[(unsigned)(role * 2 + slot) * per + n] = ((unsigned long long)clock64() << 24) | ((unsigned long long)(role & 15) << 20) |
+                                                          ((unsigned long long)(slot & 15) << 16) | ((unsigned long long)(ev & 255) << 8) | (it & 255);
+    ++n;
   }
 }
-#define TRACE_TRUNK(ev) do { if (quarter == 0 && lane == 0) trace(1, slot, ev, it); } while (0)
-#define TRACE_RAY(ev) do { if (quarter == 0 && lane == 0) trace(2, slot, ev, it); } while (0)
+#define TRACE_TRUNK(ev) do { if (quarter == 0 && lane == 0) trace(1, slot, ev, it, trace_n); } while (0)
+#define TRACE_RAY(ev) do { if (quarter == 0 && lane == 0) trace(2, slot, ev, it, trace_n); } while (0)
 
 __device__ __forceinline__ void trunk_barrier(int slot) { asm volatile("bar.sync %0, 128;" ::"r"(slot + 1) : "memory"); }
 __device__ __forceinline__ void ray_barrier(int slot) { asm volatile("bar.sync %0, 128;" ::"r"(slot + 3) : "memory"); }
@@ -256,6 +258,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
     if (lane == 0) {
       const uint32_t idesc128 = tc::umma_idesc_f16(128, 128), idesc_head = tc::umma_idesc_f16(128, kHeadN);
       uint32_t n = 0;
+      unsigned trace_n[2] = {0u, 0u};
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         const bool active1 = 2 * pair + 1 < n_tiles;
 #pragma unroll 1
@@ -266,7 +269,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
           for (int slot = 0; slot < 2; ++slot) {
             if (slot == 1 && !active1) break;
             mbar_wait_sleep(&sm.a_ready[slot], ph & 1, 20);
-            trace(0, slot, 10 + ph, (unsigned)(n & 255));
+            trace(0, slot, 10 + ph, (unsigned)(n & 255), trace_n[slot]);
             tc::tc_fence_after_sync();
             const uint32_t tb = tmem + slot * kSlotCols;
             const uint32_t d = tb + kColD;
@@ -284,7 +287,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
               for (int ks = 0; ks < 8; ++ks) tc::umma_ts(d, tb + kColH + ks * 8, bdesc(ks >> 2, ks & 3), idesc_head, ks > 0);
             }
             tc::umma_commit(&sm.d_full[slot]);
-            trace(0, slot, 30 + ph, (unsigned)(n & 255));
+            trace(0, slot, 30 + ph, (unsigned)(n & 255), trace_n[slot]);
           }
           for (int j = 0; j < nch; ++j) tc::umma_commit(&sm.w_empty[(n + j) % kNumStages]);
           n += nch;
@@ -301,6 +304,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
     const uint32_t tb = tmem + slot * kSlotCols + ((uint32_t)(quarter * 32) << 16);
     const int ray_local = row / S, s = row - ray_local * S;
     uint32_t it = 0;
+    unsigned trace_n = 0;
 
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++it) {
       const int64_t tile = 2 * pair + slot;
@@ -517,6 +521,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
     const int row = quarter * 32 + lane;
     const int ray_local = row / S, s = row - ray_local * S;
     uint32_t it = 0;
+    unsigned trace_n = 0;
 
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++it) {
       const int64_t tile = 2 * pair + slot;
@@ -871,7 +876,7 @@ extern "C" int32_t mnf_debug_decoder_trace(void* buf, int32_t cap) {
   unsigned int c = buf ? (unsigned)cap : 0u, z = 0u;
   MNF_CUDA_TRY(cudaMemcpyToSymbol(g_trace_buf, &p, sizeof(p)));
   MNF_CUDA_TRY(cudaMemcpyToSymbol(g_trace_cap, &c, sizeof(c)));
-  MNF_CUDA_TRY(cudaMemcpyToSymbol(g_trace_cnt, &z, sizeof(z)));
+  MNF_CUDA_TRY(cudaMemcpyToSymbol(g_trace_unused, &z, sizeof(z)));
   MNF_CUDA_TRY(cudaDeviceSynchronize());
   return MNF_OK;
 }

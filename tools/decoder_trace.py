@@ -54,7 +54,7 @@ def main():
     _, c16 = ctx.gather_cossim(sc, S, first_ray=first, n_rays=args.rays, want_f32=False, want_f16=True)
     ctx.decoder_composite(sc, cfg, cond_f16=c16, first_ray=first, n_rays=args.rays, impl=2)      # warm-up
     torch.cuda.synchronize()
-    cap = 1 << 17
+    cap = 6 * 4096
     buf = torch.zeros(cap, dtype=torch.int64, device=dev)
     assert lib.mnf_debug_decoder_trace(buf.data_ptr(), cap) == 0
     ctx.decoder_composite(sc, cfg, cond_f16=c16, first_ray=first, n_rays=args.rays, impl=2)
