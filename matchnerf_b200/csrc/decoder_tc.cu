@@ -317,6 +317,25 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
       // ---------------- stage this sample: geometry -> positional encoding -> fp16 A operands in tensor memory
       float depth_t = 0.f, n_views_seen = 0.f;
       {
+        // conditioning row first: its HBM latency hides behind the geometry / encoding arithmetic below
+        uint32_t cnd[16];
+        if (valid) {
+          const uint4* src = reinterpret_cast<const uint4*>(cond + n_glob * kCondPad);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 v4 = __ldg(src + j);
+            cnd[4 * j] = v4.x; cnd[4 * j + 1] = v4.y; cnd[4 * j + 2] = v4.z; cnd[4 * j + 3] = v4.w;
+          }
+          // and pull the row of this slot's NEXT tile towards the SM (next pair = gridDim.x pairs further on)
+          const int64_t next_tile = tile + 2 * (int64_t)gridDim.x;
+          if (next_tile < n_tiles) {
+            const __half* nxt = cond + ((size_t)next_tile * kTileM + row) * kCondPad;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) cnd[j] = 0u;
+        }
         float x[3] = {0.f, 0.f, 0.f};
         float dir[3] = {0.f, 0.f, 0.f};
         if (valid) {
@@ -328,9 +347,9 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
           float p[3];
 #pragma unroll
           for (int i = 0; i < 3; ++i) p[i] = __fadd_rn(o[i], __fmul_rn(d[i], depth_t));
-          project_ndc(cams, 0, p, x[0], x[1], x[2]);
-          const float nrm = fmaxf(sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]), 1e-12f);
-          const float ux = d[0] / nrm, uy = d[1] / nrm, uz = d[2] / nrm;
+          project_ndc_fast(cams, 0, p, x[0], x[1], x[2]);
+          const float rn = rsqrtf(fmaxf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2], 1e-24f));
+          const float ux = d[0] * rn, uy = d[1] * rn, uz = d[2] * rn;
           const float* E = cams.w2c[0];
           dir[0] = ux * E[0] + uy * E[1] + uz * E[2];
           dir[1] = ux * E[4] + uy * E[5] + uz * E[6];
@@ -372,18 +391,6 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
           for (int j = 0; j < 16; ++j) { lo[j] = e[j]; hi[j] = e[16 + j]; }
           tc::tmem_st16(tb + kColEnc, lo);
           tc::tmem_st16(tb + kColEnc + 16, hi);
-        }
-        uint32_t cnd[16];
-        if (valid) {
-          const uint4* src = reinterpret_cast<const uint4*>(cond + n_glob * kCondPad);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 v4 = __ldg(src + j);
-            cnd[4 * j] = v4.x; cnd[4 * j + 1] = v4.y; cnd[4 * j + 2] = v4.z; cnd[4 * j + 3] = v4.w;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) cnd[j] = 0u;
         }
         {  // visibility masks live at cond[19..21]
           const __half2 h9 = *reinterpret_cast<const __half2*>(&cnd[9]);
@@ -428,21 +435,25 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         TRACE_TRUNK(20 + l);
         tc::tc_fence_after_sync();
         const float* bl = P.bias[l];
+        // 16-column chunks, software pipelined: the TMEM load of chunk c+1 is in flight while chunk c is processed
+        uint32_t ra[16], rb[16];
+        tc::tmem_ld16(tb + kColD, ra);
 #pragma unroll
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t r[32];
-          tc::tmem_ld32(tb + kColD + c0, r);
+        for (int c = 0; c < 8; ++c) {
           tc::tmem_wait_ld();
-          uint32_t o16[16];
+          uint32_t (&cur)[16] = (c & 1) ? rb : ra;
+          uint32_t (&nxt)[16] = (c & 1) ? ra : rb;
+          if (c < 7) tc::tmem_ld16(tb + kColD + (c + 1) * 16, nxt);
+          uint32_t o8[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const ulonglong2 b4 = *reinterpret_cast<const ulonglong2*>(bl + c0 + 4 * j);
-            const pk2 s0 = pk_add(pk(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), b4.x);
-            const pk2 s1 = pk_add(pk(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), b4.y);
-            o16[2 * j] = gate_relu(pack_h2(pk_lo(s0), pk_hi(s0)), gate[c0 / 2 + 2 * j]);
-            o16[2 * j + 1] = gate_relu(pack_h2(pk_lo(s1), pk_hi(s1)), gate[c0 / 2 + 2 * j + 1]);
+          for (int j = 0; j < 4; ++j) {
+            const ulonglong2 b4 = *reinterpret_cast<const ulonglong2*>(bl + c * 16 + 4 * j);
+            const pk2 s0 = pk_add(pk(__uint_as_float(cur[4 * j]), __uint_as_float(cur[4 * j + 1])), b4.x);
+            const pk2 s1 = pk_add(pk(__uint_as_float(cur[4 * j + 2]), __uint_as_float(cur[4 * j + 3])), b4.y);
+            o8[2 * j] = gate_relu(pack_h2(pk_lo(s0), pk_hi(s0)), gate[c * 8 + 2 * j]);
+            o8[2 * j + 1] = gate_relu(pack_h2(pk_lo(s1), pk_hi(s1)), gate[c * 8 + 2 * j + 1]);
           }
-          tc::tmem_st16(tb + kColH + c0 / 2, o16);
+          tc::tmem_st8(tb + kColH + c * 8, o8);
         }
         tc::tmem_wait_st();
         tc::tc_fence_before_sync();

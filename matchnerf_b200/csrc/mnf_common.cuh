@@ -53,8 +53,10 @@ struct DevRays {
 // ---- per-ray geometry ---------------------------------------------------------------------
 // misc/camera.py:255-278 (legacy): pixel centre at integer coords; ray = c2w*[K^-1 (x,y,1), 1] - centre.
 __device__ __forceinline__ void cast_ray(const DevCams& c, int64_t pix, float o[3], float d[3]) {
-  const float x = (float)(pix % c.W);
-  const float y = (float)(pix / c.W);
+  const uint32_t pu = (uint32_t)pix, wu = (uint32_t)c.W;   // pixel ids fit 32 bits; 64-bit div/mod is ~10x dearer
+  const uint32_t yi = pu / wu;
+  const float x = (float)(pu - yi * wu);
+  const float y = (float)yi;
   float cam[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
@@ -98,6 +100,23 @@ __device__ __forceinline__ void project_ndc(const DevCams& c, int v, const float
   u = __fdiv_rn(__fdiv_rn(q[0], q[2]), (float)(c.W - 1));
   vv = __fdiv_rn(__fdiv_rn(q[1], q[2]), (float)(c.H - 1));
   z = __fdiv_rn(__fsub_rn(q[2], c.nf[v][0]), __fsub_rn(c.nf[v][1], c.nf[v][0]));
+}
+
+// Same projection with reciprocal-multiply instead of IEEE division (a few ulp).  Used only where the result feeds
+// fp16 operands (decoder positional encoding); the gather keeps the exact form because mask decisions hang on it.
+__device__ __forceinline__ void project_ndc_fast(const DevCams& c, int v, const float p[3], float& u, float& vv, float& z) {
+  const float* E = c.w2c[v];
+  const float* K = c.K[v];
+  float cam[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) cam[i] = fmaf(p[2], E[i * 4 + 2], fmaf(p[1], E[i * 4 + 1], fmaf(p[0], E[i * 4 + 0], E[i * 4 + 3])));
+  float q[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) q[i] = fmaf(cam[2], K[i * 3 + 2], fmaf(cam[1], K[i * 3 + 1], cam[0] * K[i * 3 + 0]));
+  const float rz = __frcp_rn(q[2]);
+  u = q[0] * rz * __frcp_rn((float)(c.W - 1));
+  vv = q[1] * rz * __frcp_rn((float)(c.H - 1));
+  z = (q[2] - c.nf[v][0]) * __frcp_rn(c.nf[v][1] - c.nf[v][0]);
 }
 
 // grid_sample(align_corners=True, padding_mode='border') coordinate: g = uv*2-1; i = ((g+1)/2)*(n-1), clipped.
