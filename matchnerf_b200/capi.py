@@ -13,7 +13,7 @@ from typing import Dict, Optional, Sequence
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmatchnerf_b200.so")
+LIB_PATH = os.environ.get("MNF_LIB_PATH") or os.path.join(_HERE, "libmatchnerf_b200.so")   # override: A/B builds (tools/)
 
 COND_DIM = 22
 COND_PAD = 32

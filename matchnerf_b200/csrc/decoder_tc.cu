@@ -259,21 +259,36 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
       const uint32_t idesc128 = tc::umma_idesc_f16(128, 128), idesc_head = tc::umma_idesc_f16(128, kHeadN);
       uint32_t n = 0;
       unsigned trace_n[2] = {0u, 0u};
+      // The two slots are served in whatever order they become ready (each has its own phase counter inside the pair);
+      // a weight chunk is released when every active slot has consumed it.  Slots re-synchronise only at pair
+      // boundaries, so a slow epilogue of one slot no longer delays the other slot's next layer.
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-        const bool active1 = 2 * pair + 1 < n_tiles;
+        const int n_active = 2 * pair + 1 < n_tiles ? 2 : 1;
+        int ph_of[2] = {0, n_active == 2 ? 0 : kNumPhases};
+        int used[kNumPhases];
+#pragma unroll
+        for (int i = 0; i < kNumPhases; ++i) used[i] = 0;
+        uint32_t idle = 0;
+        while (ph_of[0] < kNumPhases || ph_of[1] < kNumPhases) {
+          bool progressed = false;
 #pragma unroll 1
-        for (int ph = 0; ph < kNumPhases; ++ph) {
-          const int nch = ph <= 1 ? 1 : (ph == 6 ? 3 : 2);
-          for (int j = 0; j < nch; ++j) mbar_wait_sleep(&sm.w_full[(n + j) % kNumStages], ((n + j) / kNumStages) & 1, 20);
-#pragma unroll 1
-          for (int slot = 0; slot < 2; ++slot) {
-            if (slot == 1 && !active1) break;
-            mbar_wait_sleep(&sm.a_ready[slot], ph & 1, 20);
-            trace(0, slot, 10 + ph, (unsigned)(n & 255), trace_n[slot]);
+          for (int t = 0; t < 2; ++t) {
+            const int slot = (ph_of[0] <= ph_of[1]) ? t : 1 - t;     // the slot that is behind gets the first look
+            const int ph = ph_of[slot];
+            if (ph >= kNumPhases) continue;
+            // chunk index of this phase inside the pair: 0,1,2,4,6,8,10,13
+            const int coff = ph <= 1 ? ph : (ph <= 6 ? 2 * ph - 2 : 13);
+            const int nch = ph <= 1 ? 1 : (ph == 6 ? 3 : 2);
+            const uint32_t nb = n + coff;
+            if (!tc::mbar_try_wait(&sm.a_ready[slot], ph & 1)) continue;
+            bool wready = true;
+            for (int j = 0; j < nch; ++j) wready = wready && tc::mbar_try_wait(&sm.w_full[(nb + j) % kNumStages], ((nb + j) / kNumStages) & 1);
+            if (!wready) continue;
+            trace(0, slot, 10 + ph, (unsigned)(nb & 255), trace_n[slot]);
             tc::tc_fence_after_sync();
             const uint32_t tb = tmem + slot * kSlotCols;
             const uint32_t d = tb + kColD;
-            auto bdesc = [&](int j, int ks) { return tc::umma_desc_sw128(tc::smem_u32(sm.ring[(n + j) % kNumStages]) + ks * 32); };
+            auto bdesc = [&](int j, int ks) { return tc::umma_desc_sw128(tc::smem_u32(sm.ring[(nb + j) % kNumStages]) + ks * 32); };
             if (ph == 0) {          // gate = pts_bias(cond): K = 32
               for (int ks = 0; ks < 2; ++ks) tc::umma_ts(d, tb + kColCond + ks * 8, bdesc(0, ks), idesc128, ks > 0);
             } else if (ph == 1) {   // layer 0: K = 64 (encoding)
@@ -287,11 +302,21 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
               for (int ks = 0; ks < 8; ++ks) tc::umma_ts(d, tb + kColH + ks * 8, bdesc(ks >> 2, ks & 3), idesc_head, ks > 0);
             }
             tc::umma_commit(&sm.d_full[slot]);
-            trace(0, slot, 30 + ph, (unsigned)(n & 255), trace_n[slot]);
+            trace(0, slot, 30 + ph, (unsigned)(nb & 255), trace_n[slot]);
+            if (++used[ph] == n_active)
+              for (int j = 0; j < nch; ++j) tc::umma_commit(&sm.w_empty[(nb + j) % kNumStages]);
+            ph_of[slot] = ph + 1;
+            progressed = true;
+            break;
           }
-          for (int j = 0; j < nch; ++j) tc::umma_commit(&sm.w_empty[(n + j) % kNumStages]);
-          n += nch;
+          if (!progressed) {
+            __nanosleep(20);
+            if (++idle > (tc::kWaitTrapSpins >> 4)) __trap();
+          } else {
+            idle = 0;
+          }
         }
+        n += kNumChunks;
       }
     }
     }
