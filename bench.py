@@ -291,12 +291,21 @@ def run_ours(args):
             decoder_composite=dict(ms_per_launch=t_d, rays_per_launch=chunk, launches_per_step=n_chunks, impl=("tcgen05" if impl == 2 else "fp32"),
                                    algorithmic_TFLOPs=dec_tfs, frac_of_tensor_peak=dec_tfs / pk["tensor"]),
             encoder=dict(ms_per_call=t_e, note="torch conv/linear + 12 K-attn launches"))
+        traffic = {}
+        tp = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
+        if os.path.exists(tp):            # measured once under `ncu --set full`; scaled to this launch size
+            tj = json.load(open(tp))
+            for kname in ("gather_cossim_kernel", "decoder_tc_kernel"):
+                traffic[kname] = (tj[kname]["dram_read_bytes"] + tj[kname]["dram_write_bytes"]) * chunk / tj["captured_rays"]
         if t_g * n_chunks >= t_d * n_chunks:
             roofline = dict(kernel="gather_cossim_kernel", bound="hbm", achieved=gather_gbs, peak=pk["hbm"], unit="GB/s",
-                            frac=gather_gbs / pk["hbm"], traffic=None, peak_source=pk["source"])
+                            frac=gather_gbs / pk["hbm"], traffic=traffic.get("gather_cossim_kernel"), peak_source=pk["source"],
+                            note="feature maps are L2-resident (39 MB) and taps are reused out of L1, so algorithmic bytes exceed DRAM traffic; "
+                                 "the kernel is bound by the L1->register path (128 B/clk/SM), see DESIGN.md")
         else:
             roofline = dict(kernel="decoder_%s_kernel" % ("tc" if impl == 2 else "ref"), bound="tensor", achieved=dec_tfs, peak=pk["tensor"],
-                            unit="TFLOP/s", frac=dec_tfs / pk["tensor"], traffic=None, peak_source=pk["source"])
+                            unit="TFLOP/s", frac=dec_tfs / pk["tensor"], traffic=traffic.get("decoder_tc_kernel") if impl == 2 else None,
+                            peak_source=pk["source"])
         launches = args.steps * (n_chunks * 2 + 12 + 3)      # per step: gather+decoder per chunk, 12 K-attn, 3 pack kernels
 
     cpu_baseline = None

@@ -53,8 +53,7 @@ __host__ __device__ constexpr int chunk_bytes(int c) { return c < 13 ? kChunkByt
 __host__ __device__ constexpr int chunk_offset(int c) { return c <= 13 ? c * kChunkBytes : 13 * kChunkBytes + (c - 13) * kHeadChunkBytes; }
 constexpr int kPackedBytes = 13 * kChunkBytes + 2 * kHeadChunkBytes;
 
-struct TcParams {             // small fp32 parameters, passed BY VALUE as a __grid_constant__ kernel parameter (10.6 KB): they
-                              // live in the constant bank, so matvec weights are FFMA operands and cost no load instruction
+struct TcParams {             // small fp32 parameters, staged into shared memory once per CTA
   float bias[7][128];         // trunk layers 0..5, [6] = pts_bias.bias
   float wqkv_t[16][48];       // [in][out]: out 0..15 = w_qs * (log2(e)/2), 16..31 = w_ks, 32..47 = w_vs   (transposed)
   float fc_t[16][16];         // [in][out] ray_attention.fc
@@ -71,7 +70,7 @@ struct TcParams {             // small fp32 parameters, passed BY VALUE as a __g
 
 struct TcSmem {
   alignas(1024) unsigned char ring[kNumStages][kChunkBytes];
-  float qbuf[2][kTileM][16];                       // scaled queries in, normalised head outputs out
+  TcParams p;
   float kbuf[2][kTileM][16];
   float vbuf[2][kTileM][16];
   float dirvec[2][kMaxRaysPerTile][64];
@@ -85,24 +84,6 @@ struct TcSmem {
   uint64_t ray_empty[2][2];
   uint32_t tmem_base;
 };
-
-// ---- optional timeline trace (debug aid; mnf_debug_decoder_trace): CTA 0 records clock64() at protocol points
-__device__ unsigned long long* g_trace_buf = nullptr;
-__device__ unsigned int g_trace_cap = 0;
-__device__ unsigned int g_trace_unused = 0;
-// role: 0 mma, 1 trunk, 2 ray.  One lane per role group records into its own sixth of the buffer (no atomics, so the
-// probe costs a clock read and one store).
-__device__ __forceinline__ void trace(int role, int slot, int ev, unsigned it, unsigned& n) {
-  if (g_trace_buf != nullptr && blockIdx.x == 0) {
-    const unsigned per = g_trace_cap / 6u;
-    if (n < per)
-      g_trace_buf[(unsigned)(role * 2 + slot) * per + n] = ((unsigned long long)clock64() << 24) | ((unsigned long long)(role & 15) << 20) |
-                                                          ((unsigned long long)(slot & 15) << 16) | ((unsigned long long)(ev & 255) << 8) | (it & 255);
-    ++n;
-  }
-}
-#define TRACE_TRUNK(ev) do { if (quarter == 0 && lane == 0) trace(1, slot, ev, it, trace_n); } while (0)
-#define TRACE_RAY(ev) do { if (quarter == 0 && lane == 0) trace(2, slot, ev, it, trace_n); } while (0)
 
 __device__ __forceinline__ void trunk_barrier(int slot) { asm volatile("bar.sync %0, 128;" ::"r"(slot + 1) : "memory"); }
 __device__ __forceinline__ void ray_barrier(int slot) { asm volatile("bar.sync %0, 128;" ::"r"(slot + 3) : "memory"); }
@@ -197,14 +178,14 @@ __device__ __forceinline__ void matvec16_t(const float* __restrict__ wt, int ld,
 
 struct DecoderWeightsTC {
   unsigned char* packed = nullptr;   // device: kPackedBytes of pre-swizzled fp16 chunks
-  TcParams params;                   // host copy, handed to the kernel by value
+  TcParams* params = nullptr;        // device
 };
 
 // ------------------------------------------------------------------------------------------------------------------
 template <int kAct>
 __global__ void __launch_bounds__(kThreads, 1)
 decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, const mnf_decoder_cfg cfg,
-                  const unsigned char* __restrict__ wpacked, const __grid_constant__ TcParams P,
+                  const unsigned char* __restrict__ wpacked, const TcParams* __restrict__ gparams,
                   const __half* __restrict__ cond, const int setbg_opaque, float* __restrict__ out_rgb,
                   float* __restrict__ out_depth, float* __restrict__ out_opacity, float* __restrict__ aux) {
   extern __shared__ unsigned char smem_dyn[];
@@ -216,6 +197,8 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
   const int64_t n_pairs = (n_tiles + 1) / 2;
 
   // ---- one-time setup
+  for (int i = tid; i < (int)(sizeof(TcParams) / 4); i += blockDim.x)
+    reinterpret_cast<float*>(&sm.p)[i] = reinterpret_cast<const float*>(gparams)[i];
   if (tid == 0) {
     for (int i = 0; i < kNumStages; ++i) {
       tc::mbar_init(&sm.w_full[i], 1);
@@ -258,37 +241,20 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
     if (lane == 0) {
       const uint32_t idesc128 = tc::umma_idesc_f16(128, 128), idesc_head = tc::umma_idesc_f16(128, kHeadN);
       uint32_t n = 0;
-      unsigned trace_n[2] = {0u, 0u};
-      // The two slots are served in whatever order they become ready (each has its own phase counter inside the pair);
-      // a weight chunk is released when every active slot has consumed it.  Slots re-synchronise only at pair
-      // boundaries, so a slow epilogue of one slot no longer delays the other slot's next layer.
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-        const int n_active = 2 * pair + 1 < n_tiles ? 2 : 1;
-        int ph_of[2] = {0, n_active == 2 ? 0 : kNumPhases};
-        int used[kNumPhases];
-#pragma unroll
-        for (int i = 0; i < kNumPhases; ++i) used[i] = 0;
-        uint32_t idle = 0;
-        while (ph_of[0] < kNumPhases || ph_of[1] < kNumPhases) {
-          bool progressed = false;
+        const bool active1 = 2 * pair + 1 < n_tiles;
 #pragma unroll 1
-          for (int t = 0; t < 2; ++t) {
-            const int slot = (ph_of[0] <= ph_of[1]) ? t : 1 - t;     // the slot that is behind gets the first look
-            const int ph = ph_of[slot];
-            if (ph >= kNumPhases) continue;
-            // chunk index of this phase inside the pair: 0,1,2,4,6,8,10,13
-            const int coff = ph <= 1 ? ph : (ph <= 6 ? 2 * ph - 2 : 13);
-            const int nch = ph <= 1 ? 1 : (ph == 6 ? 3 : 2);
-            const uint32_t nb = n + coff;
-            if (!tc::mbar_try_wait(&sm.a_ready[slot], ph & 1)) continue;
-            bool wready = true;
-            for (int j = 0; j < nch; ++j) wready = wready && tc::mbar_try_wait(&sm.w_full[(nb + j) % kNumStages], ((nb + j) / kNumStages) & 1);
-            if (!wready) continue;
-            trace(0, slot, 10 + ph, (unsigned)(nb & 255), trace_n[slot]);
+        for (int ph = 0; ph < kNumPhases; ++ph) {
+          const int nch = ph <= 1 ? 1 : (ph == 6 ? 3 : 2);
+          for (int j = 0; j < nch; ++j) mbar_wait_sleep(&sm.w_full[(n + j) % kNumStages], ((n + j) / kNumStages) & 1, 20);
+#pragma unroll 1
+          for (int slot = 0; slot < 2; ++slot) {
+            if (slot == 1 && !active1) break;
+            mbar_wait_sleep(&sm.a_ready[slot], ph & 1, 20);
             tc::tc_fence_after_sync();
             const uint32_t tb = tmem + slot * kSlotCols;
             const uint32_t d = tb + kColD;
-            auto bdesc = [&](int j, int ks) { return tc::umma_desc_sw128(tc::smem_u32(sm.ring[(nb + j) % kNumStages]) + ks * 32); };
+            auto bdesc = [&](int j, int ks) { return tc::umma_desc_sw128(tc::smem_u32(sm.ring[(n + j) % kNumStages]) + ks * 32); };
             if (ph == 0) {          // gate = pts_bias(cond): K = 32
               for (int ks = 0; ks < 2; ++ks) tc::umma_ts(d, tb + kColCond + ks * 8, bdesc(0, ks), idesc128, ks > 0);
             } else if (ph == 1) {   // layer 0: K = 64 (encoding)
@@ -302,21 +268,10 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
               for (int ks = 0; ks < 8; ++ks) tc::umma_ts(d, tb + kColH + ks * 8, bdesc(ks >> 2, ks & 3), idesc_head, ks > 0);
             }
             tc::umma_commit(&sm.d_full[slot]);
-            trace(0, slot, 30 + ph, (unsigned)(nb & 255), trace_n[slot]);
-            if (++used[ph] == n_active)
-              for (int j = 0; j < nch; ++j) tc::umma_commit(&sm.w_empty[(nb + j) % kNumStages]);
-            ph_of[slot] = ph + 1;
-            progressed = true;
-            break;
           }
-          if (!progressed) {
-            __nanosleep(20);
-            if (++idle > (tc::kWaitTrapSpins >> 4)) __trap();
-          } else {
-            idle = 0;
-          }
+          for (int j = 0; j < nch; ++j) tc::umma_commit(&sm.w_empty[(n + j) % kNumStages]);
+          n += nch;
         }
-        n += kNumChunks;
       }
     }
     }
@@ -329,7 +284,6 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
     const uint32_t tb = tmem + slot * kSlotCols + ((uint32_t)(quarter * 32) << 16);
     const int ray_local = row / S, s = row - ray_local * S;
     uint32_t it = 0;
-    unsigned trace_n = 0;
 
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++it) {
       const int64_t tile = 2 * pair + slot;
@@ -338,29 +292,9 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
       const bool valid = ray < rays.n_rays;
       const size_t n_glob = valid ? (size_t)ray * S + s : 0;
 
-      TRACE_TRUNK(0);
       // ---------------- stage this sample: geometry -> positional encoding -> fp16 A operands in tensor memory
       float depth_t = 0.f, n_views_seen = 0.f;
       {
-        // conditioning row first: its HBM latency hides behind the geometry / encoding arithmetic below
-        uint32_t cnd[16];
-        if (valid) {
-          const uint4* src = reinterpret_cast<const uint4*>(cond + n_glob * kCondPad);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 v4 = __ldg(src + j);
-            cnd[4 * j] = v4.x; cnd[4 * j + 1] = v4.y; cnd[4 * j + 2] = v4.z; cnd[4 * j + 3] = v4.w;
-          }
-          // and pull the row of this slot's NEXT tile towards the SM (next pair = gridDim.x pairs further on)
-          const int64_t next_tile = tile + 2 * (int64_t)gridDim.x;
-          if (next_tile < n_tiles) {
-            const __half* nxt = cond + ((size_t)next_tile * kTileM + row) * kCondPad;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) cnd[j] = 0u;
-        }
         float x[3] = {0.f, 0.f, 0.f};
         float dir[3] = {0.f, 0.f, 0.f};
         if (valid) {
@@ -372,9 +306,9 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
           float p[3];
 #pragma unroll
           for (int i = 0; i < 3; ++i) p[i] = __fadd_rn(o[i], __fmul_rn(d[i], depth_t));
-          project_ndc_fast(cams, 0, p, x[0], x[1], x[2]);
-          const float rn = rsqrtf(fmaxf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2], 1e-24f));
-          const float ux = d[0] * rn, uy = d[1] * rn, uz = d[2] * rn;
+          project_ndc(cams, 0, p, x[0], x[1], x[2]);
+          const float nrm = fmaxf(sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]), 1e-12f);
+          const float ux = d[0] / nrm, uy = d[1] / nrm, uz = d[2] / nrm;
           const float* E = cams.w2c[0];
           dir[0] = ux * E[0] + uy * E[1] + uz * E[2];
           dir[1] = ux * E[4] + uy * E[5] + uz * E[6];
@@ -382,8 +316,8 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         }
         // direction term of the colour head, one vector per ray (the ray's threads split its 64 outputs)
         for (int o2 = s; o2 < 64; o2 += S)
-          sm.dirvec[slot][ray_local][o2] = P.views_dir[o2 * 3] * dir[0] + P.views_dir[o2 * 3 + 1] * dir[1] +
-                                           P.views_dir[o2 * 3 + 2] * dir[2] + P.views_b[o2];
+          sm.dirvec[slot][ray_local][o2] = sm.p.views_dir[o2 * 3] * dir[0] + sm.p.views_dir[o2 * 3 + 1] * dir[1] +
+                                           sm.p.views_dir[o2 * 3 + 2] * dir[2] + sm.p.views_b[o2];
         // encoding order (cond_nerf.py:108-116, :56-57): x, sin(2^k x) k-major, cos(2^k x) k-major, zero pad
         float sn[3], cs[3];
 #pragma unroll
@@ -417,6 +351,18 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
           tc::tmem_st16(tb + kColEnc, lo);
           tc::tmem_st16(tb + kColEnc + 16, hi);
         }
+        uint32_t cnd[16];
+        if (valid) {
+          const uint4* src = reinterpret_cast<const uint4*>(cond + n_glob * kCondPad);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 v4 = __ldg(src + j);
+            cnd[4 * j] = v4.x; cnd[4 * j + 1] = v4.y; cnd[4 * j + 2] = v4.z; cnd[4 * j + 3] = v4.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) cnd[j] = 0u;
+        }
         {  // visibility masks live at cond[19..21]
           const __half2 h9 = *reinterpret_cast<const __half2*>(&cnd[9]);
           const __half2 h10 = *reinterpret_cast<const __half2*>(&cnd[10]);
@@ -431,9 +377,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
 
       // ---------------- gate = pts_bias(cond) + b, kept as 64 packed-half registers for all six layers
       uint32_t gate[64];
-      TRACE_TRUNK(1);
       mbar_wait_sleep(&sm.d_full[slot], 0, 32);
-      TRACE_TRUNK(2);
       tc::tc_fence_after_sync();
 #pragma unroll
       for (int c0 = 0; c0 < 128; c0 += 32) {
@@ -442,7 +386,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         tc::tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const ulonglong2 b4 = *reinterpret_cast<const ulonglong2*>(&P.bias[6][c0 + 4 * j]);
+          const ulonglong2 b4 = *reinterpret_cast<const ulonglong2*>(&sm.p.bias[6][c0 + 4 * j]);
           const pk2 s0 = pk_add(pk(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), b4.x);
           const pk2 s1 = pk_add(pk(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), b4.y);
           gate[c0 / 2 + 2 * j] = pack_h2(pk_lo(s0), pk_hi(s0));
@@ -455,30 +399,24 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
       // ---------------- trunk: h = relu((acc + b_l) * gate) -> fp16 -> tensor memory (next layer's A operand)
 #pragma unroll 1
       for (int l = 0; l < kDepth; ++l) {
-        TRACE_TRUNK(10 + l);
         mbar_wait_sleep(&sm.d_full[slot], (l + 1) & 1, 32);
-        TRACE_TRUNK(20 + l);
         tc::tc_fence_after_sync();
-        const float* bl = P.bias[l];
-        // 16-column chunks, software pipelined: the TMEM load of chunk c+1 is in flight while chunk c is processed
-        uint32_t ra[16], rb[16];
-        tc::tmem_ld16(tb + kColD, ra);
+        const float* bl = sm.p.bias[l];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t r[32];
+          tc::tmem_ld32(tb + kColD + c0, r);
           tc::tmem_wait_ld();
-          uint32_t (&cur)[16] = (c & 1) ? rb : ra;
-          uint32_t (&nxt)[16] = (c & 1) ? ra : rb;
-          if (c < 7) tc::tmem_ld16(tb + kColD + (c + 1) * 16, nxt);
-          uint32_t o8[8];
+          uint32_t o16[16];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const ulonglong2 b4 = *reinterpret_cast<const ulonglong2*>(bl + c * 16 + 4 * j);
-            const pk2 s0 = pk_add(pk(__uint_as_float(cur[4 * j]), __uint_as_float(cur[4 * j + 1])), b4.x);
-            const pk2 s1 = pk_add(pk(__uint_as_float(cur[4 * j + 2]), __uint_as_float(cur[4 * j + 3])), b4.y);
-            o8[2 * j] = gate_relu(pack_h2(pk_lo(s0), pk_hi(s0)), gate[c * 8 + 2 * j]);
-            o8[2 * j + 1] = gate_relu(pack_h2(pk_lo(s1), pk_hi(s1)), gate[c * 8 + 2 * j + 1]);
+          for (int j = 0; j < 8; ++j) {
+            const ulonglong2 b4 = *reinterpret_cast<const ulonglong2*>(bl + c0 + 4 * j);
+            const pk2 s0 = pk_add(pk(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), b4.x);
+            const pk2 s1 = pk_add(pk(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), b4.y);
+            o16[2 * j] = gate_relu(pack_h2(pk_lo(s0), pk_hi(s0)), gate[c0 / 2 + 2 * j]);
+            o16[2 * j + 1] = gate_relu(pack_h2(pk_lo(s1), pk_hi(s1)), gate[c0 / 2 + 2 * j + 1]);
           }
-          tc::tmem_st8(tb + kColH + c * 8, o8);
+          tc::tmem_st16(tb + kColH + c0 / 2, o16);
         }
         tc::tmem_wait_st();
         tc::tc_fence_before_sync();
@@ -488,9 +426,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
       // ---------------- heads: raw alpha (16) and the colour hidden layer (64)
       float xr[16];
       float rgb[3];
-      TRACE_TRUNK(3);
       mbar_wait_sleep(&sm.d_full[slot], 1, 32);
-      TRACE_TRUNK(4);
       tc::tc_fence_after_sync();
       {
         uint32_t r16[16];
@@ -498,14 +434,14 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         tc::tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          float v = act_fn<kAct>(__uint_as_float(r16[j]) + P.alpha_b[j]);
+          float v = act_fn<kAct>(__uint_as_float(r16[j]) + sm.p.alpha_b[j]);
           if (cfg.raytrans_posenc) {   // cond_nerf.py:118-127
             const float ang = (float)s * exp2f(-(float)(j >> 1) * (13.287712379549449f / 8.f));   // s / 10000^(2*(j/2)/16)
             v += (j & 1) ? cosf(ang) : sinf(ang);
           }
           xr[j] = v;
         }
-        pk2 accrg = pk(P.rgb_b[0], P.rgb_b[1]), accb = pk(P.rgb_b[2], 0.f);
+        pk2 accrg = pk(sm.p.rgb_b[0], sm.p.rgb_b[1]), accb = pk(sm.p.rgb_b[2], 0.f);
 #pragma unroll
         for (int c0 = 16; c0 < 80; c0 += 32) {
           uint32_t r[32];
@@ -519,7 +455,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
                                  fmaxf(__uint_as_float(r[j + 2]) + dv.z, 0.f), fmaxf(__uint_as_float(r[j + 3]) + dv.w, 0.f)};
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-              const ulonglong2 w4 = *reinterpret_cast<const ulonglong2*>(P.rgb_w4[o2 + t]);
+              const ulonglong2 w4 = *reinterpret_cast<const ulonglong2*>(sm.p.rgb_w4[o2 + t]);
               const pk2 hh = pk(hv[t], hv[t]);
               accrg = pk_fma(hh, w4.x, accrg);
               accb = pk_fma(hh, w4.y, accb);
@@ -534,9 +470,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
       // ---------------- hand the per-sample ray-transformer inputs to the ray group of this slot
       {
         const uint32_t buf = it & 1;
-        TRACE_TRUNK(5);
         mbar_wait_sleep(&sm.ray_empty[slot][buf], ((it >> 1) & 1) ^ 1, 64);
-        TRACE_TRUNK(6);
         float4* h = &sm.hand[slot][buf][0][row];
         h[0 * kTileM] = make_float4(xr[0], xr[1], xr[2], xr[3]);
         h[1 * kTileM] = make_float4(xr[4], xr[5], xr[6], xr[7]);
@@ -547,7 +481,6 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         tc::mbar_arrive(&sm.ray_full[slot][buf]);       // release semantics: the stores above are visible to the waiter
       }
       trunk_barrier(slot);   // dirvec is rewritten by the next tile's staging
-      TRACE_TRUNK(7);
     }
   } else {
     // ================================================================== ray group: ray transformer + compositing
@@ -557,7 +490,6 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
     const int row = quarter * 32 + lane;
     const int ray_local = row / S, s = row - ray_local * S;
     uint32_t it = 0;
-    unsigned trace_n = 0;
 
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++it) {
       const int64_t tile = 2 * pair + slot;
@@ -568,9 +500,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
       float xr[16], rgb[3], depth_t, n_views_seen;
       {
         const uint32_t buf = it & 1;
-        TRACE_RAY(0);
         mbar_wait_sleep(&sm.ray_full[slot][buf], (it >> 1) & 1, 64);
-        TRACE_RAY(1);
         const float4* h = &sm.hand[slot][buf][0][row];
         const float4 a0 = h[0 * kTileM], a1 = h[1 * kTileM], a2 = h[2 * kTileM], a3 = h[3 * kTileM], a4 = h[4 * kTileM];
         n_views_seen = h[5 * kTileM].x;
@@ -581,136 +511,116 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
       }
 
       // ---------------- ray transformer over the S samples of this ray (ray_transformer.py:49-79)
-      // q is pre-scaled by log2(e)/temperature; q, k, v rows are laid out [dim][head], so an 8-byte load holds one dim of
-      // a head pair and every multiply-add below is a packed FFMA2.
+      // q is pre-scaled by log2(e)/temperature; k, v are laid out [dim][head], so one 16-byte load holds the 4 heads of
+      // a dim as two packed pairs (heads 0,1 | heads 2,3) and every multiply-add below is a packed FFMA2.
       const bool row_valid = n_views_seen > 1.f;    // cond_nerf.py:83; the mask disables whole QUERY rows (uniform attention)
+      pk2 q2[4][2];                                 // [dim][head pair]
       {
-        float y[48];                                // [0,16) q, [16,32) k, [32,48) v; index = head*4 + dim
+        pk2 y[24];
 #pragma unroll
-        for (int o = 0; o < 48; ++o) y[o] = 0.f;
+        for (int i = 0; i < 24; ++i) y[i] = 0ull;
+        matvec16_t<48>(&sm.p.wqkv_t[0][0], 48, xr, y);
+        float yf[48];                               // [0,16) q, [16,32) k, [32,48) v; index = head*4 + dim
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-#pragma unroll
-          for (int o = 0; o < 48; ++o) y[o] = fmaf(xr[i], P.wqkv_t[i][o], y[o]);     // weights are constant-bank operands
-        ulonglong2* qdst = reinterpret_cast<ulonglong2*>(&sm.qbuf[slot][row][0]);
+        for (int i = 0; i < 24; ++i) { yf[2 * i] = pk_lo(y[i]); yf[2 * i + 1] = pk_hi(y[i]); }
         ulonglong2* kdst = reinterpret_cast<ulonglong2*>(&sm.kbuf[slot][row][0]);
         ulonglong2* vdst = reinterpret_cast<ulonglong2*>(&sm.vbuf[slot][row][0]);
-        const float qm = row_valid ? 1.f : 0.f;     // masked query row: all scores equal -> uniform attention
 #pragma unroll
         for (int dd = 0; dd < 4; ++dd) {
-          qdst[dd] = make_ulonglong2(pk(qm * y[0 + dd], qm * y[4 + dd]), pk(qm * y[8 + dd], qm * y[12 + dd]));
-          kdst[dd] = make_ulonglong2(pk(y[16 + dd], y[20 + dd]), pk(y[24 + dd], y[28 + dd]));
-          vdst[dd] = make_ulonglong2(pk(y[32 + dd], y[36 + dd]), pk(y[40 + dd], y[44 + dd]));
+          q2[dd][0] = pk(yf[0 + dd], yf[4 + dd]);
+          q2[dd][1] = pk(yf[8 + dd], yf[12 + dd]);
+          kdst[dd] = make_ulonglong2(pk(yf[16 + dd], yf[20 + dd]), pk(yf[24 + dd], yf[28 + dd]));
+          vdst[dd] = make_ulonglong2(pk(yf[32 + dd], yf[36 + dd]), pk(yf[40 + dd], yf[44 + dd]));
         }
       }
-      TRACE_RAY(2);
       ray_barrier(slot);
-      TRACE_RAY(3);
       float sigma;
       {
-        // Exact two-pass softmax (row maxima first; a norm bound instead of the first pass underflows for 87 % of the
-        // rows on real encoder features).  Work split inside a warp: lane = (pair of adjacent query rows, pair of heads),
-        // so every 8-byte shared-memory load feeds two rows -- broadcast 16-byte loads with lane = row had made the
-        // kernel shared-memory-bandwidth bound (ncu v4: L1/TEX 78 %).
-        const int hp = lane >> 4;                                   // head pair of this lane
-        const int ra = (quarter << 5) + ((lane & 15) << 1);         // first of its two rows (same ray: S is even)
-        const pk2* qa = reinterpret_cast<const pk2*>(&sm.qbuf[slot][ra][0]) + hp;
-        const pk2* kp = reinterpret_cast<const pk2*>(&sm.kbuf[slot][(ra / S) * S][0]) + hp;
-        const pk2* vp = reinterpret_cast<const pk2*>(&sm.vbuf[slot][(ra / S) * S][0]) + hp;
-        pk2 q_a[4], q_b[4];
+        // Exact two-pass softmax (row maxima first).  A norm bound |q||k|max instead of the first pass was measured to
+        // underflow for 87 % of the rows on real encoder features (scores reach several hundred in the exp2 domain).
+        const ulonglong2* kb = reinterpret_cast<const ulonglong2*>(&sm.kbuf[slot][ray_local * S][0]);
+        const ulonglong2* vb = reinterpret_cast<const ulonglong2*>(&sm.vbuf[slot][ray_local * S][0]);
+        if (!row_valid) {
 #pragma unroll
-        for (int dd = 0; dd < 4; ++dd) { q_a[dd] = qa[dd * 2]; q_b[dd] = qa[8 + dd * 2]; }
+          for (int dd = 0; dd < 4; ++dd) q2[dd][0] = q2[dd][1] = 0ull;   // masked query row: all scores equal -> uniform attention
+        }
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 2
         for (int j = 0; j < S; ++j) {
-          pk2 sa = 0ull, sb = 0ull;
+          pk2 sc0 = 0ull, sc1 = 0ull;
 #pragma unroll
           for (int dd = 0; dd < 4; ++dd) {
-            const pk2 k2 = kp[j * 8 + dd * 2];
-            sa = pk_fma(q_a[dd], k2, sa);
-            sb = pk_fma(q_b[dd], k2, sb);
+            const ulonglong2 k4 = kb[j * 4 + dd];
+            sc0 = pk_fma(q2[dd][0], k4.x, sc0);
+            sc1 = pk_fma(q2[dd][1], k4.y, sc1);
           }
-          mx[0] = fmaxf(mx[0], pk_lo(sa)); mx[1] = fmaxf(mx[1], pk_hi(sa));
-          mx[2] = fmaxf(mx[2], pk_lo(sb)); mx[3] = fmaxf(mx[3], pk_hi(sb));
+          mx[0] = fmaxf(mx[0], pk_lo(sc0)); mx[1] = fmaxf(mx[1], pk_hi(sc0));
+          mx[2] = fmaxf(mx[2], pk_lo(sc1)); mx[3] = fmaxf(mx[3], pk_hi(sc1));
         }
-        TRACE_RAY(4);
-        const pk2 nma = pk(-mx[0], -mx[1]), nmb = pk(-mx[2], -mx[3]);
-        pk2 den_a = 0ull, den_b = 0ull, o_a[4], o_b[4];
+        const pk2 negm[2] = {pk(-mx[0], -mx[1]), pk(-mx[2], -mx[3])};
+        pk2 den[2] = {0ull, 0ull}, o2[4][2];
 #pragma unroll
-        for (int dd = 0; dd < 4; ++dd) o_a[dd] = o_b[dd] = 0ull;
+        for (int dd = 0; dd < 4; ++dd) o2[dd][0] = o2[dd][1] = 0ull;
 #pragma unroll 2
         for (int j = 0; j < S; ++j) {
-          pk2 sa = nma, sb = nmb;
+          pk2 sc0 = negm[0], sc1 = negm[1];
 #pragma unroll
           for (int dd = 0; dd < 4; ++dd) {
-            const pk2 k2 = kp[j * 8 + dd * 2];
-            sa = pk_fma(q_a[dd], k2, sa);
-            sb = pk_fma(q_b[dd], k2, sb);
+            const ulonglong2 k4 = kb[j * 4 + dd];
+            sc0 = pk_fma(q2[dd][0], k4.x, sc0);
+            sc1 = pk_fma(q2[dd][1], k4.y, sc1);
           }
-          const pk2 pa = pk(ex2_fast(pk_lo(sa)), ex2_fast(pk_hi(sa)));
-          const pk2 pb = pk(ex2_fast(pk_lo(sb)), ex2_fast(pk_hi(sb)));
-          den_a = pk_add(den_a, pa);
-          den_b = pk_add(den_b, pb);
+          const pk2 p0 = pk(ex2_fast(pk_lo(sc0)), ex2_fast(pk_hi(sc0)));
+          const pk2 p1 = pk(ex2_fast(pk_lo(sc1)), ex2_fast(pk_hi(sc1)));
+          den[0] = pk_add(den[0], p0);
+          den[1] = pk_add(den[1], p1);
 #pragma unroll
           for (int dd = 0; dd < 4; ++dd) {
-            const pk2 v2 = vp[j * 8 + dd * 2];
-            o_a[dd] = pk_fma(pa, v2, o_a[dd]);
-            o_b[dd] = pk_fma(pb, v2, o_b[dd]);
+            const ulonglong2 v4 = vb[j * 4 + dd];
+            o2[dd][0] = pk_fma(p0, v4.x, o2[dd][0]);
+            o2[dd][1] = pk_fma(p1, v4.y, o2[dd][1]);
           }
         }
-        TRACE_RAY(5);
-        // normalised head outputs back through shared memory in [head*4 + dim] order (all within this warp)
-        __syncwarp();
+        // att[head*4 + dim] = o / den
+        float att[16];
         {
-          const float ia0 = 1.f / pk_lo(den_a), ia1 = 1.f / pk_hi(den_a), ib0 = 1.f / pk_lo(den_b), ib1 = 1.f / pk_hi(den_b);
-          float* da = &sm.qbuf[slot][ra][hp * 8];
-          float* db = &sm.qbuf[slot][ra + 1][hp * 8];
-          *reinterpret_cast<float4*>(da) = make_float4(pk_lo(o_a[0]) * ia0, pk_lo(o_a[1]) * ia0, pk_lo(o_a[2]) * ia0, pk_lo(o_a[3]) * ia0);
-          *reinterpret_cast<float4*>(da + 4) = make_float4(pk_hi(o_a[0]) * ia1, pk_hi(o_a[1]) * ia1, pk_hi(o_a[2]) * ia1, pk_hi(o_a[3]) * ia1);
-          *reinterpret_cast<float4*>(db) = make_float4(pk_lo(o_b[0]) * ib0, pk_lo(o_b[1]) * ib0, pk_lo(o_b[2]) * ib0, pk_lo(o_b[3]) * ib0);
-          *reinterpret_cast<float4*>(db + 4) = make_float4(pk_hi(o_b[0]) * ib1, pk_hi(o_b[1]) * ib1, pk_hi(o_b[2]) * ib1, pk_hi(o_b[3]) * ib1);
-        }
-        __syncwarp();
-        float att[16];                                              // att[head*4 + dim] of this thread's own row
-        {
-          const float4* src = reinterpret_cast<const float4*>(&sm.qbuf[slot][row][0]);
+          const float inv[4] = {1.f / pk_lo(den[0]), 1.f / pk_hi(den[0]), 1.f / pk_lo(den[1]), 1.f / pk_hi(den[1])};
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 t4 = src[i];
-            att[4 * i] = t4.x; att[4 * i + 1] = t4.y; att[4 * i + 2] = t4.z; att[4 * i + 3] = t4.w;
+          for (int dd = 0; dd < 4; ++dd) {
+            att[0 + dd] = pk_lo(o2[dd][0]) * inv[0];
+            att[4 + dd] = pk_hi(o2[dd][0]) * inv[1];
+            att[8 + dd] = pk_lo(o2[dd][1]) * inv[2];
+            att[12 + dd] = pk_hi(o2[dd][1]) * inv[3];
           }
         }
+        pk2 y2[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y2[i] = pk(xr[2 * i], xr[2 * i + 1]);     // residual
+        matvec16_t<16>(&sm.p.fc_t[0][0], 16, att, y2);
         float y[16], mu = 0.f;
 #pragma unroll
-        for (int o = 0; o < 16; ++o) y[o] = xr[o];                  // residual
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-#pragma unroll
-          for (int o = 0; o < 16; ++o) y[o] = fmaf(att[i], P.fc_t[i][o], y[o]);
-#pragma unroll
-        for (int o = 0; o < 16; ++o) mu += y[o];
+        for (int i = 0; i < 8; ++i) { y[2 * i] = pk_lo(y2[i]); y[2 * i + 1] = pk_hi(y2[i]); mu += y[2 * i] + y[2 * i + 1]; }
         mu *= (1.f / 16.f);
         float var = 0.f;
 #pragma unroll
         for (int i = 0; i < 16; ++i) var += (y[i] - mu) * (y[i] - mu);
         const float rstd = rsqrtf(var * (1.f / 16.f) + 1e-6f);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) y[i] = (y[i] - mu) * rstd * P.ln_w[i] + P.ln_b[i];
-        float a1[16];
+        for (int i = 0; i < 16; ++i) y[i] = (y[i] - mu) * rstd * sm.p.ln_w[i] + sm.p.ln_b[i];
+        pk2 a2[8];
 #pragma unroll
-        for (int o = 0; o < 16; ++o) a1[o] = P.oa0_b[o];
+        for (int i = 0; i < 8; ++i) a2[i] = pk(sm.p.oa0_b[2 * i], sm.p.oa0_b[2 * i + 1]);
+        matvec16_t<16>(&sm.p.oa0_t[0][0], 16, y, a2);
+        float acc = sm.p.oa2_b;
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-#pragma unroll
-          for (int o = 0; o < 16; ++o) a1[o] = fmaf(y[i], P.oa0_t[i][o], a1[o]);
-        float acc = P.oa2_b;
-#pragma unroll
-        for (int o = 0; o < 16; ++o) acc = fmaf(act_fn<kAct>(a1[o]), P.oa2_w[o], acc);
+        for (int i = 0; i < 8; ++i) {
+          acc = fmaf(act_fn<kAct>(pk_lo(a2[i])), sm.p.oa2_w[2 * i], acc);
+          acc = fmaf(act_fn<kAct>(pk_hi(a2[i])), sm.p.oa2_w[2 * i + 1], acc);
+        }
         sigma = fmaxf(acc, 0.f);
         if (cfg.density_maskfill && n_views_seen < 1.f) sigma = 0.f;
         if (!valid) sigma = 0.f;
       }
-      TRACE_RAY(6);
       if (aux && valid) {
         float4* a4 = reinterpret_cast<float4*>(aux) + n_glob;
         *a4 = make_float4(rgb[0], rgb[1], rgb[2], sigma);
@@ -765,7 +675,6 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
           out_opacity[ray] = part[4];
         }
         ray_barrier(slot);   // kbuf / vbuf / red / dirvec are rewritten by the next tile
-        TRACE_RAY(7);
       }
     }
   }
@@ -858,7 +767,8 @@ int decoder_tc_pack(const float* P, const ParamOffsets& off, DecoderWeightsTC** 
   DecoderWeightsTC* w = new DecoderWeightsTC();
   MNF_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&w->packed), kPackedBytes));
   MNF_CUDA_TRY(cudaMemcpy(w->packed, buf.data(), kPackedBytes, cudaMemcpyHostToDevice));
-  w->params = tp;
+  MNF_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&w->params), sizeof(TcParams)));
+  MNF_CUDA_TRY(cudaMemcpy(w->params, &tp, sizeof(TcParams), cudaMemcpyHostToDevice));
   *out = w;
   return MNF_OK;
 }
@@ -866,6 +776,7 @@ int decoder_tc_pack(const float* P, const ParamOffsets& off, DecoderWeightsTC** 
 void decoder_tc_free(DecoderWeightsTC* w) {
   if (!w) return;
   cudaFree(w->packed);
+  cudaFree(w->params);
   delete w;
 }
 
@@ -903,16 +814,3 @@ int launch_decoder_tc(const DevCams& cams, const DevRays& rays, const mnf_decode
 }
 
 }  // namespace mnf
-
-// Debug aid (not part of the reference-facing ABI): arm / disarm the decoder timeline trace.  buf = device array of
-// `cap` u64 records ([clock:40 | role:4 | slot:4 | event:8 | iteration:8]); buf = NULL disarms.  Synchronises.
-extern "C" int32_t mnf_debug_decoder_trace(void* buf, int32_t cap) {
-  using namespace mnf;
-  unsigned long long* p = reinterpret_cast<unsigned long long*>(buf);
-  unsigned int c = buf ? (unsigned)cap : 0u, z = 0u;
-  MNF_CUDA_TRY(cudaMemcpyToSymbol(g_trace_buf, &p, sizeof(p)));
-  MNF_CUDA_TRY(cudaMemcpyToSymbol(g_trace_cap, &c, sizeof(c)));
-  MNF_CUDA_TRY(cudaMemcpyToSymbol(g_trace_unused, &z, sizeof(z)));
-  MNF_CUDA_TRY(cudaDeviceSynchronize());
-  return MNF_OK;
-}
