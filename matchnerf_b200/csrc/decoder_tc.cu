@@ -237,9 +237,13 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         }
       }
     } else if (warp == 1) {
-    // ================================================================== MMA issuer
-    if (lane == 0) {
+      // ================================================================== MMA issuer
+      // The whole warp runs this loop convergently and one elected lane issues the tcgen05 instructions: descriptor and
+      // address arithmetic is then warp-uniform (uniform datapath) instead of per-thread values that need a
+      // register -> uniform-register move in front of every MMA (the single-lane version spent ~1000 cycles issuing
+      // the 8 MMAs of a 512-cycle layer).
       const uint32_t idesc128 = tc::umma_idesc_f16(128, 128), idesc_head = tc::umma_idesc_f16(128, kHeadN);
+      const bool leader = tc::elect_one();
       uint32_t n = 0;
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         const bool active1 = 2 * pair + 1 < n_tiles;
@@ -247,6 +251,9 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         for (int ph = 0; ph < kNumPhases; ++ph) {
           const int nch = ph <= 1 ? 1 : (ph == 6 ? 3 : 2);
           for (int j = 0; j < nch; ++j) mbar_wait_sleep(&sm.w_full[(n + j) % kNumStages], ((n + j) / kNumStages) & 1, 20);
+          uint32_t ring_addr[3];
+#pragma unroll
+          for (int j = 0; j < 3; ++j) ring_addr[j] = tc::smem_u32(sm.ring[(n + (j < nch ? j : 0)) % kNumStages]);
 #pragma unroll 1
           for (int slot = 0; slot < 2; ++slot) {
             if (slot == 1 && !active1) break;
@@ -254,26 +261,35 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
             tc::tc_fence_after_sync();
             const uint32_t tb = tmem + slot * kSlotCols;
             const uint32_t d = tb + kColD;
-            auto bdesc = [&](int j, int ks) { return tc::umma_desc_sw128(tc::smem_u32(sm.ring[(n + j) % kNumStages]) + ks * 32); };
-            if (ph == 0) {          // gate = pts_bias(cond): K = 32
-              for (int ks = 0; ks < 2; ++ks) tc::umma_ts(d, tb + kColCond + ks * 8, bdesc(0, ks), idesc128, ks > 0);
-            } else if (ph == 1) {   // layer 0: K = 64 (encoding)
-              for (int ks = 0; ks < 4; ++ks) tc::umma_ts(d, tb + kColEnc + ks * 8, bdesc(0, ks), idesc128, ks > 0);
-            } else if (ph <= 5) {   // layers 1..4: K = 128
-              for (int ks = 0; ks < 8; ++ks) tc::umma_ts(d, tb + kColH + ks * 8, bdesc(ks >> 2, ks & 3), idesc128, ks > 0);
-            } else if (ph == 6) {   // layer 5 on [enc, h]: K = 64 + 128
-              for (int ks = 0; ks < 4; ++ks) tc::umma_ts(d, tb + kColEnc + ks * 8, bdesc(0, ks), idesc128, ks > 0);
-              for (int ks = 0; ks < 8; ++ks) tc::umma_ts(d, tb + kColH + ks * 8, bdesc(1 + (ks >> 2), ks & 3), idesc128, 1);
-            } else {                // heads: [alpha_linear | views(feature_linear(.))], N = 80, K = 128
-              for (int ks = 0; ks < 8; ++ks) tc::umma_ts(d, tb + kColH + ks * 8, bdesc(ks >> 2, ks & 3), idesc_head, ks > 0);
+            if (leader) {
+              if (ph == 0) {          // gate = pts_bias(cond): K = 32
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) tc::umma_ts(d, tb + kColCond + ks * 8, tc::umma_desc_sw128(ring_addr[0] + ks * 32), idesc128, ks > 0);
+              } else if (ph == 1) {   // layer 0: K = 64 (encoding)
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) tc::umma_ts(d, tb + kColEnc + ks * 8, tc::umma_desc_sw128(ring_addr[0] + ks * 32), idesc128, ks > 0);
+              } else if (ph <= 5) {   // layers 1..4: K = 128
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) tc::umma_ts(d, tb + kColH + ks * 8, tc::umma_desc_sw128(ring_addr[ks >> 2] + (ks & 3) * 32), idesc128, ks > 0);
+              } else if (ph == 6) {   // layer 5 on [enc, h]: K = 64 + 128
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) tc::umma_ts(d, tb + kColEnc + ks * 8, tc::umma_desc_sw128(ring_addr[0] + ks * 32), idesc128, ks > 0);
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) tc::umma_ts(d, tb + kColH + ks * 8, tc::umma_desc_sw128(ring_addr[1 + (ks >> 2)] + (ks & 3) * 32), idesc128, 1);
+              } else {                // heads: [alpha_linear | views(feature_linear(.))], N = 80, K = 128
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) tc::umma_ts(d, tb + kColH + ks * 8, tc::umma_desc_sw128(ring_addr[ks >> 2] + (ks & 3) * 32), idesc_head, ks > 0);
+              }
+              tc::umma_commit(&sm.d_full[slot]);
             }
-            tc::umma_commit(&sm.d_full[slot]);
+            __syncwarp();
           }
-          for (int j = 0; j < nch; ++j) tc::umma_commit(&sm.w_empty[(n + j) % kNumStages]);
+          if (leader)
+            for (int j = 0; j < nch; ++j) tc::umma_commit(&sm.w_empty[(n + j) % kNumStages]);
+          __syncwarp();
           n += nch;
         }
       }
-    }
     }
   } else if (wg <= 2) {
     // ================================================================== trunk slot: staging, epilogues, heads

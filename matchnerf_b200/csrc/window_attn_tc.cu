@@ -146,15 +146,18 @@ window_attn_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, 
     tc::fence_proxy_async_smem();
     tc::tc_fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {       // warp-uniform descriptor arithmetic, one elected lane issues (no per-MMA R2UR moves)
       tc::tc_fence_after_sync();
+      if (tc::elect_one()) {
 #pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {
-        const uint64_t ad = tc::umma_desc_sw128(tc::smem_u32(&sm.q[ks >> 2][0]) + (ks & 3) * 32);
-        const uint64_t bd = tc::umma_desc_sw128(tc::smem_u32(&sm.k[ks >> 2][0]) + (ks & 3) * 32);
-        tc::umma_ss(tmem + kColS, ad, bd, idesc_qk, ks > 0);
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t ad = tc::umma_desc_sw128(tc::smem_u32(&sm.q[ks >> 2][0]) + (ks & 3) * 32);
+          const uint64_t bd = tc::umma_desc_sw128(tc::smem_u32(&sm.k[ks >> 2][0]) + (ks & 3) * 32);
+          tc::umma_ss(tmem + kColS, ad, bd, idesc_qk, ks > 0);
+        }
+        tc::umma_commit(&sm.bar_s);
       }
-      tc::umma_commit(&sm.bar_s);
+      __syncwarp();
     }
     if (warp < 4) {
       tc::mbar_wait(&sm.bar_s, kt & 1);
@@ -216,14 +219,17 @@ window_attn_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, 
       tc::tc_fence_before_sync();
     }
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
       tc::tc_fence_after_sync();
+      if (tc::elect_one()) {
 #pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {   // 16 keys per step: A = P columns [8 ks, 8 ks + 8), B = V rows [16 ks, 16 ks + 16)
-        const uint64_t bd = tc::umma_desc_sw128_mn(tc::smem_u32(&sm.v[0][0]) + ks * 2048, kBlockBytes);
-        tc::umma_ts(tmem + kColO, tmem + kColS + ks * 8, bd, idesc_pv, (kt | ks) ? 1u : 0u);
+        for (int ks = 0; ks < 8; ++ks) {   // 16 keys per step: A = P columns [8 ks, 8 ks + 8), B = V rows [16 ks, 16 ks + 16)
+          const uint64_t bd = tc::umma_desc_sw128_mn(tc::smem_u32(&sm.v[0][0]) + ks * 2048, kBlockBytes);
+          tc::umma_ts(tmem + kColO, tmem + kColS + ks * 8, bd, idesc_pv, (kt | ks) ? 1u : 0u);
+        }
+        tc::umma_commit(&sm.bar_o);
       }
-      tc::umma_commit(&sm.bar_o);
+      __syncwarp();
     }
     // K / V shared memory and the S / P columns are reused by the next tile: wait for this tile's MMAs
     tc::mbar_wait(&sm.bar_o, kt & 1);
