@@ -139,3 +139,47 @@ extern "C" int32_t mnf_selftest_umma(const void* a_f16, const void* b_f16, float
   MNF_CUDA_TRY(cudaGetLastError());
   return MNF_OK;
 }
+
+// ---- micro-benchmark: tensor-memory read (tcgen05.ld) throughput of one SM ------------------------------------------
+// `warps` warps (4 or 8; two warps share a lane quarter when 8) each read `cols` columns `iters` times; out[0] = cycles.
+namespace mnf {
+__global__ void __launch_bounds__(256, 1) tmem_bw_kernel(int iters, int cols, long long* out) {
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) tc::tmem_alloc<512>(&slot);
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  tc::tc_fence_after_sync();
+  const uint32_t tb = slot + ((uint32_t)((warp & 3) * 32) << 16) + (warp >= 4 ? 256 : 0);
+  uint32_t acc = 0;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) {
+    for (int c0 = 0; c0 < cols; c0 += 32) {
+      uint32_t r[32];
+      tc::tmem_ld32(tb + c0, r);
+      tc::tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc ^= r[j];
+    }
+  }
+  __syncthreads();
+  const long long t1 = clock64();
+  if (threadIdx.x == 0) { out[0] = t1 - t0; }
+  if (acc == 0x12345678u) out[1] = acc;   // keep the loads alive
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<512>(slot);
+}
+}  // namespace mnf
+
+extern "C" int32_t mnf_selftest_tmem_bw(int32_t warps, int32_t iters, int32_t cols, long long* cycles_out_dev, void* stream) {
+  using namespace mnf;
+  if ((warps != 4 && warps != 8) || iters <= 0 || cols <= 0 || cols > 256 || cols % 32 || !cycles_out_dev) {
+    set_error("mnf_selftest_tmem_bw: bad arguments");
+    return MNF_EINVAL;
+  }
+  tmem_bw_kernel<<<1, warps * 32, 0, (cudaStream_t)stream>>>(iters, cols, cycles_out_dev);
+  MNF_CUDA_TRY(cudaGetLastError());
+  return MNF_OK;
+}
