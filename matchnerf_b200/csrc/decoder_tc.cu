@@ -85,6 +85,24 @@ struct TcSmem {
   uint32_t tmem_base;
 };
 
+// ---- optional timeline trace (debug aid; mnf_debug_decoder_trace): CTA 0 records clock64() at protocol points
+__device__ unsigned long long* g_trace_buf = nullptr;
+__device__ unsigned int g_trace_cap = 0;
+// role: 0 mma, 1 trunk, 2 ray.  One lane per role group records into its own sixth of the buffer (no atomics, so a
+// probe costs a clock read and one store).
+__device__ __forceinline__ void trace(int role, int slot, int ev, unsigned it, unsigned& n) {
+  if (g_trace_buf != nullptr && blockIdx.x == 0) {
+    const unsigned per = g_trace_cap / 6u;
+    if (n < per)
+      g_trace_buf[(unsigned)(role * 2 + slot) * per + n] = ((unsigned long long)clock64() << 24) | ((unsigned long long)(role & 15) << 20) |
+                                                          ((unsigned long long)(slot & 15) << 16) | ((unsigned long long)(ev & 255) << 8) | (it & 255);
+    ++n;
+  }
+}
+#define TRACE_TRUNK(ev) do { if (quarter == 0 && lane == 0) trace(1, slot, ev, it, trace_n); } while (0)
+#define TRACE_RAY(ev) do { if (quarter == 0 && lane == 0) trace(2, slot, ev, it, trace_n); } while (0)
+#define TRACE_MMA(sl, ev) do { if (leader) trace(0, sl, ev, (unsigned)(n & 255), trace_m[sl]); } while (0)
+
 __device__ __forceinline__ void trunk_barrier(int slot) { asm volatile("bar.sync %0, 128;" ::"r"(slot + 1) : "memory"); }
 __device__ __forceinline__ void ray_barrier(int slot) { asm volatile("bar.sync %0, 128;" ::"r"(slot + 3) : "memory"); }
 using tc::mbar_wait_sleep;
@@ -244,6 +262,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
       // the 8 MMAs of a 512-cycle layer).
       const uint32_t idesc128 = tc::umma_idesc_f16(128, 128), idesc_head = tc::umma_idesc_f16(128, kHeadN);
       const bool leader = tc::elect_one();
+      unsigned trace_m[2] = {0u, 0u};
       uint32_t n = 0;
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         const bool active1 = 2 * pair + 1 < n_tiles;
@@ -251,6 +270,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         for (int ph = 0; ph < kNumPhases; ++ph) {
           const int nch = ph <= 1 ? 1 : (ph == 6 ? 3 : 2);
           for (int j = 0; j < nch; ++j) mbar_wait_sleep(&sm.w_full[(n + j) % kNumStages], ((n + j) / kNumStages) & 1, 20);
+          TRACE_MMA(0, 50 + ph);
           uint32_t ring_addr[3];
 #pragma unroll
           for (int j = 0; j < 3; ++j) ring_addr[j] = tc::smem_u32(sm.ring[(n + (j < nch ? j : 0)) % kNumStages]);
@@ -258,6 +278,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
           for (int slot = 0; slot < 2; ++slot) {
             if (slot == 1 && !active1) break;
             mbar_wait_sleep(&sm.a_ready[slot], ph & 1, 20);
+            TRACE_MMA(slot, 10 + ph);
             tc::tc_fence_after_sync();
             const uint32_t tb = tmem + slot * kSlotCols;
             const uint32_t d = tb + kColD;
@@ -282,6 +303,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
               }
               tc::umma_commit(&sm.d_full[slot]);
             }
+            TRACE_MMA(slot, 30 + ph);
             __syncwarp();
           }
           if (leader)
@@ -300,6 +322,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
     const uint32_t tb = tmem + slot * kSlotCols + ((uint32_t)(quarter * 32) << 16);
     const int ray_local = row / S, s = row - ray_local * S;
     uint32_t it = 0;
+    unsigned trace_n = 0;
 
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++it) {
       const int64_t tile = 2 * pair + slot;
@@ -308,6 +331,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
       const bool valid = ray < rays.n_rays;
       const size_t n_glob = valid ? (size_t)ray * S + s : 0;
 
+      TRACE_TRUNK(0);
       // ---------------- stage this sample: geometry -> positional encoding -> fp16 A operands in tensor memory
       float depth_t = 0.f, n_views_seen = 0.f;
       {
@@ -393,7 +417,9 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
 
       // ---------------- gate = pts_bias(cond) + b, kept as 64 packed-half registers for all six layers
       uint32_t gate[64];
+      TRACE_TRUNK(1);
       mbar_wait_sleep(&sm.d_full[slot], 0, 32);
+      TRACE_TRUNK(2);
       tc::tc_fence_after_sync();
 #pragma unroll
       for (int c0 = 0; c0 < 128; c0 += 32) {
@@ -415,7 +441,9 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
       // ---------------- trunk: h = relu((acc + b_l) * gate) -> fp16 -> tensor memory (next layer's A operand)
 #pragma unroll 1
       for (int l = 0; l < kDepth; ++l) {
+        TRACE_TRUNK(10 + l);
         mbar_wait_sleep(&sm.d_full[slot], (l + 1) & 1, 32);
+        TRACE_TRUNK(20 + l);
         tc::tc_fence_after_sync();
         const float* bl = sm.p.bias[l];
 #pragma unroll
@@ -442,7 +470,9 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
       // ---------------- heads: raw alpha (16) and the colour hidden layer (64)
       float xr[16];
       float rgb[3];
+      TRACE_TRUNK(3);
       mbar_wait_sleep(&sm.d_full[slot], 1, 32);
+      TRACE_TRUNK(4);
       tc::tc_fence_after_sync();
       {
         uint32_t r16[16];
@@ -486,7 +516,9 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
       // ---------------- hand the per-sample ray-transformer inputs to the ray group of this slot
       {
         const uint32_t buf = it & 1;
+        TRACE_TRUNK(5);
         mbar_wait_sleep(&sm.ray_empty[slot][buf], ((it >> 1) & 1) ^ 1, 64);
+        TRACE_TRUNK(6);
         float4* h = &sm.hand[slot][buf][0][row];
         h[0 * kTileM] = make_float4(xr[0], xr[1], xr[2], xr[3]);
         h[1 * kTileM] = make_float4(xr[4], xr[5], xr[6], xr[7]);
@@ -496,6 +528,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         h[5 * kTileM] = make_float4(n_views_seen, 0.f, 0.f, 0.f);
         tc::mbar_arrive(&sm.ray_full[slot][buf]);       // release semantics: the stores above are visible to the waiter
       }
+      TRACE_TRUNK(7);
       trunk_barrier(slot);   // dirvec is rewritten by the next tile's staging
     }
   } else {
@@ -506,6 +539,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
     const int row = quarter * 32 + lane;
     const int ray_local = row / S, s = row - ray_local * S;
     uint32_t it = 0;
+    unsigned trace_n = 0;
 
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++it) {
       const int64_t tile = 2 * pair + slot;
@@ -516,7 +550,9 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
       float xr[16], rgb[3], depth_t, n_views_seen;
       {
         const uint32_t buf = it & 1;
+        TRACE_RAY(0);
         mbar_wait_sleep(&sm.ray_full[slot][buf], (it >> 1) & 1, 64);
+        TRACE_RAY(1);
         const float4* h = &sm.hand[slot][buf][0][row];
         const float4 a0 = h[0 * kTileM], a1 = h[1 * kTileM], a2 = h[2 * kTileM], a3 = h[3 * kTileM], a4 = h[4 * kTileM];
         n_views_seen = h[5 * kTileM].x;
@@ -549,7 +585,9 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
           vdst[dd] = make_ulonglong2(pk(yf[32 + dd], yf[36 + dd]), pk(yf[40 + dd], yf[44 + dd]));
         }
       }
+      TRACE_RAY(2);
       ray_barrier(slot);
+      TRACE_RAY(3);
       float sigma;
       {
         // Exact two-pass softmax (row maxima first).  A norm bound |q||k|max instead of the first pass was measured to
@@ -573,6 +611,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
           mx[0] = fmaxf(mx[0], pk_lo(sc0)); mx[1] = fmaxf(mx[1], pk_hi(sc0));
           mx[2] = fmaxf(mx[2], pk_lo(sc1)); mx[3] = fmaxf(mx[3], pk_hi(sc1));
         }
+        TRACE_RAY(4);
         const pk2 negm[2] = {pk(-mx[0], -mx[1]), pk(-mx[2], -mx[3])};
         pk2 den[2] = {0ull, 0ull}, o2[4][2];
 #pragma unroll
@@ -597,6 +636,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
             o2[dd][1] = pk_fma(p1, v4.y, o2[dd][1]);
           }
         }
+        TRACE_RAY(5);
         // att[head*4 + dim] = o / den
         float att[16];
         {
@@ -637,6 +677,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         if (cfg.density_maskfill && n_views_seen < 1.f) sigma = 0.f;
         if (!valid) sigma = 0.f;
       }
+      TRACE_RAY(6);
       if (aux && valid) {
         float4* a4 = reinterpret_cast<float4*>(aux) + n_glob;
         *a4 = make_float4(rgb[0], rgb[1], rgb[2], sigma);
@@ -691,6 +732,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
           out_opacity[ray] = part[4];
         }
         ray_barrier(slot);   // kbuf / vbuf / red / dirvec are rewritten by the next tile
+        TRACE_RAY(7);
       }
     }
   }
@@ -830,3 +872,15 @@ int launch_decoder_tc(const DevCams& cams, const DevRays& rays, const mnf_decode
 }
 
 }  // namespace mnf
+
+// Debug aid (not part of the reference-facing ABI): arm / disarm the decoder timeline trace.  buf = device array of
+// `cap` u64 records ([clock:40 | role:4 | slot:4 | event:8 | iteration:8]); buf = NULL disarms.  Synchronises.
+extern "C" int32_t mnf_debug_decoder_trace(void* buf, int32_t cap) {
+  using namespace mnf;
+  unsigned long long* p = reinterpret_cast<unsigned long long*>(buf);
+  unsigned int c = buf ? (unsigned)cap : 0u;
+  MNF_CUDA_TRY(cudaMemcpyToSymbol(g_trace_buf, &p, sizeof(p)));
+  MNF_CUDA_TRY(cudaMemcpyToSymbol(g_trace_cap, &c, sizeof(c)));
+  MNF_CUDA_TRY(cudaDeviceSynchronize());
+  return MNF_OK;
+}

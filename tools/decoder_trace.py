@@ -21,6 +21,10 @@ TRUNK = {0: "tile start", 1: "staged (A operands written)", 2: "gate acc ready",
          5: "heads epilogue done", 6: "hand-off buffer free", 7: "tile end"}
 TRUNK.update({10 + l: f"L{l}: gate/prev epilogue done -> wait acc" for l in range(6)})
 TRUNK.update({20 + l: f"L{l}: acc ready" for l in range(6)})
+MMA = {}
+MMA.update({50 + p: f"ph{p}: weights resident" for p in range(8)})
+MMA.update({10 + p: f"ph{p}: slot A operand ready" for p in range(8)})
+MMA.update({30 + p: f"ph{p}: MMAs issued + committed" for p in range(8)})
 RAY = {0: "wait hand-off", 1: "hand-off received", 2: "qkv done", 3: "ray barrier passed", 4: "pass 1 (max) done",
        5: "pass 2 (softmax.V) done", 6: "fc/LN/sigma done", 7: "composite + tile end"}
 
@@ -79,7 +83,7 @@ def main():
             if not (3 <= (i1 if role else 0) or role == 0):
                 continue
             acc.setdefault((e0, e1), []).append(c1 - c0)
-        names = TRUNK if role == 1 else (RAY if role == 2 else {})
+        names = TRUNK if role == 1 else (RAY if role == 2 else MMA)
         tot = 0.0
         for (e0, e1), v in acc.items():
             if len(v) < 4:
