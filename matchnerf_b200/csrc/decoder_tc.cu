@@ -38,6 +38,9 @@ namespace {
 constexpr int kTileM = 128;
 constexpr int kNumStages = 6;
 constexpr int kChunkBytes = 128 * 128;            // [128 rows][64 fp16]
+constexpr int kWRow = 24;                         // halves per row of the small fp16 matrices / of kbuf (48 B)
+constexpr int kVRow = 40;                         // halves per key of vbuf (4 heads x 8 columns + pad = 80 B)
+constexpr int kHandRow = 20;                      // floats per row of the trunk -> ray hand-off (80 B)
 constexpr int kHeadN = 80;                        // 16 alpha + 64 colour-hidden outputs
 constexpr int kHeadChunkBytes = kHeadN * 128;
 constexpr int kNumChunks = 15;                    // gate, L0, 4 x 2, 3 (L5), 2 (heads)
@@ -55,9 +58,12 @@ constexpr int kPackedBytes = 13 * kChunkBytes + 2 * kHeadChunkBytes;
 
 struct TcParams {             // small fp32 parameters, staged into shared memory once per CTA
   float bias[7][128];         // trunk layers 0..5, [6] = pts_bias.bias
-  float wqkv_t[16][48];       // [in][out]: out 0..15 = w_qs * (log2(e)/2), 16..31 = w_ks, 32..47 = w_vs   (transposed)
-  float fc_t[16][16];         // [in][out] ray_attention.fc
-  float oa0_t[16][16];        // [in][out] out_alpha_linear.0
+  // ray-transformer matrices as mma.sync B operands: fp16, [out][in] rows padded to kWRow halves (48 B: the 8 rows a
+  // quad-group reads land in distinct banks).  rows 0..15 = w_qs * (log2(e)/2), 16..31 = w_ks, 32..47 = w_vs
+  __half wqkv_h[48][kWRow];
+  __half wqkv_l[48][kWRow];   // fp16 remainder W - fp16(W): the q/k/v projection runs as a 3-term split product (~fp32 accurate)
+  __half fc_h[16][kWRow];     // ray_attention.fc
+  __half oa0_h[16][kWRow];    // out_alpha_linear.0
   float ln_w[16], ln_b[16];
   float oa0_b[16], oa2_w[16];
   float alpha_b[16];
@@ -71,11 +77,13 @@ struct TcParams {             // small fp32 parameters, staged into shared memor
 struct TcSmem {
   alignas(1024) unsigned char ring[kNumStages][kChunkBytes];
   TcParams p;
-  float kbuf[2][kTileM][16];
-  float vbuf[2][kTileM][16];
+  alignas(16) __half kbuf[2][kTileM][kWRow];                   // keys, [row][head*4 + dim]
+  alignas(16) __half vbuf[2][kTileM][kVRow];                   // values, [row][head][8]: even heads (v0..v3, 1, 0, 0, 0), odd heads (1, 0, 0, 0, v0..v3)
+  float sig[2][kTileM];
   float dirvec[2][kMaxRaysPerTile][64];
   float red[2][4][8];
-  float4 hand[2][2][6][kTileM];                    // trunk -> ray hand-off: [slot][buffer][xr0-3, xr4-7, xr8-11, xr12-15, rgb+depth, nviews][row]
+  alignas(16) float hand[2][2][kTileM][kHandRow];              // trunk -> ray hand-off: [slot][buffer][row][raw alpha 0..15, r, g, b, depth]
+  float hand_nv[2][2][kTileM];                     // views that see the sample
   alignas(8) uint64_t w_full[kNumStages];
   uint64_t w_empty[kNumStages];
   uint64_t a_ready[2];
@@ -113,6 +121,8 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
+__device__ __forceinline__ float h2_lo(uint32_t v) { return __low2float(*reinterpret_cast<const __half2*>(&v)); }
+__device__ __forceinline__ float h2_hi(uint32_t v) { return __high2float(*reinterpret_cast<const __half2*>(&v)); }
 __device__ __forceinline__ uint32_t gate_relu(uint32_t t, uint32_t g) {  // relu(t * g) on packed halves
   const __half2 r = __hfma2_relu(*reinterpret_cast<const __half2*>(&t), *reinterpret_cast<const __half2*>(&g), __float2half2_rn(0.f));
   return *reinterpret_cast<const uint32_t*>(&r);
@@ -176,20 +186,202 @@ __device__ __forceinline__ float ex2_fast(float x) {   // MUFU.EX2 without the d
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// y[0..kOut) (+)= W_t[in][out] . x   with W_t rows of `ld` floats in shared memory (broadcast LDS.128 + FFMA2)
-template <int kOut>
-__device__ __forceinline__ void matvec16_t(const float* __restrict__ wt, int ld, const float (&x)[16], pk2 (&y)[kOut / 2]) {
+// ---- warp-level tensor-core pieces of the ray transformer (mma.sync m16n8k16, fp16 operands, fp32 accumulate).
+// Fragment coordinates (g = lane >> 2, t = lane & 3):  A: a0 (row g, k 2t..2t+1), a1 (row g+8, same k), a2 (row g, k 8+2t..),
+// a3 (row g+8, k 8+2t..);  B: b0 (k 2t..2t+1, n g), b1 (k 8+2t.., n g);  C: c0,c1 (row g, n 2t, 2t+1), c2,c3 (row g+8, same n).
+__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void ldsm_x2_trans(uint32_t& r0, uint32_t& r1, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+
+// ---- ray transformer for the 32 rows of one warp (ray_transformer.py:49-79, cond_nerf.py:83-99), on mma.sync.
+// Phase A: [q | k | v] = raw . Wqkv^T (6 n-tiles per 16-row m-tile); q stays in registers as the A fragment of the
+// score product, k and v go to shared memory as fp16 B operands.  Phase B, per m-tile and head: scores = Q_h . K^T
+// with the other heads' columns of Q zeroed (so all four heads share the same K fragments, K = 16 = 4 heads x 4 dims),
+// row maxima (pass 1), then the same product again with the accumulator initialised to -max, exp2, and P . V_h where
+// V_h carries a column of ones: the softmax denominator drops out of the same MMA.  fc (+ residual), LayerNorm,
+// out_alpha_linear.0 are two more MMAs on C-layout registers; sigma is written to sm.sig for the compositing scan.
+template <int kAct, int kS>
+__device__ __forceinline__ void ray_transformer_mma(TcSmem& sm, const int slot, const uint32_t buf, const int quarter, const int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  const bool lo = t < 2;
+  const float* hand = &sm.hand[slot][buf][0][0];
+  const float* hand_nv = &sm.hand_nv[slot][buf][0];
+  uint32_t qa[2][4];                               // Q as A fragments (fp16 pairs), per m-tile
+  // ---------------- phase A
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const pk2 xi = pk(x[i], x[i]);
-    const ulonglong2* row = reinterpret_cast<const ulonglong2*>(wt + i * ld);
+  for (int mt = 0; mt < 2; ++mt) {
+    const int r0 = quarter * 32 + mt * 16 + g;     // fragment rows r0 and r0 + 8
+    const float2 x00 = *reinterpret_cast<const float2*>(hand + r0 * kHandRow + 2 * t);
+    const float2 x10 = *reinterpret_cast<const float2*>(hand + (r0 + 8) * kHandRow + 2 * t);
+    const float2 x01 = *reinterpret_cast<const float2*>(hand + r0 * kHandRow + 8 + 2 * t);
+    const float2 x11 = *reinterpret_cast<const float2*>(hand + (r0 + 8) * kHandRow + 8 + 2 * t);
+    const uint32_t a0 = pack_h2(x00.x, x00.y), a1 = pack_h2(x10.x, x10.y), a2 = pack_h2(x01.x, x01.y), a3 = pack_h2(x11.x, x11.y);
+    // x = hi + lo in fp16 pairs: scores reach ~1e3 (exp2 domain), so q and k want more than one fp16 of the inputs
+    const uint32_t l0 = pack_h2(x00.x - h2_lo(a0), x00.y - h2_hi(a0)), l1 = pack_h2(x10.x - h2_lo(a1), x10.y - h2_hi(a1));
+    const uint32_t l2 = pack_h2(x01.x - h2_lo(a2), x01.y - h2_hi(a2)), l3 = pack_h2(x11.x - h2_lo(a3), x11.y - h2_hi(a3));
+    // cond_nerf.py:83: the mask disables whole QUERY rows (all scores equal -> uniform attention): zero their q
+    const bool v0 = hand_nv[r0] > 1.f, v1 = hand_nv[r0 + 8] > 1.f;
+    float c[6][4];
 #pragma unroll
-    for (int o4 = 0; o4 < kOut / 4; ++o4) {
-      const ulonglong2 w = row[o4];
-      y[2 * o4] = pk_fma(xi, w.x, y[2 * o4]);
-      y[2 * o4 + 1] = pk_fma(xi, w.y, y[2 * o4 + 1]);
+    for (int j = 0; j < 6; ++j) {
+      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&sm.p.wqkv_h[8 * j + g][2 * t]);
+      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&sm.p.wqkv_h[8 * j + g][8 + 2 * t]);
+      const uint32_t e0 = *reinterpret_cast<const uint32_t*>(&sm.p.wqkv_l[8 * j + g][2 * t]);
+      const uint32_t e1 = *reinterpret_cast<const uint32_t*>(&sm.p.wqkv_l[8 * j + g][8 + 2 * t]);
+      c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
+      mma16816(c[j], a0, a1, a2, a3, e0, e1);
+      mma16816(c[j], l0, l1, l2, l3, b0, b1);
+      mma16816(c[j], a0, a1, a2, a3, b0, b1);
+    }
+    qa[mt][0] = v0 ? pack_h2(c[0][0], c[0][1]) : 0u;
+    qa[mt][1] = v1 ? pack_h2(c[0][2], c[0][3]) : 0u;
+    qa[mt][2] = v0 ? pack_h2(c[1][0], c[1][1]) : 0u;
+    qa[mt][3] = v1 ? pack_h2(c[1][2], c[1][3]) : 0u;
+    __half* k0 = &sm.kbuf[slot][r0][0];
+    __half* k1 = &sm.kbuf[slot][r0 + 8][0];
+    *reinterpret_cast<uint32_t*>(k0 + 2 * t) = pack_h2(c[2][0], c[2][1]);
+    *reinterpret_cast<uint32_t*>(k1 + 2 * t) = pack_h2(c[2][2], c[2][3]);
+    *reinterpret_cast<uint32_t*>(k0 + 8 + 2 * t) = pack_h2(c[3][0], c[3][1]);
+    *reinterpret_cast<uint32_t*>(k1 + 8 + 2 * t) = pack_h2(c[3][2], c[3][3]);
+    // value columns: n-tile 4 = heads 0,1, n-tile 5 = heads 2,3; thread t holds dims 2(t&1).. of head (t>>1) (+2)
+    const int vcol = (t >> 1) * 8 + (t >> 1) * 4 + (t & 1) * 2;   // odd heads keep their dims in columns 4..7
+    __half* v0p = &sm.vbuf[slot][r0][vcol];
+    __half* v1p = &sm.vbuf[slot][r0 + 8][vcol];
+    *reinterpret_cast<uint32_t*>(v0p) = pack_h2(c[4][0], c[4][1]);
+    *reinterpret_cast<uint32_t*>(v1p) = pack_h2(c[4][2], c[4][3]);
+    *reinterpret_cast<uint32_t*>(v0p + 16) = pack_h2(c[5][0], c[5][1]);
+    *reinterpret_cast<uint32_t*>(v1p + 16) = pack_h2(c[5][2], c[5][3]);
+  }
+  ray_barrier(slot);                               // a ray's keys / values come from up to four warps
+
+  // ---------------- phase B
+  const float2 lnw0 = *reinterpret_cast<const float2*>(&sm.p.ln_w[2 * t]), lnw1 = *reinterpret_cast<const float2*>(&sm.p.ln_w[8 + 2 * t]);
+  const float2 lnb0 = *reinterpret_cast<const float2*>(&sm.p.ln_b[2 * t]), lnb1 = *reinterpret_cast<const float2*>(&sm.p.ln_b[8 + 2 * t]);
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    const int rbase = quarter * 32 + mt * 16;      // first row of the m-tile; it lies inside one ray (kS >= 16)
+    const int key0 = rbase & ~(kS - 1);            // first key row of that ray
+    // ldmatrix lane addresses.  K (x4): matrices (n-tile 2np, k 0-7), (2np, k 8-15), (2np+1, k 0-7), (2np+1, k 8-15).
+    const uint32_t kaddr = tc::smem_u32(&sm.kbuf[slot][key0 + (lane >> 4) * 8 + (lane & 7)][((lane >> 3) & 1) * 8]);
+    // V (x2, transposed): matrices (keys 16np .. +7), (keys 16np + 8 .. +15), 8 columns of one head
+    const uint32_t vaddr = tc::smem_u32(&sm.vbuf[slot][key0 + ((lane >> 3) & 1) * 8 + (lane & 7)][0]);
+    uint32_t att[4];                               // normalised attention output as the A fragment of fc
+#pragma unroll
+    for (int hp = 0; hp < 2; ++hp) {               // head pair (0,1) / (2,3)
+      float o[2][4];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int h = 2 * hp + hh;
+        // Q_h: only the 4 k-columns of head h survive (k 0-3: t<2 of a0/a1; 4-7: t>=2; 8-11: t<2 of a2/a3; 12-15: t>=2)
+        const bool mine = (hh == 0) ? lo : !lo;
+        const uint32_t q0 = mine ? qa[mt][2 * hp] : 0u, q1 = mine ? qa[mt][2 * hp + 1] : 0u;
+        const uint32_t a0 = hp == 0 ? q0 : 0u, a1 = hp == 0 ? q1 : 0u, a2 = hp == 0 ? 0u : q0, a3 = hp == 0 ? 0u : q1;
+        float m0 = -INFINITY, m1 = -INFINITY;      // rows g, g + 8
+#pragma unroll
+        for (int np = 0; np < kS / 16; ++np) {
+          uint32_t kf[4];
+          ldsm_x4(kf, kaddr + np * 16 * kWRow * 2);
+          float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+          mma16816(c0, a0, a1, a2, a3, kf[0], kf[1]);
+          mma16816(c1, a0, a1, a2, a3, kf[2], kf[3]);
+          m0 = fmax3(m0, c0[0], c0[1]); m0 = fmax3(m0, c1[0], c1[1]);
+          m1 = fmax3(m1, c0[2], c0[3]); m1 = fmax3(m1, c1[2], c1[3]);
+        }
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+        o[hh][0] = o[hh][1] = o[hh][2] = o[hh][3] = 0.f;
+#pragma unroll
+        for (int np = 0; np < kS / 16; ++np) {
+          uint32_t kf[4];
+          ldsm_x4(kf, kaddr + np * 16 * kWRow * 2);
+          float c0[4] = {-m0, -m0, -m1, -m1}, c1[4] = {-m0, -m0, -m1, -m1};
+          mma16816(c0, a0, a1, a2, a3, kf[0], kf[1]);
+          mma16816(c1, a0, a1, a2, a3, kf[2], kf[3]);
+          const uint32_t p0 = pack_h2(ex2_fast(c0[0]), ex2_fast(c0[1])), p1 = pack_h2(ex2_fast(c0[2]), ex2_fast(c0[3]));
+          const uint32_t p2 = pack_h2(ex2_fast(c1[0]), ex2_fast(c1[1])), p3 = pack_h2(ex2_fast(c1[2]), ex2_fast(c1[3]));
+          uint32_t vf0, vf1;
+          ldsm_x2_trans(vf0, vf1, vaddr + np * 16 * kVRow * 2 + h * 16);
+          mma16816(o[hh], p0, p1, p2, p3, vf0, vf1);
+        }
+      }
+      // even head: (o0,o1 | o2,o3 | den,0 | 0,0) over t = 0..3; odd head: (den,0 | 0,0 | o0,o1 | o2,o3).  fc wants
+      // k = head*4 + dim, i.e. exactly the even head's values for t < 2 and the odd head's for t >= 2.
+      const int src = (lane & ~3) + (lo ? 2 : 0);
+      const float den0 = __shfl_sync(0xffffffffu, t == 0 ? o[1][0] : o[0][0], src);
+      const float den1 = __shfl_sync(0xffffffffu, t == 0 ? o[1][2] : o[0][2], src);
+      const float i0 = rcp_fast(den0), i1 = rcp_fast(den1);
+      att[2 * hp] = pack_h2((lo ? o[0][0] : o[1][0]) * i0, (lo ? o[0][1] : o[1][1]) * i0);
+      att[2 * hp + 1] = pack_h2((lo ? o[0][2] : o[1][2]) * i1, (lo ? o[0][3] : o[1][3]) * i1);
+    }
+    // fc + residual (C layout: y[j] = columns 8j + 2t, 8j + 2t + 1 of rows g | g + 8)
+    const int r0 = rbase + g;
+    float y[2][4];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float2 xa = *reinterpret_cast<const float2*>(hand + r0 * kHandRow + 8 * j + 2 * t);
+      const float2 xb = *reinterpret_cast<const float2*>(hand + (r0 + 8) * kHandRow + 8 * j + 2 * t);
+      y[j][0] = xa.x; y[j][1] = xa.y; y[j][2] = xb.x; y[j][3] = xb.y;
+      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&sm.p.fc_h[8 * j + g][2 * t]);
+      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&sm.p.fc_h[8 * j + g][8 + 2 * t]);
+      mma16816(y[j], att[0], att[1], att[2], att[3], b0, b1);
+    }
+    // LayerNorm(eps 1e-6) over the 16 columns: 4 per thread, the quad holds the row
+    float s0 = (y[0][0] + y[0][1]) + (y[1][0] + y[1][1]), s1 = (y[0][2] + y[0][3]) + (y[1][2] + y[1][3]);
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    const float mu0 = s0 * (1.f / 16.f), mu1 = s1 * (1.f / 16.f);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { y[j][0] -= mu0; y[j][1] -= mu0; y[j][2] -= mu1; y[j][3] -= mu1; }
+    float q0 = y[0][0] * y[0][0] + y[0][1] * y[0][1] + y[1][0] * y[1][0] + y[1][1] * y[1][1];
+    float q1 = y[0][2] * y[0][2] + y[0][3] * y[0][3] + y[1][2] * y[1][2] + y[1][3] * y[1][3];
+    q0 += __shfl_xor_sync(0xffffffffu, q0, 1); q0 += __shfl_xor_sync(0xffffffffu, q0, 2);
+    q1 += __shfl_xor_sync(0xffffffffu, q1, 1); q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
+    const float rs0 = rsqrtf(q0 * (1.f / 16.f) + 1e-6f), rs1 = rsqrtf(q1 * (1.f / 16.f) + 1e-6f);
+    const uint32_t n0 = pack_h2(fmaf(y[0][0] * rs0, lnw0.x, lnb0.x), fmaf(y[0][1] * rs0, lnw0.y, lnb0.y));
+    const uint32_t n1 = pack_h2(fmaf(y[0][2] * rs1, lnw0.x, lnb0.x), fmaf(y[0][3] * rs1, lnw0.y, lnb0.y));
+    const uint32_t n2 = pack_h2(fmaf(y[1][0] * rs0, lnw1.x, lnb1.x), fmaf(y[1][1] * rs0, lnw1.y, lnb1.y));
+    const uint32_t n3 = pack_h2(fmaf(y[1][2] * rs1, lnw1.x, lnb1.x), fmaf(y[1][3] * rs1, lnw1.y, lnb1.y));
+    // out_alpha_linear: 16 -> 16 (MMA, bias as the initial accumulator), activation, 16 -> 1
+    float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float2 bj = *reinterpret_cast<const float2*>(&sm.p.oa0_b[8 * j + 2 * t]);
+      const float2 wj = *reinterpret_cast<const float2*>(&sm.p.oa2_w[8 * j + 2 * t]);
+      float c[4] = {bj.x, bj.y, bj.x, bj.y};
+      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&sm.p.oa0_h[8 * j + g][2 * t]);
+      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&sm.p.oa0_h[8 * j + g][8 + 2 * t]);
+      mma16816(c, n0, n1, n2, n3, b0, b1);
+      d0 = fmaf(act_fn<kAct>(c[0]), wj.x, fmaf(act_fn<kAct>(c[1]), wj.y, d0));
+      d1 = fmaf(act_fn<kAct>(c[2]), wj.x, fmaf(act_fn<kAct>(c[3]), wj.y, d1));
+    }
+    d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
+    d1 += __shfl_xor_sync(0xffffffffu, d1, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
+    if (t == 0) {
+      sm.sig[slot][r0] = fmaxf(d0 + sm.p.oa2_b, 0.f);
+      sm.sig[slot][r0 + 8] = fmaxf(d1 + sm.p.oa2_b, 0.f);
     }
   }
+  __syncwarp();
 }
 
 }  // namespace
@@ -217,6 +409,11 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
   // ---- one-time setup
   for (int i = tid; i < (int)(sizeof(TcParams) / 4); i += blockDim.x)
     reinterpret_cast<float*>(&sm.p)[i] = reinterpret_cast<const float*>(gparams)[i];
+  for (int i = tid; i < 2 * kTileM * kVRow; i += blockDim.x) {   // the constant columns of the value operand (see vbuf)
+    const int c = i % kVRow, head = c >> 3, e = c & 7;
+    const bool one = head < 4 && ((head & 1) ? e == 0 : e == 4);
+    (&sm.vbuf[0][0][0])[i] = __float2half_rn(one ? 1.f : 0.f);
+  }
   if (tid == 0) {
     for (int i = 0; i < kNumStages; ++i) {
       tc::mbar_init(&sm.w_full[i], 1);
@@ -519,13 +716,13 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         TRACE_TRUNK(5);
         mbar_wait_sleep(&sm.ray_empty[slot][buf], ((it >> 1) & 1) ^ 1, 64);
         TRACE_TRUNK(6);
-        float4* h = &sm.hand[slot][buf][0][row];
-        h[0 * kTileM] = make_float4(xr[0], xr[1], xr[2], xr[3]);
-        h[1 * kTileM] = make_float4(xr[4], xr[5], xr[6], xr[7]);
-        h[2 * kTileM] = make_float4(xr[8], xr[9], xr[10], xr[11]);
-        h[3 * kTileM] = make_float4(xr[12], xr[13], xr[14], xr[15]);
-        h[4 * kTileM] = make_float4(rgb[0], rgb[1], rgb[2], depth_t);
-        h[5 * kTileM] = make_float4(n_views_seen, 0.f, 0.f, 0.f);
+        float4* h = reinterpret_cast<float4*>(&sm.hand[slot][buf][row][0]);   // 80-byte rows: conflict-free 16-byte stores
+        h[0] = make_float4(xr[0], xr[1], xr[2], xr[3]);
+        h[1] = make_float4(xr[4], xr[5], xr[6], xr[7]);
+        h[2] = make_float4(xr[8], xr[9], xr[10], xr[11]);
+        h[3] = make_float4(xr[12], xr[13], xr[14], xr[15]);
+        h[4] = make_float4(rgb[0], rgb[1], rgb[2], depth_t);
+        sm.hand_nv[slot][buf][row] = n_views_seen;
         tc::mbar_arrive(&sm.ray_full[slot][buf]);       // release semantics: the stores above are visible to the waiter
       }
       TRACE_TRUNK(7);
@@ -547,133 +744,25 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
       const int64_t ray = tile * rays_per_tile + ray_local;
       const bool valid = ray < rays.n_rays;
       const size_t n_glob = valid ? (size_t)ray * S + s : 0;
-      float xr[16], rgb[3], depth_t, n_views_seen;
+      float rgb[3], depth_t, sigma;
       {
         const uint32_t buf = it & 1;
         TRACE_RAY(0);
         mbar_wait_sleep(&sm.ray_full[slot][buf], (it >> 1) & 1, 64);
         TRACE_RAY(1);
-        const float4* h = &sm.hand[slot][buf][0][row];
-        const float4 a0 = h[0 * kTileM], a1 = h[1 * kTileM], a2 = h[2 * kTileM], a3 = h[3 * kTileM], a4 = h[4 * kTileM];
-        n_views_seen = h[5 * kTileM].x;
-        xr[0] = a0.x; xr[1] = a0.y; xr[2] = a0.z; xr[3] = a0.w; xr[4] = a1.x; xr[5] = a1.y; xr[6] = a1.z; xr[7] = a1.w;
-        xr[8] = a2.x; xr[9] = a2.y; xr[10] = a2.z; xr[11] = a2.w; xr[12] = a3.x; xr[13] = a3.y; xr[14] = a3.z; xr[15] = a3.w;
-        rgb[0] = a4.x; rgb[1] = a4.y; rgb[2] = a4.z; depth_t = a4.w;
-        tc::mbar_arrive(&sm.ray_empty[slot][buf]);
-      }
-
-      // ---------------- ray transformer over the S samples of this ray (ray_transformer.py:49-79)
-      // q is pre-scaled by log2(e)/temperature; k, v are laid out [dim][head], so one 16-byte load holds the 4 heads of
-      // a dim as two packed pairs (heads 0,1 | heads 2,3) and every multiply-add below is a packed FFMA2.
-      const bool row_valid = n_views_seen > 1.f;    // cond_nerf.py:83; the mask disables whole QUERY rows (uniform attention)
-      pk2 q2[4][2];                                 // [dim][head pair]
-      {
-        pk2 y[24];
-#pragma unroll
-        for (int i = 0; i < 24; ++i) y[i] = 0ull;
-        matvec16_t<48>(&sm.p.wqkv_t[0][0], 48, xr, y);
-        float yf[48];                               // [0,16) q, [16,32) k, [32,48) v; index = head*4 + dim
-#pragma unroll
-        for (int i = 0; i < 24; ++i) { yf[2 * i] = pk_lo(y[i]); yf[2 * i + 1] = pk_hi(y[i]); }
-        ulonglong2* kdst = reinterpret_cast<ulonglong2*>(&sm.kbuf[slot][row][0]);
-        ulonglong2* vdst = reinterpret_cast<ulonglong2*>(&sm.vbuf[slot][row][0]);
-#pragma unroll
-        for (int dd = 0; dd < 4; ++dd) {
-          q2[dd][0] = pk(yf[0 + dd], yf[4 + dd]);
-          q2[dd][1] = pk(yf[8 + dd], yf[12 + dd]);
-          kdst[dd] = make_ulonglong2(pk(yf[16 + dd], yf[20 + dd]), pk(yf[24 + dd], yf[28 + dd]));
-          vdst[dd] = make_ulonglong2(pk(yf[32 + dd], yf[36 + dd]), pk(yf[40 + dd], yf[44 + dd]));
-        }
-      }
-      TRACE_RAY(2);
-      ray_barrier(slot);
-      TRACE_RAY(3);
-      float sigma;
-      {
-        // Exact two-pass softmax (row maxima first).  A norm bound |q||k|max instead of the first pass was measured to
-        // underflow for 87 % of the rows on real encoder features (scores reach several hundred in the exp2 domain).
-        const ulonglong2* kb = reinterpret_cast<const ulonglong2*>(&sm.kbuf[slot][ray_local * S][0]);
-        const ulonglong2* vb = reinterpret_cast<const ulonglong2*>(&sm.vbuf[slot][ray_local * S][0]);
-        if (!row_valid) {
-#pragma unroll
-          for (int dd = 0; dd < 4; ++dd) q2[dd][0] = q2[dd][1] = 0ull;   // masked query row: all scores equal -> uniform attention
-        }
-        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll 2
-        for (int j = 0; j < S; ++j) {
-          pk2 sc0 = 0ull, sc1 = 0ull;
-#pragma unroll
-          for (int dd = 0; dd < 4; ++dd) {
-            const ulonglong2 k4 = kb[j * 4 + dd];
-            sc0 = pk_fma(q2[dd][0], k4.x, sc0);
-            sc1 = pk_fma(q2[dd][1], k4.y, sc1);
-          }
-          mx[0] = fmaxf(mx[0], pk_lo(sc0)); mx[1] = fmaxf(mx[1], pk_hi(sc0));
-          mx[2] = fmaxf(mx[2], pk_lo(sc1)); mx[3] = fmaxf(mx[3], pk_hi(sc1));
-        }
-        TRACE_RAY(4);
-        const pk2 negm[2] = {pk(-mx[0], -mx[1]), pk(-mx[2], -mx[3])};
-        pk2 den[2] = {0ull, 0ull}, o2[4][2];
-#pragma unroll
-        for (int dd = 0; dd < 4; ++dd) o2[dd][0] = o2[dd][1] = 0ull;
-#pragma unroll 2
-        for (int j = 0; j < S; ++j) {
-          pk2 sc0 = negm[0], sc1 = negm[1];
-#pragma unroll
-          for (int dd = 0; dd < 4; ++dd) {
-            const ulonglong2 k4 = kb[j * 4 + dd];
-            sc0 = pk_fma(q2[dd][0], k4.x, sc0);
-            sc1 = pk_fma(q2[dd][1], k4.y, sc1);
-          }
-          const pk2 p0 = pk(ex2_fast(pk_lo(sc0)), ex2_fast(pk_hi(sc0)));
-          const pk2 p1 = pk(ex2_fast(pk_lo(sc1)), ex2_fast(pk_hi(sc1)));
-          den[0] = pk_add(den[0], p0);
-          den[1] = pk_add(den[1], p1);
-#pragma unroll
-          for (int dd = 0; dd < 4; ++dd) {
-            const ulonglong2 v4 = vb[j * 4 + dd];
-            o2[dd][0] = pk_fma(p0, v4.x, o2[dd][0]);
-            o2[dd][1] = pk_fma(p1, v4.y, o2[dd][1]);
-          }
+        switch (S) {
+          case 16: ray_transformer_mma<kAct, 16>(sm, slot, buf, quarter, lane); break;
+          case 32: ray_transformer_mma<kAct, 32>(sm, slot, buf, quarter, lane); break;
+          case 64: ray_transformer_mma<kAct, 64>(sm, slot, buf, quarter, lane); break;
+          default: ray_transformer_mma<kAct, 128>(sm, slot, buf, quarter, lane); break;
         }
         TRACE_RAY(5);
-        // att[head*4 + dim] = o / den
-        float att[16];
-        {
-          const float inv[4] = {1.f / pk_lo(den[0]), 1.f / pk_hi(den[0]), 1.f / pk_lo(den[1]), 1.f / pk_hi(den[1])};
-#pragma unroll
-          for (int dd = 0; dd < 4; ++dd) {
-            att[0 + dd] = pk_lo(o2[dd][0]) * inv[0];
-            att[4 + dd] = pk_hi(o2[dd][0]) * inv[1];
-            att[8 + dd] = pk_lo(o2[dd][1]) * inv[2];
-            att[12 + dd] = pk_hi(o2[dd][1]) * inv[3];
-          }
-        }
-        pk2 y2[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) y2[i] = pk(xr[2 * i], xr[2 * i + 1]);     // residual
-        matvec16_t<16>(&sm.p.fc_t[0][0], 16, att, y2);
-        float y[16], mu = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { y[2 * i] = pk_lo(y2[i]); y[2 * i + 1] = pk_hi(y2[i]); mu += y[2 * i] + y[2 * i + 1]; }
-        mu *= (1.f / 16.f);
-        float var = 0.f;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) var += (y[i] - mu) * (y[i] - mu);
-        const float rstd = rsqrtf(var * (1.f / 16.f) + 1e-6f);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) y[i] = (y[i] - mu) * rstd * sm.p.ln_w[i] + sm.p.ln_b[i];
-        pk2 a2[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) a2[i] = pk(sm.p.oa0_b[2 * i], sm.p.oa0_b[2 * i + 1]);
-        matvec16_t<16>(&sm.p.oa0_t[0][0], 16, y, a2);
-        float acc = sm.p.oa2_b;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          acc = fmaf(act_fn<kAct>(pk_lo(a2[i])), sm.p.oa2_w[2 * i], acc);
-          acc = fmaf(act_fn<kAct>(pk_hi(a2[i])), sm.p.oa2_w[2 * i + 1], acc);
-        }
-        sigma = fmaxf(acc, 0.f);
+        // back to lane = row for the compositing scan
+        const float4 a4 = *reinterpret_cast<const float4*>(&sm.hand[slot][buf][row][16]);
+        const float n_views_seen = sm.hand_nv[slot][buf][row];
+        rgb[0] = a4.x; rgb[1] = a4.y; rgb[2] = a4.z; depth_t = a4.w;
+        sigma = sm.sig[slot][row];
+        tc::mbar_arrive(&sm.ray_empty[slot][buf]);
         if (cfg.density_maskfill && n_views_seen < 1.f) sigma = 0.f;
         if (!valid) sigma = 0.f;
       }
@@ -800,13 +889,17 @@ int decoder_tc_pack(const float* P, const ParamOffsets& off, DecoderWeightsTC** 
   for (int l = 0; l < kDepth; ++l) memcpy(tp.bias[l], P + off.pts_b[l], 128 * sizeof(float));
   memcpy(tp.bias[6], P + off.gate_b, 128 * sizeof(float));
   const float qscale = 0.5f * 1.4426950408889634f;    // 1/temperature (sqrt(d_k) = 2) and log2(e) for exp2
-  for (int i = 0; i < 16; ++i)
-    for (int o = 0; o < 16; ++o) {
-      tp.wqkv_t[i][o] = P[off.att_q + o * 16 + i] * qscale;
-      tp.wqkv_t[i][16 + o] = P[off.att_k + o * 16 + i];
-      tp.wqkv_t[i][32 + o] = P[off.att_v + o * 16 + i];
-      tp.fc_t[i][o] = P[off.att_fc + o * 16 + i];
-      tp.oa0_t[i][o] = P[off.oa0_w + o * 16 + i];
+  for (int o = 0; o < 16; ++o)
+    for (int i = 0; i < kWRow; ++i) {
+      const bool in = i < 16;
+      const float w3[3] = {in ? P[off.att_q + o * 16 + i] * qscale : 0.f, in ? P[off.att_k + o * 16 + i] : 0.f,
+                           in ? P[off.att_v + o * 16 + i] : 0.f};
+      for (int m = 0; m < 3; ++m) {
+        tp.wqkv_h[16 * m + o][i] = __float2half_rn(w3[m]);
+        tp.wqkv_l[16 * m + o][i] = __float2half_rn(w3[m] - __half2float(tp.wqkv_h[16 * m + o][i]));
+      }
+      tp.fc_h[o][i] = __float2half_rn(in ? P[off.att_fc + o * 16 + i] : 0.f);
+      tp.oa0_h[o][i] = __float2half_rn(in ? P[off.oa0_w + o * 16 + i] : 0.f);
     }
   memcpy(tp.ln_w, P + off.ln_w, sizeof(tp.ln_w));
   memcpy(tp.ln_b, P + off.ln_b, sizeof(tp.ln_b));

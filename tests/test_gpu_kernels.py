@@ -144,7 +144,7 @@ def tc_available(ctx, S):
     return True
 
 
-@pytest.mark.parametrize("S", [64, 128])
+@pytest.mark.parametrize("S", [16, 32, 64, 128])
 def test_decoder_tcgen05_config1(ctx, S):
     """fp16-operand tensor-core kernel vs the fp32 oracle: mixed-precision budget rgb RMS <= 2e-3 (0.01 dB)."""
     feats, imgs, extr, intr, nf, ray_idx = config1_inputs()
