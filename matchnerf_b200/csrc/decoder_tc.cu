@@ -53,11 +53,11 @@ constexpr int kColD = 0, kColH = 128, kColEnc = 192, kColCond = 224, kSlotCols =
 constexpr int kMaxRaysPerTile = 8;                // S >= 16
 
 __host__ __device__ constexpr int chunk_bytes(int c) { return c < 13 ? kChunkBytes : kHeadChunkBytes; }
-__host__ __device__ constexpr int chunk_offset(int c) { return c <= 13 ? c * kChunkBytes : 13 * kChunkBytes + (c - 13) * kHeadChunkBytes; }
-constexpr int kPackedBytes = 13 * kChunkBytes + 2 * kHeadChunkBytes;
+__host__ __device__ constexpr int chunk_offset(int c) { return c <= 13 ? c * kChunkBytes : 13 * kChunkBytes + (c - 13) * kHeadChunkBytes; }   // c = 15: the bias tile
+constexpr int kBiasOffset = 13 * kChunkBytes + 2 * kHeadChunkBytes;   // resident bias tile (layers 1..4), not part of the ring stream
+constexpr int kPackedBytes = kBiasOffset + kChunkBytes;
 
 struct TcParams {             // small fp32 parameters, staged into shared memory once per CTA
-  float bias[7][128];         // trunk layers 0..5, [6] = pts_bias.bias
   // ray-transformer matrices as mma.sync B operands: fp16, [out][in] rows padded to kWRow halves (48 B: the 8 rows a
   // quad-group reads land in distinct banks).  rows 0..15 = w_qs * (log2(e)/2), 16..31 = w_ks, 32..47 = w_vs
   __half wqkv_h[48][kWRow];
@@ -74,8 +74,14 @@ struct TcParams {             // small fp32 parameters, staged into shared memor
   float oa2_b;
 };
 
+struct TraceCtl { unsigned long long* buf; unsigned per; };
 struct TcSmem {
   alignas(1024) unsigned char ring[kNumStages][kChunkBytes];
+  // Biases ride on the tensor pipe.  The positional-encoding tile carries 1.0 in its pad column 63 and the conditioning
+  // tile in its pad column 22, so gate / layer 0 / layer 5 (which consume those tiles anyway) find their bias as one
+  // more weight column.  Layers 1..4 (K = 128, no spare column) get one extra K=16 step: A = encoding columns 48..63,
+  // B = columns 16j..16j+15 of this resident [128][64] tile, zero except column 16j+15 = bias of layer 1+j.
+  alignas(1024) unsigned char biasw[kChunkBytes];
   TcParams p;
   alignas(16) __half kbuf[2][kTileM][kWRow];                   // keys, [row][head*4 + dim]
   alignas(16) __half vbuf[2][kTileM][kVRow];                   // values, [row][head][8]: even heads (v0..v3, 1, 0, 0, 0), odd heads (1, 0, 0, 0, v0..v3)
@@ -87,29 +93,38 @@ struct TcSmem {
   alignas(8) uint64_t w_full[kNumStages];
   uint64_t w_empty[kNumStages];
   uint64_t a_ready[2];
+  uint64_t bias_full;
   uint64_t d_full[2];
   uint64_t ray_full[2][2];
   uint64_t ray_empty[2][2];
   uint32_t tmem_base;
+  TraceCtl trace;
 };
 
 // ---- optional timeline trace (debug aid; mnf_debug_decoder_trace): CTA 0 records clock64() at protocol points
 __device__ unsigned long long* g_trace_buf = nullptr;
 __device__ unsigned int g_trace_cap = 0;
-// role: 0 mma, 1 trunk, 2 ray.  One lane per role group records into its own sixth of the buffer (no atomics, so a
-// probe costs a clock read and one store).
-__device__ __forceinline__ void trace(int role, int slot, int ev, unsigned it, unsigned& n) {
-  if (g_trace_buf != nullptr && blockIdx.x == 0) {
-    const unsigned per = g_trace_cap / 6u;
-    if (n < per)
-      g_trace_buf[(unsigned)(role * 2 + slot) * per + n] = ((unsigned long long)clock64() << 24) | ((unsigned long long)(role & 15) << 20) |
-                                                          ((unsigned long long)(slot & 15) << 16) | ((unsigned long long)(ev & 255) << 8) | (it & 255);
+// role: 0 mma, 1 trunk, 2 ray.  Lane 0 of every warp records into that warp's own twentieth of the buffer (no atomics,
+// so a probe costs a clock read and one store); the slot field carries slot | quarter << 2.
+// The armed buffer is latched into shared memory at kernel start: a probe must not cost a global-memory round trip
+// (it sits on the MMA issuer's critical path).
+__device__ __forceinline__ void trace(const TraceCtl& tc_, int role, int slot, int ev, unsigned it, unsigned& n) {
+  if (tc_.per != 0u) {
+    if (n < tc_.per)
+      tc_.buf[(threadIdx.x >> 5) * tc_.per + n] = ((unsigned long long)clock64() << 24) | ((unsigned long long)(role & 15) << 20) |
+                                                 ((unsigned long long)(slot & 15) << 16) | ((unsigned long long)(ev & 255) << 8) | (it & 255);
     ++n;
   }
 }
-#define TRACE_TRUNK(ev) do { if (quarter == 0 && lane == 0) trace(1, slot, ev, it, trace_n); } while (0)
-#define TRACE_RAY(ev) do { if (quarter == 0 && lane == 0) trace(2, slot, ev, it, trace_n); } while (0)
-#define TRACE_MMA(sl, ev) do { if (leader) trace(0, sl, ev, (unsigned)(n & 255), trace_m[sl]); } while (0)
+#ifdef MNF_DECODER_TRACE
+#define TRACE_TRUNK(ev) do { if (lane == 0) trace(sm.trace, 1, slot | (quarter << 2), ev, it, trace_n); } while (0)
+#define TRACE_RAY(ev) do { if (lane == 0) trace(sm.trace, 2, slot | (quarter << 2), ev, it, trace_n); } while (0)
+#define TRACE_MMA(sl, ev) do { if (leader) trace(sm.trace, 0, sl, ev, (unsigned)(n & 255), trace_m); } while (0)
+#else   // probes compile to nothing unless the library is built with -DMNF_DECODER_TRACE (tools/decoder_trace.py)
+#define TRACE_TRUNK(ev) do { (void)trace_n; } while (0)
+#define TRACE_RAY(ev) do { (void)trace_n; } while (0)
+#define TRACE_MMA(sl, ev) do { } while (0)
+#endif
 
 __device__ __forceinline__ void trunk_barrier(int slot) { asm volatile("bar.sync %0, 128;" ::"r"(slot + 1) : "memory"); }
 __device__ __forceinline__ void ray_barrier(int slot) { asm volatile("bar.sync %0, 128;" ::"r"(slot + 3) : "memory"); }
@@ -415,10 +430,13 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
     (&sm.vbuf[0][0][0])[i] = __float2half_rn(one ? 1.f : 0.f);
   }
   if (tid == 0) {
+    sm.trace.buf = g_trace_buf;
+    sm.trace.per = (g_trace_buf != nullptr && blockIdx.x == 0) ? g_trace_cap / 20u : 0u;
     for (int i = 0; i < kNumStages; ++i) {
       tc::mbar_init(&sm.w_full[i], 1);
       tc::mbar_init(&sm.w_empty[i], 1);
     }
+    tc::mbar_init(&sm.bias_full, 1);
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&sm.a_ready[i], kTileM);
       tc::mbar_init(&sm.d_full[i], 1);
@@ -441,6 +459,8 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
     if (warp == 0) {
       // ================================================================== weight streamer
       if (lane == 0) {
+        tc::mbar_arrive_expect_tx(&sm.bias_full, kChunkBytes);
+        tc::bulk_g2s(sm.biasw, wpacked + kBiasOffset, kChunkBytes, &sm.bias_full);
         uint32_t n = 0;
         for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
           for (int c = 0; c < kNumChunks; ++c, ++n) {
@@ -453,62 +473,90 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
       }
     } else if (warp == 1) {
       // ================================================================== MMA issuer
-      // The whole warp runs this loop convergently and one elected lane issues the tcgen05 instructions: descriptor and
-      // address arithmetic is then warp-uniform (uniform datapath) instead of per-thread values that need a
-      // register -> uniform-register move in front of every MMA (the single-lane version spent ~1000 cycles issuing
-      // the 8 MMAs of a 512-cycle layer).
+      // The tensor pipe idles whenever this warp is between "operand ready" and the next tcgen05.mma, so its loop is
+      // kept lean: the 8 phases are unrolled (K-step structure is compile-time), a shared-memory descriptor is
+      // (constant high word | low word), low word = ring base + stage * 1024 + K-step * 2 (units of 16 B), stages and
+      // barrier parities are tracked incrementally (no div/mod by 6).  The whole warp runs the loop convergently and one
+      // elected lane issues the tcgen05 instructions.
       const uint32_t idesc128 = tc::umma_idesc_f16(128, 128), idesc_head = tc::umma_idesc_f16(128, kHeadN);
       const bool leader = tc::elect_one();
-      unsigned trace_m[2] = {0u, 0u};
-      uint32_t n = 0;
+      constexpr uint64_t kDescHi = ((uint64_t)2 << 61) | ((uint64_t)1 << 46) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 16);
+      const uint32_t ring_lo = (tc::smem_u32(sm.ring[0]) >> 4) & 0x3FFFu;
+      const uint32_t bias_lo = (tc::smem_u32(sm.biasw) >> 4) & 0x3FFFu;
+      auto bdesc = [](uint32_t lo) { return kDescHi | (uint64_t)lo; };
+      unsigned trace_m = 0u;
+      uint32_t n = 0;            // chunk counter (trace only)
+      uint32_t st = 0;           // ring stage of the next chunk
+      uint32_t full_par = 0;     // bit s = parity of the next w_full[s] phase to wait for
+      mbar_wait_sleep(&sm.bias_full, 0, 20);
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         const bool active1 = 2 * pair + 1 < n_tiles;
-#pragma unroll 1
+#pragma unroll
         for (int ph = 0; ph < kNumPhases; ++ph) {
           const int nch = ph <= 1 ? 1 : (ph == 6 ? 3 : 2);
-          for (int j = 0; j < nch; ++j) mbar_wait_sleep(&sm.w_full[(n + j) % kNumStages], ((n + j) / kNumStages) & 1, 20);
-          TRACE_MMA(0, 50 + ph);
-          uint32_t ring_addr[3];
+          uint32_t stage[3], lo[3];
 #pragma unroll
-          for (int j = 0; j < 3; ++j) ring_addr[j] = tc::smem_u32(sm.ring[(n + (j < nch ? j : 0)) % kNumStages]);
-#pragma unroll 1
+          for (int j = 0; j < 3; ++j) {
+            if (j < nch) {
+              stage[j] = st;
+              st = (st == kNumStages - 1) ? 0u : st + 1u;
+            } else {
+              stage[j] = stage[0];
+            }
+            lo[j] = ring_lo + stage[j] * (uint32_t)(kChunkBytes >> 4);
+          }
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+            if (j < nch) {
+              mbar_wait_sleep(&sm.w_full[stage[j]], (full_par >> stage[j]) & 1u, 20);
+              full_par ^= 1u << stage[j];
+            }
+          TRACE_MMA(0, 50 + ph);
+#pragma unroll
           for (int slot = 0; slot < 2; ++slot) {
-            if (slot == 1 && !active1) break;
+            if (slot == 1 && !active1) continue;
             mbar_wait_sleep(&sm.a_ready[slot], ph & 1, 20);
             TRACE_MMA(slot, 10 + ph);
             tc::tc_fence_after_sync();
-            const uint32_t tb = tmem + slot * kSlotCols;
+            uint32_t tb = tmem + slot * kSlotCols;
+            asm volatile("" : "+r"(tb));   // opaque: keeps the 20-odd operand addresses of a phase from being hoisted into registers
             const uint32_t d = tb + kColD;
             if (leader) {
               if (ph == 0) {          // gate = pts_bias(cond): K = 32
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks) tc::umma_ts(d, tb + kColCond + ks * 8, tc::umma_desc_sw128(ring_addr[0] + ks * 32), idesc128, ks > 0);
+                for (int ks = 0; ks < 2; ++ks) tc::umma_ts(d, tb + kColCond + ks * 8, bdesc(lo[0] + ks * 2), idesc128, ks > 0);
               } else if (ph == 1) {   // layer 0: K = 64 (encoding)
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) tc::umma_ts(d, tb + kColEnc + ks * 8, tc::umma_desc_sw128(ring_addr[0] + ks * 32), idesc128, ks > 0);
-              } else if (ph <= 5) {   // layers 1..4: K = 128
+                for (int ks = 0; ks < 4; ++ks) tc::umma_ts(d, tb + kColEnc + ks * 8, bdesc(lo[0] + ks * 2), idesc128, ks > 0);
+              } else if (ph <= 5) {   // layers 1..4: K = 128, then the bias step (A = encoding columns 48..63, see biasw)
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) tc::umma_ts(d, tb + kColH + ks * 8, tc::umma_desc_sw128(ring_addr[ks >> 2] + (ks & 3) * 32), idesc128, ks > 0);
+                for (int ks = 0; ks < 8; ++ks) tc::umma_ts(d, tb + kColH + ks * 8, bdesc(lo[ks >> 2] + (ks & 3) * 2), idesc128, ks > 0);
+                tc::umma_ts(d, tb + kColEnc + 3 * 8, bdesc(bias_lo + (ph - 2) * 2), idesc128, 1);
               } else if (ph == 6) {   // layer 5 on [enc, h]: K = 64 + 128
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) tc::umma_ts(d, tb + kColEnc + ks * 8, tc::umma_desc_sw128(ring_addr[0] + ks * 32), idesc128, ks > 0);
+                for (int ks = 0; ks < 4; ++ks) tc::umma_ts(d, tb + kColEnc + ks * 8, bdesc(lo[0] + ks * 2), idesc128, ks > 0);
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) tc::umma_ts(d, tb + kColH + ks * 8, tc::umma_desc_sw128(ring_addr[1 + (ks >> 2)] + (ks & 3) * 32), idesc128, 1);
+                for (int ks = 0; ks < 8; ++ks) tc::umma_ts(d, tb + kColH + ks * 8, bdesc(lo[1 + (ks >> 2)] + (ks & 3) * 2), idesc128, 1);
               } else {                // heads: [alpha_linear | views(feature_linear(.))], N = 80, K = 128
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) tc::umma_ts(d, tb + kColH + ks * 8, tc::umma_desc_sw128(ring_addr[ks >> 2] + (ks & 3) * 32), idesc_head, ks > 0);
+                for (int ks = 0; ks < 8; ++ks) tc::umma_ts(d, tb + kColH + ks * 8, bdesc(lo[ks >> 2] + (ks & 3) * 2), idesc_head, ks > 0);
               }
               tc::umma_commit(&sm.d_full[slot]);
             }
             TRACE_MMA(slot, 30 + ph);
             __syncwarp();
           }
-          if (leader)
-            for (int j = 0; j < nch; ++j) tc::umma_commit(&sm.w_empty[(n + j) % kNumStages]);
+          if (leader) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+              if (j < nch) tc::umma_commit(&sm.w_empty[stage[j]]);
+          }
+          TRACE_MMA(0, 60 + ph);
           __syncwarp();
           n += nch;
         }
       }
+      (void)n; (void)trace_m;
     }
   } else if (wg <= 2) {
     // ================================================================== trunk slot: staging, epilogues, heads
@@ -580,7 +628,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         }
 #pragma unroll
         for (int j = 0; j < 30; ++j) put(33 + j, cosv[j]);
-        put(63, 0.f);
+        put(63, 1.f);   // pad column = 1: multiplies the bias column of the layer-0 / layer-5 weights
         {
           uint32_t lo[16], hi[16];
 #pragma unroll
@@ -605,6 +653,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
           const __half2 h10 = *reinterpret_cast<const __half2*>(&cnd[10]);
           n_views_seen = __high2float(h9) + __low2float(h10) + __high2float(h10);
         }
+        cnd[11] = (cnd[11] & 0xffff0000u) | 0x3c00u;   // pad column 22 = 1.0: multiplies the gate's bias column
         tc::tmem_st16(tb + kColCond, cnd);
         tc::tmem_wait_st();
         tc::tc_fence_before_sync();
@@ -612,7 +661,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         tc::mbar_arrive(&sm.a_ready[slot]);
       }
 
-      // ---------------- gate = pts_bias(cond) + b, kept as 64 packed-half registers for all six layers
+      // ---------------- gate = pts_bias(cond) (bias folded into the MMA), kept as 64 packed-half registers for all six layers
       uint32_t gate[64];
       TRACE_TRUNK(1);
       mbar_wait_sleep(&sm.d_full[slot], 0, 32);
@@ -624,25 +673,18 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         tc::tmem_ld32(tb + kColD + c0, r);
         tc::tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const ulonglong2 b4 = *reinterpret_cast<const ulonglong2*>(&sm.p.bias[6][c0 + 4 * j]);
-          const pk2 s0 = pk_add(pk(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), b4.x);
-          const pk2 s1 = pk_add(pk(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), b4.y);
-          gate[c0 / 2 + 2 * j] = pack_h2(pk_lo(s0), pk_hi(s0));
-          gate[c0 / 2 + 2 * j + 1] = pack_h2(pk_lo(s1), pk_hi(s1));
-        }
+        for (int j = 0; j < 16; ++j) gate[c0 / 2 + j] = pack_h2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
       }
       tc::tc_fence_before_sync();
       tc::mbar_arrive(&sm.a_ready[slot]);
 
-      // ---------------- trunk: h = relu((acc + b_l) * gate) -> fp16 -> tensor memory (next layer's A operand)
+      // ---------------- trunk: h = relu(acc * gate), acc = W h + b from the tensor pipe, -> fp16 -> tensor memory (next layer's A operand)
 #pragma unroll 1
       for (int l = 0; l < kDepth; ++l) {
         TRACE_TRUNK(10 + l);
         mbar_wait_sleep(&sm.d_full[slot], (l + 1) & 1, 32);
         TRACE_TRUNK(20 + l);
         tc::tc_fence_after_sync();
-        const float* bl = sm.p.bias[l];
 #pragma unroll
         for (int c0 = 0; c0 < 128; c0 += 32) {
           uint32_t r[32];
@@ -650,13 +692,8 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
           tc::tmem_wait_ld();
           uint32_t o16[16];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const ulonglong2 b4 = *reinterpret_cast<const ulonglong2*>(bl + c0 + 4 * j);
-            const pk2 s0 = pk_add(pk(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), b4.x);
-            const pk2 s1 = pk_add(pk(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), b4.y);
-            o16[2 * j] = gate_relu(pack_h2(pk_lo(s0), pk_hi(s0)), gate[c0 / 2 + 2 * j]);
-            o16[2 * j + 1] = gate_relu(pack_h2(pk_lo(s1), pk_hi(s1)), gate[c0 / 2 + 2 * j + 1]);
-          }
+          for (int j = 0; j < 16; ++j)
+            o16[j] = gate_relu(pack_h2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])), gate[c0 / 2 + j]);
           tc::tmem_st16(tb + kColH + c0 / 2, o16);
         }
         tc::tmem_wait_st();
@@ -853,13 +890,23 @@ int decoder_tc_pack(const float* P, const ParamOffsets& off, DecoderWeightsTC** 
       for (int k = 0; k < kn; ++k) t[(size_t)n * 64 + k] = W[(size_t)n * K + k0 + k];
     return t;
   };
-  put_chunk(buf, 0, 128, slice(P + off.gate_w, 128, kCond, 0, kCond));
-  put_chunk(buf, 1, 128, slice(P + off.pts_w[0], 128, kEnc, 0, kEnc));
+  auto with_bias = [&](std::vector<double> t, int col, const float* b) {   // bias as the weight column of a constant-1 input
+    for (int n = 0; n < 128; ++n) t[(size_t)n * 64 + col] = b[n];
+    return t;
+  };
+  put_chunk(buf, 0, 128, with_bias(slice(P + off.gate_w, 128, kCond, 0, kCond), kCond, P + off.gate_b));
+  put_chunk(buf, 1, 128, with_bias(slice(P + off.pts_w[0], 128, kEnc, 0, kEnc), kEnc, P + off.pts_b[0]));
   for (int l = 1; l <= 4; ++l) {
     put_chunk(buf, 2 * l, 128, slice(P + off.pts_w[l], 128, 128, 0, 64));
     put_chunk(buf, 2 * l + 1, 128, slice(P + off.pts_w[l], 128, 128, 64, 64));
   }
-  put_chunk(buf, 10, 128, slice(P + off.pts_w[5], 128, kEnc + 128, 0, kEnc));
+  put_chunk(buf, 10, 128, with_bias(slice(P + off.pts_w[5], 128, kEnc + 128, 0, kEnc), kEnc, P + off.pts_b[5]));
+  {
+    std::vector<double> t((size_t)128 * 64, 0.0);
+    for (int j = 0; j < 4; ++j)
+      for (int n = 0; n < 128; ++n) t[(size_t)n * 64 + 16 * j + 15] = P[off.pts_b[1 + j] + n];
+    put_chunk(buf, 15, 128, t);
+  }
   put_chunk(buf, 11, 128, slice(P + off.pts_w[5], 128, kEnc + 128, kEnc, 64));
   put_chunk(buf, 12, 128, slice(P + off.pts_w[5], 128, kEnc + 128, kEnc + 64, 64));
   // heads: rows 0..15 alpha_linear; rows 16..79 views_linears.0[:, :128] @ feature_linear (no nonlinearity between them)
@@ -886,8 +933,6 @@ int decoder_tc_pack(const float* P, const ParamOffsets& off, DecoderWeightsTC** 
       for (int k = 0; k < 64; ++k) t[(size_t)n * 64 + k] = head[(size_t)n * 128 + half * 64 + k];
     put_chunk(buf, 13 + half, kHeadN, t);
   }
-  for (int l = 0; l < kDepth; ++l) memcpy(tp.bias[l], P + off.pts_b[l], 128 * sizeof(float));
-  memcpy(tp.bias[6], P + off.gate_b, 128 * sizeof(float));
   const float qscale = 0.5f * 1.4426950408889634f;    // 1/temperature (sqrt(d_k) = 2) and log2(e) for exp2
   for (int o = 0; o < 16; ++o)
     for (int i = 0; i < kWRow; ++i) {
@@ -972,6 +1017,9 @@ extern "C" int32_t mnf_debug_decoder_trace(void* buf, int32_t cap) {
   using namespace mnf;
   unsigned long long* p = reinterpret_cast<unsigned long long*>(buf);
   unsigned int c = buf ? (unsigned)cap : 0u;
+#ifndef MNF_DECODER_TRACE
+  if (buf) { set_error("library built without -DMNF_DECODER_TRACE"); return MNF_EUNSUPPORTED; }
+#endif
   MNF_CUDA_TRY(cudaMemcpyToSymbol(g_trace_buf, &p, sizeof(p)));
   MNF_CUDA_TRY(cudaMemcpyToSymbol(g_trace_cap, &c, sizeof(c)));
   MNF_CUDA_TRY(cudaDeviceSynchronize());

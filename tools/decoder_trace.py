@@ -25,14 +25,16 @@ MMA = {}
 MMA.update({50 + p: f"ph{p}: weights resident" for p in range(8)})
 MMA.update({10 + p: f"ph{p}: slot A operand ready" for p in range(8)})
 MMA.update({30 + p: f"ph{p}: MMAs issued + committed" for p in range(8)})
-RAY = {0: "wait hand-off", 1: "hand-off received", 2: "qkv done", 3: "ray barrier passed", 4: "pass 1 (max) done",
-       5: "pass 2 (softmax.V) done", 6: "fc/LN/sigma done", 7: "composite + tile end"}
+MMA.update({60 + p: f"ph{p}: weight stages released" for p in range(8)})
+RAY = {0: "wait hand-off", 1: "hand-off received", 5: "ray transformer (mma.sync) done", 6: "sigma read back, buffer released",
+       7: "composite + tile end"}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rays", type=int, default=40960)
     ap.add_argument("--samples", type=int, default=64)
+    ap.add_argument("--timeline", type=int, default=-1, help="also print the merged event timeline of this tile iteration of CTA 0")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     ctx = capi.get_context(dev)
@@ -58,7 +60,7 @@ def main():
     _, c16 = ctx.gather_cossim(sc, S, first_ray=first, n_rays=args.rays, want_f32=False, want_f16=True)
     ctx.decoder_composite(sc, cfg, cond_f16=c16, first_ray=first, n_rays=args.rays, impl=2)      # warm-up
     torch.cuda.synchronize()
-    cap = 6 * 4096
+    cap = 20 * 2048
     buf = torch.zeros(cap, dtype=torch.int64, device=dev)
     assert lib.mnf_debug_decoder_trace(buf.data_ptr(), cap) == 0
     ctx.decoder_composite(sc, cfg, cond_f16=c16, first_ray=first, n_rays=args.rays, impl=2)
@@ -71,7 +73,21 @@ def main():
     t0 = min(e[0] for e in ev)
     per = collections.defaultdict(list)
     for clk, role, slot, e, it in ev:
-        per[(role, slot)].append((clk - t0, e, it))
+        if role == 0 or (slot >> 2) == 0:
+            per[(role, slot & 3)].append((clk - t0, e, it))
+    if args.timeline >= 0:
+        starts = sorted(c for c, e, it in per[(1, 0)] if e == 0 and it in (args.timeline, args.timeline + 1))
+        if len(starts) == 2:
+            print(f"\n== merged timeline of iteration {args.timeline} (cycles since slot 0 tile start)")
+            allev = sorted((clk - t0, role, slot, e) for clk, role, slot, e, it in ev)
+            tag = {0: "MMA", 1: "TRUNK", 2: "RAY"}
+            for c, role, slot, e in allev:
+                if starts[0] <= c < starts[1]:
+                    names = TRUNK if role == 1 else (RAY if role == 2 else MMA)
+                    label = names.get(e, e)
+                    if role == 0:
+                        label = str(label).replace("slot A", "slot %s" % "AB"[slot & 1])
+                    print(f"   {c - starts[0]:7d}  {tag[role]:5s} {slot & 3} q{slot >> 2}  {label}")
     for key in sorted(per):
         role, slot = key
         seq = sorted(per[key])
