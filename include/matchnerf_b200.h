@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MNF_ABI_VERSION 1
+#define MNF_ABI_VERSION 2
 
 typedef enum mnf_status {
   MNF_OK = 0,
@@ -104,7 +104,10 @@ int64_t mnf_decoder_param_count(void);
 /* ---- layout packing (once per encoded scene) -------------------------------------------- */
 /* fp32 NCHW feature maps [V][256][h][w] (the layout get_img_feat returns, models/matchnerf.py:183-207)
  * -> fp16 channels-last [V][h][w][256] with the two 128-channel halves interleaved in groups of 4
- * (see DESIGN.md "feature map layout").  out must hold V*h*w*256 halves. */
+ * (see DESIGN.md "feature map layout"), followed by a zero tail of (w + 1) texels so that the
+ * zero-weight bilinear taps of samples on the last row / column of a map stay in bounds.
+ * out must hold mnf_packed_feature_halves(V, h, w) = (V*h*w + w + 1) * 256 halves, 16-byte aligned. */
+int64_t mnf_packed_feature_halves(int32_t V, int32_t h, int32_t w);
 int32_t mnf_pack_features(mnf_ctx* ctx, const float* feat_nchw, int32_t V, int32_t h, int32_t w,
                           void* out_packed, void* stream);
 /* fp32 [V][3][H][W] images in [0,1] -> fp32 [V][H][W][4].  out must hold V*H*W*4 floats. */

@@ -67,6 +67,8 @@ def load() -> C.CDLL:
     lib.mnf_ctx_create.argtypes = [i32, C.POINTER(vp)]
     lib.mnf_ctx_destroy.argtypes = [vp]
     lib.mnf_decoder_load_host.argtypes = [vp, fp, i64]
+    lib.mnf_packed_feature_halves.argtypes = [i32, i32, i32]
+    lib.mnf_packed_feature_halves.restype = i64
     lib.mnf_pack_features.argtypes = [vp, fp, i32, i32, i32, vp, vp]
     lib.mnf_pack_images.argtypes = [vp, fp, i32, i32, i32, vp, vp]
     lib.mnf_gather_cossim_fwd.argtypes = [vp, C.POINTER(Scene), C.POINTER(Rays), i32, fp, vp, vp]
@@ -82,8 +84,8 @@ def load() -> C.CDLL:
                  "mnf_gather_cossim_fwd", "mnf_decoder_composite_fwd", "mnf_render_rays_fwd", "mnf_window_attn_fwd",
                  "mnf_selftest_umma"):
         getattr(lib, name).restype = i32
-    if lib.mnf_abi_version() != 1:
-        raise RuntimeError(f"libmatchnerf_b200.so ABI {lib.mnf_abi_version()} != 1")
+    if lib.mnf_abi_version() != 2:
+        raise RuntimeError(f"libmatchnerf_b200.so ABI {lib.mnf_abi_version()} != 2")
     _lib = lib
     return lib
 
@@ -196,8 +198,11 @@ class Context:
         _, _, H, W = im.shape
         if V != 3 or ch != FEAT_CH or f1.shape[1] != FEAT_CH or im.shape[1] != 3:
             raise ValueError("expected 3 views x 256 channels feature maps and RGB images")
-        p0 = torch.empty((V, h0, w0, FEAT_CH), dtype=torch.float16, device=self.device)
-        p1 = torch.empty((V, h1, w1, FEAT_CH), dtype=torch.float16, device=self.device)
+        # flat buffers incl. the zero tail the library appends; feat0 / feat1 are [V,h,w,256] views of their heads
+        b0 = torch.empty(self.lib.mnf_packed_feature_halves(V, h0, w0), dtype=torch.float16, device=self.device)
+        b1 = torch.empty(self.lib.mnf_packed_feature_halves(V, h1, w1), dtype=torch.float16, device=self.device)
+        p0 = b0[:V * h0 * w0 * FEAT_CH].view(V, h0, w0, FEAT_CH)
+        p1 = b1[:V * h1 * w1 * FEAT_CH].view(V, h1, w1, FEAT_CH)
         pi = torch.empty((V, H, W, 4), dtype=torch.float32, device=self.device)
         st = _stream(self.device)
         _check(self.lib.mnf_pack_features(self._h, f0.data_ptr(), V, h0, w0, p0.data_ptr(), st), "mnf_pack_features")

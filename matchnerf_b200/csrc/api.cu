@@ -218,6 +218,11 @@ int32_t mnf_decoder_load_host(mnf_ctx* ctx, const float* P, int64_t n_floats) {
   return MNF_OK;
 }
 
+int64_t mnf_packed_feature_halves(int32_t V, int32_t h, int32_t w) {
+  if (V <= 0 || h <= 0 || w <= 0) return 0;
+  return ((int64_t)V * h * w + w + 1) * kFeatCh;
+}
+
 int32_t mnf_pack_features(mnf_ctx* ctx, const float* feat_nchw, int32_t V, int32_t h, int32_t w, void* out_packed, void* stream) {
   if (!ctx || !feat_nchw || !out_packed || V <= 0 || h <= 0 || w <= 0) { set_error("mnf_pack_features: bad argument"); return MNF_EINVAL; }
   if (((uintptr_t)out_packed & 15) != 0) { set_error("mnf_pack_features: out must be 16-byte aligned"); return MNF_EINVAL; }

@@ -1,19 +1,22 @@
 // Layout packing kernels: reference NCHW fp32 tensors -> the channels-last layouts the gather kernel reads.
 //
-// Feature map layout ("interleaved halves"): a source view's 256 channels are two 128-channel halves,
-// one per image pair the view takes part in (models/matchnerf.py:192-205).  A texel is stored as 256
-// fp16 = 512 B; the gather kernel reads it with 8 lanes x 4 loads of 16 B, load j of lane l being the 16-byte slot
-// 8*j + l (so one load instruction of a lane group covers 128 contiguous bytes); lane l thereby holds channels
-//   half0[16l .. 16l+15] (loads 0,1) and half1[16l .. 16l+15] (loads 2,3)
-// i.e. packed position p = 64*j + 8*l + e  <->  channel (j < 2 ? 0 : 128) + 16*l + 8*(j & 1) + e.
-// Every lane therefore owns the same channel indices of both halves of every view, which makes all three
-// pair products (v0h0.v1h0, v0h1.v2h0, v1h1.v2h1) lane-local; a fine-scale cosine group (16 channels) is
-// lane-local and a coarse group (64 channels) is a run of 4 lanes.
+// Feature map layout: a source view's 256 channels are two 128-channel halves, one per image pair the view takes part
+// in (models/matchnerf.py:192-205).  A texel is stored as 256 fp16 = 512 B = 32 slots of 16 B.
+//
+// Packing v3 (default, gather v3): slot l (= lane l of the gathering warp, one 512 B load instruction per texel) holds
+//   half0[4l .. 4l+3] and half1[4l .. 4l+3]
+// i.e. packed position p = 8*l + e  <->  channel (e < 4 ? 0 : 128) + 4*l + (e & 3).
+// Every lane therefore owns the same channel indices of both halves of every view, which makes all three pair products
+// (v0h0.v1h0, v0h1.v2h0, v1h1.v2h1) lane-local; a fine-scale cosine group (16 channels) is a run of 4 lanes and a
+// coarse group (64 channels) a run of 16 lanes.
+//
+// Packing v2 (MNF_GATHER_IMPL=2, the A/B baseline): 8 lanes x 4 loads of 16 B per texel, load j of lane l being slot
+// 8*j + l: p = 64*j + 8*l + e  <->  channel (j < 2 ? 0 : 128) + 16*l + 8*(j & 1) + e.
 #include "mnf_common.cuh"
 
 namespace mnf {
 
-__global__ void pack_features_kernel(const float* __restrict__ in, __half* __restrict__ out, int hw) {
+__global__ void pack_features_kernel(const float* __restrict__ in, __half* __restrict__ out, int hw, int layout) {
   // grid: (ceil(hw/32), V); block 256 threads.  Tile = 32 pixels x 256 channels through shared memory.
   __shared__ float tile[kFeatCh][33];
   const int v = blockIdx.y;
@@ -33,8 +36,13 @@ __global__ void pack_features_kernel(const float* __restrict__ in, __half* __res
     __align__(16) __half vals[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int ld = slot >> 3, l = slot & 7;      // 16-byte slot = 8 * load + lane
-      const int c = (ld < 2 ? 0 : 128) + 16 * l + 8 * (ld & 1) + j;
+      int c;
+      if (layout == 2) {
+        const int ld = slot >> 3, l = slot & 7;    // 16-byte slot = 8 * load + lane
+        c = (ld < 2 ? 0 : 128) + 16 * l + 8 * (ld & 1) + j;
+      } else {
+        c = (j < 4 ? 0 : 128) + 4 * slot + (j & 3);
+      }
       vals[j] = __float2half_rn(tile[c][pix]);
     }
     *reinterpret_cast<uint4*>(out + ((size_t)v * hw + p) * kFeatCh + slot * 8) = *reinterpret_cast<const uint4*>(vals);
@@ -52,8 +60,10 @@ __global__ void pack_images_kernel(const float* __restrict__ in, float4* __restr
 int launch_pack_features(const float* nchw, int V, int h, int w, __half* out, cudaStream_t s) {
   const int hw = h * w;
   dim3 grid((hw + 31) / 32, V);
-  pack_features_kernel<<<grid, 256, 0, s>>>(nchw, out, hw);
+  pack_features_kernel<<<grid, 256, 0, s>>>(nchw, out, hw, gather_impl());
   MNF_CUDA_TRY(cudaGetLastError());
+  // zero tail of (w + 1) texels: the zero-weight taps of samples on the last row / column stay in bounds (gather v3)
+  MNF_CUDA_TRY(cudaMemsetAsync(out + (size_t)V * hw * kFeatCh, 0, (size_t)(w + 1) * kFeatCh * sizeof(__half), s));
   return MNF_OK;
 }
 

@@ -7,6 +7,8 @@ Tolerances (fp32 reference arithmetic; the kernels read fp16 feature maps):
   * kernel vs reference goldens (fp32 feature maps): the north-star budget, rgb RMS <= 2e-3 (== 0.01 dB at 27 dB
     PSNR) -- measured values are ~1e-4.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -63,8 +65,12 @@ def test_pack_features_layout(ctx):
     packed, _ = make_scene(ctx, [f[None], torch.randn(1, 3, 256, 10, 14, generator=g)], imgs, *synth.synthetic_cameras(40, 56))
     p = packed.feat0.cpu().float()                                   # [V,h,w,256] packed order
     pos = torch.arange(256)
-    ld, lane, e = pos // 64, (pos // 8) % 8, pos % 8
-    chan = torch.where(ld < 2, 0, 128) + 16 * lane + 8 * (ld & 1) + e    # DESIGN.md "feature map layout"
+    if os.environ.get("MNF_GATHER_IMPL") == "2":                       # v2 packing (A/B baseline kernel)
+        ld, lane, e = pos // 64, (pos // 8) % 8, pos % 8
+        chan = torch.where(ld < 2, 0, 128) + 16 * lane + 8 * (ld & 1) + e
+    else:                                                              # v3 packing: DESIGN.md "feature map layout"
+        lane, e = pos // 8, pos % 8
+        chan = torch.where(e < 4, 0, 128) + 4 * lane + (e & 3)
     assert torch.equal(p, f.half().float().permute(0, 2, 3, 1)[..., chan])
     assert torch.equal(packed.images.cpu()[..., :3].permute(0, 3, 1, 2), imgs[0])
 
@@ -102,6 +108,32 @@ def test_gather_config1_and_ray_range(ctx):
     a, _ = ctx.gather_cossim(sc, S, first_ray=first, n_rays=96)
     b, _ = ctx.gather_cossim(sc, S, ray_idx=torch.arange(first, first + 96))
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("S,first,n", [(13, 0, 7), (64, 40 * 56 - 9, 9), (8, 56 * 17 + 50, 23), (2, 5, 1)])
+def test_gather_borders_ragged(ctx, S, first, n):
+    """Image corners (taps on the last row / column of the maps, clipped coordinates), sample counts that are not a
+    multiple of the 8-sample chunk, ray counts that are not a multiple of the 4-ray quad; wide baseline so that many
+    samples leave the source views."""
+    H, W = 40, 56
+    g = torch.Generator().manual_seed(S * 7 + n)
+    feats = [torch.randn(1, 3, 256, H // 8, W // 8, generator=g), torch.randn(1, 3, 256, H // 4, W // 4, generator=g)]
+    imgs = torch.rand(1, 3, 3, H, W, generator=g)
+    extr, intr, nf = synth.synthetic_cameras(H, W, baseline_deg=25.0)
+    _, sc = make_scene(ctx, feats, imgs, extr, intr, nf)
+    c32, c16 = ctx.gather_cossim(sc, S, first_ray=first, n_rays=n, want_f32=True, want_f16=True)
+    torch.cuda.synchronize()
+    ray_idx = torch.arange(first, first + n)
+    aux = oracle_render(synth.synthetic_decoder(0), feats, imgs, extr, intr, nf, ray_idx, S, quantize_feats=True, return_aux=True)[3]
+    cond = aux["cond"]
+    assert c32.shape == (n * S, 22) and c16.shape == (n * S, 32)
+    assert 0.02 < float(cond[:, 19:].mean()) < 0.98                   # both inside and outside samples are present
+    assert frac_above(c32[:, 19:], cond[:, 19:], 0.5) < 5e-3
+    assert rms(c32[:, 10:19], cond[:, 10:19]) < 2e-5
+    assert rms(c32[:, :10], cond[:, :10]) < 5e-4, rms(c32[:, :10], cond[:, :10])
+    assert rms(c16[:, :22].float(), c32) < 5e-4 and float(c16[:, 22:].abs().max()) == 0.0
+    b32, _ = ctx.gather_cossim(sc, S, ray_idx=ray_idx, want_f32=True)
+    assert torch.equal(b32, c32)
 
 
 # ------------------------------------------------------------------------------------------- K-mlp-composite
