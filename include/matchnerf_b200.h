@@ -146,6 +146,22 @@ int32_t mnf_render_rays_fwd(mnf_ctx* ctx, const mnf_scene* scene, const mnf_rays
                             float* out_rgb, float* out_depth, float* out_opacity,
                             void* workspace, int64_t workspace_bytes, int32_t impl, void* stream);
 
+/* ---- the reference's unfused per-sample methods on explicit tensors -------------------------- */
+/* MatchNeRF.query_cond_info (models/matchnerf.py:209-293) on explicit world-space sample points
+ * [R*S][3] (ray-major): same outputs as mnf_gather_cossim_fwd; the target camera of `scene` is unused. */
+int32_t mnf_query_cond_points_fwd(mnf_ctx* ctx, const mnf_scene* scene, const float* points_world, int64_t n_rays,
+                                  int32_t n_samples, float* cond_f32, void* cond_f16, void* stream);
+/* CondNeRF.forward (models/rfdecoder/cond_nerf.py:52-100) on explicit tensors: pts_ndc [R*S][3] (points_3D),
+ * ray_unit [R*S][3] (per-sample view direction), cond_f32 [R*S][22] (cat[feat_info, color_info, mask_info])
+ * -> out_rgb_sigma [R*S][4] = (r, g, b, density) per sample.  fp32 CUDA-core kernel. */
+int32_t mnf_decoder_samples_fwd(mnf_ctx* ctx, const mnf_decoder_cfg* cfg, const float* pts_ndc, const float* ray_unit,
+                                const float* cond_f32, int64_t n_rays, float* out_rgb_sigma, void* stream);
+/* NeRF.composite (models/rfdecoder/nerf.py:101-124, wo_render_interval): rgb [R][S][3], sigma [R][S], depth [R][S]
+ * -> out_rgb [R][3], out_depth [R], out_opacity [R], out_prob [R][S] (or NULL). */
+int32_t mnf_composite_fwd(mnf_ctx* ctx, const float* rgb, const float* sigma, const float* depth, int64_t n_rays,
+                          int32_t n_samples, int32_t setbg_opaque, float* out_rgb, float* out_depth, float* out_opacity,
+                          float* out_prob, void* stream);
+
 /* ---- K-attn: GMFlow split-window single-head attention ----------------------------------- */
 /* Replaces single_head_split_window_attention / single_head_full_attention
  * (models/gmflow/transformer.py:46-105 / :8-16) including the roll, the window partition and the

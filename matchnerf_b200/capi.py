@@ -74,6 +74,9 @@ def load() -> C.CDLL:
     lib.mnf_gather_cossim_fwd.argtypes = [vp, C.POINTER(Scene), C.POINTER(Rays), i32, fp, vp, vp]
     lib.mnf_decoder_composite_fwd.argtypes = [vp, C.POINTER(Scene), C.POINTER(Rays), C.POINTER(DecoderCfg), fp, vp, i32,
                                               fp, fp, fp, fp, i32, vp]
+    lib.mnf_query_cond_points_fwd.argtypes = [vp, C.POINTER(Scene), fp, i64, i32, fp, vp, vp]
+    lib.mnf_decoder_samples_fwd.argtypes = [vp, C.POINTER(DecoderCfg), fp, fp, fp, i64, fp, vp]
+    lib.mnf_composite_fwd.argtypes = [vp, fp, fp, fp, i64, i32, i32, fp, fp, fp, fp, vp]
     lib.mnf_render_workspace_bytes.argtypes = [i64, i32]
     lib.mnf_render_workspace_bytes.restype = i64
     lib.mnf_render_rays_fwd.argtypes = [vp, C.POINTER(Scene), C.POINTER(Rays), C.POINTER(DecoderCfg), i32, fp, fp, fp,
@@ -82,7 +85,7 @@ def load() -> C.CDLL:
     lib.mnf_selftest_umma.argtypes = [vp, vp, fp, i32, i32, i32, vp]
     for name in ("mnf_ctx_create", "mnf_ctx_destroy", "mnf_decoder_load_host", "mnf_pack_features", "mnf_pack_images",
                  "mnf_gather_cossim_fwd", "mnf_decoder_composite_fwd", "mnf_render_rays_fwd", "mnf_window_attn_fwd",
-                 "mnf_selftest_umma"):
+                 "mnf_selftest_umma", "mnf_query_cond_points_fwd", "mnf_decoder_samples_fwd", "mnf_composite_fwd"):
         getattr(lib, name).restype = i32
     if lib.mnf_abi_version() != 2:
         raise RuntimeError(f"libmatchnerf_b200.so ABI {lib.mnf_abi_version()} != 2")
@@ -256,6 +259,47 @@ class Context:
                                                   opac.data_ptr(), _ptr(aux), impl, _stream(self.device)),
                "mnf_decoder_composite_fwd")
         return rgb, depth, opac, aux
+
+    # ---- the reference's unfused per-sample methods on explicit tensors
+    def query_cond_points(self, scene: Scene, points: torch.Tensor, want_f16=False):
+        """points [R,S,3] world-space samples -> cond [R*S,22] fp32 (and [R*S,32] fp16): query_cond_info on explicit points."""
+        pts = _dev_f32(points, self.device, "points")
+        R, S = pts.shape[0], pts.shape[1]
+        c32 = torch.empty((R * S, COND_DIM), dtype=torch.float32, device=self.device)
+        c16 = torch.empty((R * S, COND_PAD), dtype=torch.float16, device=self.device) if want_f16 else None
+        _check(self.lib.mnf_query_cond_points_fwd(self._h, C.byref(scene), pts.data_ptr(), R, S, c32.data_ptr(), _ptr(c16),
+                                                  _stream(self.device)), "mnf_query_cond_points_fwd")
+        return c32, c16
+
+    def decoder_samples(self, cfg: DecoderCfg, pts_ndc: torch.Tensor, ray_unit: torch.Tensor, cond_f32: torch.Tensor):
+        """CondNeRF.forward on explicit tensors: pts_ndc / ray_unit [R,S,3], cond [R*S,22] -> [R*S,4] (rgb, density)."""
+        ndc = _dev_f32(pts_ndc, self.device, "pts_ndc")
+        dirs = _dev_f32(ray_unit, self.device, "ray_unit")
+        cond = _dev_f32(cond_f32, self.device, "cond")
+        R, S = ndc.shape[0], ndc.shape[1]
+        if S != cfg.n_samples or dirs.shape != ndc.shape or cond.numel() != R * S * COND_DIM:
+            raise ValueError(f"decoder_samples: shapes {tuple(ndc.shape)} / {tuple(dirs.shape)} / {tuple(cond.shape)} do not match S={cfg.n_samples}")
+        out = torch.empty((R * S, 4), dtype=torch.float32, device=self.device)
+        _check(self.lib.mnf_decoder_samples_fwd(self._h, C.byref(cfg), ndc.data_ptr(), dirs.data_ptr(), cond.data_ptr(), R,
+                                                out.data_ptr(), _stream(self.device)), "mnf_decoder_samples_fwd")
+        return out
+
+    def composite(self, rgb: torch.Tensor, sigma: torch.Tensor, depth: torch.Tensor, setbg_opaque=False, want_prob=True):
+        """NeRF.composite: rgb [R,S,3], sigma [R,S], depth [R,S] -> rgb [R,3], depth [R], opacity [R], prob [R,S]."""
+        c = _dev_f32(rgb, self.device, "rgb")
+        sg = _dev_f32(sigma, self.device, "sigma")
+        d = _dev_f32(depth, self.device, "depth")
+        R, S = sg.shape
+        if c.shape != (R, S, 3) or d.shape != (R, S):
+            raise ValueError(f"composite: shapes {tuple(c.shape)} / {tuple(sg.shape)} / {tuple(d.shape)} do not match")
+        o_rgb = torch.empty((R, 3), dtype=torch.float32, device=self.device)
+        o_d = torch.empty((R,), dtype=torch.float32, device=self.device)
+        o_o = torch.empty((R,), dtype=torch.float32, device=self.device)
+        prob = torch.empty((R, S), dtype=torch.float32, device=self.device) if want_prob else None
+        _check(self.lib.mnf_composite_fwd(self._h, c.data_ptr(), sg.data_ptr(), d.data_ptr(), R, S, int(setbg_opaque),
+                                          o_rgb.data_ptr(), o_d.data_ptr(), o_o.data_ptr(), _ptr(prob), _stream(self.device)),
+               "mnf_composite_fwd")
+        return o_rgb, o_d, o_o, prob
 
     def render_rays(self, scene: Scene, cfg: DecoderCfg, ray_idx=None, first_ray=0, n_rays=0, jitter=None,
                     setbg_opaque=False, impl=0, out=None, workspace=None):

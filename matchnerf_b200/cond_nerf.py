@@ -85,24 +85,37 @@ class CondNeRF(nn.Module):
         cfg.density_maskfill = int(bool(get_opt(opt, "decoder.density_maskfill", False)))
         return cfg
 
-    def forward(self, *args, **kwargs):
-        raise NotImplementedError(
-            "matchnerf_b200: the decoder runs fused with ray casting and compositing inside "
-            "MatchNeRF.render (mnf_render_rays_fwd); a standalone CondNeRF.forward on explicit sample tensors is not built")
+    def forward(self, opt, points_3D, ray_unit=None, cond_info=None, mode=None):
+        """models/rfdecoder/cond_nerf.py:52-100 on explicit tensors: points_3D [B,R,S,3] (view-0 NDC), ray_unit [B,R,S,3],
+        cond_info = dict(feat_info [B,R,S,10], color_info [B,R,S,9], mask_info [B,R,S,3]) -> (rgb [B,R,S,3], alpha [B,R,S]).
+        Runs the fp32 CUDA kernel (mnf_decoder_samples_fwd); MatchNeRF.render uses the fused tcgen05 kernel instead."""
+        if not points_3D.is_cuda:
+            raise RuntimeError("matchnerf_b200: the decoder only exists as CUDA kernels (no CPU path)")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("matchnerf_b200: the backward kernels are not built yet; call under torch.no_grad()")
+        if ray_unit is None or cond_info is None:
+            raise ValueError("CondNeRF.forward needs ray_unit (nerf.view_dep) and cond_info")
+        ctx = self.sync_to_library()
+        cfg = self.decoder_cfg(opt)
+        B, R, S, _ = points_3D.shape
+        cfg.n_samples = S
+        cond = torch.cat([cond_info["feat_info"], cond_info["color_info"], cond_info["mask_info"]], dim=-1).float()
+        out = ctx.decoder_samples(cfg, points_3D.float().reshape(B * R, S, 3), ray_unit.float().expand(B, R, S, 3).reshape(B * R, S, 3),
+                                  cond.reshape(B * R * S, -1))
+        out = out.view(B, R, S, 4)
+        return out[..., :3], out[..., 3]
 
     @staticmethod
     def composite(opt, ray, rgb_samples, density_samples, depth_samples, setbg_opaque):
-        """Alpha compositing on explicit sample tensors (models/rfdecoder/nerf.py:101-124).  Compatibility helper for
-        callers of the unfused API; MatchNeRF.render composites inside the CUDA kernel."""
+        """Alpha compositing on explicit sample tensors (models/rfdecoder/nerf.py:101-124) through mnf_composite_fwd:
+        rgb_samples [B,R,S,3], density_samples [B,R,S], depth_samples [B,R,S,1] -> rgb [B,R,3], depth [B,R,1],
+        opacity [B,R,1], prob [B,R,S,1].  (MatchNeRF.render composites inside the fused kernel.)"""
         if not get_opt(opt, "nerf.wo_render_interval", True):
             raise NotImplementedError("only wo_render_interval=True (all shipped configs) is built")
-        sigma = density_samples
-        alpha = 1.0 - torch.exp(-sigma)
-        trans = torch.exp(-(torch.cumsum(sigma, dim=2) - sigma))
-        prob = (trans * alpha)[..., None]
-        depth = (depth_samples * prob).sum(dim=2)
-        rgb = (rgb_samples * prob).sum(dim=2)
-        opacity = prob.sum(dim=2)
-        if setbg_opaque:
-            rgb = rgb + (1.0 - opacity)
-        return rgb, depth, opacity, prob
+        if not rgb_samples.is_cuda:
+            raise RuntimeError("matchnerf_b200: compositing only exists as a CUDA kernel (no CPU path)")
+        B, R, S, _ = rgb_samples.shape
+        ctx = capi.get_context(rgb_samples.device)
+        rgb, depth, opac, prob = ctx.composite(rgb_samples.float().reshape(B * R, S, 3), density_samples.float().reshape(B * R, S),
+                                               depth_samples.float().reshape(B * R, S), bool(setbg_opaque))
+        return rgb.view(B, R, 3), depth.view(B, R, 1), opac.view(B, R, 1), prob.view(B, R, S, 1)

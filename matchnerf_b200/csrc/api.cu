@@ -239,7 +239,7 @@ int32_t mnf_gather_cossim_fwd(mnf_ctx* ctx, const mnf_scene* scene, const mnf_ra
                               void* cond_f16, void* stream) {
   if (!ctx) { set_error("ctx is NULL"); return MNF_EINVAL; }
   DevCams cams;
-  DevRays dr;
+  DevRays dr{};
   int rc;
   if ((rc = fill_cams(scene, &cams))) return rc;
   if ((rc = fill_rays(scene, rays, &dr))) return rc;
@@ -258,7 +258,7 @@ int32_t mnf_decoder_composite_fwd(mnf_ctx* ctx, const mnf_scene* scene, const mn
   if (!ctx) { set_error("ctx is NULL"); return MNF_EINVAL; }
   if (!ctx->loaded) { set_error("decoder weights not loaded (call mnf_decoder_load_host)"); return MNF_ESTATE; }
   DevCams cams;
-  DevRays dr;
+  DevRays dr{};
   int rc;
   if ((rc = fill_cams(scene, &cams))) return rc;
   if ((rc = fill_rays(scene, rays, &dr))) return rc;
@@ -276,6 +276,56 @@ int32_t mnf_decoder_composite_fwd(mnf_ctx* ctx, const mnf_scene* scene, const mn
   if (!cond_f32) { set_error("fp32 decoder needs cond_f32"); return MNF_EINVAL; }
   return launch_decoder_ref(cams, dr, *cfg, ctx->wf32, cond_f32, setbg_opaque, out_rgb, out_depth, out_opacity, aux_rgb_sigma,
                             (cudaStream_t)stream);
+}
+
+int32_t mnf_query_cond_points_fwd(mnf_ctx* ctx, const mnf_scene* scene, const float* points_world, int64_t n_rays, int32_t n_samples,
+                                  float* cond_f32, void* cond_f16, void* stream) {
+  if (!ctx) { set_error("ctx is NULL"); return MNF_EINVAL; }
+  DevCams cams;
+  int rc;
+  if ((rc = fill_cams(scene, &cams))) return rc;
+  if (n_rays < 0) { set_error("n_rays < 0"); return MNF_EINVAL; }
+  if (n_samples < 1 || n_samples > kMaxSamples) { set_error("n_samples = %d outside [1, %d]", n_samples, kMaxSamples); return MNF_EUNSUPPORTED; }
+  if (n_rays == 0) return MNF_OK;
+  if (!points_world) { set_error("points_world is NULL"); return MNF_EINVAL; }
+  if (!scene->feat0 || !scene->feat1 || !scene->images) { set_error("scene feature maps / images missing"); return MNF_EINVAL; }
+  if (!cond_f32 && !cond_f16) { set_error("no output buffer"); return MNF_EINVAL; }
+  DevRays dr{};
+  dr.n_rays = n_rays;
+  dr.points = points_world;
+  return launch_gather(cams, dr, n_samples, reinterpret_cast<const __half*>(scene->feat0), scene->h0, scene->w0,
+                       reinterpret_cast<const __half*>(scene->feat1), scene->h1, scene->w1,
+                       reinterpret_cast<const float*>(scene->images), cond_f32, reinterpret_cast<__half*>(cond_f16),
+                       (cudaStream_t)stream);
+}
+
+int32_t mnf_decoder_samples_fwd(mnf_ctx* ctx, const mnf_decoder_cfg* cfg, const float* pts_ndc, const float* ray_unit,
+                                const float* cond_f32, int64_t n_rays, float* out_rgb_sigma, void* stream) {
+  if (!ctx) { set_error("ctx is NULL"); return MNF_EINVAL; }
+  if (!ctx->loaded) { set_error("decoder weights not loaded (call mnf_decoder_load_host)"); return MNF_ESTATE; }
+  int rc;
+  if ((rc = check_cfg(cfg))) return rc;
+  if (n_rays < 0) { set_error("n_rays < 0"); return MNF_EINVAL; }
+  if (n_rays == 0) return MNF_OK;
+  if (!pts_ndc || !ray_unit || !cond_f32 || !out_rgb_sigma) { set_error("mnf_decoder_samples_fwd: NULL tensor"); return MNF_EINVAL; }
+  DevCams cams{};          // geometry comes from the explicit tensors; keep the unused camera block benign
+  cams.W = cams.H = 2;
+  DevRays dr{};
+  dr.n_rays = n_rays;
+  dr.ndc = pts_ndc;
+  dr.dirs = ray_unit;
+  return launch_decoder_ref(cams, dr, *cfg, ctx->wf32, cond_f32, 0, nullptr, nullptr, nullptr, out_rgb_sigma, (cudaStream_t)stream);
+}
+
+int32_t mnf_composite_fwd(mnf_ctx* ctx, const float* rgb, const float* sigma, const float* depth, int64_t n_rays,
+                          int32_t n_samples, int32_t setbg_opaque, float* out_rgb, float* out_depth, float* out_opacity,
+                          float* out_prob, void* stream) {
+  if (!ctx) { set_error("ctx is NULL"); return MNF_EINVAL; }
+  if (n_rays < 0 || n_samples < 1) { set_error("mnf_composite_fwd: bad shape R=%lld S=%d", (long long)n_rays, n_samples); return MNF_EINVAL; }
+  if (n_rays == 0) return MNF_OK;
+  if (!rgb || !sigma || !depth || !out_rgb || !out_depth || !out_opacity) { set_error("mnf_composite_fwd: NULL tensor"); return MNF_EINVAL; }
+  return launch_composite(rgb, sigma, depth, n_rays, n_samples, setbg_opaque, out_rgb, out_depth, out_opacity, out_prob,
+                          (cudaStream_t)stream);
 }
 
 int64_t mnf_render_workspace_bytes(int64_t n_rays, int32_t n_samples) {

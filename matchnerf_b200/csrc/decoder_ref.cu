@@ -34,6 +34,7 @@ struct Smem {
   float sigma[kMaxSamples];
   float scan[8];
   float dirvec[64];          // views_linears.0.weight[:,128:] . dir + bias  (per ray)
+  float dir3[kRows][4];      // explicit per-sample view directions (CondNeRF.forward ray_unit), else unused
 };
 
 // acc[r][c] += sum_k in[(ty*4+r)][k] * Wt[k][tx*CPT + c]
@@ -84,7 +85,8 @@ decoder_ref_kernel(const __grid_constant__ DevCams cams, const DevRays rays, con
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const int S = cfg.n_samples;
   const int64_t ray = blockIdx.x;
-  const int64_t pix = rays.ray_idx ? rays.ray_idx[ray] : rays.first_ray + ray;
+  const bool explicit_in = rays.ndc != nullptr;   // CondNeRF.forward on explicit tensors: NDC points + per-sample directions
+  const int64_t pix = explicit_in ? 0 : (rays.ray_idx ? rays.ray_idx[ray] : rays.first_ray + ray);
   float o[3], d[3];
   cast_ray(cams, pix, o, d);
 
@@ -104,7 +106,14 @@ decoder_ref_kernel(const __grid_constant__ DevCams cams, const DevRays rays, con
     if (tid < kRows) {
       const int s = row0 + tid;
       float x[3] = {0.f, 0.f, 0.f};
-      if (s < S) {
+      if (s < S && explicit_in) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          x[i] = rays.ndc[((size_t)ray * S + s) * 3 + i];
+          sm.dir3[tid][i] = rays.dirs[((size_t)ray * S + s) * 3 + i];
+        }
+        sm.depth[s] = 0.f;
+      } else if (s < S) {
         const float u = rays.jitter ? rays.jitter[ray * S + s] : 0.f;
         const float t = sample_depth(cams, s, S, u);
         float p[3];
@@ -197,7 +206,15 @@ decoder_ref_kernel(const __grid_constant__ DevCams cams, const DevRays rays, con
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) sm.e[ty * 4 + r][tx * 4 + c] = fmaxf(acc2[r][c] + sm.dirvec[tx * 4 + c], 0.f);
+        for (int c = 0; c < 4; ++c) {
+          const int col = tx * 4 + c;
+          float dterm = sm.dirvec[col];
+          if (explicit_in) {
+            const float* d3 = sm.dir3[ty * 4 + r];
+            dterm = hp.views_dir[col * 3 + 0] * d3[0] + hp.views_dir[col * 3 + 1] * d3[1] + hp.views_dir[col * 3 + 2] * d3[2] + hp.views_b[col];
+          }
+          sm.e[ty * 4 + r][col] = fmaxf(acc2[r][c] + dterm, 0.f);
+        }
       __syncthreads();
       if (tid < kRows * 3) {
         const int r = tid / 3, c = tid - r * 3;
@@ -320,7 +337,7 @@ decoder_ref_kernel(const __grid_constant__ DevCams cams, const DevRays rays, con
 #pragma unroll
     for (int i = 0; i < 5; ++i) sm.kk[wid][i] = part[i];
   __syncthreads();
-  if (tid == 0) {
+  if (tid == 0 && out_rgb) {
     float tot[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     for (int wv = 0; wv < 8; ++wv)
       for (int i = 0; i < 5; ++i) tot[i] += sm.kk[wv][i];

@@ -390,7 +390,7 @@ gather_cossim_kernel(const __grid_constant__ DevCams cams, const DevRays rays, c
   const int rq = lane >> 3;        // geometry phase: ray of the quad
   const int sj = lane & 7;         // geometry phase: sample inside the chunk
   const int64_t my_ray = min(ray0 + rq, rays.n_rays - 1);       // rays past the end repeat the last one (not stored)
-  const int64_t pix = rays.ray_idx ? rays.ray_idx[my_ray] : rays.first_ray + my_ray;
+  const int64_t pix = rays.points ? 0 : (rays.ray_idx ? rays.ray_idx[my_ray] : rays.first_ray + my_ray);
   float o[3], d[3];
   cast_ray(cams, pix, o, d);
   const int HW = cams.H * cams.W;
@@ -407,11 +407,16 @@ gather_cossim_kernel(const __grid_constant__ DevCams cams, const DevRays rays, c
     // ------------------------------------------------------------ geometry phase: lane = (ray rq, sample s0 + sj)
     {
       const int s = min(s0 + sj, S - 1);
-      const float u = rays.jitter ? rays.jitter[my_ray * S + s] : 0.f;
-      const float t = sample_depth(cams, s, S, u);
       float p[3];
+      if (rays.points) {                                                         // explicit sample points (query_cond_info)
 #pragma unroll
-      for (int i = 0; i < 3; ++i) p[i] = __fadd_rn(o[i], __fmul_rn(d[i], t));   // misc/camera.py:281-286
+        for (int i = 0; i < 3; ++i) p[i] = __ldg(rays.points + ((size_t)my_ray * S + s) * 3 + i);
+      } else {
+        const float u = rays.jitter ? rays.jitter[my_ray * S + s] : 0.f;
+        const float t = sample_depth(cams, s, S, u);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) p[i] = __fadd_rn(o[i], __fmul_rn(d[i], t));   // misc/camera.py:281-286
+      }
 #pragma unroll
       for (int v = 0; v < kViews; ++v) {
         float uu, vv, zz;
@@ -562,6 +567,7 @@ int launch_gather(const DevCams& cams, const DevRays& rays, int S, const __half*
                   const __half* f1, int h1, int w1, const float* images, float* cond_f32, __half* cond_f16,
                   cudaStream_t s) {
   if (rays.n_rays <= 0) return MNF_OK;
+  if (gather_impl() == 2 && rays.points) { set_error("explicit sample points need the v3 gather kernel (unset MNF_GATHER_IMPL)"); return MNF_EUNSUPPORTED; }
   if (gather_impl() == 2) return launch_gather_v2(cams, rays, S, f0, h0, w0, f1, h1, w1, images, cond_f32, cond_f16, s);
   const int64_t quads = (rays.n_rays + kQuad - 1) / kQuad;
   const int64_t blocks = (quads + kWarps3 - 1) / kWarps3;

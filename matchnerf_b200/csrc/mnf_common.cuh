@@ -48,6 +48,10 @@ struct DevRays {
   int64_t first_ray;
   const float* jitter;
   int64_t n_rays;
+  // explicit-tensor variants (the reference's unfused public methods); all NULL on the fused render path
+  const float* points = nullptr;   // [R*S][3] world-space sample points  (query_cond_info, models/matchnerf.py:209)
+  const float* ndc = nullptr;      // [R*S][3] view-0 NDC sample points   (CondNeRF.forward points_3D, cond_nerf.py:52)
+  const float* dirs = nullptr;     // [R*S][3] per-sample view direction  (CondNeRF.forward ray_unit)
 };
 
 // ---- per-ray geometry ---------------------------------------------------------------------
@@ -137,6 +141,9 @@ struct DecoderWeightsF32;  // decoder_ref.cu
 int launch_decoder_ref(const DevCams& cams, const DevRays& rays, const mnf_decoder_cfg& cfg,
                        const DecoderWeightsF32& w, const float* cond_f32, int setbg_opaque, float* out_rgb,
                        float* out_depth, float* out_opacity, float* aux, cudaStream_t s);
+
+int launch_composite(const float* rgb, const float* sigma, const float* depth, int64_t n_rays, int S, int setbg_opaque,
+                     float* out_rgb, float* out_depth, float* out_opacity, float* out_prob, cudaStream_t s);
 
 int launch_window_attn_ref(const float* q, const float* k, const float* v, float* out, int B, int h, int w, int C,
                            int num_splits, int with_shift, cudaStream_t s);

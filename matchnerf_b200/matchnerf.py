@@ -5,7 +5,7 @@ per-ray work handed to the CUDA library through the C ABI.
     render(opt, tgt_pose, ray_idx, ...)  models/matchnerf.py:88-143   -> mnf_render_rays_fwd
     render_by_slices(...)                models/matchnerf.py:145-161
     get_img_feat(imgs, ...)              models/matchnerf.py:183-207  -> GMFlow (K-attn inside)
-    query_cond_info(points, ...)         models/matchnerf.py:209-293  -> (fused; explicit-point variant not built)
+    query_cond_info(points, ...)         models/matchnerf.py:209-293  -> mnf_query_cond_points_fwd (explicit points)
     render_rays(...)                     alias of ``render`` (the name BASELINE.json uses)
 
 PyTorch is the tensor plumbing (device memory, streams, the encoder's conv / linear library calls); there is no
@@ -135,8 +135,20 @@ class MatchNeRF(nn.Module):
         return AttrDict({k: torch.cat([p[k] for p in parts], dim=1) for k in ("rgb", "depth", "opacity")})
 
     def query_cond_info(self, point_samples, ref_poses, ref_images, ref_feats_list):
-        raise NotImplementedError("matchnerf_b200: the conditioning query runs fused with ray casting inside render(); "
-                                  "the explicit-point variant of models/matchnerf.py:209-293 is not built")
+        """models/matchnerf.py:209-293 on explicit world-space points [B,R,S,3] -> dict(feat_info [B,R,S,10],
+        color_info [B,R,S,9], mask_info [B,R,S,3]).  (MatchNeRF.render runs the same kernel fused with ray casting.)"""
+        if not point_samples.is_cuda:
+            raise RuntimeError("matchnerf_b200: the conditioning query only exists as a CUDA kernel (no CPU path)")
+        B, R, S, _ = point_samples.shape
+        scenes = self._packed_scenes(ref_poses, ref_images, ref_feats_list)
+        ctx = self._unwrap(self.nerf_dec).sync_to_library()
+        conds = []
+        for b in range(B):
+            # the target camera is not used by the point query; hand the kernel source view 0 as a placeholder
+            sc = scenes[b].c_scene(ref_poses["extrinsics"][b, 0], ref_poses["intrinsics"][b, 0], ref_poses["near_fars"][b, 0])
+            conds.append(ctx.query_cond_points(sc, point_samples[b].float())[0].view(R, S, -1))
+        cond = torch.stack(conds)
+        return {"feat_info": cond[..., :10], "color_info": cond[..., 10:19], "mask_info": cond[..., 19:22]}
 
     # ------------------------------------------------------------------ entry point used by Coach
     def forward(self, batch, mode=None, render_video=False, render_path_mode="interpolate"):
