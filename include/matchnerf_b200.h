@@ -106,7 +106,7 @@ int64_t mnf_decoder_param_count(void);
  * -> fp16 channels-last [V][h][w][256] with the two 128-channel halves interleaved in groups of 4
  * (see DESIGN.md "feature map layout"), followed by a zero tail of (w + 1) texels so that the
  * zero-weight bilinear taps of samples on the last row / column of a map stay in bounds.
- * out must hold mnf_packed_feature_halves(V, h, w) = (V*h*w + w + 1) * 256 halves, 16-byte aligned. */
+ * out must hold mnf_packed_feature_halves(V, h, w) halves (slightly more than V*h*w*256), 16-byte aligned. */
 int64_t mnf_packed_feature_halves(int32_t V, int32_t h, int32_t w);
 int32_t mnf_pack_features(mnf_ctx* ctx, const float* feat_nchw, int32_t V, int32_t h, int32_t w,
                           void* out_packed, void* stream);

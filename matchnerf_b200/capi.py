@@ -201,11 +201,9 @@ class Context:
         _, _, H, W = im.shape
         if V != 3 or ch != FEAT_CH or f1.shape[1] != FEAT_CH or im.shape[1] != 3:
             raise ValueError("expected 3 views x 256 channels feature maps and RGB images")
-        # flat buffers incl. the zero tail the library appends; feat0 / feat1 are [V,h,w,256] views of their heads
-        b0 = torch.empty(self.lib.mnf_packed_feature_halves(V, h0, w0), dtype=torch.float16, device=self.device)
-        b1 = torch.empty(self.lib.mnf_packed_feature_halves(V, h1, w1), dtype=torch.float16, device=self.device)
-        p0 = b0[:V * h0 * w0 * FEAT_CH].view(V, h0, w0, FEAT_CH)
-        p1 = b1[:V * h1 * w1 * FEAT_CH].view(V, h1, w1, FEAT_CH)
+        # flat fp16 buffers in the library's packed layout (opaque to the caller; the size includes the tail padding)
+        p0 = torch.empty(self.lib.mnf_packed_feature_halves(V, h0, w0), dtype=torch.float16, device=self.device)
+        p1 = torch.empty(self.lib.mnf_packed_feature_halves(V, h1, w1), dtype=torch.float16, device=self.device)
         pi = torch.empty((V, H, W, 4), dtype=torch.float32, device=self.device)
         st = _stream(self.device)
         _check(self.lib.mnf_pack_features(self._h, f0.data_ptr(), V, h0, w0, p0.data_ptr(), st), "mnf_pack_features")

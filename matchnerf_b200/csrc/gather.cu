@@ -541,9 +541,13 @@ gather_cossim_kernel(const __grid_constant__ DevCams cams, const DevRays rays, c
 }
 
 int gather_impl() {
-  static const int impl = [] { const char* e = getenv("MNF_GATHER_IMPL"); return e ? atoi(e) : 3; }();   // A/B knob: 2 = v2, 3 = v3
-  return impl == 2 ? 2 : 3;
+  static const int impl = [] { const char* e = getenv("MNF_GATHER_IMPL"); return e ? atoi(e) : 3; }();   // A/B knob: 2 = v2, 3 = v3, 4 = v4 (tensor-core blend)
+  return (impl == 2 || impl == 4) ? impl : 3;
 }
+
+int launch_gather_mma(const DevCams& cams, const DevRays& rays, int S, const __half* f0, int h0, int w0,
+                      const __half* f1, int h1, int w1, const float* images, float* cond_f32, __half* cond_f16,
+                      cudaStream_t s);
 
 static int launch_gather_v2(const DevCams& cams, const DevRays& rays, int S, const __half* f0, int h0, int w0,
                   const __half* f1, int h1, int w1, const float* images, float* cond_f32, __half* cond_f16,
@@ -567,6 +571,7 @@ int launch_gather(const DevCams& cams, const DevRays& rays, int S, const __half*
                   const __half* f1, int h1, int w1, const float* images, float* cond_f32, __half* cond_f16,
                   cudaStream_t s) {
   if (rays.n_rays <= 0) return MNF_OK;
+  if (gather_impl() == 4) return launch_gather_mma(cams, rays, S, f0, h0, w0, f1, h1, w1, images, cond_f32, cond_f16, s);
   if (gather_impl() == 2 && rays.points) { set_error("explicit sample points need the v3 gather kernel (unset MNF_GATHER_IMPL)"); return MNF_EUNSUPPORTED; }
   if (gather_impl() == 2) return launch_gather_v2(cams, rays, S, f0, h0, w0, f1, h1, w1, images, cond_f32, cond_f16, s);
   const int64_t quads = (rays.n_rays + kQuad - 1) / kQuad;

@@ -20,6 +20,7 @@ from tests.helpers import (config1_inputs, dec_from_npz, frac_above, half_round,
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
+GATHER_IMPL_DEFAULT = 3       # csrc/gather.cu gather_impl()
 
 
 def make_scene(ctx, feats, imgs, extr, intr, nf):
@@ -59,19 +60,34 @@ def test_umma_selftest_mn_major_b(ctx, N, K):
 
 # ------------------------------------------------------------------------------------------- K-gather
 def test_pack_features_layout(ctx):
+    """The packed fp16 layout the gather kernel reads (DESIGN.md "feature map layout"), for an odd and an even width."""
     g = torch.Generator().manual_seed(3)
     f = torch.randn(3, 256, 5, 7, generator=g)
+    f1 = torch.randn(3, 256, 10, 14, generator=g)
     imgs = torch.rand(1, 3, 3, 40, 56, generator=g)
-    packed, _ = make_scene(ctx, [f[None], torch.randn(1, 3, 256, 10, 14, generator=g)], imgs, *synth.synthetic_cameras(40, 56))
-    p = packed.feat0.cpu().float()                                   # [V,h,w,256] packed order
-    pos = torch.arange(256)
-    if os.environ.get("MNF_GATHER_IMPL") == "2":                       # v2 packing (A/B baseline kernel)
-        ld, lane, e = pos // 64, (pos // 8) % 8, pos % 8
-        chan = torch.where(ld < 2, 0, 128) + 16 * lane + 8 * (ld & 1) + e
-    else:                                                              # v3 packing: DESIGN.md "feature map layout"
-        lane, e = pos // 8, pos % 8
-        chan = torch.where(e < 4, 0, 128) + 4 * lane + (e & 3)
-    assert torch.equal(p, f.half().float().permute(0, 2, 3, 1)[..., chan])
+    packed, _ = make_scene(ctx, [f[None], f1[None]], imgs, *synth.synthetic_cameras(40, 56))
+    impl = os.environ.get("MNF_GATHER_IMPL", str(GATHER_IMPL_DEFAULT))
+    for src, buf in ((f, packed.feat0), (f1, packed.feat1)):
+        V, _, h, w = src.shape
+        want = src.half().float().permute(0, 2, 3, 1)                      # [V,h,w,256] natural channel order
+        flat = buf.cpu().float()
+        if impl == "4":                                                    # x-pair interleaved blocks [V][h][ceil(w/2)][256][2]
+            wp = (w + 1) // 2
+            body = flat[: V * h * wp * 512].view(V, h, wp, 256, 2)
+            got = body.permute(0, 1, 2, 4, 3).reshape(V, h, 2 * wp, 256)
+            assert torch.equal(got[:, :, :w], want)
+            assert float(got[:, :, w:].abs().max() if 2 * wp > w else 0.0) == 0.0      # unpaired texel of an odd width
+            assert float(flat[V * h * wp * 512: V * h * wp * 512 + (wp + 2) * 512].abs().max()) == 0.0   # zero tail
+        else:
+            p = flat[: V * h * w * 256].view(V, h, w, 256)
+            pos = torch.arange(256)
+            if impl == "2":                                                # v2 packing (A/B baseline kernel)
+                ld, lane, e = pos // 64, (pos // 8) % 8, pos % 8
+                chan = torch.where(ld < 2, 0, 128) + 16 * lane + 8 * (ld & 1) + e
+            else:                                                          # v3 packing
+                lane, e = pos // 8, pos % 8
+                chan = torch.where(e < 4, 0, 128) + 4 * lane + (e & 3)
+            assert torch.equal(p, want[..., chan])
     assert torch.equal(packed.images.cpu()[..., :3].permute(0, 3, 1, 2), imgs[0])
 
 
