@@ -35,6 +35,8 @@ struct AttnTcSmem {
   int qtok[kTile];
   int ktok[kTile];
   int kreg[kTile];
+  uint32_t kmask[9][4];            // per query region: bit j of word c = key 32 c + j lies in ANOTHER shift region
+  uint32_t kinval[4];              // bit j of word c = key 32 c + j is past the end of the window (partial last tile)
   alignas(8) uint64_t bar_s;
   uint64_t bar_o;
   uint32_t tmem_base;
@@ -59,23 +61,40 @@ __device__ __forceinline__ uint32_t pack_h2f(float a, float b) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-// gather 128 rows x 128 fp32 channels (token ids in tok[], -1 = zero row) into two swizzled [128][64] fp16 blocks
+// gather 128 rows x 128 fp32 channels (token ids in tok[], -1 = zero row) into two swizzled [128][64] fp16 blocks.
+// A thread owns one 8-channel chunk (tid & 15) of rows (tid >> 4) + 16 i: all 16 of its 16-byte loads are issued before
+// the first conversion, so the tile costs one L2 round trip instead of eight (v1 walked the rows one dependent load at
+// a time and spent ~13k of its ~29k cycles per key tile waiting here).
 __device__ __forceinline__ void load_rows_swizzled(const float* __restrict__ src, const int* tok, unsigned char* dst,
                                                    float scale, int tid) {
-  for (int item = tid; item < kTile * 16; item += kAttnThreads) {
-    const int row = item >> 4, ch = item & 15;          // 16 chunks of 8 channels per row
-    uint4 out = make_uint4(0u, 0u, 0u, 0u);
-    const int t = tok[row];
-    if (t >= 0) {
-      const float4* p = reinterpret_cast<const float4*>(src + (size_t)t * kC + ch * 8);
-      const float4 a = __ldg(p), b = __ldg(p + 1);
-      out.x = pack_h2f(a.x * scale, a.y * scale);
-      out.y = pack_h2f(a.z * scale, a.w * scale);
-      out.z = pack_h2f(b.x * scale, b.y * scale);
-      out.w = pack_h2f(b.z * scale, b.w * scale);
-    }
-    *reinterpret_cast<uint4*>(dst + (ch >> 3) * kBlockBytes + tc::sw128_offset(row, (ch & 7) * 8)) = out;
+  const int ch = tid & 15, r0 = tid >> 4;
+  int t[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t[i] = tok[r0 + 16 * i];
+  float4 a[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4* p = reinterpret_cast<const float4*>(src + (size_t)max(t[i], 0) * kC + ch * 8);
+    a[i] = __ldg(p);
+    b[i] = __ldg(p + 1);
   }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    uint4 out = make_uint4(0u, 0u, 0u, 0u);
+    if (t[i] >= 0) {
+      out.x = pack_h2f(a[i].x * scale, a[i].y * scale);
+      out.y = pack_h2f(a[i].z * scale, a[i].w * scale);
+      out.z = pack_h2f(b[i].x * scale, b[i].y * scale);
+      out.w = pack_h2f(b[i].z * scale, b[i].w * scale);
+    }
+    *reinterpret_cast<uint4*>(dst + (ch >> 3) * kBlockBytes + tc::sw128_offset(r0 + 16 * i, (ch & 7) * 8)) = out;
+  }
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -141,6 +160,18 @@ window_attn_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, 
       sm.kreg[tid] = reg;
     }
     __syncthreads();                                            // ktok visible; previous tile's MMAs were waited for below
+    if (warp < 4) {        // key masks of this tile as bit sets (one ballot per region instead of a shared-memory read per score)
+      const int kr = sm.kreg[warp * 32 + lane];
+      if (shifted) {
+#pragma unroll
+        for (int r = 0; r < 9; ++r) {
+          const uint32_t other = __ballot_sync(0xffffffffu, kr != r);
+          if (lane == 0) sm.kmask[r][warp] = other;
+        }
+      }
+      const uint32_t inval = __ballot_sync(0xffffffffu, k0 + warp * 32 + lane >= Lw);
+      if (lane == 0) sm.kinval[warp] = inval;
+    }
     load_rows_swizzled(k + boff, sm.ktok, &sm.k[0][0], 1.0f, tid);
     load_rows_swizzled(v + boff, sm.ktok, &sm.v[0][0], 1.0f, tid);
     tc::fence_proxy_async_smem();
@@ -163,41 +194,59 @@ window_attn_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, 
       tc::mbar_wait(&sm.bar_s, kt & 1);
       tc::tc_fence_after_sync();
       // sweep 1: row maximum of the masked scores
+      const bool partial = n_valid < kTile;                     // warp-uniform
+      const float kMaskAdd = -100.0f * kLog2e;                  // transformer.py:41, :90
       float mx = -INFINITY;
 #pragma unroll
       for (int c0 = 0; c0 < kTile; c0 += 32) {
         uint32_t r[32];
         tc::tmem_ld32(tb + kColS + c0, r);
+        const uint32_t mk = shifted ? sm.kmask[my_qreg][c0 >> 5] : 0u;
+        const uint32_t iv = partial ? sm.kinval[c0 >> 5] : 0u;
         tc::tmem_wait_ld();
+        if (mk | iv) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float s = __uint_as_float(r[j]);
-          if (shifted && sm.kreg[c0 + j] != my_qreg) s += -100.0f * kLog2e;    // transformer.py:41, :90
-          if (c0 + j >= n_valid) s = -INFINITY;
-          mx = fmaxf(mx, s);
+          for (int j = 0; j < 32; ++j) {
+            float sc = __uint_as_float(r[j]);
+            if ((mk >> j) & 1u) sc += kMaskAdd;
+            if ((iv >> j) & 1u) sc = -INFINITY;
+            mx = fmaxf(mx, sc);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
         }
       }
       const float m_new = fmaxf(m_run, mx);
-      const float alpha = exp2f(m_run - m_new);                // 0 on the first tile (m_run = -inf)
+      const float alpha = ex2_approx(m_run - m_new);            // 0 on the first tile (m_run = -inf)
       // sweep 2: P = exp2(S - m) -> fp16, written over the S columns already consumed (P col = S col / 2)
       float sum = 0.f;
 #pragma unroll
       for (int c0 = 0; c0 < kTile; c0 += 32) {
         uint32_t r[32];
         tc::tmem_ld32(tb + kColS + c0, r);
+        const uint32_t mk = shifted ? sm.kmask[my_qreg][c0 >> 5] : 0u;
+        const uint32_t iv = partial ? sm.kinval[c0 >> 5] : 0u;
         tc::tmem_wait_ld();
         uint32_t p16[16];
+        if (mk | iv) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float s0 = __uint_as_float(r[j]), s1 = __uint_as_float(r[j + 1]);
-          if (shifted) {
-            if (sm.kreg[c0 + j] != my_qreg) s0 += -100.0f * kLog2e;
-            if (sm.kreg[c0 + j + 1] != my_qreg) s1 += -100.0f * kLog2e;
+          for (int j = 0; j < 32; j += 2) {
+            float s0 = __uint_as_float(r[j]), s1 = __uint_as_float(r[j + 1]);
+            if ((mk >> j) & 1u) s0 += kMaskAdd;
+            if ((mk >> (j + 1)) & 1u) s1 += kMaskAdd;
+            const float p0 = ((iv >> j) & 1u) ? 0.f : ex2_approx(s0 - m_new);
+            const float p1 = ((iv >> (j + 1)) & 1u) ? 0.f : ex2_approx(s1 - m_new);
+            sum += p0 + p1;
+            p16[j >> 1] = pack_h2f(p0, p1);
           }
-          const float p0 = c0 + j < n_valid ? exp2f(s0 - m_new) : 0.f;
-          const float p1 = c0 + j + 1 < n_valid ? exp2f(s1 - m_new) : 0.f;
-          sum += p0 + p1;
-          p16[j >> 1] = pack_h2f(p0, p1);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float p0 = ex2_approx(__uint_as_float(r[j]) - m_new), p1 = ex2_approx(__uint_as_float(r[j + 1]) - m_new);
+            sum += p0 + p1;
+            p16[j >> 1] = pack_h2f(p0, p1);
+          }
         }
         tc::tmem_st16(tb + kColS + c0 / 2, p16);
       }

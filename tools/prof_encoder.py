@@ -80,24 +80,26 @@ def main():
             print("graph capture failed:", repr(e))
 
         # channels_last convolutions
-        if hasattr(enc, "conv_memory_format"):
-            enc.conv_memory_format = torch.channels_last
+        if hasattr(enc, "backbone_memory_format"):
+            enc.backbone_memory_format = torch.channels_last
             f = m.get_img_feat(images)
             print(f"  channels_last: rel diff {rel(f[0], ref[0]):.2e} / {rel(f[1], ref[1]):.2e}")
             timeit("encoder channels_last", lambda: m.get_img_feat(images), args.reps)
             x = enc.normalize_images(images).reshape(3, 3, H, W)
             timeit("  backbone channels_last", lambda: enc.backbone(x.contiguous(memory_format=torch.channels_last)), args.reps)
-            enc.conv_memory_format = torch.contiguous_format
+            enc.backbone_memory_format = torch.contiguous_format
         x = enc.normalize_images(images).reshape(3, 3, H, W)
         timeit("  backbone default", lambda: enc.backbone(x), args.reps)
         base = enc.backbone(x)
         f0 = torch.stack([base[0], base[0], base[1]])
         f1 = torch.stack([base[1], base[2], base[2]])
-        timeit("  transformer", lambda: enc.transformer(f0, f1, 2), args.reps)
+        from matchnerf_b200.gmflow import _matmul_precision
+        with _matmul_precision("tf32"):
+            timeit("  transformer (tf32)", lambda: enc.transformer(f0, f1, 2), args.reps)
         t0, t1 = enc.transformer(f0, f1, 2)
         up_in = torch.cat([t0, t1], 0)
         timeit("  upsampler default", lambda: enc.featup_net(up_in), args.reps)
-        if hasattr(enc, "conv_memory_format"):
+        if hasattr(enc, "upsampler_memory_format"):
             up_cl = up_in.contiguous(memory_format=torch.channels_last)
             timeit("  upsampler channels_last", lambda: enc.featup_net(up_cl), args.reps)
         timeit("  regroup + pack (get_img_feat tail): full - parts", lambda: None, 1)
