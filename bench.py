@@ -300,8 +300,9 @@ def run_ours(args):
         if t_g * n_chunks >= t_d * n_chunks:
             roofline = dict(kernel="gather_cossim_kernel", bound="hbm", achieved=gather_gbs, peak=pk["hbm"], unit="GB/s",
                             frac=gather_gbs / pk["hbm"], traffic=traffic.get("gather_cossim_kernel"), peak_source=pk["source"],
-                            note="feature maps are L2-resident (39 MB) and taps are reused out of L1, so algorithmic bytes exceed DRAM traffic; "
-                                 "the kernel is bound by the L1->register path (128 B/clk/SM), see DESIGN.md")
+                            note="feature maps are L2-resident (39 MB) and a fetched texel cell is reused from registers by the rays of a "
+                                 "quad, so algorithmic bytes exceed DRAM traffic by two orders of magnitude (frac > 1); ncu shows the kernel "
+                                 "bound by the half-rate fp16 FMA pipe and instruction issue (68 %), not by any memory level -- DESIGN.md 4")
         else:
             roofline = dict(kernel="decoder_%s_kernel" % ("tc" if impl == 2 else "ref"), bound="tensor", achieved=dec_tfs, peak=pk["tensor"],
                             unit="TFLOP/s", frac=dec_tfs / pk["tensor"], traffic=traffic.get("decoder_tc_kernel") if impl == 2 else None,
