@@ -162,6 +162,13 @@ int32_t mnf_composite_fwd(mnf_ctx* ctx, const float* rgb, const float* sigma, co
                           int32_t n_samples, int32_t setbg_opaque, float* out_rgb, float* out_depth, float* out_opacity,
                           float* out_prob, void* stream);
 
+/* ---- encoder helper: fused InstanceNorm2d + ReLU (+ residual) of the CNN backbone --------- */
+/* x, y (and residual): fp32 [n_planes][hw] = contiguous NCHW with n_planes = N*C.  eps 1e-5, biased variance, no affine
+ * (nn.InstanceNorm2d defaults, models/gmflow/backbone.py:13-25).
+ *   mode 0: y = IN(x);  mode 1: y = relu(IN(x));  mode 2: y = relu(residual + relu(IN(x)))   (backbone.py:28-36) */
+int32_t mnf_instance_norm_fwd(mnf_ctx* ctx, const float* x, const float* residual, float* y, int64_t n_planes,
+                              int32_t hw, int32_t mode, float eps, void* stream);
+
 /* ---- K-attn: GMFlow split-window single-head attention ----------------------------------- */
 /* Replaces single_head_split_window_attention / single_head_full_attention
  * (models/gmflow/transformer.py:46-105 / :8-16) including the roll, the window partition and the

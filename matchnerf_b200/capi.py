@@ -77,6 +77,7 @@ def load() -> C.CDLL:
     lib.mnf_query_cond_points_fwd.argtypes = [vp, C.POINTER(Scene), fp, i64, i32, fp, vp, vp]
     lib.mnf_decoder_samples_fwd.argtypes = [vp, C.POINTER(DecoderCfg), fp, fp, fp, i64, fp, vp]
     lib.mnf_composite_fwd.argtypes = [vp, fp, fp, fp, i64, i32, i32, fp, fp, fp, fp, vp]
+    lib.mnf_instance_norm_fwd.argtypes = [vp, fp, fp, fp, i64, i32, i32, C.c_float, vp]
     lib.mnf_render_workspace_bytes.argtypes = [i64, i32]
     lib.mnf_render_workspace_bytes.restype = i64
     lib.mnf_render_rays_fwd.argtypes = [vp, C.POINTER(Scene), C.POINTER(Rays), C.POINTER(DecoderCfg), i32, fp, fp, fp,
@@ -85,7 +86,8 @@ def load() -> C.CDLL:
     lib.mnf_selftest_umma.argtypes = [vp, vp, fp, i32, i32, i32, vp]
     for name in ("mnf_ctx_create", "mnf_ctx_destroy", "mnf_decoder_load_host", "mnf_pack_features", "mnf_pack_images",
                  "mnf_gather_cossim_fwd", "mnf_decoder_composite_fwd", "mnf_render_rays_fwd", "mnf_window_attn_fwd",
-                 "mnf_selftest_umma", "mnf_query_cond_points_fwd", "mnf_decoder_samples_fwd", "mnf_composite_fwd"):
+                 "mnf_selftest_umma", "mnf_query_cond_points_fwd", "mnf_decoder_samples_fwd", "mnf_composite_fwd",
+                 "mnf_instance_norm_fwd"):
         getattr(lib, name).restype = i32
     if lib.mnf_abi_version() != 2:
         raise RuntimeError(f"libmatchnerf_b200.so ABI {lib.mnf_abi_version()} != 2")
@@ -315,6 +317,18 @@ class Context:
                                             out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), workspace.data_ptr(),
                                             workspace.numel(), impl, _stream(self.device)), "mnf_render_rays_fwd")
         return out
+
+    def instance_norm(self, x: torch.Tensor, mode: int = 1, residual: Optional[torch.Tensor] = None, eps: float = 1e-5):
+        """Fused InstanceNorm2d(+ReLU)(+residual, ReLU) on a contiguous NCHW fp32 tensor; see mnf_instance_norm_fwd."""
+        xc = _dev_f32(x, self.device, "x")
+        rc = _dev_f32(residual, self.device, "residual") if residual is not None else None
+        if rc is not None and rc.shape != xc.shape:
+            raise ValueError(f"residual {tuple(rc.shape)} != x {tuple(xc.shape)}")
+        N, Cc, H, W = xc.shape
+        y = torch.empty_like(xc)
+        _check(self.lib.mnf_instance_norm_fwd(self._h, xc.data_ptr(), _ptr(rc), y.data_ptr(), N * Cc, H * W, mode, eps,
+                                              _stream(self.device)), "mnf_instance_norm_fwd")
+        return y
 
     def window_attn(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, h: int, w: int, num_splits: int,
                     with_shift: bool, impl: int = 0) -> torch.Tensor:

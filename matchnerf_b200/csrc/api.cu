@@ -362,6 +362,14 @@ int32_t mnf_render_rays_fwd(mnf_ctx* ctx, const mnf_scene* scene, const mnf_rays
                                    out_rgb, out_depth, out_opacity, nullptr, impl, stream);
 }
 
+int32_t mnf_instance_norm_fwd(mnf_ctx* ctx, const float* x, const float* residual, float* y, int64_t n_planes, int32_t hw,
+                              int32_t mode, float eps, void* stream) {
+  if (!ctx || !x || !y) { set_error("mnf_instance_norm_fwd: NULL argument"); return MNF_EINVAL; }
+  if (n_planes < 0 || hw <= 0) { set_error("mnf_instance_norm_fwd: bad shape planes=%lld hw=%d", (long long)n_planes, hw); return MNF_EINVAL; }
+  if (mode < 0 || mode > 2 || (mode == 2 && !residual)) { set_error("mnf_instance_norm_fwd: mode must be 0, 1 or 2 (2 needs a residual)"); return MNF_EINVAL; }
+  return launch_instance_norm(x, mode == 2 ? residual : nullptr, y, n_planes, hw, mode, eps, (cudaStream_t)stream);
+}
+
 int32_t mnf_window_attn_fwd(mnf_ctx* ctx, const float* q, const float* k, const float* v, float* out, int32_t B, int32_t h,
                             int32_t w, int32_t C, int32_t num_splits, int32_t with_shift, int32_t impl, void* stream) {
   if (!ctx || !q || !k || !v || !out) { set_error("mnf_window_attn_fwd: NULL argument"); return MNF_EINVAL; }

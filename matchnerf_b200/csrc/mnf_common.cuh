@@ -145,6 +145,8 @@ int launch_decoder_ref(const DevCams& cams, const DevRays& rays, const mnf_decod
 int launch_composite(const float* rgb, const float* sigma, const float* depth, int64_t n_rays, int S, int setbg_opaque,
                      float* out_rgb, float* out_depth, float* out_opacity, float* out_prob, cudaStream_t s);
 
+int launch_instance_norm(const float* x, const float* res, float* y, int64_t planes, int hw, int mode, float eps, cudaStream_t s);
+
 int launch_window_attn_ref(const float* q, const float* k, const float* v, float* out, int B, int h, int w, int C,
                            int num_splits, int with_shift, cudaStream_t s);
 

@@ -24,6 +24,20 @@ from . import capi
 # CNN backbone (models/gmflow/backbone.py) -- parameter names: conv1, layer{1,2,3}.{0,1}.{conv1,conv2,
 # downsample.0}, conv2
 # ----------------------------------------------------------------------------------------------
+def _in_relu(x, mode: int, residual=None):
+    """InstanceNorm2d (no affine) fused with what follows it in the backbone: mode 0 = norm only, 1 = norm + ReLU,
+    2 = relu(residual + relu(norm(x))).  On a CUDA tensor (inference) this is one kernel of this repo's library
+    (mnf_instance_norm_fwd); elsewhere (CPU tensors, autograd) the PyTorch ops the reference uses."""
+    if x.is_cuda and not (torch.is_grad_enabled() and x.requires_grad) and x.dtype == torch.float32:
+        return capi.get_context(x.device).instance_norm(x.contiguous(), mode, residual.contiguous() if residual is not None else None)
+    y = F.instance_norm(x)
+    if mode >= 1:
+        y = F.relu(y)
+    if mode == 2:
+        y = F.relu(residual + y)
+    return y
+
+
 class ResidualBlock(nn.Module):
     """Two 3x3 convs with instance norm + identity/1x1 shortcut (models/gmflow/backbone.py:6-36)."""
 
@@ -36,11 +50,11 @@ class ResidualBlock(nn.Module):
             self.downsample = nn.Sequential(nn.Conv2d(c_in, c_out, 1, stride), nn.InstanceNorm2d(c_out))
 
     def forward(self, x):
-        y = F.relu(F.instance_norm(self.conv1(x)))
-        y = F.relu(F.instance_norm(self.conv2(y)))
+        y = _in_relu(self.conv1(x), 1)
+        y2 = self.conv2(y)
         if self.downsample is not None:
-            x = self.downsample(x)
-        return F.relu(x + y)
+            x = _in_relu(self.downsample[0](x), 0)
+        return _in_relu(y2, 2, x)                 # relu(x + relu(IN(conv2(y))))
 
 
 class CNNEncoder(nn.Module):
@@ -59,7 +73,7 @@ class CNNEncoder(nn.Module):
                 nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
 
     def forward(self, x):
-        x = F.relu(F.instance_norm(self.conv1(x)))
+        x = _in_relu(self.conv1(x), 1)
         x = self.layer3(self.layer2(self.layer1(x)))
         return self.conv2(x)
 

@@ -319,3 +319,21 @@ def test_window_attn_dtu_shape(ctx, impl, shift):
     lhs = ctx.window_attn(q.to(DEV), k.to(DEV), 0.5 * v.to(DEV) + v2, 64, 80, 2, shift, impl=impl)
     rhs = 0.5 * out + ctx.window_attn(q.to(DEV), k.to(DEV), v2, 64, 80, 2, shift, impl=impl)
     assert rms(lhs, rhs) < (1e-5 if impl == 1 else 3e-3)
+
+
+# ------------------------------------------------------------------------------------------- backbone instance norm
+@pytest.mark.parametrize("shape", [(3, 64, 32, 40), (2, 96, 7, 9), (1, 5, 1, 3), (3, 128, 64, 80)])
+def test_instance_norm_fused_modes(ctx, shape):
+    """mnf_instance_norm_fwd vs the PyTorch ops of the reference backbone (models/gmflow/backbone.py:28-36): fp32
+    round-off only; odd plane sizes take the scalar path."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(sum(shape))
+    x = (torch.randn(*shape, generator=g) * 3 + 0.5).to(DEV)
+    res = torch.randn(*shape, generator=g).to(DEV)
+    ref0 = F.instance_norm(x.double()).float()
+    assert max_abs(ctx.instance_norm(x, 0), ref0) < 2e-5
+    assert max_abs(ctx.instance_norm(x, 1), F.relu(ref0)) < 2e-5
+    assert max_abs(ctx.instance_norm(x, 2, res), F.relu(res + F.relu(ref0))) < 2e-5
+    # a constant plane: variance 0 -> output 0 (eps keeps it finite)
+    c = torch.full(shape, 2.5, device=DEV)
+    assert float(ctx.instance_norm(c, 0).abs().max()) < 1e-3

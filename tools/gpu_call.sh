@@ -5,9 +5,7 @@ mkdir -p gpurun_out
 L=gpurun_out/call.log
 : > $L
 run() { echo "=== $*" >> $L; ( "$@" ) >> $L 2>&1; echo "--- exit $?" >> $L; }
-run timeout 600 python -m pytest tests/test_gpu_kernels.py -q -m gpu -k "window_attn"
-run timeout 600 python -m pytest tests/test_gpu_model.py -q -m gpu
-run timeout 300 python tools/prof_kernels.py --which attn --reps 10 --impl 2
+run timeout 900 python -m pytest tests -q -m gpu -x
 run timeout 300 python tools/prof_encoder.py
-run timeout 600 ncu --set full --clock-control none --import-source on -k regex:window_attn_tc_kernel -c 2 -f -o gpurun_out/attn_v2 python tools/prof_kernels.py --which attn --impl 2 --reps 1
+run timeout 600 python bench.py
 tail -5 $L
