@@ -92,6 +92,16 @@ class MatchNeRF(nn.Module):
         self._scene_cache = (key, scenes)
         return scenes
 
+    def _c_scene(self, scene, tgt_pose, b):
+        """mnf_scene struct of batch item b for one target camera, built once per (scene, pose) and reused by every slice."""
+        key = (id(scene), id(tgt_pose), b, tgt_pose["extrinsics"]._version, tgt_pose["extrinsics"].data_ptr())
+        hit = getattr(self, "_c_scene_cache", None)
+        if hit is not None and hit[0] == key and hit[1] is tgt_pose:
+            return hit[2]
+        sc = scene.c_scene(tgt_pose["extrinsics"][b], tgt_pose["intrinsics"][b], tgt_pose["near_fars"][b])
+        self._c_scene_cache = (key, tgt_pose, sc)
+        return sc
+
     # ------------------------------------------------------------------ the per-slice pipeline
     def render(self, opt, tgt_pose=None, ray_idx=None, mode=None, ref_poses=None, ref_images=None, ref_feats_list=None):
         """models/matchnerf.py:88-143.  Returns AttrDict(rgb [B,R,3], depth [B,R,1], opacity [B,R,1])."""
@@ -117,7 +127,7 @@ class MatchNeRF(nn.Module):
         stratified = mode == "train" and bool(get_opt(opt, "nerf.sample_stratified", False))
         outs = []
         for b in range(B):
-            sc = scenes[b].c_scene(tgt_pose["extrinsics"][b], tgt_pose["intrinsics"][b], tgt_pose["near_fars"][b])
+            sc = self._c_scene(scenes[b], tgt_pose, b)
             jitter = torch.rand(n_rays, S, device=ctx.device) if stratified else None     # matchnerf.py:168-169
             rgb, depth, opac = ctx.render_rays(sc, cfg, ray_idx=ray_idx, first_ray=first_ray, n_rays=n_rays, jitter=jitter,
                                                setbg_opaque=self.nerf_setbg_opaque)
@@ -158,9 +168,14 @@ class MatchNeRF(nn.Module):
             raise NotImplementedError("matchnerf_b200: video path rendering (models/matchnerf.py:295-325) is not built yet")
         V = self.n_src_views
         ref_images = batch["images"][:, :V]
+        # The kernels take the cameras as host values inside mnf_scene.  Fetch them BEFORE queueing any GPU work: one
+        # device->host read on an idle stream, after which the encoder and every render launch are queued without a
+        # host synchronisation in between (a .cpu() per slice made the GPU idle ~1 ms per DTU image).
+        tgt_pose, ref_poses = self.extract_poses(batch)
+        tgt_pose = {k: v.detach().cpu() for k, v in tgt_pose.items()}
+        ref_poses = {k: v.detach().cpu() for k, v in ref_poses.items()}
         ref_feats_list = self.get_img_feat(ref_images, attn_splits_list=get_opt(self.opts, "encoder.attn_splits_list", [2]),
                                            cur_n_src_views=V)
-        tgt_pose, ref_poses = self.extract_poses(batch)
         B, _, _, H, W = ref_images.shape
         n_rand = int(get_opt(self.opts, f"nerf.rand_rays_{mode}", 0) or 0)
         if n_rand and mode in ("train", "test-optim"):
