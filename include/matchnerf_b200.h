@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MNF_ABI_VERSION 2
+#define MNF_ABI_VERSION 3
 
 typedef enum mnf_status {
   MNF_OK = 0,
@@ -175,10 +175,14 @@ int32_t mnf_instance_norm_fwd(mnf_ctx* ctx, const float* x, const float* residua
  * shifted-window mask (:19-43), none of which are materialised.
  *   q, k, v, out: [B][h*w][128] fp32, token order row-major over (h, w).
  *   num_splits: windows per axis (1 = full attention); with_shift: Swin shift of half a window.
- *   impl: 0 = auto, 1 = fp32 CUDA-core kernel, 2 = tcgen05 kernel. */
+ *   impl: 0 = auto, 1 = fp32 CUDA-core kernel, 2 = tcgen05 kernel.
+ *   workspace: device scratch of mnf_window_attn_workspace_bytes(B, h, w, num_splits) bytes, 16-byte aligned, or NULL.
+ *     With it the tcgen05 path pre-packs every Q / K / V tile once per call (fp16, swizzled operand images) and feeds
+ *     the attention kernel with TMA-unit bulk copies; without it every CTA gathers and converts its own tiles. */
+int64_t mnf_window_attn_workspace_bytes(int32_t B, int32_t h, int32_t w, int32_t num_splits);
 int32_t mnf_window_attn_fwd(mnf_ctx* ctx, const float* q, const float* k, const float* v, float* out,
                             int32_t B, int32_t h, int32_t w, int32_t C, int32_t num_splits, int32_t with_shift,
-                            int32_t impl, void* stream);
+                            int32_t impl, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- self tests of the tcgen05 building blocks (used by tests/ on the GPU box) ------------- */
 /* D[128][N] = A[128][K] * B[N][K]^T with fp16 operands, fp32 accumulate, one CTA.

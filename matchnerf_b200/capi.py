@@ -82,15 +82,17 @@ def load() -> C.CDLL:
     lib.mnf_render_workspace_bytes.restype = i64
     lib.mnf_render_rays_fwd.argtypes = [vp, C.POINTER(Scene), C.POINTER(Rays), C.POINTER(DecoderCfg), i32, fp, fp, fp,
                                         vp, i64, i32, vp]
-    lib.mnf_window_attn_fwd.argtypes = [vp, fp, fp, fp, fp, i32, i32, i32, i32, i32, i32, i32, vp]
+    lib.mnf_window_attn_workspace_bytes.argtypes = [i32, i32, i32, i32]
+    lib.mnf_window_attn_workspace_bytes.restype = i64
+    lib.mnf_window_attn_fwd.argtypes = [vp, fp, fp, fp, fp, i32, i32, i32, i32, i32, i32, i32, vp, i64, vp]
     lib.mnf_selftest_umma.argtypes = [vp, vp, fp, i32, i32, i32, vp]
     for name in ("mnf_ctx_create", "mnf_ctx_destroy", "mnf_decoder_load_host", "mnf_pack_features", "mnf_pack_images",
                  "mnf_gather_cossim_fwd", "mnf_decoder_composite_fwd", "mnf_render_rays_fwd", "mnf_window_attn_fwd",
                  "mnf_selftest_umma", "mnf_query_cond_points_fwd", "mnf_decoder_samples_fwd", "mnf_composite_fwd",
                  "mnf_instance_norm_fwd"):
         getattr(lib, name).restype = i32
-    if lib.mnf_abi_version() != 2:
-        raise RuntimeError(f"libmatchnerf_b200.so ABI {lib.mnf_abi_version()} != 2")
+    if lib.mnf_abi_version() != 3:
+        raise RuntimeError(f"libmatchnerf_b200.so ABI {lib.mnf_abi_version()} != 3")
     _lib = lib
     return lib
 
@@ -331,7 +333,7 @@ class Context:
         return y
 
     def window_attn(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, h: int, w: int, num_splits: int,
-                    with_shift: bool, impl: int = 0) -> torch.Tensor:
+                    with_shift: bool, impl: int = 0, use_workspace: bool = True) -> torch.Tensor:
         q = _dev_f32(q, self.device, "q")
         k = _dev_f32(k, self.device, "k")
         v = _dev_f32(v, self.device, "v")
@@ -339,8 +341,13 @@ class Context:
         if L != h * w:
             raise ValueError("q.shape[1] != h*w")
         out = torch.empty_like(q)
+        ws = None
+        if impl != 1 and use_workspace:
+            need = self.lib.mnf_window_attn_workspace_bytes(B, h, w, num_splits)
+            ws = torch.empty((max(need, 16),), dtype=torch.uint8, device=self.device)
         _check(self.lib.mnf_window_attn_fwd(self._h, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, h, w, Cc,
-                                            num_splits, int(with_shift), impl, _stream(self.device)), "mnf_window_attn_fwd")
+                                            num_splits, int(with_shift), impl, _ptr(ws), ws.numel() if ws is not None else 0,
+                                            _stream(self.device)), "mnf_window_attn_fwd")
         return out
 
     def selftest_umma(self, a: torch.Tensor, b: torch.Tensor, mode: int) -> torch.Tensor:

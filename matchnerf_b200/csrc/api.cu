@@ -35,7 +35,8 @@ bool decoder_tc_supports(const mnf_decoder_cfg& cfg);
 // window_attn_tc.cu
 bool window_attn_tc_supports(int B, int h, int w, int C, int num_splits);
 int launch_window_attn_tc(const float* q, const float* k, const float* v, float* out, int B, int h, int w, int C,
-                          int num_splits, int with_shift, cudaStream_t s);
+                          int num_splits, int with_shift, void* workspace, int64_t workspace_bytes, cudaStream_t s);
+int64_t window_attn_tc_workspace_bytes(int B, int h, int w, int num_splits);
 
 }  // namespace mnf
 
@@ -370,8 +371,13 @@ int32_t mnf_instance_norm_fwd(mnf_ctx* ctx, const float* x, const float* residua
   return launch_instance_norm(x, mode == 2 ? residual : nullptr, y, n_planes, hw, mode, eps, (cudaStream_t)stream);
 }
 
+int64_t mnf_window_attn_workspace_bytes(int32_t B, int32_t h, int32_t w, int32_t num_splits) {
+  return window_attn_tc_workspace_bytes(B, h, w, num_splits);
+}
+
 int32_t mnf_window_attn_fwd(mnf_ctx* ctx, const float* q, const float* k, const float* v, float* out, int32_t B, int32_t h,
-                            int32_t w, int32_t C, int32_t num_splits, int32_t with_shift, int32_t impl, void* stream) {
+                            int32_t w, int32_t C, int32_t num_splits, int32_t with_shift, int32_t impl, void* workspace,
+                            int64_t workspace_bytes, void* stream) {
   if (!ctx || !q || !k || !v || !out) { set_error("mnf_window_attn_fwd: NULL argument"); return MNF_EINVAL; }
   if (C != 128) { set_error("mnf_window_attn_fwd: C = %d unsupported (feature_channels is 128)", C); return MNF_EUNSUPPORTED; }
   if (B <= 0 || h <= 0 || w <= 0 || num_splits <= 0 || h % num_splits || w % num_splits) {
@@ -381,7 +387,7 @@ int32_t mnf_window_attn_fwd(mnf_ctx* ctx, const float* q, const float* k, const 
   if (impl == 0) impl = window_attn_tc_supports(B, h, w, C, num_splits) ? 2 : 1;
   if (impl == 2) {
     if (!window_attn_tc_supports(B, h, w, C, num_splits)) { set_error("tcgen05 attention does not cover this shape"); return MNF_EUNSUPPORTED; }
-    return launch_window_attn_tc(q, k, v, out, B, h, w, C, num_splits, with_shift, (cudaStream_t)stream);
+    return launch_window_attn_tc(q, k, v, out, B, h, w, C, num_splits, with_shift, workspace, workspace_bytes, (cudaStream_t)stream);
   }
   if (impl != 1) { set_error("impl must be 0, 1 or 2"); return MNF_EINVAL; }
   return launch_window_attn_ref(q, k, v, out, B, h, w, C, num_splits, with_shift, (cudaStream_t)stream);

@@ -15,6 +15,8 @@
 // Tensor memory: S / P columns [0,128), O columns [128,256).
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "mnf_common.cuh"
 #include "tcgen05.cuh"
 
@@ -111,7 +113,7 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
 }  // namespace
 
 __global__ void __launch_bounds__(kAttnThreads, 2)
-window_attn_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+window_attn_tc_v2_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                       float* __restrict__ out, const WinGeomTc g) {
   extern __shared__ unsigned char smem_dyn[];
   AttnTcSmem& sm = *reinterpret_cast<AttnTcSmem*>(smem_dyn + ((1024u - (tc::smem_u32(smem_dyn) & 1023u)) & 1023u));
@@ -307,26 +309,590 @@ window_attn_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, 
   if (warp == 1) tc::tmem_dealloc<256>(tmem);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// v3: warp-specialised pipeline.  ncu of v2: issue 20 %, 4.2 barrier + 5.3 long-scoreboard stalls per issue -- every key
+// tile ran load -> QK -> softmax -> PV strictly one after the other, with half the warps idle in each phase.  Here
+//   warps 0-3  softmax: thread = query row, as before;
+//   warps 4-7  loaders: gather K of tile t+1 as soon as QK(t) has consumed the K buffer (i.e. underneath softmax(t)),
+//              then V of tile t+1 as soon as PV(t) has consumed the V buffer; they also own the token / shift-region
+//              bookkeeping (double-buffered bit masks);
+//   warp 8     one elected lane issues the MMAs and commits them to mbarriers.
+// Single K / V buffers (2 CTAs per SM still fit), five mbarriers, no __syncthreads inside the loop.
+constexpr int kPipeThreads = 288;
+
+struct AttnPipeSmem {
+  alignas(1024) unsigned char q[2][kBlockBytes];
+  unsigned char k[2][kBlockBytes];
+  unsigned char v[2][kBlockBytes];
+  int qtok[kTile];
+  int ktok[kTile];
+  uint32_t kmask[2][9][4];         // [tile parity][query region][word]: key lies in ANOTHER shift region
+  uint32_t kinval[2][4];           // [tile parity][word]: key past the end of the window
+  alignas(8) uint64_t bar_s;       // QK(t) complete            (tcgen05.commit)
+  uint64_t bar_o;                  // PV(t) complete            (tcgen05.commit)
+  uint64_t k_full;                 // K(t) in shared memory     (4 loader warps)
+  uint64_t v_full;                 // V(t) in shared memory     (4 loader warps)
+  uint64_t p_ready;                // P(t) in tensor memory, O rescaled   (4 softmax warps)
+  uint32_t tmem_base;
+};
+
+// rows r0 + 8 i (i < 16) of a 128-row tile, one 8-channel chunk per thread, for a group of 128 loader threads; two batches
+// of 8 rows so that at most 16 16-byte loads (64 registers) are in flight per thread
+__device__ __forceinline__ void load_rows_swizzled_128(const float* __restrict__ src, const int* tok, unsigned char* dst, int ltid) {
+  const int ch = ltid & 15, r0 = ltid >> 4;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    int t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = tok[r0 + 8 * (half * 8 + i)];
+    float4 a[8], b[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4* p = reinterpret_cast<const float4*>(src + (size_t)max(t[i], 0) * kC + ch * 8);
+      a[i] = __ldg(p);
+      b[i] = __ldg(p + 1);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      uint4 out = make_uint4(0u, 0u, 0u, 0u);
+      if (t[i] >= 0) {
+        out.x = pack_h2f(a[i].x, a[i].y);
+        out.y = pack_h2f(a[i].z, a[i].w);
+        out.z = pack_h2f(b[i].x, b[i].y);
+        out.w = pack_h2f(b[i].z, b[i].w);
+      }
+      *reinterpret_cast<uint4*>(dst + (ch >> 3) * kBlockBytes + tc::sw128_offset(r0 + 8 * (half * 8 + i), (ch & 7) * 8)) = out;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kPipeThreads, 2)
+window_attn_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                      float* __restrict__ out, const WinGeomTc g) {
+  extern __shared__ unsigned char smem_dyn[];
+  AttnPipeSmem& sm = *reinterpret_cast<AttnPipeSmem*>(smem_dyn + ((1024u - (tc::smem_u32(smem_dyn) & 1023u)) & 1023u));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Lw = g.wh * g.ww;
+  const int win = blockIdx.y % (g.splits * g.splits), b = blockIdx.y / (g.splits * g.splits);
+  const int wy = win / g.splits, wx = win - wy * g.splits;
+  const int q0 = blockIdx.x * kTile;
+  const size_t boff = (size_t)b * g.h * g.w * kC;
+  const bool shifted = (g.sh | g.sw) != 0;
+  const float kLog2e = 1.4426950408889634f;
+  const int n_kt = (Lw + kTile - 1) / kTile;
+
+  if (tid == 0) {
+    tc::mbar_init(&sm.bar_s, 1);
+    tc::mbar_init(&sm.bar_o, 1);
+    tc::mbar_init(&sm.k_full, 4);
+    tc::mbar_init(&sm.v_full, 4);
+    tc::mbar_init(&sm.p_ready, 4);
+    tc::fence_mbar_init();
+  }
+  if (warp == 8) tc::tmem_alloc<256>(&sm.tmem_base);
+  int my_qreg = 0;
+  if (tid < kTile) {
+    int tok = -1, reg = 0;
+    if (q0 + tid < Lw) window_token(g, wy, wx, q0 + tid, tok, reg);
+    sm.qtok[tid] = tok;
+    my_qreg = reg;
+  }
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  tc::tc_fence_after_sync();
+  const uint32_t tmem = sm.tmem_base;
+  // Q, pre-scaled so that scores come out in the exp2 domain: (q . k) / sqrt(C) * log2(e)
+  if (tid < 256) load_rows_swizzled(q + boff, sm.qtok, &sm.q[0][0], rsqrtf((float)kC) * kLog2e, tid);
+  tc::fence_proxy_async_smem();
+  __syncthreads();
+
+  if (warp >= 4 && warp < 8) {
+    // ================================================================== loaders
+    const int ltid = tid - 128, lw = warp - 4;
+    for (int t = 0; t < n_kt; ++t) {
+      const int par = t & 1;
+      // K buffer, token list and mask buffers of parity `par` are free once QK(t-1) is complete: that MMA was issued
+      // after PV(t-2), which waited for softmax(t-2), the last reader of kmask[par]
+      if (t > 0) tc::mbar_wait(&sm.bar_s, (t - 1) & 1);
+      int tok = -1, reg = 0;
+      if (t * kTile + ltid < Lw) window_token(g, wy, wx, t * kTile + ltid, tok, reg);
+      sm.ktok[ltid] = tok;
+      if (shifted) {
+#pragma unroll
+        for (int r = 0; r < 9; ++r) {
+          const uint32_t other = __ballot_sync(0xffffffffu, reg != r);
+          if (lane == 0) sm.kmask[par][r][lw] = other;
+        }
+      }
+      const uint32_t inval = __ballot_sync(0xffffffffu, tok < 0);
+      if (lane == 0) sm.kinval[par][lw] = inval;
+      asm volatile("bar.sync 1, 128;" ::: "memory");             // token list complete (loader warps only)
+      load_rows_swizzled_128(k + boff, sm.ktok, &sm.k[0][0], ltid);
+      tc::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&sm.k_full);
+      if (t > 0) tc::mbar_wait(&sm.bar_o, (t - 1) & 1);          // V buffer free: PV(t-1) complete
+      load_rows_swizzled_128(v + boff, sm.ktok, &sm.v[0][0], ltid);
+      tc::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&sm.v_full);
+      asm volatile("bar.sync 1, 128;" ::: "memory");             // everyone is done with ktok before the next tile rewrites it
+    }
+  } else if (warp == 8) {
+    // ================================================================== MMA issuer
+    const uint32_t idesc_qk = tc::umma_idesc_f16(128, 128, 0), idesc_pv = tc::umma_idesc_f16(128, 128, 1);
+    for (int kt = 0; kt < n_kt; ++kt) {
+      tc::mbar_wait(&sm.k_full, kt & 1);
+      if (kt > 0) tc::mbar_wait(&sm.bar_o, (kt - 1) & 1);        // S / P columns free, O accumulation ordered
+      tc::tc_fence_after_sync();
+      if (tc::elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t ad = tc::umma_desc_sw128(tc::smem_u32(&sm.q[ks >> 2][0]) + (ks & 3) * 32);
+          const uint64_t bd = tc::umma_desc_sw128(tc::smem_u32(&sm.k[ks >> 2][0]) + (ks & 3) * 32);
+          tc::umma_ss(tmem + kColS, ad, bd, idesc_qk, ks > 0);
+        }
+        tc::umma_commit(&sm.bar_s);
+      }
+      __syncwarp();
+      tc::mbar_wait(&sm.p_ready, kt & 1);
+      tc::mbar_wait(&sm.v_full, kt & 1);
+      tc::tc_fence_after_sync();
+      if (tc::elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {   // 16 keys per step: A = P columns [8 ks, 8 ks + 8), B = V rows [16 ks, 16 ks + 16)
+          const uint64_t bd = tc::umma_desc_sw128_mn(tc::smem_u32(&sm.v[0][0]) + ks * 2048, kBlockBytes);
+          tc::umma_ts(tmem + kColO, tmem + kColS + ks * 8, bd, idesc_pv, (kt | ks) ? 1u : 0u);
+        }
+        tc::umma_commit(&sm.bar_o);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================================================================== softmax: thread = query row
+    const int row = warp * 32 + lane;
+    const uint32_t tb = tmem + ((uint32_t)(warp * 32) << 16);
+    const float kMaskAdd = -100.0f * kLog2e;                     // transformer.py:41, :90
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int kt = 0; kt < n_kt; ++kt) {
+      const int par = kt & 1;
+      const bool partial = Lw - kt * kTile < kTile;              // warp-uniform
+      tc::mbar_wait(&sm.bar_s, par);
+      tc::tc_fence_after_sync();
+      // sweep 1: row maximum of the masked scores
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c0 = 0; c0 < kTile; c0 += 32) {
+        uint32_t r[32];
+        tc::tmem_ld32(tb + kColS + c0, r);
+        const uint32_t mk = shifted ? sm.kmask[par][my_qreg][c0 >> 5] : 0u;
+        const uint32_t iv = partial ? sm.kinval[par][c0 >> 5] : 0u;
+        tc::tmem_wait_ld();
+        if (mk | iv) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float sc = __uint_as_float(r[j]);
+            if ((mk >> j) & 1u) sc += kMaskAdd;
+            if ((iv >> j) & 1u) sc = -INFINITY;
+            mx = fmaxf(mx, sc);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+        }
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float alpha = ex2_approx(m_run - m_new);             // 0 on the first tile (m_run = -inf)
+      // sweep 2: P = exp2(S - m) -> fp16, written over the S columns already consumed (P col = S col / 2)
+      float sum = 0.f;
+#pragma unroll
+      for (int c0 = 0; c0 < kTile; c0 += 32) {
+        uint32_t r[32];
+        tc::tmem_ld32(tb + kColS + c0, r);
+        const uint32_t mk = shifted ? sm.kmask[par][my_qreg][c0 >> 5] : 0u;
+        const uint32_t iv = partial ? sm.kinval[par][c0 >> 5] : 0u;
+        tc::tmem_wait_ld();
+        uint32_t p16[16];
+        if (mk | iv) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float s0 = __uint_as_float(r[j]), s1 = __uint_as_float(r[j + 1]);
+            if ((mk >> j) & 1u) s0 += kMaskAdd;
+            if ((mk >> (j + 1)) & 1u) s1 += kMaskAdd;
+            const float p0 = ((iv >> j) & 1u) ? 0.f : ex2_approx(s0 - m_new);
+            const float p1 = ((iv >> (j + 1)) & 1u) ? 0.f : ex2_approx(s1 - m_new);
+            sum += p0 + p1;
+            p16[j >> 1] = pack_h2f(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float p0 = ex2_approx(__uint_as_float(r[j]) - m_new), p1 = ex2_approx(__uint_as_float(r[j + 1]) - m_new);
+            sum += p0 + p1;
+            p16[j >> 1] = pack_h2f(p0, p1);
+          }
+        }
+        tc::tmem_st16(tb + kColS + c0 / 2, p16);
+      }
+      l_run = l_run * alpha + sum;
+      m_run = m_new;
+      // rescale the running output when some row of this warp moved its maximum (warp-collective TMEM access); PV(kt-1)
+      // is complete: QK(kt) was only issued after it
+      if (kt > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll
+        for (int c0 = 0; c0 < kC; c0 += 32) {
+          uint32_t r[32];
+          tc::tmem_ld32(tb + kColO + c0, r);
+          tc::tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * alpha);
+          tmem_st32(tb + kColO + c0, r);
+        }
+      }
+      tc::tmem_wait_st();
+      tc::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&sm.p_ready);
+    }
+    tc::mbar_wait(&sm.bar_o, (n_kt - 1) & 1);
+    tc::tc_fence_after_sync();
+    const int tok = sm.qtok[row];
+    const float inv = 1.f / l_run;
+#pragma unroll
+    for (int c0 = 0; c0 < kC; c0 += 32) {
+      uint32_t r[32];
+      tc::tmem_ld32(tb + kColO + c0, r);
+      tc::tmem_wait_ld();
+      if (tok >= 0) {
+        float4* dst = reinterpret_cast<float4*>(out + boff + (size_t)tok * kC + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          dst[j] = make_float4(__uint_as_float(r[4 * j]) * inv, __uint_as_float(r[4 * j + 1]) * inv,
+                               __uint_as_float(r[4 * j + 2]) * inv, __uint_as_float(r[4 * j + 3]) * inv);
+      }
+    }
+  }
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 8) tc::tmem_dealloc<256>(tmem);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// v4: pre-packed operand tiles + TMA-unit bulk copies.  ncu of v3: the loader warps became the critical path (11 long-
+// scoreboard stalls per issue): every one of the 10 query-tile CTAs of a window re-gathers and re-converts the same fp32
+// K / V rows, four dependent L2 round trips per key tile.  v4 does that work ONCE per call: a pre-pass writes every
+// 128-row Q / K / V tile of every window as a ready-made operand image (fp16, SWIZZLE_128B, Q pre-scaled, rows past the
+// window end zero) into a caller-provided workspace; the attention kernel then feeds its shared-memory operand buffers
+// with cp.async.bulk (one elected lane, mbarrier complete_tx) -- no registers, no conversions, K(t+1) in flight
+// underneath softmax(t) and V(t+1) underneath QK(t+1) + softmax(t+1).
+//   warps 0-3 softmax | warp 4 producer (bulk copies + shift-region bit masks) | warp 5 MMA issuer
+constexpr int kPackThreads = 256;
+constexpr int kV4Threads = 192;
+constexpr int kImageBytes = 2 * kBlockBytes;      // one [128][128] fp16 operand tile = two swizzled [128][64] blocks
+
+// grid (n_tiles, B * n_windows, 3): image (b, window, tile, matrix) of the workspace
+__global__ void __launch_bounds__(kPackThreads)
+attn_pack_tiles_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                       unsigned char* __restrict__ ws, const WinGeomTc g) {
+  __shared__ int tok_s[kTile];
+  const int tid = threadIdx.x;
+  const int Lw = g.wh * g.ww;
+  const int n_tiles = gridDim.x;
+  const int win = blockIdx.y % (g.splits * g.splits), b = blockIdx.y / (g.splits * g.splits);
+  const int wy = win / g.splits, wx = win - wy * g.splits;
+  const int mat = blockIdx.z;
+  const float* src = (mat == 0 ? q : (mat == 1 ? k : v)) + (size_t)b * g.h * g.w * kC;
+  const float scale = mat == 0 ? rsqrtf((float)kC) * 1.4426950408889634f : 1.0f;   // scores in the exp2 domain
+  if (tid < kTile) {
+    int tok = -1, reg = 0;
+    if (blockIdx.x * kTile + tid < Lw) window_token(g, wy, wx, blockIdx.x * kTile + tid, tok, reg);
+    tok_s[tid] = tok;
+  }
+  __syncthreads();
+  unsigned char* img = ws + (((size_t)blockIdx.y * n_tiles + blockIdx.x) * 3 + mat) * kImageBytes;
+  load_rows_swizzled(src, tok_s, img, scale, tid);       // same image the v2 / v3 kernels build in shared memory
+}
+
+struct AttnV4Smem {
+  alignas(1024) unsigned char q[2][kBlockBytes];
+  unsigned char k[2][kBlockBytes];
+  unsigned char v[2][kBlockBytes];
+  int qtok[kTile];
+  uint32_t kmask[2][9][4];         // [tile parity][query region][word]: key lies in ANOTHER shift region
+  uint32_t kinval[2][4];           // [tile parity][word]: key past the end of the window
+  alignas(8) uint64_t bar_s;       // QK(t) complete            (tcgen05.commit)
+  uint64_t bar_o;                  // PV(t) complete            (tcgen05.commit)
+  uint64_t k_full;                 // K(t) (and Q, for t = 0) landed   (complete_tx)
+  uint64_t v_full;                 // V(t) landed                      (complete_tx)
+  uint64_t p_ready;                // P(t) in tensor memory, O rescaled   (4 softmax warps)
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kV4Threads, 2)
+window_attn_tc_v4_kernel(const unsigned char* __restrict__ ws, float* __restrict__ out, const WinGeomTc g) {
+  extern __shared__ unsigned char smem_dyn[];
+  AttnV4Smem& sm = *reinterpret_cast<AttnV4Smem*>(smem_dyn + ((1024u - (tc::smem_u32(smem_dyn) & 1023u)) & 1023u));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Lw = g.wh * g.ww;
+  const int win = blockIdx.y % (g.splits * g.splits), b = blockIdx.y / (g.splits * g.splits);
+  const int wy = win / g.splits, wx = win - wy * g.splits;
+  const int q0 = blockIdx.x * kTile;
+  const size_t boff = (size_t)b * g.h * g.w * kC;
+  const bool shifted = (g.sh | g.sw) != 0;
+  const float kLog2e = 1.4426950408889634f;
+  const int n_kt = (Lw + kTile - 1) / kTile;
+  const unsigned char* wbase = ws + (size_t)blockIdx.y * n_kt * 3 * kImageBytes;     // this window's images: [tile][q, k, v]
+
+  if (tid == 0) {
+    tc::mbar_init(&sm.bar_s, 1);
+    tc::mbar_init(&sm.bar_o, 1);
+    tc::mbar_init(&sm.k_full, 1);
+    tc::mbar_init(&sm.v_full, 1);
+    tc::mbar_init(&sm.p_ready, 4);
+    tc::fence_mbar_init();
+  }
+  if (warp == 5) tc::tmem_alloc<256>(&sm.tmem_base);
+  int my_qreg = 0;
+  if (tid < kTile) {
+    int tok = -1, reg = 0;
+    if (q0 + tid < Lw) window_token(g, wy, wx, q0 + tid, tok, reg);
+    sm.qtok[tid] = tok;
+    my_qreg = reg;
+  }
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  tc::tc_fence_after_sync();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp == 4) {
+    // ================================================================== producer
+    for (int t = 0; t < n_kt; ++t) {
+      const int par = t & 1;
+      // K buffer and the mask buffers of parity `par` are free once QK(t-1) is complete (it was issued after PV(t-2),
+      // which waited for softmax(t-2), the last reader of kmask[par])
+      if (t > 0) tc::mbar_wait(&sm.bar_s, (t - 1) & 1);
+#pragma unroll
+      for (int w4 = 0; w4 < 4; ++w4) {
+        int tok = -1, reg = 0;
+        if (t * kTile + w4 * 32 + lane < Lw) window_token(g, wy, wx, t * kTile + w4 * 32 + lane, tok, reg);
+        if (shifted) {
+#pragma unroll
+          for (int r = 0; r < 9; ++r) {
+            const uint32_t other = __ballot_sync(0xffffffffu, reg != r);
+            if (lane == 0) sm.kmask[par][r][w4] = other;
+          }
+        }
+        const uint32_t inval = __ballot_sync(0xffffffffu, tok < 0);
+        if (lane == 0) sm.kinval[par][w4] = inval;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        const unsigned char* timg = wbase + (size_t)t * 3 * kImageBytes;
+        if (t == 0) {
+          tc::mbar_arrive_expect_tx(&sm.k_full, 2 * kImageBytes);
+          const unsigned char* qimg = wbase + (size_t)blockIdx.x * 3 * kImageBytes;
+          tc::bulk_g2s(&sm.q[0][0], qimg, kBlockBytes, &sm.k_full);
+          tc::bulk_g2s(&sm.q[1][0], qimg + kBlockBytes, kBlockBytes, &sm.k_full);
+        } else {
+          tc::mbar_arrive_expect_tx(&sm.k_full, kImageBytes);
+        }
+        tc::bulk_g2s(&sm.k[0][0], timg + kImageBytes, kBlockBytes, &sm.k_full);
+        tc::bulk_g2s(&sm.k[1][0], timg + kImageBytes + kBlockBytes, kBlockBytes, &sm.k_full);
+      }
+      if (t > 0) tc::mbar_wait(&sm.bar_o, (t - 1) & 1);          // V buffer free: PV(t-1) complete
+      if (lane == 0) {
+        const unsigned char* timg = wbase + (size_t)t * 3 * kImageBytes;
+        tc::mbar_arrive_expect_tx(&sm.v_full, kImageBytes);
+        tc::bulk_g2s(&sm.v[0][0], timg + 2 * kImageBytes, kBlockBytes, &sm.v_full);
+        tc::bulk_g2s(&sm.v[1][0], timg + 2 * kImageBytes + kBlockBytes, kBlockBytes, &sm.v_full);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 5) {
+    // ================================================================== MMA issuer
+    const uint32_t idesc_qk = tc::umma_idesc_f16(128, 128, 0), idesc_pv = tc::umma_idesc_f16(128, 128, 1);
+    for (int kt = 0; kt < n_kt; ++kt) {
+      tc::mbar_wait(&sm.k_full, kt & 1);
+      if (kt > 0) tc::mbar_wait(&sm.bar_o, (kt - 1) & 1);        // S / P columns free, O accumulation ordered
+      tc::tc_fence_after_sync();
+      if (tc::elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t ad = tc::umma_desc_sw128(tc::smem_u32(&sm.q[ks >> 2][0]) + (ks & 3) * 32);
+          const uint64_t bd = tc::umma_desc_sw128(tc::smem_u32(&sm.k[ks >> 2][0]) + (ks & 3) * 32);
+          tc::umma_ss(tmem + kColS, ad, bd, idesc_qk, ks > 0);
+        }
+        tc::umma_commit(&sm.bar_s);
+      }
+      __syncwarp();
+      tc::mbar_wait(&sm.p_ready, kt & 1);
+      tc::mbar_wait(&sm.v_full, kt & 1);
+      tc::tc_fence_after_sync();
+      if (tc::elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {   // 16 keys per step: A = P columns [8 ks, 8 ks + 8), B = V rows [16 ks, 16 ks + 16)
+          const uint64_t bd = tc::umma_desc_sw128_mn(tc::smem_u32(&sm.v[0][0]) + ks * 2048, kBlockBytes);
+          tc::umma_ts(tmem + kColO, tmem + kColS + ks * 8, bd, idesc_pv, (kt | ks) ? 1u : 0u);
+        }
+        tc::umma_commit(&sm.bar_o);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================================================================== softmax: thread = query row
+    const int row = warp * 32 + lane;
+    const uint32_t tb = tmem + ((uint32_t)(warp * 32) << 16);
+    const float kMaskAdd = -100.0f * kLog2e;                     // transformer.py:41, :90
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int kt = 0; kt < n_kt; ++kt) {
+      const int par = kt & 1;
+      const bool partial = Lw - kt * kTile < kTile;              // warp-uniform
+      tc::mbar_wait(&sm.bar_s, par);
+      tc::tc_fence_after_sync();
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c0 = 0; c0 < kTile; c0 += 32) {
+        uint32_t r[32];
+        tc::tmem_ld32(tb + kColS + c0, r);
+        const uint32_t mk = shifted ? sm.kmask[par][my_qreg][c0 >> 5] : 0u;
+        const uint32_t iv = partial ? sm.kinval[par][c0 >> 5] : 0u;
+        tc::tmem_wait_ld();
+        if (mk | iv) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float sc = __uint_as_float(r[j]);
+            if ((mk >> j) & 1u) sc += kMaskAdd;
+            if ((iv >> j) & 1u) sc = -INFINITY;
+            mx = fmaxf(mx, sc);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+        }
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float alpha = ex2_approx(m_run - m_new);             // 0 on the first tile (m_run = -inf)
+      float sum = 0.f;
+#pragma unroll
+      for (int c0 = 0; c0 < kTile; c0 += 32) {
+        uint32_t r[32];
+        tc::tmem_ld32(tb + kColS + c0, r);
+        const uint32_t mk = shifted ? sm.kmask[par][my_qreg][c0 >> 5] : 0u;
+        const uint32_t iv = partial ? sm.kinval[par][c0 >> 5] : 0u;
+        tc::tmem_wait_ld();
+        uint32_t p16[16];
+        if (mk | iv) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float s0 = __uint_as_float(r[j]), s1 = __uint_as_float(r[j + 1]);
+            if ((mk >> j) & 1u) s0 += kMaskAdd;
+            if ((mk >> (j + 1)) & 1u) s1 += kMaskAdd;
+            const float p0 = ((iv >> j) & 1u) ? 0.f : ex2_approx(s0 - m_new);
+            const float p1 = ((iv >> (j + 1)) & 1u) ? 0.f : ex2_approx(s1 - m_new);
+            sum += p0 + p1;
+            p16[j >> 1] = pack_h2f(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float p0 = ex2_approx(__uint_as_float(r[j]) - m_new), p1 = ex2_approx(__uint_as_float(r[j + 1]) - m_new);
+            sum += p0 + p1;
+            p16[j >> 1] = pack_h2f(p0, p1);
+          }
+        }
+        tc::tmem_st16(tb + kColS + c0 / 2, p16);
+      }
+      l_run = l_run * alpha + sum;
+      m_run = m_new;
+      if (kt > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {    // PV(kt-1) is complete: QK(kt) was only issued after it
+#pragma unroll
+        for (int c0 = 0; c0 < kC; c0 += 32) {
+          uint32_t r[32];
+          tc::tmem_ld32(tb + kColO + c0, r);
+          tc::tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * alpha);
+          tmem_st32(tb + kColO + c0, r);
+        }
+      }
+      tc::tmem_wait_st();
+      tc::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&sm.p_ready);
+    }
+    tc::mbar_wait(&sm.bar_o, (n_kt - 1) & 1);
+    tc::tc_fence_after_sync();
+    const int tok = sm.qtok[row];
+    const float inv = 1.f / l_run;
+#pragma unroll
+    for (int c0 = 0; c0 < kC; c0 += 32) {
+      uint32_t r[32];
+      tc::tmem_ld32(tb + kColO + c0, r);
+      tc::tmem_wait_ld();
+      if (tok >= 0) {
+        float4* dst = reinterpret_cast<float4*>(out + boff + (size_t)tok * kC + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          dst[j] = make_float4(__uint_as_float(r[4 * j]) * inv, __uint_as_float(r[4 * j + 1]) * inv,
+                               __uint_as_float(r[4 * j + 2]) * inv, __uint_as_float(r[4 * j + 3]) * inv);
+      }
+    }
+  }
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 5) tc::tmem_dealloc<256>(tmem);
+}
+
+int64_t window_attn_tc_workspace_bytes(int B, int h, int w, int num_splits) {
+  if (B <= 0 || h <= 0 || w <= 0 || num_splits <= 0 || h % num_splits || w % num_splits) return 0;
+  const int64_t Lw = (int64_t)(h / num_splits) * (w / num_splits);
+  const int64_t n_tiles = (Lw + kTile - 1) / kTile;
+  return (int64_t)B * num_splits * num_splits * n_tiles * 3 * kImageBytes;
+}
+
 bool window_attn_tc_supports(int B, int h, int w, int C, int num_splits) {
   return C == kC && B > 0 && h % num_splits == 0 && w % num_splits == 0;
 }
 
 int launch_window_attn_tc(const float* q, const float* k, const float* v, float* out, int B, int h, int w, int C,
-                          int num_splits, int with_shift, cudaStream_t s) {
+                          int num_splits, int with_shift, void* workspace, int64_t workspace_bytes, cudaStream_t s) {
   WinGeomTc g;
   g.h = h; g.w = w; g.splits = num_splits;
   g.wh = h / num_splits; g.ww = w / num_splits;
   g.sh = (with_shift && num_splits > 1) ? g.wh / 2 : 0;
   g.sw = (with_shift && num_splits > 1) ? g.ww / 2 : 0;
   const int Lw = g.wh * g.ww;
-  const size_t smem = sizeof(AttnTcSmem) + 1024;
-  static bool configured = false;
-  if (!configured) {
-    MNF_CUDA_TRY(cudaFuncSetAttribute(window_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  static const int pipe = [] { const char* e = getenv("MNF_ATTN_PIPE"); return e ? atoi(e) : 2; }();   // A/B knob: 0 = v2 (serial phases), 1 = v3, 2 = v4
   dim3 grid((Lw + kTile - 1) / kTile, B * num_splits * num_splits);
-  window_attn_tc_kernel<<<grid, kAttnThreads, smem, s>>>(q, k, v, out, g);
+  if (pipe >= 2 && workspace && workspace_bytes >= window_attn_tc_workspace_bytes(B, h, w, num_splits) &&
+      ((uintptr_t)workspace & 15) == 0) {
+    const size_t smem = sizeof(AttnV4Smem) + 1024;
+    static bool configured = false;
+    if (!configured) {
+      MNF_CUDA_TRY(cudaFuncSetAttribute(window_attn_tc_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = true;
+    }
+    dim3 pgrid(grid.x, grid.y, 3);
+    attn_pack_tiles_kernel<<<pgrid, kPackThreads, 0, s>>>(q, k, v, reinterpret_cast<unsigned char*>(workspace), g);
+    MNF_CUDA_TRY(cudaGetLastError());
+    window_attn_tc_v4_kernel<<<grid, kV4Threads, smem, s>>>(reinterpret_cast<const unsigned char*>(workspace), out, g);
+  } else if (pipe) {
+    const size_t smem = sizeof(AttnPipeSmem) + 1024;
+    static bool configured = false;
+    if (!configured) {
+      MNF_CUDA_TRY(cudaFuncSetAttribute(window_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = true;
+    }
+    window_attn_tc_kernel<<<grid, kPipeThreads, smem, s>>>(q, k, v, out, g);
+  } else {
+    const size_t smem = sizeof(AttnTcSmem) + 1024;
+    static bool configured = false;
+    if (!configured) {
+      MNF_CUDA_TRY(cudaFuncSetAttribute(window_attn_tc_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = true;
+    }
+    window_attn_tc_v2_kernel<<<grid, kAttnThreads, smem, s>>>(q, k, v, out, g);
+  }
   MNF_CUDA_TRY(cudaGetLastError());
   return MNF_OK;
 }

@@ -5,9 +5,11 @@ mkdir -p gpurun_out
 L=gpurun_out/call.log
 : > $L
 run() { echo "=== $*" >> $L; ( "$@" ) >> $L 2>&1; echo "--- exit $?" >> $L; }
-run timeout 900 python -m pytest tests -q -m gpu -x
-run timeout 600 python bench.py
-run timeout 600 python bench.py --impl reference --steps 2 --warmup 1
-run timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline
-run timeout 600 ncu --set full --clock-control none --import-source on -k regex:decoder_tc_kernel -c 1 -f -o gpurun_out/decoder_r01_final python tools/prof_kernels.py --which decoder --impl 2 --rays 40960 --reps 1
+run timeout 300 python -m pytest tests/test_gpu_kernels.py -q -m gpu -k "window_attn" -x
+run timeout 300 python -m pytest tests/test_gpu_model.py -q -m gpu -x
+run timeout 300 python tools/prof_kernels.py --which attn --reps 10 --impl 2
+MNF_ATTN_PIPE=1 run timeout 300 python tools/prof_kernels.py --which attn --reps 10 --impl 2
+run timeout 600 ncu --set full --clock-control none --import-source on -k regex:window_attn_tc_v4_kernel -c 1 -f -o gpurun_out/attn_v4 python tools/prof_kernels.py --which attn --impl 2 --reps 1
+run timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"attn" -c 8 python tools/prof_kernels.py --which attn --impl 2 --reps 1
+run timeout 300 python tools/prof_encoder.py
 tail -5 $L
