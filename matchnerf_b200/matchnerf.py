@@ -161,11 +161,35 @@ class MatchNeRF(nn.Module):
         return {"feat_info": cond[..., :10], "color_info": cond[..., 10:19], "mask_info": cond[..., 19:22]}
 
     # ------------------------------------------------------------------ entry point used by Coach
+    def get_video_rendering_path(self, tgt_pose, ref_poses, mode, n_frames=30, batch=None):
+        """models/matchnerf.py:295-325: a list of target-pose dicts, one per video frame.  'interpolate' loops through the
+        source cameras; 'spiral' needs ``batch['c2ws_all']`` (all scene cameras) and uses the target near / far."""
+        from . import camera_paths
+        paths = []
+        for b, w2cs in enumerate(ref_poses["extrinsics"]):
+            if mode == "interpolate":
+                sq = torch.eye(4, dtype=torch.float64).repeat(w2cs.shape[0], 1, 1)
+                sq[:, :3, :] = w2cs.detach().to("cpu", torch.float64)
+                c2ws = torch.linalg.inv(sq)[:, :3, :].to(torch.float32).numpy()          # float64 inverse, as :302-303
+                path = camera_paths.interpolate_path(c2ws, n_frames)
+            elif mode == "spiral":
+                assert batch is not None, "Must provide all c2ws and near_far for getting spiral rendering path."
+                c2ws_all = batch["c2ws_all"][b].detach().cpu().numpy()
+                near_far = tgt_pose["near_fars"][b].detach().cpu().numpy().tolist()
+                path = camera_paths.spiral_path(c2ws_all, near_far, rads_scale=float(get_opt(self.opts, "nerf.video_rads_scale", 0.1)),
+                                                n_frames=n_frames)
+            else:
+                raise Exception(f"Unknown video rendering path mode {mode}")
+            paths.append(torch.linalg.inv(torch.tensor(path))[:, :3].to(torch.float32))      # back to world->camera, :317
+        paths = torch.stack(paths, dim=0)                                                     # [B, n_frames, 3, 4]
+        return [dict(extrinsics=paths[:, f], intrinsics=tgt_pose["intrinsics"].clone().detach(),
+                     near_fars=tgt_pose["near_fars"].clone().detach()) for f in range(paths.shape[1])]
+
+    # ------------------------------------------------------------------ entry point used by Coach
     def forward(self, batch, mode=None, render_video=False, render_path_mode="interpolate"):
-        """models/matchnerf.py:32-73: encoder once, then random rays (train) or the full image; appends
-        rgb / depth / opacity (and ray_idx in train mode) to ``batch`` and returns it."""
-        if render_video:
-            raise NotImplementedError("matchnerf_b200: video path rendering (models/matchnerf.py:295-325) is not built yet")
+        """models/matchnerf.py:32-73: encoder once, then random rays (train), the full image, or -- with ``render_video`` --
+        every frame of a camera path (one encoder pass amortised over all frames); appends rgb / depth / opacity (and
+        ray_idx in train mode) to ``batch`` and returns it.  Video frames are moved to the host and concatenated on dim 0."""
         V = self.n_src_views
         ref_images = batch["images"][:, :V]
         # The kernels take the cameras as host values inside mnf_scene.  Fetch them BEFORE queueing any GPU work: one
@@ -174,22 +198,34 @@ class MatchNeRF(nn.Module):
         tgt_pose, ref_poses = self.extract_poses(batch)
         tgt_pose = {k: v.detach().cpu() for k, v in tgt_pose.items()}
         ref_poses = {k: v.detach().cpu() for k, v in ref_poses.items()}
+        if render_video:
+            assert mode in ["test", "val"], f"Do NOT render video in mode {mode}, change to either 'test' or 'val'."
+            frames = self.get_video_rendering_path(tgt_pose, ref_poses, render_path_mode,
+                                                   int(get_opt(self.opts, "nerf.video_n_frames", 30)), batch)
+        else:
+            frames = [tgt_pose]
         ref_feats_list = self.get_img_feat(ref_images, attn_splits_list=get_opt(self.opts, "encoder.attn_splits_list", [2]),
                                            cur_n_src_views=V)
         B, _, _, H, W = ref_images.shape
         n_rand = int(get_opt(self.opts, f"nerf.rand_rays_{mode}", 0) or 0)
-        if n_rand and mode in ("train", "test-optim"):
-            batch["ray_idx"] = torch.randperm(H * W, device=ref_images.device)[: n_rand // B]
-            ret = self.render(self.opts, tgt_pose, ray_idx=batch["ray_idx"], mode=mode, ref_poses=ref_poses,
-                              ref_images=ref_images, ref_feats_list=ref_feats_list)
-        elif n_rand:
-            ret = self.render_by_slices(self.opts, tgt_pose, mode=mode, ref_poses=ref_poses, ref_images=ref_images,
-                                        ref_feats_list=ref_feats_list)
-        else:
-            ret = self.render(self.opts, tgt_pose, mode=mode, ref_poses=ref_poses, ref_images=ref_images,
-                              ref_feats_list=ref_feats_list)
-        for k, v in ret.items():
-            batch[k] = v
+        collected: Dict[str, list] = {}
+        for cur_pose in frames:
+            if n_rand and mode in ("train", "test-optim"):
+                batch["ray_idx"] = torch.randperm(H * W, device=ref_images.device)[: n_rand // B]
+                ret = self.render(self.opts, cur_pose, ray_idx=batch["ray_idx"], mode=mode, ref_poses=ref_poses,
+                                  ref_images=ref_images, ref_feats_list=ref_feats_list)
+            elif n_rand:
+                ret = self.render_by_slices(self.opts, cur_pose, mode=mode, ref_poses=ref_poses, ref_images=ref_images,
+                                            ref_feats_list=ref_feats_list)
+            else:
+                ret = self.render(self.opts, cur_pose, mode=mode, ref_poses=ref_poses, ref_images=ref_images,
+                                  ref_feats_list=ref_feats_list)
+            for k, v in ret.items():
+                collected.setdefault(k, []).append(v.detach().to("cpu", non_blocking=True) if render_video else v)
+        if render_video and ref_images.is_cuda:
+            torch.cuda.current_stream(ref_images.device).synchronize()      # the per-frame device->host copies
+        for k, v in collected.items():
+            batch[k] = torch.cat(v, dim=0) if len(v) > 1 else v[0]
         return batch
 
 

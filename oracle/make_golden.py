@@ -228,10 +228,40 @@ def main():
                         images=imgs.numpy(), feat8=ref_feats[0][0].numpy(),
                         feat4_ch0mod8=ref_feats[1][0][:, ::8].contiguous().numpy())
 
+    report.append(video_path_goldens(out_dir))
+
     with open(os.path.join(out_dir, "REPORT.txt"), "w") as f:
         f.write("generated by oracle/make_golden.py against the reference at %s (torch %s)\n" % (REF, torch.__version__))
         f.write("\n".join(report) + "\n")
     print("\n".join(report))
+
+
+def video_path_goldens(out_dir: str) -> str:
+    """Camera paths of the video mode (misc/camera.py:382-468) from the unmodified reference, for
+    tests/test_host_cpu.py::test_video_paths_match_reference (host-side numpy, no GPU involved)."""
+    from misc import camera as refcam                           # the reference
+    from scipy.spatial.transform import Rotation
+    from oracle import synth
+    extr, _, _ = synth.synthetic_cameras(64, 96)
+    w2c = torch.eye(4)[None].repeat(3, 1, 1)
+    w2c[:, :3] = extr[0, :3, :3]
+    c2w = torch.linalg.inv(w2c.double()).float().numpy()
+    g = {"interp_in": c2w}
+    for n in (6, 30):
+        g[f"interp_{n}"] = refcam.get_interpolate_render_path(c2w[:, :3], n)
+    rng = np.random.default_rng(0)
+    eul = np.array([[170., 5., -175.], [-175., -3., 178.], [160., 10., 170.]])      # Euler angles straddling +-180 degrees
+    c2w2 = np.tile(np.eye(4), (3, 1, 1))
+    c2w2[:, :3, :3] = Rotation.from_euler("xyz", eul, degrees=True).as_matrix()
+    c2w2[:, :3, 3] = rng.normal(size=(3, 3))
+    g["interp_wrap_in"], g["interp_wrap_9"] = c2w2, refcam.get_interpolate_render_path(c2w2[:, :3], 9)
+    M = 12
+    c2wa = np.tile(np.eye(4), (M, 1, 1))
+    c2wa[:, :3, :3] = Rotation.from_euler("xyz", rng.normal(scale=8, size=(M, 3)), degrees=True).as_matrix()
+    c2wa[:, :3, 3] = rng.normal(scale=0.5, size=(M, 3))
+    g["spiral_in"], g["spiral_10"] = c2wa, refcam.get_spiral_render_path(c2wa[:, :3], [2.0, 6.0], rads_scale=0.1, N_views=10)
+    np.savez_compressed(os.path.join(out_dir, "video_paths.npz"), **g)
+    return "video paths: interpolate (6, 30, wrap-around 9 frames) and spiral (10 frames) from misc/camera.py"
 
 
 if __name__ == "__main__":

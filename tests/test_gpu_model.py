@@ -92,3 +92,27 @@ def test_full_size_dtu_properties():
     idx = torch.arange(1000, H * W, 4099)
     o = oracle_render(synth.synthetic_decoder(0), feats, imgs, extr, intr, nf, idx, S)
     assert rms(a.rgb[0, idx], o[0]) < 2e-3
+
+
+def test_video_mode_renders_every_frame_of_the_path():
+    """forward(render_video=True) (models/matchnerf.py:42-71): one encoder pass, one full render per path pose, frames
+    moved to the host and concatenated on dim 0; each frame equals a stand-alone render at that pose."""
+    H, W, S = 64, 96, 16
+    m, opt = build_model(S, **{"nerf.rand_rays_test": 2000})
+    opt.nerf["video_n_frames"] = 6
+    g = torch.Generator().manual_seed(8)
+    images = torch.rand(1, 4, 3, H, W, generator=g)
+    extr, intr, nf = synth.synthetic_cameras(H, W)
+    batch = AttrDict(images=images.to(DEV), extrinsics=extr.to(DEV), intrinsics=intr.to(DEV), near_fars=nf.to(DEV))
+    with torch.no_grad():
+        out = m(AttrDict(batch), mode="test", render_video=True, render_path_mode="interpolate")
+        assert out.rgb.shape == (6, H * W, 3) and out.depth.shape == (6, H * W, 1) and not out.rgb.is_cuda
+        tgt, ref = m.extract_poses(batch)
+        frames = m.get_video_rendering_path(tgt, ref, "interpolate", 6, batch)
+        feats = m.get_img_feat(batch["images"][:, :3])
+        for f in (0, 3, 5):
+            one = m.render_by_slices(opt, frames[f], mode="test", ref_poses=ref, ref_images=batch["images"][:, :3], ref_feats_list=feats)
+            assert rms(one.rgb[0], out.rgb[f]) < 1e-5 and rms(one.opacity[0], out.opacity[f]) < 1e-5
+    assert 0.02 < float(out.opacity.mean()) < 0.98
+    with pytest.raises(AssertionError):
+        m(AttrDict(batch), mode="train", render_video=True)

@@ -2,6 +2,8 @@
 feature regrouping, and the guarantee that nothing silently runs on the CPU."""
 import os
 
+import numpy as np
+
 import pytest
 import torch
 import yaml
@@ -114,3 +116,37 @@ def test_sine_position_matches_oracle():
     from matchnerf_b200.gmflow import sine_position
     from oracle.encoder_oracle import sine_position as ref
     assert torch.allclose(sine_position(4, 6, 128, "cpu"), ref(4, 6, 128), atol=1e-6)
+
+
+def test_video_paths_match_reference(golden_dir):
+    """camera_paths restates misc/camera.py:382-468; goldens come from the unmodified reference (oracle/make_golden.py)."""
+    from matchnerf_b200 import camera_paths as cp
+    from tests.helpers import load_npz
+    z = load_npz(golden_dir, "video_paths.npz")
+    for n in (6, 30):
+        got = cp.interpolate_path(z["interp_in"][:, :3], n)
+        assert got.shape == (3 * (n // 3), 4, 4) and np.abs(got - z[f"interp_{n}"]).max() < 1e-9
+    assert np.abs(cp.interpolate_path(z["interp_wrap_in"][:, :3], 9) - z["interp_wrap_9"]).max() < 1e-9   # +-180 degree unwrap
+    assert np.abs(cp.spiral_path(z["spiral_in"][:, :3], [2.0, 6.0], 0.1, 10) - z["spiral_10"]).max() < 1e-9
+
+
+def test_video_rendering_path_poses():
+    """get_video_rendering_path (models/matchnerf.py:295-325): n_frames pose dicts; the first interpolated frame is
+    source view 0, frame n/3 is source view 1; spiral mode needs batch['c2ws_all']."""
+    from matchnerf_b200.matchnerf import MatchNeRF
+    m = MatchNeRF(make_opts()).eval()
+    extr, intr, nf = synth.synthetic_cameras(32, 48)
+    batch = AttrDict(images=torch.rand(1, 4, 3, 32, 48), extrinsics=extr, intrinsics=intr, near_fars=nf)
+    tgt, ref = m.extract_poses(batch)
+    frames = m.get_video_rendering_path(tgt, ref, "interpolate", n_frames=6, batch=batch)
+    assert len(frames) == 6 and frames[0]["extrinsics"].shape == (1, 3, 4) and frames[0]["intrinsics"].shape == (1, 3, 3)
+    assert torch.allclose(frames[0]["extrinsics"][0], extr[0, 0, :3], atol=1e-5)
+    assert torch.allclose(frames[2]["extrinsics"][0], extr[0, 1, :3], atol=1e-5)
+    assert torch.equal(frames[3]["near_fars"], tgt["near_fars"])
+    with pytest.raises(Exception):
+        m.get_video_rendering_path(tgt, ref, "zigzag", n_frames=6, batch=batch)
+    sq = torch.eye(4).repeat(4, 1, 1)
+    sq[:, :3] = extr[0, :, :3]
+    batch["c2ws_all"] = torch.linalg.inv(sq)[None]
+    sp = m.get_video_rendering_path(tgt, ref, "spiral", n_frames=5, batch=batch)
+    assert len(sp) == 5 and torch.isfinite(sp[4]["extrinsics"]).all()
