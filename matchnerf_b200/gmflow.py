@@ -114,8 +114,26 @@ class TransformerLayer(nn.Module):
                                attn_num_splits, shift)
         msg = self.norm1(self.merge(msg))
         if not self.no_ffn:
-            msg = self.norm2(self.mlp(torch.cat([source, msg], dim=-1)))
+            msg = self.norm2(self._ffn(torch.cat([source, msg], dim=-1)))
         return source + msg
+
+    # dtype of the FFN's operands and 1024-wide hidden tensor.  The TF32 path (None) already rounds every GEMM operand to a
+    # 10-bit mantissa; storing the hidden activations as fp16 (same mantissa, fp32 accumulation in both GEMMs, GELU
+    # evaluated in fp32 inside the kernel) halves the 126 MB-per-layer hidden round trips.  Inference only.
+    ffn_dtype = torch.float16
+
+    def _ffn(self, x):
+        dt = self.ffn_dtype
+        if dt is None or not x.is_cuda or (torch.is_grad_enabled() and x.requires_grad):
+            return self.mlp(x)
+        w1, w2 = self._ffn_weights(dt)
+        return F.linear(F.gelu(F.linear(x.to(dt), w1)), w2).float()
+
+    def _ffn_weights(self, dt):
+        key = (dt, self.mlp[0].weight._version, self.mlp[2].weight._version, self.mlp[0].weight.data_ptr())
+        if getattr(self, "_ffn_cache", None) is None or self._ffn_cache[0] != key:
+            self._ffn_cache = (key, self.mlp[0].weight.detach().to(dt), self.mlp[2].weight.detach().to(dt))
+        return self._ffn_cache[1], self._ffn_cache[2]
 
 
 class TransformerBlock(nn.Module):
@@ -231,11 +249,18 @@ class GMFlow(nn.Module):
         if feature_upsampler == "network":
             self.featup_net = UpSampler(feature_channels, upsample_factor)
 
+    _norm_consts = {}
+
     @staticmethod
     def normalize_images(images):
-        mean = torch.tensor([0.485, 0.456, 0.406], device=images.device).view(1, 1, 3, 1, 1)
-        std = torch.tensor([0.229, 0.224, 0.225], device=images.device).view(1, 1, 3, 1, 1)
-        return (images - mean) / std
+        """ImageNet mean / std normalisation (models/gmflow/gmflow.py:82-89).  The two constant tensors are created once per
+        device: a fresh torch.tensor(...) per call is a pageable host->device copy in the middle of the launch stream."""
+        c = GMFlow._norm_consts.get(images.device)
+        if c is None:
+            c = (torch.tensor([0.485, 0.456, 0.406], device=images.device).view(1, 1, 3, 1, 1),
+                 torch.tensor([0.229, 0.224, 0.225], device=images.device).view(1, 1, 3, 1, 1))
+            GMFlow._norm_consts[images.device] = c
+        return (images - c[0]) / c[1]
 
     matmul_precision = "tf32"      # "tf32" | "fp32" for the cuBLAS / cuDNN calls of the encoder
     # memory formats of the cuDNN convolution stacks (measured on B200, DTU size, tools/prof_encoder.py): the up-sampler
@@ -264,7 +289,10 @@ class GMFlow(nn.Module):
         h, w = f0.shape[-2:]
         if h % splits or w % splits:
             raise ValueError(f"feature map {h}x{w} not divisible by attn_splits {splits}")
-        pos = sine_position(h // splits, w // splits, self.feature_channels, f0.device).repeat(1, splits, splits)
+        pkey = (h, w, splits, f0.device)
+        if getattr(self, "_pos_cache", None) is None or self._pos_cache[0] != pkey:
+            self._pos_cache = (pkey, sine_position(h // splits, w // splits, self.feature_channels, f0.device).repeat(1, splits, splits))
+        pos = self._pos_cache[1]
         f0, f1 = self.transformer(f0 + pos, f1 + pos, splits, wo_self_attn)
         P = len(pairs)
         out0, out1 = [], []

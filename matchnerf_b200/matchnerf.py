@@ -60,11 +60,43 @@ class MatchNeRF(nn.Module):
                    near_fars=batch["near_fars"][:, :-1])
         return tgt, ref
 
+    # Replay the encoder as a CUDA graph in inference (one graph per input shape / device / parameter state): its ~250
+    # launches average 20 us of GPU work each, so eager launching leaves the GPU idle between them (5.0 -> 4.5 ms at DTU
+    # size).  The returned feature tensors are then the graph's static outputs: valid until the next get_img_feat call.
+    encoder_cuda_graph = True
+
     def get_img_feat(self, imgs, attn_splits_list=None, cur_n_src_views=3) -> List[torch.Tensor]:
         """[B,V,3,H,W] -> [[B,V,256,H/8,W/8], [B,V,256,H/4,W/4]]: view i holds the features it got as a member of
         each of its pairs (models/matchnerf.py:183-207)."""
         if attn_splits_list is None:
             attn_splits_list = get_opt(self.opts, "encoder.attn_splits_list", [2])
+        if not (self.encoder_cuda_graph and imgs.is_cuda and imgs.dtype == torch.float32 and not torch.is_grad_enabled()
+                and not torch.cuda.is_current_stream_capturing()):
+            return self._get_img_feat_eager(imgs, attn_splits_list, cur_n_src_views)
+        enc = self._unwrap(self.feat_enc)
+        params = tuple(enc.parameters())
+        key = (tuple(imgs.shape), imgs.device, tuple(attn_splits_list), cur_n_src_views, enc.matmul_precision,
+               tuple(p.data_ptr() for p in params), sum(p._version for p in params))
+        hit = getattr(self, "_enc_graph", None)
+        if hit is None or hit[0] != key:
+            static_in = imgs.detach().clone()
+            side = torch.cuda.Stream(device=imgs.device)
+            side.wait_stream(torch.cuda.current_stream(imgs.device))
+            with torch.cuda.stream(side):                       # warm-up outside the capture: lazy handles, autotuning, caches
+                for _ in range(2):
+                    self._get_img_feat_eager(static_in, attn_splits_list, cur_n_src_views)
+            torch.cuda.current_stream(imgs.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = self._get_img_feat_eager(static_in, attn_splits_list, cur_n_src_views)
+            hit = (key, graph, static_in, static_out)
+            self._enc_graph = hit
+        hit[2].copy_(imgs)
+        hit[1].replay()
+        self._feat_epoch = getattr(self, "_feat_epoch", 0) + 1     # static outputs rewritten in place: invalidates packed scenes
+        return hit[3]
+
+    def _get_img_feat_eager(self, imgs, attn_splits_list, cur_n_src_views=3) -> List[torch.Tensor]:
         V = cur_n_src_views
         out = self.feat_enc(imgs=imgs[:, :V], attn_splits_list=attn_splits_list, keep_raw_feats=True,
                             wo_self_attn=bool(get_opt(self.opts, "encoder.wo_self_attn", False)))
@@ -81,7 +113,7 @@ class MatchNeRF(nn.Module):
     def _packed_scenes(self, ref_poses, ref_images, ref_feats_list):
         """Pack (once per set of feature maps) the per-batch-item scenes the kernels read."""
         key = (ref_feats_list[0].data_ptr(), ref_feats_list[1].data_ptr(), ref_images.data_ptr(),
-               ref_feats_list[0]._version, ref_images._version, ref_poses["extrinsics"].data_ptr())
+               ref_feats_list[0]._version, ref_images._version, ref_poses["extrinsics"].data_ptr(), getattr(self, "_feat_epoch", 0))
         if self._scene_cache is not None and self._scene_cache[0] == key:
             return self._scene_cache[1]
         ctx = self._unwrap(self.nerf_dec).sync_to_library()
@@ -91,6 +123,19 @@ class MatchNeRF(nn.Module):
                                          ref_poses["extrinsics"][b], ref_poses["intrinsics"][b], ref_poses["near_fars"][b]))
         self._scene_cache = (key, scenes)
         return scenes
+
+    def _host_poses(self, batch):
+        """(tgt_pose, ref_poses) as HOST tensors.  Camera tensors that already live on the host cost nothing (callers may
+        leave extrinsics / intrinsics / near_fars there: only the images are consumed on the device); device tensors are
+        read back once and remembered by identity, so re-rendering from the same resident batch never synchronises."""
+        cams = tuple(batch[k] for k in ("extrinsics", "intrinsics", "near_fars"))
+        key = tuple((t.data_ptr(), t._version, t.device, tuple(t.shape)) for t in cams)
+        hit = getattr(self, "_pose_cache", None)
+        if hit is None or hit[0] != key or any(a is not b for a, b in zip(hit[1], cams)):
+            tgt, ref = self.extract_poses(batch)
+            hit = (key, cams, {k: v.detach().cpu() for k, v in tgt.items()}, {k: v.detach().cpu() for k, v in ref.items()})
+            self._pose_cache = hit
+        return hit[2], hit[3]
 
     def _c_scene(self, scene, tgt_pose, b):
         """mnf_scene struct of batch item b for one target camera, built once per (scene, pose) and reused by every slice."""
@@ -195,9 +240,7 @@ class MatchNeRF(nn.Module):
         # The kernels take the cameras as host values inside mnf_scene.  Fetch them BEFORE queueing any GPU work: one
         # device->host read on an idle stream, after which the encoder and every render launch are queued without a
         # host synchronisation in between (a .cpu() per slice made the GPU idle ~1 ms per DTU image).
-        tgt_pose, ref_poses = self.extract_poses(batch)
-        tgt_pose = {k: v.detach().cpu() for k, v in tgt_pose.items()}
-        ref_poses = {k: v.detach().cpu() for k, v in ref_poses.items()}
+        tgt_pose, ref_poses = self._host_poses(batch)
         if render_video:
             assert mode in ["test", "val"], f"Do NOT render video in mode {mode}, change to either 'test' or 'val'."
             frames = self.get_video_rendering_path(tgt_pose, ref_poses, render_path_mode,

@@ -52,13 +52,31 @@ def main():
 
     with torch.no_grad():
         ref = [f.clone() for f in m.get_img_feat(images)]
-        timeit("encoder default (eager, NCHW)", lambda: m.get_img_feat(images), args.reps)
+        timeit("encoder default (CUDA graph replay inside get_img_feat)", lambda: m.get_img_feat(images), args.reps)
+        m.encoder_cuda_graph = False
+        timeit("encoder eager", lambda: m.get_img_feat(images), args.reps)
         for mode in ("fp32",):
             enc.matmul_precision = mode
             f = m.get_img_feat(images)
             print(f"  precision {mode}: rel diff vs tf32 default {rel(f[0], ref[0]):.2e} / {rel(f[1], ref[1]):.2e}")
             timeit(f"encoder {mode}", lambda: m.get_img_feat(images), args.reps)
         enc.matmul_precision = "tf32"
+        from matchnerf_b200.gmflow import TransformerLayer
+        for dt in (None, torch.float16):
+            TransformerLayer.ffn_dtype = dt
+            f = m.get_img_feat(images)
+            print(f"  ffn_dtype {dt}: rel diff vs default {rel(f[0], ref[0]):.2e} / {rel(f[1], ref[1]):.2e}")
+            timeit(f"encoder ffn_dtype={dt}", lambda: m.get_img_feat(images), args.reps)
+        # fp32 reference for the error budget of both variants
+        enc.matmul_precision = "fp32"
+        TransformerLayer.ffn_dtype = None
+        f32 = [x.clone() for x in m.get_img_feat(images)]
+        enc.matmul_precision = "tf32"
+        for dt in (None, torch.float16):
+            TransformerLayer.ffn_dtype = dt
+            f = m.get_img_feat(images)
+            print(f"  ffn_dtype {dt}: rel diff vs fp32 encoder {rel(f[0], f32[0]):.2e} / {rel(f[1], f32[1]):.2e}")
+        TransformerLayer.ffn_dtype = torch.float16
 
         # CUDA graph of the default path
         static_in = images.clone()
