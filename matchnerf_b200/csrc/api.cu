@@ -221,9 +221,9 @@ int32_t mnf_decoder_load_host(mnf_ctx* ctx, const float* P, int64_t n_floats) {
 
 int64_t mnf_packed_feature_halves(int32_t V, int32_t h, int32_t w) {
   if (V <= 0 || h <= 0 || w <= 0) return 0;
-  // covers every packing: v3 = V*h*w + w + 1 texels; v4 = (V*h + 1) * 2*ceil(w/2) + 4 texels (x-pair blocks + tail)
+  // covers every packing: v3 = V*h*w + w + 1 texels; x-pair blocks = (V*h + 1) * 2*ceil(w/2) + 8 texels (blocks + tail)
   const int64_t w2 = 2 * (((int64_t)w + 1) / 2);
-  return (((int64_t)V * h + 1) * w2 + 4) * kFeatCh;
+  return (((int64_t)V * h + 1) * w2 + 8) * kFeatCh;
 }
 
 int32_t mnf_pack_features(mnf_ctx* ctx, const float* feat_nchw, int32_t V, int32_t h, int32_t w, void* out_packed, void* stream) {

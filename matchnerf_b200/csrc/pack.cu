@@ -102,10 +102,10 @@ int launch_pack_features(const float* nchw, int V, int h, int w, __half* out, cu
   if (gather_impl() == 4) {
     const int wp = (w + 1) / 2;
     const size_t body = (size_t)V * h * wp * 2 * kFeatCh;
-    // zero tail (one block row + 2 blocks: windows touching the last row / column stay in bounds); with an odd width
+    // zero tail (one block row + 4 blocks: 8 x 2 texel windows touching the last row / column stay in bounds); with an odd width
     // the unpaired texels of every row are zero as well
     if (w & 1) MNF_CUDA_TRY(cudaMemsetAsync(out, 0, body * sizeof(__half), s));
-    MNF_CUDA_TRY(cudaMemsetAsync(out + body, 0, (size_t)(wp + 2) * 2 * kFeatCh * sizeof(__half), s));
+    MNF_CUDA_TRY(cudaMemsetAsync(out + body, 0, (size_t)(wp + 4) * 2 * kFeatCh * sizeof(__half), s));
     pack_features_v4_kernel<<<grid, 256, 0, s>>>(nchw, out, h, w, wp);
     MNF_CUDA_TRY(cudaGetLastError());
     return MNF_OK;

@@ -77,7 +77,7 @@ def test_pack_features_layout(ctx):
             got = body.permute(0, 1, 2, 4, 3).reshape(V, h, 2 * wp, 256)
             assert torch.equal(got[:, :, :w], want)
             assert float(got[:, :, w:].abs().max() if 2 * wp > w else 0.0) == 0.0      # unpaired texel of an odd width
-            assert float(flat[V * h * wp * 512: V * h * wp * 512 + (wp + 2) * 512].abs().max()) == 0.0   # zero tail
+            assert float(flat[V * h * wp * 512: V * h * wp * 512 + (wp + 4) * 512].abs().max()) == 0.0   # zero tail
         else:
             p = flat[: V * h * w * 256].view(V, h, w, 256)
             pos = torch.arange(256)

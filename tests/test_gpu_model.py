@@ -1,5 +1,7 @@
 """GPU (B200): the reference-facing model interface end to end -- encoder (K-attn inside) + renderer -- against the
 oracle and the reference goldens, plus full-image properties at BASELINE config-2 size."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -67,7 +69,10 @@ def test_train_mode_random_rays_and_slicing_invariance():
         full = m(AttrDict(batch), mode="test")
         m.render_chunk = 999                         # different slicing must not change any pixel
         full2 = m(AttrDict(batch), mode="test")
-    assert torch.equal(full.rgb, full2.rgb) and torch.equal(full.depth, full2.depth)
+    if os.environ.get("MNF_GATHER_IMPL") == "4":     # tensor-core gather experiment: a ray's result depends on its 16-ray batch in the last bits
+        assert rms(full.rgb, full2.rgb) < 1e-5 and rms(full.depth, full2.depth) < 1e-4
+    else:
+        assert torch.equal(full.rgb, full2.rgb) and torch.equal(full.depth, full2.depth)
 
 
 def test_full_size_dtu_properties():
