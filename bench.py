@@ -187,6 +187,8 @@ def run_ours(args):
     model.feat_enc.load_state_dict(synth.synthetic_encoder(1))
     model.nerf_dec.load_state_dict(synth.synthetic_decoder(0))
     model.to(dev)
+    if args.chunk:
+        model.render_chunk = args.chunk
     ctx = capi.get_context(dev)
     hw = H_IMG * W_IMG
 
@@ -393,6 +395,7 @@ def main():
     ap.add_argument("--samples", type=int, default=64)
     ap.add_argument("--ref-rays", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chunk", type=int, default=0, help="rays per render launch (default: MatchNeRF.render_chunk)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -374,8 +374,8 @@ __device__ __forceinline__ void pair_products4_mixed(const uint4& a0, const uint
 
 }  // namespace
 
-template <bool kMixed>
-__global__ void __launch_bounds__(kWarps3 * 32, 4)
+template <bool kMixed, int kMinBlocks = 4>
+__global__ void __launch_bounds__(kWarps3 * 32, kMinBlocks)
 gather_cossim_kernel(const __grid_constant__ DevCams cams, const DevRays rays, const int S,
                      const __half* __restrict__ f0, const int h0, const int w0,
                      const __half* __restrict__ f1, const int h1, const int w1,
@@ -578,7 +578,14 @@ int launch_gather(const DevCams& cams, const DevRays& rays, int S, const __half*
   const int64_t blocks = (quads + kWarps3 - 1) / kWarps3;
   if ((int64_t)h0 * w0 >= (1 << 23) || (int64_t)h1 * w1 >= (1 << 23)) { set_error("feature map too large for 32-bit texel offsets"); return MNF_EUNSUPPORTED; }
   static const int mixed = [] { const char* e = getenv("MNF_GATHER_MIXED"); return e ? atoi(e) : 1; }();   // A/B knob: FHFMA pair products
-  if (mixed)
+  static const int occ = [] { const char* e = getenv("MNF_GATHER_OCC"); return e ? atoi(e) : 5; }();   // CTAs (of 4 warps) per SM: 4 -> 2.44 ms, 5 -> 2.35 ms (96 registers, no spills), 6 -> 2.34 ms per 81,920 rays x 64
+  if (mixed && occ == 5)
+    gather_cossim_kernel<true, 5><<<(unsigned)blocks, kWarps3 * 32, 0, s>>>(cams, rays, S, f0, h0, w0, f1, h1, w1,
+                                                                           reinterpret_cast<const float4*>(images), cond_f32, cond_f16);
+  else if (mixed && occ == 6)
+    gather_cossim_kernel<true, 6><<<(unsigned)blocks, kWarps3 * 32, 0, s>>>(cams, rays, S, f0, h0, w0, f1, h1, w1,
+                                                                           reinterpret_cast<const float4*>(images), cond_f32, cond_f16);
+  else if (mixed)
     gather_cossim_kernel<true><<<(unsigned)blocks, kWarps3 * 32, 0, s>>>(cams, rays, S, f0, h0, w0, f1, h1, w1,
                                                                         reinterpret_cast<const float4*>(images), cond_f32, cond_f16);
   else

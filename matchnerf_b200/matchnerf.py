@@ -27,7 +27,8 @@ from .utils import AttrDict, get_opt
 class MatchNeRF(nn.Module):
     # rays handed to one kernel launch when rendering a full image.  The reference's ``rand_rays_{mode}`` slice
     # size is a memory device (models/matchnerf.py:151-152); rays are independent, so results do not depend on it.
-    render_chunk = 81920
+    # One launch per DTU image (327,680 rays, 3.2 GB of conditioning workspace): 22.23 -> 21.95 ms per image vs 81,920.
+    render_chunk = 327680
 
     def __init__(self, opts):
         super().__init__()
