@@ -311,7 +311,7 @@ def run_ours(args):
             roofline = dict(kernel="decoder_%s_kernel" % ("tc" if impl == 2 else "ref"), bound="tensor", achieved=dec_tfs, peak=pk["tensor"],
                             unit="TFLOP/s", frac=dec_tfs / pk["tensor"], traffic=traffic.get("decoder_tc_kernel") if impl == 2 else None,
                             peak_source=pk["source"])
-        launches = args.steps * (n_chunks * 2 + 12 + 3 + 15)  # per step: gather+decoder per chunk, 12 K-attn, 3 pack kernels, 15 instance norms
+        launches = args.steps * (n_chunks * 2 + 24 + 3 + 15)  # per step: gather+decoder per chunk, 12 x (K-attn pre-pack + K-attn), 3 pack kernels, 15 instance norms
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

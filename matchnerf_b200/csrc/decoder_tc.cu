@@ -108,7 +108,7 @@ __device__ unsigned int g_trace_cap = 0;
 // so a probe costs a clock read and one store); the slot field carries slot | quarter << 2.
 // The armed buffer is latched into shared memory at kernel start: a probe must not cost a global-memory round trip
 // (it sits on the MMA issuer's critical path).
-__device__ __forceinline__ void trace(const TraceCtl& tc_, int role, int slot, int ev, unsigned it, unsigned& n) {
+[[maybe_unused]] __device__ __forceinline__ void trace(const TraceCtl& tc_, int role, int slot, int ev, unsigned it, unsigned& n) {
   if (tc_.per != 0u) {
     if (n < tc_.per)
       tc_.buf[(threadIdx.x >> 5) * tc_.per + n] = ((unsigned long long)clock64() << 24) | ((unsigned long long)(role & 15) << 20) |
@@ -147,27 +147,6 @@ __device__ __forceinline__ float act_fn(float x) {
   if constexpr (kAct == 0) return fmaxf(x, 0.f);
   else return x > 0.f ? x : expm1f(x);
 }
-// packed fp32 math (sm_100: FFMA2 / FADD2)
-__device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const float2 c) {
-  float2 d;
-  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
-      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
-      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
-      "mov.b64 {%0, %1}, rd;\n\t}"
-      : "=f"(d.x), "=f"(d.y)
-      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
-  return d;
-}
-__device__ __forceinline__ float2 fadd2(const float2 a, const float2 b) {
-  float2 d;
-  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
-      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
-      "add.rn.f32x2 rd, ra, rb;\n\t"
-      "mov.b64 {%0, %1}, rd;\n\t}"
-      : "=f"(d.x), "=f"(d.y)
-      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-  return d;
-}
 // Packed pairs of fp32 kept in ONE 64-bit register for their whole life, so that FFMA2 / FADD2 need no re-packing
 // moves (ncu of v3: 25 MOVs per 32 FFMA2 in the attention loop when pairs were rebuilt from scalar registers).
 typedef unsigned long long pk2;
@@ -176,24 +155,11 @@ __device__ __forceinline__ pk2 pk(float lo, float hi) {
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
   return r;
 }
-__device__ __forceinline__ float pk_lo(pk2 v) {
-  float lo, hi;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-  return lo;
-}
-__device__ __forceinline__ float pk_hi(pk2 v) {
-  float lo, hi;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-  return hi;
-}
+__device__ __forceinline__ float pk_lo(pk2 v) { return __uint_as_float((uint32_t)(v & 0xffffffffull)); }
+__device__ __forceinline__ float pk_hi(pk2 v) { return __uint_as_float((uint32_t)(v >> 32)); }
 __device__ __forceinline__ pk2 pk_fma(pk2 a, pk2 b, pk2 c) {
   pk2 d;
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ pk2 pk_add(pk2 a, pk2 b) {
-  pk2 d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
 __device__ __forceinline__ float ex2_fast(float x) {   // MUFU.EX2 without the denormal-range fix-up of exp2f()

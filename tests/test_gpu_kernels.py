@@ -337,3 +337,18 @@ def test_instance_norm_fused_modes(ctx, shape):
     # a constant plane: variance 0 -> output 0 (eps keeps it finite)
     c = torch.full(shape, 2.5, device=DEV)
     assert float(ctx.instance_norm(c, 0).abs().max()) < 1e-3
+
+
+@pytest.mark.parametrize("h,w,splits,shift", [(100, 100, 2, True), (96, 128, 2, False)])
+def test_window_attn_blender_llff_shapes(ctx, h, w, splits, shift):
+    """BASELINE configs[3] (Blender 800x800: 100x100 tokens, windows of 2500 keys = 19 full + 1 partial key tile) and the
+    LLFF / IBRNet size (768x1024: 96x128 tokens): tcgen05 kernel (pre-packed tiles + bulk copies) vs the fp32 CUDA-core
+    kernel on the same inputs."""
+    g = torch.Generator().manual_seed(h + w)
+    q, k, v = (torch.randn(2, h * w, 128, generator=g).to(DEV) for _ in range(3))
+    ref = ctx.window_attn(q, k, v, h, w, splits, shift, impl=1)
+    got = ctx.window_attn(q, k, v, h, w, splits, shift, impl=2)
+    nows = ctx.window_attn(q, k, v, h, w, splits, shift, impl=2, use_workspace=False)
+    torch.cuda.synchronize()
+    assert rms(got, ref) < 2e-3 * float(ref.std()) and rms(nows, ref) < 2e-3 * float(ref.std())
+    assert max_abs(got, ref) < 2e-2
