@@ -130,7 +130,7 @@ __device__ __forceinline__ float grid_unnormalize(float g, int n) {
 }
 
 // kernel launchers (defined in the .cu files; called from api.cu)
-int gather_impl();   // 3 (default) or 2 (MNF_GATHER_IMPL=2): selects the gather kernel AND the feature packing it reads
+int gather_impl();   // 3 (default) or 4 (MNF_GATHER_IMPL=4, tensor-core experiment): selects the gather kernel AND the feature packing it reads
 int launch_pack_features(const float* nchw, int V, int h, int w, __half* out, cudaStream_t s);
 int launch_pack_images(const float* nchw, int V, int H, int W, float* out, cudaStream_t s);
 int launch_gather(const DevCams& cams, const DevRays& rays, int S, const __half* f0, int h0, int w0,

@@ -13,14 +13,11 @@
 // Packing v4 (gather v4, gather_mma.cu): x-pair interleaved blocks, [V][h][ceil(w/2)][256 channels][2 texels] fp16:
 // one 32-bit word holds the same channel of texels (2i, 2i+1) of a row, i.e. one k-pair of an mma.sync B fragment;
 // channels in natural order (half0 = words 0..127, half1 = words 128..255).  A missing odd texel (w odd) is zero.
-//
-// Packing v2 (MNF_GATHER_IMPL=2, the A/B baseline): 8 lanes x 4 loads of 16 B per texel, load j of lane l being slot
-// 8*j + l: p = 64*j + 8*l + e  <->  channel (j < 2 ? 0 : 128) + 16*l + 8*(j & 1) + e.
 #include "mnf_common.cuh"
 
 namespace mnf {
 
-__global__ void pack_features_kernel(const float* __restrict__ in, __half* __restrict__ out, int hw, int layout) {
+__global__ void pack_features_kernel(const float* __restrict__ in, __half* __restrict__ out, int hw) {
   // grid: (ceil(hw/32), V); block 256 threads.  Tile = 32 pixels x 256 channels through shared memory.
   __shared__ float tile[kFeatCh][33];
   const int v = blockIdx.y;
@@ -40,13 +37,7 @@ __global__ void pack_features_kernel(const float* __restrict__ in, __half* __res
     __align__(16) __half vals[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      int c;
-      if (layout == 2) {
-        const int ld = slot >> 3, l = slot & 7;    // 16-byte slot = 8 * load + lane
-        c = (ld < 2 ? 0 : 128) + 16 * l + 8 * (ld & 1) + j;
-      } else {
-        c = (j < 4 ? 0 : 128) + 4 * slot + (j & 3);
-      }
+      const int c = (j < 4 ? 0 : 128) + 4 * slot + (j & 3);
       vals[j] = __float2half_rn(tile[c][pix]);
     }
     *reinterpret_cast<uint4*>(out + ((size_t)v * hw + p) * kFeatCh + slot * 8) = *reinterpret_cast<const uint4*>(vals);
@@ -110,7 +101,7 @@ int launch_pack_features(const float* nchw, int V, int h, int w, __half* out, cu
     MNF_CUDA_TRY(cudaGetLastError());
     return MNF_OK;
   }
-  pack_features_kernel<<<grid, 256, 0, s>>>(nchw, out, hw, gather_impl());
+  pack_features_kernel<<<grid, 256, 0, s>>>(nchw, out, hw);
   MNF_CUDA_TRY(cudaGetLastError());
   // zero tail of (w + 1) texels: the zero-weight taps of samples on the last row / column stay in bounds (gather v3)
   MNF_CUDA_TRY(cudaMemsetAsync(out + (size_t)V * hw * kFeatCh, 0, (size_t)(w + 1) * kFeatCh * sizeof(__half), s));

@@ -6,13 +6,14 @@
 // mask (:19-43) are index arithmetic on token ids; the L x L score matrix only ever exists as 128 x 128 tiles in
 // tensor memory.
 //
-// One CTA (256 threads, 2 CTAs per SM) = one 128-query tile of one window; it walks the window's keys in 128-key tiles:
-//   all threads  gather K / V rows of the tile (fp32 global -> fp16 -> SWIZZLE_128B shared-memory tiles);
-//   thread 0     S = Q K^T          tcgen05.mma  A = Q (smem, K-major)   B = K (smem, K-major)   D = S in tensor memory
-//   warps 0-3    thread = query row: online softmax on S (exp2 domain), P -> fp16 written over the dead S columns,
-//                running output O rescaled in tensor memory when a row maximum moved;
-//   thread 0     O += P V           tcgen05.mma  A = P (tensor memory)    B = V (smem, MN-major: rows = keys)
-// Tensor memory: S / P columns [0,128), O columns [128,256).
+// One CTA = one 128-query tile of one window (2 CTAs per SM); it walks the window's keys in 128-key tiles:
+//   S = Q K^T          tcgen05.mma  A = Q (smem, K-major)   B = K (smem, K-major)   D = S in tensor memory
+//   softmax warps      thread = query row: online softmax on S (exp2 domain), P -> fp16 written over the dead S columns,
+//                      running output O rescaled in tensor memory when a row maximum moved;
+//   O += P V           tcgen05.mma  A = P (tensor memory)    B = V (smem, MN-major: rows = keys)
+// Tensor memory: S / P columns [0,128), O columns [128,256).  Two kernels share this core: v3 gathers / converts its fp32
+// operand rows itself (loader warps), v4 (default, needs the caller's workspace) is fed pre-packed operand images by
+// cp.async.bulk.  (v1 / v2, the serial-phase versions, are described in DESIGN.md 4 and profiles/r01_ncu_summary.md.)
 #include <cuda_fp16.h>
 
 #include <cstdlib>
@@ -28,21 +29,6 @@ constexpr int kC = 128;
 constexpr int kTile = 128;
 constexpr int kBlockBytes = kTile * 128;    // [128 rows][64 fp16]
 constexpr int kColS = 0, kColO = 128;
-constexpr int kAttnThreads = 256;
-
-struct AttnTcSmem {
-  alignas(1024) unsigned char q[2][kBlockBytes];
-  unsigned char k[2][kBlockBytes];
-  unsigned char v[2][kBlockBytes];
-  int qtok[kTile];
-  int ktok[kTile];
-  int kreg[kTile];
-  uint32_t kmask[9][4];            // per query region: bit j of word c = key 32 c + j lies in ANOTHER shift region
-  uint32_t kinval[4];              // bit j of word c = key 32 c + j is past the end of the window (partial last tile)
-  alignas(8) uint64_t bar_s;
-  uint64_t bar_o;
-  uint32_t tmem_base;
-};
 
 struct WinGeomTc {
   int h, w, wh, ww, sh, sw, splits;
@@ -66,7 +52,7 @@ __device__ __forceinline__ uint32_t pack_h2f(float a, float b) {
 // gather 128 rows x 128 fp32 channels (token ids in tok[], -1 = zero row) into two swizzled [128][64] fp16 blocks.
 // A thread owns one 8-channel chunk (tid & 15) of rows (tid >> 4) + 16 i: all 16 of its 16-byte loads are issued before
 // the first conversion, so the tile costs one L2 round trip instead of eight (v1 walked the rows one dependent load at
-// a time and spent ~13k of its ~29k cycles per key tile waiting here).
+// a time and spent ~13k of its ~29k cycles per key tile waiting here).  256 threads.
 __device__ __forceinline__ void load_rows_swizzled(const float* __restrict__ src, const int* tok, unsigned char* dst,
                                                    float scale, int tid) {
   const int ch = tid & 15, r0 = tid >> 4;
@@ -111,203 +97,6 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
 }
 
 }  // namespace
-
-__global__ void __launch_bounds__(kAttnThreads, 2)
-window_attn_tc_v2_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
-                      float* __restrict__ out, const WinGeomTc g) {
-  extern __shared__ unsigned char smem_dyn[];
-  AttnTcSmem& sm = *reinterpret_cast<AttnTcSmem*>(smem_dyn + ((1024u - (tc::smem_u32(smem_dyn) & 1023u)) & 1023u));
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int Lw = g.wh * g.ww;
-  const int win = blockIdx.y % (g.splits * g.splits), b = blockIdx.y / (g.splits * g.splits);
-  const int wy = win / g.splits, wx = win - wy * g.splits;
-  const int q0 = blockIdx.x * kTile;
-  const size_t boff = (size_t)b * g.h * g.w * kC;
-  const bool shifted = (g.sh | g.sw) != 0;
-  const float kLog2e = 1.4426950408889634f;
-
-  if (tid == 0) {
-    tc::mbar_init(&sm.bar_s, 1);
-    tc::mbar_init(&sm.bar_o, 1);
-    tc::fence_mbar_init();
-  }
-  if (warp == 1) tc::tmem_alloc<256>(&sm.tmem_base);
-  int my_qreg = 0;
-  if (tid < kTile) {
-    int tok = -1, reg = 0;
-    if (q0 + tid < Lw) window_token(g, wy, wx, q0 + tid, tok, reg);
-    sm.qtok[tid] = tok;
-    my_qreg = reg;
-  }
-  tc::tc_fence_before_sync();
-  __syncthreads();
-  tc::tc_fence_after_sync();
-  const uint32_t tmem = sm.tmem_base;
-  // Q, pre-scaled so that scores come out in the exp2 domain: (q . k) / sqrt(C) * log2(e)
-  load_rows_swizzled(q + boff, sm.qtok, &sm.q[0][0], rsqrtf((float)kC) * kLog2e, tid);
-
-  const int row = (warp & 3) * 32 + lane;                      // softmax threads: warps 0-3
-  const uint32_t tb = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-  float m_run = -INFINITY, l_run = 0.f;
-  const int n_kt = (Lw + kTile - 1) / kTile;
-  const uint32_t idesc_qk = tc::umma_idesc_f16(128, 128, 0), idesc_pv = tc::umma_idesc_f16(128, 128, 1);
-
-  for (int kt = 0; kt < n_kt; ++kt) {
-    const int k0 = kt * kTile;
-    const int n_valid = min(kTile, Lw - k0);
-    if (tid < kTile) {
-      int tok = -1, reg = 0;
-      if (k0 + tid < Lw) window_token(g, wy, wx, k0 + tid, tok, reg);
-      sm.ktok[tid] = tok;
-      sm.kreg[tid] = reg;
-    }
-    __syncthreads();                                            // ktok visible; previous tile's MMAs were waited for below
-    if (warp < 4) {        // key masks of this tile as bit sets (one ballot per region instead of a shared-memory read per score)
-      const int kr = sm.kreg[warp * 32 + lane];
-      if (shifted) {
-#pragma unroll
-        for (int r = 0; r < 9; ++r) {
-          const uint32_t other = __ballot_sync(0xffffffffu, kr != r);
-          if (lane == 0) sm.kmask[r][warp] = other;
-        }
-      }
-      const uint32_t inval = __ballot_sync(0xffffffffu, k0 + warp * 32 + lane >= Lw);
-      if (lane == 0) sm.kinval[warp] = inval;
-    }
-    load_rows_swizzled(k + boff, sm.ktok, &sm.k[0][0], 1.0f, tid);
-    load_rows_swizzled(v + boff, sm.ktok, &sm.v[0][0], 1.0f, tid);
-    tc::fence_proxy_async_smem();
-    tc::tc_fence_before_sync();
-    __syncthreads();
-    if (warp == 0) {       // warp-uniform descriptor arithmetic, one elected lane issues (no per-MMA R2UR moves)
-      tc::tc_fence_after_sync();
-      if (tc::elect_one()) {
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t ad = tc::umma_desc_sw128(tc::smem_u32(&sm.q[ks >> 2][0]) + (ks & 3) * 32);
-          const uint64_t bd = tc::umma_desc_sw128(tc::smem_u32(&sm.k[ks >> 2][0]) + (ks & 3) * 32);
-          tc::umma_ss(tmem + kColS, ad, bd, idesc_qk, ks > 0);
-        }
-        tc::umma_commit(&sm.bar_s);
-      }
-      __syncwarp();
-    }
-    if (warp < 4) {
-      tc::mbar_wait(&sm.bar_s, kt & 1);
-      tc::tc_fence_after_sync();
-      // sweep 1: row maximum of the masked scores
-      const bool partial = n_valid < kTile;                     // warp-uniform
-      const float kMaskAdd = -100.0f * kLog2e;                  // transformer.py:41, :90
-      float mx = -INFINITY;
-#pragma unroll
-      for (int c0 = 0; c0 < kTile; c0 += 32) {
-        uint32_t r[32];
-        tc::tmem_ld32(tb + kColS + c0, r);
-        const uint32_t mk = shifted ? sm.kmask[my_qreg][c0 >> 5] : 0u;
-        const uint32_t iv = partial ? sm.kinval[c0 >> 5] : 0u;
-        tc::tmem_wait_ld();
-        if (mk | iv) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float sc = __uint_as_float(r[j]);
-            if ((mk >> j) & 1u) sc += kMaskAdd;
-            if ((iv >> j) & 1u) sc = -INFINITY;
-            mx = fmaxf(mx, sc);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
-        }
-      }
-      const float m_new = fmaxf(m_run, mx);
-      const float alpha = ex2_approx(m_run - m_new);            // 0 on the first tile (m_run = -inf)
-      // sweep 2: P = exp2(S - m) -> fp16, written over the S columns already consumed (P col = S col / 2)
-      float sum = 0.f;
-#pragma unroll
-      for (int c0 = 0; c0 < kTile; c0 += 32) {
-        uint32_t r[32];
-        tc::tmem_ld32(tb + kColS + c0, r);
-        const uint32_t mk = shifted ? sm.kmask[my_qreg][c0 >> 5] : 0u;
-        const uint32_t iv = partial ? sm.kinval[c0 >> 5] : 0u;
-        tc::tmem_wait_ld();
-        uint32_t p16[16];
-        if (mk | iv) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float s0 = __uint_as_float(r[j]), s1 = __uint_as_float(r[j + 1]);
-            if ((mk >> j) & 1u) s0 += kMaskAdd;
-            if ((mk >> (j + 1)) & 1u) s1 += kMaskAdd;
-            const float p0 = ((iv >> j) & 1u) ? 0.f : ex2_approx(s0 - m_new);
-            const float p1 = ((iv >> (j + 1)) & 1u) ? 0.f : ex2_approx(s1 - m_new);
-            sum += p0 + p1;
-            p16[j >> 1] = pack_h2f(p0, p1);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const float p0 = ex2_approx(__uint_as_float(r[j]) - m_new), p1 = ex2_approx(__uint_as_float(r[j + 1]) - m_new);
-            sum += p0 + p1;
-            p16[j >> 1] = pack_h2f(p0, p1);
-          }
-        }
-        tc::tmem_st16(tb + kColS + c0 / 2, p16);
-      }
-      l_run = l_run * alpha + sum;
-      m_run = m_new;
-      // rescale the running output when some row of this warp moved its maximum (warp-collective TMEM access)
-      if (kt > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
-#pragma unroll
-        for (int c0 = 0; c0 < kC; c0 += 32) {
-          uint32_t r[32];
-          tc::tmem_ld32(tb + kColO + c0, r);
-          tc::tmem_wait_ld();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * alpha);
-          tmem_st32(tb + kColO + c0, r);
-        }
-      }
-      tc::tmem_wait_st();
-      tc::tc_fence_before_sync();
-    }
-    __syncthreads();
-    if (warp == 0) {
-      tc::tc_fence_after_sync();
-      if (tc::elect_one()) {
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {   // 16 keys per step: A = P columns [8 ks, 8 ks + 8), B = V rows [16 ks, 16 ks + 16)
-          const uint64_t bd = tc::umma_desc_sw128_mn(tc::smem_u32(&sm.v[0][0]) + ks * 2048, kBlockBytes);
-          tc::umma_ts(tmem + kColO, tmem + kColS + ks * 8, bd, idesc_pv, (kt | ks) ? 1u : 0u);
-        }
-        tc::umma_commit(&sm.bar_o);
-      }
-      __syncwarp();
-    }
-    // K / V shared memory and the S / P columns are reused by the next tile: wait for this tile's MMAs
-    tc::mbar_wait(&sm.bar_o, kt & 1);
-    tc::tc_fence_after_sync();
-  }
-
-  if (warp < 4) {
-    const int tok = sm.qtok[row];
-    const float inv = 1.f / l_run;
-#pragma unroll
-    for (int c0 = 0; c0 < kC; c0 += 32) {
-      uint32_t r[32];
-      tc::tmem_ld32(tb + kColO + c0, r);
-      tc::tmem_wait_ld();
-      if (tok >= 0) {
-        float4* dst = reinterpret_cast<float4*>(out + boff + (size_t)tok * kC + c0);
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          dst[j] = make_float4(__uint_as_float(r[4 * j]) * inv, __uint_as_float(r[4 * j + 1]) * inv,
-                               __uint_as_float(r[4 * j + 2]) * inv, __uint_as_float(r[4 * j + 3]) * inv);
-      }
-    }
-  }
-  tc::tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 1) tc::tmem_dealloc<256>(tmem);
-}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // v3: warp-specialised pipeline.  ncu of v2: issue 20 %, 4.2 barrier + 5.3 long-scoreboard stalls per issue -- every key
@@ -862,7 +651,7 @@ int launch_window_attn_tc(const float* q, const float* k, const float* v, float*
   g.sh = (with_shift && num_splits > 1) ? g.wh / 2 : 0;
   g.sw = (with_shift && num_splits > 1) ? g.ww / 2 : 0;
   const int Lw = g.wh * g.ww;
-  static const int pipe = [] { const char* e = getenv("MNF_ATTN_PIPE"); return e ? atoi(e) : 2; }();   // A/B knob: 0 = v2 (serial phases), 1 = v3, 2 = v4
+  static const int pipe = [] { const char* e = getenv("MNF_ATTN_PIPE"); return e ? atoi(e) : 2; }();   // A/B knob: 1 = v3 even with a workspace
   dim3 grid((Lw + kTile - 1) / kTile, B * num_splits * num_splits);
   if (pipe >= 2 && workspace && workspace_bytes >= window_attn_tc_workspace_bytes(B, h, w, num_splits) &&
       ((uintptr_t)workspace & 15) == 0) {
@@ -876,7 +665,7 @@ int launch_window_attn_tc(const float* q, const float* k, const float* v, float*
     attn_pack_tiles_kernel<<<pgrid, kPackThreads, 0, s>>>(q, k, v, reinterpret_cast<unsigned char*>(workspace), g);
     MNF_CUDA_TRY(cudaGetLastError());
     window_attn_tc_v4_kernel<<<grid, kV4Threads, smem, s>>>(reinterpret_cast<const unsigned char*>(workspace), out, g);
-  } else if (pipe) {
+  } else {              // no workspace: every CTA gathers and converts its own operand tiles (v3)
     const size_t smem = sizeof(AttnPipeSmem) + 1024;
     static bool configured = false;
     if (!configured) {
@@ -884,14 +673,6 @@ int launch_window_attn_tc(const float* q, const float* k, const float* v, float*
       configured = true;
     }
     window_attn_tc_kernel<<<grid, kPipeThreads, smem, s>>>(q, k, v, out, g);
-  } else {
-    const size_t smem = sizeof(AttnTcSmem) + 1024;
-    static bool configured = false;
-    if (!configured) {
-      MNF_CUDA_TRY(cudaFuncSetAttribute(window_attn_tc_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = true;
-    }
-    window_attn_tc_v2_kernel<<<grid, kAttnThreads, smem, s>>>(q, k, v, out, g);
   }
   MNF_CUDA_TRY(cudaGetLastError());
   return MNF_OK;

@@ -80,13 +80,9 @@ def test_pack_features_layout(ctx):
             assert float(flat[V * h * wp * 512: V * h * wp * 512 + (wp + 4) * 512].abs().max()) == 0.0   # zero tail
         else:
             p = flat[: V * h * w * 256].view(V, h, w, 256)
-            pos = torch.arange(256)
-            if impl == "2":                                                # v2 packing (A/B baseline kernel)
-                ld, lane, e = pos // 64, (pos // 8) % 8, pos % 8
-                chan = torch.where(ld < 2, 0, 128) + 16 * lane + 8 * (ld & 1) + e
-            else:                                                          # v3 packing
-                lane, e = pos // 8, pos % 8
-                chan = torch.where(e < 4, 0, 128) + 4 * lane + (e & 3)
+            pos = torch.arange(256)                                        # v3 packing: slot l = channels 4l..4l+3 of both halves
+            lane, e = pos // 8, pos % 8
+            chan = torch.where(e < 4, 0, 128) + 4 * lane + (e & 3)
             assert torch.equal(p, want[..., chan])
     assert torch.equal(packed.images.cpu()[..., :3].permute(0, 3, 1, 2), imgs[0])
 
