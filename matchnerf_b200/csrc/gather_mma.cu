@@ -106,8 +106,7 @@ __device__ __forceinline__ float pair_cosine(const float2 (&acc)[2][3], const bo
     f[k] = (odd ? hi : lo) + __shfl_xor_sync(0xffffffffu, odd ? lo : hi, 1);
     if (SC == 0) f[k] += __shfl_xor_sync(0xffffffffu, f[k], 2);
   }
-  const float na = fmaxf(sqrtf(f[1]), 1e-8f), nb = fmaxf(sqrtf(f[2]), 1e-8f);
-  return __fdividef(f[0], na * nb);
+  return f[0] * rsqrtf(fmaxf(f[1], 1e-16f)) * rsqrtf(fmaxf(f[2], 1e-16f));      // max(sqrt(x), 1e-8) == sqrt(max(x, 1e-16))
 }
 
 __device__ __forceinline__ void pair_accumulate(float2 (&acc)[2][3], const float (&dA)[4][4], const float (&dB)[4][4], const bool first) {

@@ -4,8 +4,8 @@ mkdir -p gpurun_out
 L=gpurun_out/call.log
 : > $L
 run() { echo "=== $*" >> $L; ( "$@" ) >> $L 2>&1; echo "--- exit $?" >> $L; }
-run timeout 900 python -m pytest tests -q -m gpu -x
-MNF_GATHER_IMPL=4 run timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_model.py -q -m gpu -k "gather or pack or render or forward or train_mode"
-MNF_ATTN_PIPE=1 run timeout 600 python -m pytest tests/test_gpu_kernels.py -q -m gpu -k "window_attn"
-run timeout 600 python bench.py --no-cpu-baseline --steps 10
+run timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_unfused_api.py tests/test_gpu_model.py -q -m gpu -k "gather or render or unfused or forward or full_size"
+run timeout 300 python tools/prof_kernels.py --which gather --reps 10
+MNF_GATHER_OCC=6 run timeout 300 python tools/prof_kernels.py --which gather --reps 10
+run timeout 300 python tools/prof_kernels.py --which gather --reps 10 --rays 327680
 tail -5 $L
