@@ -121,3 +121,28 @@ def test_video_mode_renders_every_frame_of_the_path():
     assert 0.02 < float(out.opacity.mean()) < 0.98
     with pytest.raises(AssertionError):
         m(AttrDict(batch), mode="train", render_video=True)
+
+
+def test_blender_size_render_properties():
+    """BASELINE configs[3] size (Blender 800x800, wide baseline, white background): full-image render from given feature
+    maps (100x100 and 200x200, i.e. not L2-resident in fp32), background identity, and a strided subset vs the oracle."""
+    H, W, S = 800, 800, 32
+    m, opt = build_model(S)
+    g = torch.Generator().manual_seed(21)
+    feats = [torch.randn(1, 3, 256, H // 8, W // 8, generator=g), torch.randn(1, 3, 256, H // 4, W // 4, generator=g)]
+    imgs = torch.rand(1, 3, 3, H, W, generator=g)
+    extr, intr, nf = synth.synthetic_cameras(H, W, baseline_deg=30.0, near=2.0, far=6.0)
+    tgt = dict(extrinsics=extr[:, 3, :3].to(DEV), intrinsics=intr[:, 3].to(DEV), near_fars=nf[:, 3].to(DEV))
+    ref = dict(extrinsics=extr[:, :3, :3].to(DEV), intrinsics=intr[:, :3].to(DEV), near_fars=nf[:, :3].to(DEV))
+    fd = [f.to(DEV) for f in feats]
+    with torch.no_grad():
+        a = m.render_by_slices(opt, tgt, mode="test", ref_poses=ref, ref_images=imgs.to(DEV), ref_feats_list=fd)
+        m.nerf_setbg_opaque = True
+        b = m.render_by_slices(opt, tgt, mode="test", ref_poses=ref, ref_images=imgs.to(DEV), ref_feats_list=fd)
+    assert a.rgb.shape == (1, H * W, 3)
+    assert float(a.opacity.min()) >= 0 and float(a.opacity.max()) <= 1 + 1e-5
+    assert rms(b.rgb, a.rgb + (1 - a.opacity)) < 1e-6
+    idx = torch.arange(777, H * W, 9973)
+    o = oracle_render(synth.synthetic_decoder(0), feats, imgs, extr, intr, nf, idx, S)
+    assert rms(a.rgb[0, idx], o[0]) < 2e-3 and rms(a.opacity[0, idx], o[2]) < 4e-3
+    assert 0.02 < float(a.opacity.mean()) < 0.98
