@@ -376,7 +376,7 @@ window_attn_tc_kernel(const float* __restrict__ q, const float* __restrict__ k, 
 // underneath softmax(t) and V(t+1) underneath QK(t+1) + softmax(t+1).
 //   warps 0-3 softmax | warp 4 producer (bulk copies + shift-region bit masks) | warp 5 MMA issuer
 constexpr int kPackThreads = 256;
-constexpr int kV4Threads = 192;
+constexpr int kV4Threads = 320;              // 8 softmax warps (2 threads per query row) + producer + MMA issuer
 constexpr int kImageBytes = 2 * kBlockBytes;      // one [128][128] fp16 operand tile = two swizzled [128][64] blocks
 
 // grid (n_tiles, B * n_windows, 3): image (b, window, tile, matrix) of the workspace
@@ -413,8 +413,10 @@ struct AttnV4Smem {
   uint64_t bar_o;                  // PV(t) complete            (tcgen05.commit)
   uint64_t k_full;                 // K(t) (and Q, for t = 0) landed   (complete_tx)
   uint64_t v_full;                 // V(t) landed                      (complete_tx)
-  uint64_t p_ready;                // P(t) in tensor memory, O rescaled   (4 softmax warps)
+  uint64_t p_ready;                // P(t) in tensor memory, O rescaled   (8 softmax warps)
   uint32_t tmem_base;
+  float pmax[2][2][kTile];         // [tile parity][column half][row]: row maxima of the two threads of a row
+  float lsum[2][kTile];            // final exchange of the two partial row sums
 };
 
 __global__ void __launch_bounds__(kV4Threads, 2)
@@ -437,15 +439,15 @@ window_attn_tc_v4_kernel(const unsigned char* __restrict__ ws, float* __restrict
     tc::mbar_init(&sm.bar_o, 1);
     tc::mbar_init(&sm.k_full, 1);
     tc::mbar_init(&sm.v_full, 1);
-    tc::mbar_init(&sm.p_ready, 4);
+    tc::mbar_init(&sm.p_ready, 8);
     tc::fence_mbar_init();
   }
-  if (warp == 5) tc::tmem_alloc<256>(&sm.tmem_base);
+  if (warp == 9) tc::tmem_alloc<256>(&sm.tmem_base);
   int my_qreg = 0;
-  if (tid < kTile) {
+  if (tid < 2 * kTile) {                      // both threads of a query row need its shift region
     int tok = -1, reg = 0;
-    if (q0 + tid < Lw) window_token(g, wy, wx, q0 + tid, tok, reg);
-    sm.qtok[tid] = tok;
+    if (q0 + (tid & (kTile - 1)) < Lw) window_token(g, wy, wx, q0 + (tid & (kTile - 1)), tok, reg);
+    if (tid < kTile) sm.qtok[tid] = tok;
     my_qreg = reg;
   }
   tc::tc_fence_before_sync();
@@ -453,7 +455,7 @@ window_attn_tc_v4_kernel(const unsigned char* __restrict__ ws, float* __restrict
   tc::tc_fence_after_sync();
   const uint32_t tmem = sm.tmem_base;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ================================================================== producer
     for (int t = 0; t < n_kt; ++t) {
       const int par = t & 1;
@@ -497,7 +499,7 @@ window_attn_tc_v4_kernel(const unsigned char* __restrict__ ws, float* __restrict
       }
       __syncwarp();
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ================================================================== MMA issuer
     const uint32_t idesc_qk = tc::umma_idesc_f16(128, 128, 0), idesc_pv = tc::umma_idesc_f16(128, 128, 1);
     for (int kt = 0; kt < n_kt; ++kt) {
@@ -528,9 +530,14 @@ window_attn_tc_v4_kernel(const unsigned char* __restrict__ ws, float* __restrict
       __syncwarp();
     }
   } else {
-    // ================================================================== softmax: thread = query row
-    const int row = warp * 32 + lane;
-    const uint32_t tb = tmem + ((uint32_t)(warp * 32) << 16);
+    // ================================================================== softmax: two threads per query row
+    // warp w works on TMEM lanes 32 (w & 3) .. +31 (rows) and on column half hc = w >> 2: S columns [64 hc, 64 hc + 64),
+    // P columns [32 hc, 32 hc + 32), O columns [64 hc, 64 hc + 64).  The two threads of a row exchange their partial
+    // row maxima through shared memory (one 256-thread named barrier per key tile, buffers alternate with the tile
+    // parity); each keeps its own partial row sum until the end.
+    const int hc = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t tb = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const float kMaskAdd = -100.0f * kLog2e;                     // transformer.py:41, :90
     float m_run = -INFINITY, l_run = 0.f;
     for (int kt = 0; kt < n_kt; ++kt) {
@@ -540,7 +547,8 @@ window_attn_tc_v4_kernel(const unsigned char* __restrict__ ws, float* __restrict
       tc::tc_fence_after_sync();
       float mx = -INFINITY;
 #pragma unroll
-      for (int c0 = 0; c0 < kTile; c0 += 32) {
+      for (int c1 = 0; c1 < 64; c1 += 32) {
+        const int c0 = hc * 64 + c1;
         uint32_t r[32];
         tc::tmem_ld32(tb + kColS + c0, r);
         const uint32_t mk = shifted ? sm.kmask[par][my_qreg][c0 >> 5] : 0u;
@@ -559,17 +567,26 @@ window_attn_tc_v4_kernel(const unsigned char* __restrict__ ws, float* __restrict
           for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
         }
       }
+      sm.pmax[par][hc][row] = mx;
+      asm volatile("bar.sync 2, 256;" ::: "memory");             // the 8 softmax warps
+      mx = fmaxf(mx, sm.pmax[par][hc ^ 1][row]);
       const float m_new = fmaxf(m_run, mx);
       const float alpha = ex2_approx(m_run - m_new);             // 0 on the first tile (m_run = -inf)
+      // sweep 2: P = exp2(S - m) -> fp16.  P of key columns [c, c + 32) is stored over tensor-memory columns [c / 2, c / 2 + 16):
+      // the hc = 0 thread's P lands on S columns it has already consumed, but the hc = 1 thread's P (columns [32, 64)) lands on
+      // S columns the hc = 0 thread still has to read in its second chunk.  So hc = 1 computes both of its chunks into
+      // registers and stores them only after a barrier that hc = 0 reaches once its second chunk is in registers.
       float sum = 0.f;
+      uint32_t p16[2][16];
 #pragma unroll
-      for (int c0 = 0; c0 < kTile; c0 += 32) {
+      for (int ci = 0; ci < 2; ++ci) {
+        const int c0 = hc * 64 + ci * 32;
         uint32_t r[32];
         tc::tmem_ld32(tb + kColS + c0, r);
         const uint32_t mk = shifted ? sm.kmask[par][my_qreg][c0 >> 5] : 0u;
         const uint32_t iv = partial ? sm.kinval[par][c0 >> 5] : 0u;
         tc::tmem_wait_ld();
-        uint32_t p16[16];
+        if (ci == 1 && hc == 0) asm volatile("bar.sync 3, 256;" ::: "memory");      // all of this thread's S reads are done
         if (mk | iv) {
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
@@ -579,29 +596,34 @@ window_attn_tc_v4_kernel(const unsigned char* __restrict__ ws, float* __restrict
             const float p0 = ((iv >> j) & 1u) ? 0.f : ex2_approx(s0 - m_new);
             const float p1 = ((iv >> (j + 1)) & 1u) ? 0.f : ex2_approx(s1 - m_new);
             sum += p0 + p1;
-            p16[j >> 1] = pack_h2f(p0, p1);
+            p16[ci][j >> 1] = pack_h2f(p0, p1);
           }
         } else {
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
             const float p0 = ex2_approx(__uint_as_float(r[j]) - m_new), p1 = ex2_approx(__uint_as_float(r[j + 1]) - m_new);
             sum += p0 + p1;
-            p16[j >> 1] = pack_h2f(p0, p1);
+            p16[ci][j >> 1] = pack_h2f(p0, p1);
           }
         }
-        tc::tmem_st16(tb + kColS + c0 / 2, p16);
+        if (hc == 0) tc::tmem_st16(tb + kColS + c0 / 2, p16[ci]);
+      }
+      if (hc == 1) {
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        tc::tmem_st16(tb + kColS + 32, p16[0]);
+        tc::tmem_st16(tb + kColS + 48, p16[1]);
       }
       l_run = l_run * alpha + sum;
       m_run = m_new;
       if (kt > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {    // PV(kt-1) is complete: QK(kt) was only issued after it
 #pragma unroll
-        for (int c0 = 0; c0 < kC; c0 += 32) {
+        for (int c1 = 0; c1 < 64; c1 += 32) {
           uint32_t r[32];
-          tc::tmem_ld32(tb + kColO + c0, r);
+          tc::tmem_ld32(tb + kColO + hc * 64 + c1, r);
           tc::tmem_wait_ld();
 #pragma unroll
           for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * alpha);
-          tmem_st32(tb + kColO + c0, r);
+          tmem_st32(tb + kColO + hc * 64 + c1, r);
         }
       }
       tc::tmem_wait_st();
@@ -609,12 +631,16 @@ window_attn_tc_v4_kernel(const unsigned char* __restrict__ ws, float* __restrict
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&sm.p_ready);
     }
+    sm.lsum[hc][row] = l_run;
+    asm volatile("bar.sync 2, 256;" ::: "memory");
+    const float l_tot = sm.lsum[0][row] + sm.lsum[1][row];
     tc::mbar_wait(&sm.bar_o, (n_kt - 1) & 1);
     tc::tc_fence_after_sync();
     const int tok = sm.qtok[row];
-    const float inv = 1.f / l_run;
+    const float inv = 1.f / l_tot;
 #pragma unroll
-    for (int c0 = 0; c0 < kC; c0 += 32) {
+    for (int c1 = 0; c1 < 64; c1 += 32) {
+      const int c0 = hc * 64 + c1;
       uint32_t r[32];
       tc::tmem_ld32(tb + kColO + c0, r);
       tc::tmem_wait_ld();
@@ -629,7 +655,7 @@ window_attn_tc_v4_kernel(const unsigned char* __restrict__ ws, float* __restrict
   }
   tc::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 5) tc::tmem_dealloc<256>(tmem);
+  if (warp == 9) tc::tmem_dealloc<256>(tmem);
 }
 
 int64_t window_attn_tc_workspace_bytes(int B, int h, int w, int num_splits) {
