@@ -88,8 +88,15 @@ class MatchNeRF(nn.Module):
                     self._get_img_feat_eager(static_in, attn_splits_list, cur_n_src_views)
             torch.cuda.current_stream(imgs.device).wait_stream(side)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                static_out = self._get_img_feat_eager(static_in, attn_splits_list, cur_n_src_views)
+            try:
+                with torch.cuda.graph(graph):
+                    static_out = self._get_img_feat_eager(static_in, attn_splits_list, cur_n_src_views)
+            except RuntimeError as e:            # an op that cannot be captured on this torch build: stay eager (same kernels)
+                import warnings
+                warnings.warn(f"matchnerf_b200: encoder CUDA-graph capture failed ({e}); running the encoder eagerly")
+                self.encoder_cuda_graph = False
+                torch.cuda.synchronize(imgs.device)
+                return self._get_img_feat_eager(imgs, attn_splits_list, cur_n_src_views)
             hit = (key, graph, static_in, static_out)
             self._enc_graph = hit
         hit[2].copy_(imgs)
