@@ -402,6 +402,19 @@ attn_pack_tiles_kernel(const float* __restrict__ q, const float* __restrict__ k,
   load_rows_swizzled(src, tok_s, img, scale, tid);       // same image the v2 / v3 kernels build in shared memory
 }
 
+// ---- optional timeline trace of CTA (0, 0) (debug aid, tools/attn_trace.py): lane 0 of the MMA-issuer warp, the producer
+// warp and the two softmax warps of rows 0-31 record clock64() at protocol points.  Armed by mnf_debug_attn_trace(); a probe
+// costs one uniform branch when not armed.
+__device__ unsigned long long* g_attn_trace_buf = nullptr;
+constexpr int kAttnTraceRoles = 4, kAttnTracePer = 256;
+struct AttnTrace {
+  unsigned long long* buf;      // this role's slice, or nullptr
+  unsigned n;
+  __device__ __forceinline__ void hit(int ev) {
+    if (buf != nullptr && n < kAttnTracePer) buf[n++] = ((unsigned long long)clock64() << 8) | (unsigned)(ev & 255);
+  }
+};
+
 struct AttnV4Smem {
   alignas(1024) unsigned char q[2][kBlockBytes];
   unsigned char k[2][kBlockBytes];
@@ -454,6 +467,12 @@ window_attn_tc_v4_kernel(const unsigned char* __restrict__ ws, float* __restrict
   __syncthreads();
   tc::tc_fence_after_sync();
   const uint32_t tmem = sm.tmem_base;
+  AttnTrace tr{nullptr, 0u};
+  {
+    const int role = warp == 9 ? 0 : (warp == 8 ? 1 : (warp == 0 ? 2 : (warp == 4 ? 3 : -1)));
+    unsigned long long* tb_ = g_attn_trace_buf;
+    if (tb_ != nullptr && role >= 0 && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0) tr.buf = tb_ + role * kAttnTracePer;
+  }
 
   if (warp == 8) {
     // ================================================================== producer
@@ -462,6 +481,7 @@ window_attn_tc_v4_kernel(const unsigned char* __restrict__ ws, float* __restrict
       // K buffer and the mask buffers of parity `par` are free once QK(t-1) is complete (it was issued after PV(t-2),
       // which waited for softmax(t-2), the last reader of kmask[par])
       if (t > 0) tc::mbar_wait(&sm.bar_s, (t - 1) & 1);
+      tr.hit(20);
 #pragma unroll
       for (int w4 = 0; w4 < 4; ++w4) {
         int tok = -1, reg = 0;
@@ -490,7 +510,9 @@ window_attn_tc_v4_kernel(const unsigned char* __restrict__ ws, float* __restrict
         tc::bulk_g2s(&sm.k[0][0], timg + kImageBytes, kBlockBytes, &sm.k_full);
         tc::bulk_g2s(&sm.k[1][0], timg + kImageBytes + kBlockBytes, kBlockBytes, &sm.k_full);
       }
+      tr.hit(21);
       if (t > 0) tc::mbar_wait(&sm.bar_o, (t - 1) & 1);          // V buffer free: PV(t-1) complete
+      tr.hit(22);
       if (lane == 0) {
         const unsigned char* timg = wbase + (size_t)t * 3 * kImageBytes;
         tc::mbar_arrive_expect_tx(&sm.v_full, kImageBytes);
@@ -504,7 +526,9 @@ window_attn_tc_v4_kernel(const unsigned char* __restrict__ ws, float* __restrict
     const uint32_t idesc_qk = tc::umma_idesc_f16(128, 128, 0), idesc_pv = tc::umma_idesc_f16(128, 128, 1);
     for (int kt = 0; kt < n_kt; ++kt) {
       tc::mbar_wait(&sm.k_full, kt & 1);
+      tr.hit(1);
       if (kt > 0) tc::mbar_wait(&sm.bar_o, (kt - 1) & 1);        // S / P columns free, O accumulation ordered
+      tr.hit(2);
       tc::tc_fence_after_sync();
       if (tc::elect_one()) {
 #pragma unroll
@@ -516,8 +540,11 @@ window_attn_tc_v4_kernel(const unsigned char* __restrict__ ws, float* __restrict
         tc::umma_commit(&sm.bar_s);
       }
       __syncwarp();
+      tr.hit(3);
       tc::mbar_wait(&sm.p_ready, kt & 1);
+      tr.hit(4);
       tc::mbar_wait(&sm.v_full, kt & 1);
+      tr.hit(5);
       tc::tc_fence_after_sync();
       if (tc::elect_one()) {
 #pragma unroll
@@ -528,6 +555,7 @@ window_attn_tc_v4_kernel(const unsigned char* __restrict__ ws, float* __restrict
         tc::umma_commit(&sm.bar_o);
       }
       __syncwarp();
+      tr.hit(6);
     }
   } else {
     // ================================================================== softmax: two threads per query row
@@ -544,6 +572,7 @@ window_attn_tc_v4_kernel(const unsigned char* __restrict__ ws, float* __restrict
       const int par = kt & 1;
       const bool partial = Lw - kt * kTile < kTile;              // warp-uniform
       tc::mbar_wait(&sm.bar_s, par);
+      tr.hit(10);
       tc::tc_fence_after_sync();
       float mx = -INFINITY;
 #pragma unroll
@@ -568,7 +597,9 @@ window_attn_tc_v4_kernel(const unsigned char* __restrict__ ws, float* __restrict
         }
       }
       sm.pmax[par][hc][row] = mx;
+      tr.hit(11);
       asm volatile("bar.sync 2, 256;" ::: "memory");             // the 8 softmax warps
+      tr.hit(12);
       mx = fmaxf(mx, sm.pmax[par][hc ^ 1][row]);
       const float m_new = fmaxf(m_run, mx);
       const float alpha = ex2_approx(m_run - m_new);             // 0 on the first tile (m_run = -inf)
@@ -615,6 +646,7 @@ window_attn_tc_v4_kernel(const unsigned char* __restrict__ ws, float* __restrict
       }
       l_run = l_run * alpha + sum;
       m_run = m_new;
+      tr.hit(13);
       if (kt > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {    // PV(kt-1) is complete: QK(kt) was only issued after it
 #pragma unroll
         for (int c1 = 0; c1 < 64; c1 += 32) {
@@ -629,6 +661,7 @@ window_attn_tc_v4_kernel(const unsigned char* __restrict__ ws, float* __restrict
       tc::tmem_wait_st();
       tc::tc_fence_before_sync();
       __syncwarp();
+      tr.hit(14);
       if (lane == 0) tc::mbar_arrive(&sm.p_ready);
     }
     sm.lsum[hc][row] = l_run;
@@ -705,3 +738,10 @@ int launch_window_attn_tc(const float* q, const float* k, const float* v, float*
 }
 
 }  // namespace mnf
+
+// Debug aid (tools/attn_trace.py; not part of include/matchnerf_b200.h): arm (device buffer of 4 x 256 uint64) or disarm (NULL)
+// the timeline trace of the v4 attention kernel.
+extern "C" int32_t mnf_debug_attn_trace(void* dev_buf) {
+  unsigned long long* p = reinterpret_cast<unsigned long long*>(dev_buf);
+  return cudaMemcpyToSymbol(mnf::g_attn_trace_buf, &p, sizeof(p)) == cudaSuccess ? 0 : -3;
+}

@@ -4,5 +4,7 @@ mkdir -p gpurun_out
 L=gpurun_out/call.log
 : > $L
 run() { echo "=== $*" >> $L; ( "$@" ) >> $L 2>&1; echo "--- exit $?" >> $L; }
-run timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 4 --steps 10 --warmup 3
+run timeout 300 python tools/attn_trace.py
+run timeout 300 python tools/attn_trace.py --shift
+run timeout 300 python tools/prof_kernels.py --which attn --reps 10 --impl 2
 tail -5 $L
