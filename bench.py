@@ -313,6 +313,10 @@ def run_ours(args):
                             peak_source=pk["source"])
         launches = args.steps * (n_chunks * 2 + 24 + 3 + 15)  # per step: gather+decoder per chunk, 12 x (K-attn pre-pack + K-attn), 3 pack kernels, 15 instance norms
 
+    parity = None
+    if rank == 0 and world == 1:
+        parity = parity_vs_reference_golden(ctx, S)
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline = cpu_baseline_sample(S)
@@ -330,10 +334,42 @@ def run_ours(args):
                                    % (hw * S * 64 / 1e9)),
                     clocks=clocks,
                     e2e=dict(value=e2e_value, unit="rays/s", ms_per_step=ms_e2e, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
-                    gpu_launches=launches, roofline=roofline, kernels=kernels, cpu_baseline=cpu_baseline)
+                    gpu_launches=launches, roofline=roofline, kernels=kernels, cpu_baseline=cpu_baseline, parity=parity)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def parity_vs_reference_golden(ctx, S):
+    """BASELINE configs[0] (1024 rays x S samples x 3 views, random feature maps) through the C ABI against the committed outputs of
+    the UNMODIFIED reference (tests/golden/config1_synth_S*.npz, made by oracle/make_golden.py): rgb RMS and the PSNR delta
+    against a common pseudo ground truth (misc/metrics.py:35-41 formula) -- the north-star bar is 0.01 dB.  Untimed."""
+    import numpy as np
+    from matchnerf_b200 import capi
+    from oracle import synth
+    path = os.path.join(ROOT, "tests", "golden", f"config1_synth_S{S}.npz")
+    if not os.path.exists(path):
+        return None
+    z = np.load(path)
+    feats, imgs, g = synth.synthetic_scene(H_IMG, W_IMG, seed=1234)
+    extr, intr, nf = synth.synthetic_cameras(H_IMG, W_IMG)
+    ray_idx = torch.randperm(H_IMG * W_IMG, generator=g)[:1024]
+    dev = ctx.device
+    ctx.load_decoder(synth.synthetic_decoder(0))
+    packed = ctx.pack_scene([feats[0][0].to(dev), feats[1][0].to(dev)], imgs[0].to(dev), extr[0, :3], intr[0, :3], nf[0, :3])
+    sc = packed.c_scene(extr[0, 3, :3], intr[0, 3], nf[0, 3])
+    cfg = capi.DecoderCfg()
+    cfg.n_samples, cfg.raytrans_act, cfg.raytrans_posenc, cfg.density_maskfill = S, 0, 0, 0
+    rgb = ctx.render_rays(sc, cfg, ray_idx=ray_idx.to(dev))[0].cpu().double()
+    ref = torch.from_numpy(z["rgb"]).double()
+    gt = ref + 0.045 * torch.randn(ref.shape, generator=torch.Generator().manual_seed(0), dtype=torch.float32).double()
+
+    def psnr(a):
+        return -10.0 * float(torch.log10(((a - gt) ** 2).mean()))
+
+    return dict(case=f"BASELINE configs[0]: 1024 rays x {S} samples vs the unmodified reference's fp32 outputs (tests/golden)",
+                rgb_rms=float(((rgb - ref) ** 2).mean().sqrt()), psnr_ref_db=psnr(ref), psnr_ours_db=psnr(rgb),
+                psnr_delta_db=psnr(rgb) - psnr(ref), bar_db=0.01)
 
 
 def _tc_decoder_ok(ctx, sc, cfg) -> bool:
