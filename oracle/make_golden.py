@@ -82,7 +82,7 @@ def main():
     from oracle import render_oracle as RO
     from oracle import synth
 
-    out_dir = os.path.join(ROOT, "tests", "golden")
+    out_dir = os.environ.get("MATCHNERF_GOLDEN_OUT") or os.path.join(ROOT, "tests", "golden")   # override: reproducibility check
     os.makedirs(out_dir, exist_ok=True)
     torch.set_grad_enabled(False)
     report = []
