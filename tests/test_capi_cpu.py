@@ -86,3 +86,12 @@ def test_calls_fail_loudly_without_gpu(lib_path):
     with pytest.raises(RuntimeError):
         capi.Context()
     assert lib.mnf_render_workspace_bytes(1024, 64) >= 1024 * 64 * (22 * 4 + 32 * 2)
+
+
+def test_integration_doc_covers_every_compute_entry_point():
+    """INTEGRATION.md must say, for every compute entry point of the header, which reference code it replaces."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    compute = [n for n in declared_functions() if n.endswith("_fwd") or n in ("mnf_pack_features", "mnf_pack_images", "mnf_decoder_load_host")]
+    assert len(compute) >= 10
+    missing = [n for n in compute if f"`{n}`" not in doc]
+    assert not missing, f"INTEGRATION.md lacks {missing}"
