@@ -565,14 +565,17 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
           dir[1] = ux * E[4] + uy * E[5] + uz * E[6];
           dir[2] = ux * E[8] + uy * E[9] + uz * E[10];
         }
+        TRACE_TRUNK(30);
         // direction term of the colour head, one vector per ray (the ray's threads split its 64 outputs)
         for (int o2 = s; o2 < 64; o2 += S)
           sm.dirvec[slot][ray_local][o2] = sm.p.views_dir[o2 * 3] * dir[0] + sm.p.views_dir[o2 * 3 + 1] * dir[1] +
                                            sm.p.views_dir[o2 * 3 + 2] * dir[2] + sm.p.views_b[o2];
+        TRACE_TRUNK(31);
         // encoding order (cond_nerf.py:108-116, :56-57): x, sin(2^k x) k-major, cos(2^k x) k-major, zero pad
         float sn[3], cs[3];
 #pragma unroll
         for (int i = 0; i < 3; ++i) sincosf(x[i], &sn[i], &cs[i]);
+        TRACE_TRUNK(32);
         uint32_t e[32];
         float prev = 0.f;  // pairs are emitted in index order: idx 0..63
         auto put = [&](int idx, float v) {
@@ -602,6 +605,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
           tc::tmem_st16(tb + kColEnc, lo);
           tc::tmem_st16(tb + kColEnc + 16, hi);
         }
+        TRACE_TRUNK(33);
         uint32_t cnd[16];
         if (valid) {
           const uint4* src = reinterpret_cast<const uint4*>(cond + n_glob * kCondPad);
@@ -614,6 +618,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
 #pragma unroll
           for (int j = 0; j < 16; ++j) cnd[j] = 0u;
         }
+        TRACE_TRUNK(34);
         {  // visibility masks live at cond[19..21]
           const __half2 h9 = *reinterpret_cast<const __half2*>(&cnd[9]);
           const __half2 h10 = *reinterpret_cast<const __half2*>(&cnd[10]);
@@ -621,9 +626,11 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         }
         cnd[11] = (cnd[11] & 0xffff0000u) | 0x3c00u;   // pad column 22 = 1.0: multiplies the gate's bias column
         tc::tmem_st16(tb + kColCond, cnd);
+        TRACE_TRUNK(35);
         tc::tmem_wait_st();
         tc::tc_fence_before_sync();
         trunk_barrier(slot);          // dirvec visible to the whole slot before the heads epilogue
+        TRACE_TRUNK(36);
         tc::mbar_arrive(&sm.a_ready[slot]);
       }
 
@@ -687,6 +694,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
           }
           xr[j] = v;
         }
+        TRACE_TRUNK(40);
         pk2 accrg = pk(sm.p.rgb_b[0], sm.p.rgb_b[1]), accb = pk(sm.p.rgb_b[2], 0.f);
 #pragma unroll
         for (int c0 = 16; c0 < 80; c0 += 32) {
@@ -708,6 +716,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
             }
           }
         }
+        TRACE_TRUNK(41);
         rgb[0] = 1.f / (1.f + __expf(-pk_lo(accrg)));
         rgb[1] = 1.f / (1.f + __expf(-pk_hi(accrg)));
         rgb[2] = 1.f / (1.f + __expf(-pk_lo(accb)));

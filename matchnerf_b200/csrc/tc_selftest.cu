@@ -183,3 +183,94 @@ extern "C" int32_t mnf_selftest_tmem_bw(int32_t warps, int32_t iters, int32_t co
   MNF_CUDA_TRY(cudaGetLastError());
   return MNF_OK;
 }
+
+// ---- micro-benchmark: tcgen05.mma issue / execution rate of one SM --------------------------------------------------
+// One CTA.  `iters` back-to-back groups of 8 K=16 steps (M = 128, N columns, fp16, fp32 accumulate) are issued by one
+// thread and committed once; out[0] = cycles from the first issue to the commit's arrival, out[1] = cycles the issue loop
+// itself took.  mode 0: A and B from shared memory; mode 1: A from tensor memory.  `readers` > 0: that many extra warps
+// (1..4, one per TMEM lane quarter) stream tcgen05.ld over 128 accumulator columns of another region meanwhile.
+namespace mnf {
+__global__ void __launch_bounds__(256, 1) umma_rate_kernel(int iters, int N, int mode, int readers, long long* out) {
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  unsigned char* smem = smem_dyn + ((1024u - (tc::smem_u32(smem_dyn) & 1023u)) & 1023u);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  __shared__ volatile int done;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (128 * 128 + 256 * 128) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    tc::mbar_init(&bar, 1);
+    tc::fence_mbar_init();
+    done = 0;
+  }
+  if (warp == 0) tc::tmem_alloc<512>(&slot);
+  tc::fence_proxy_async_smem();
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  tc::tc_fence_after_sync();
+  const uint32_t tmem = slot;
+  if (warp < 4) {   // zero the A operand columns [256, 320)
+    uint32_t z[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) z[j] = 0u;
+    for (int c0 = 0; c0 < 64; c0 += 16) tc::tmem_st16(tmem + ((uint32_t)(warp * 32) << 16) + 256 + c0, z);
+    tc::tmem_wait_st();
+  }
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  tc::tc_fence_after_sync();
+  if (tid == 0) {
+    const uint32_t idesc = tc::umma_idesc_f16(128, N);
+    unsigned char* sA = smem;
+    unsigned char* sB = smem + 128 * 128;
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint64_t bdesc = tc::umma_desc_sw128(tc::smem_u32(sB) + (ks & 3) * 32);
+        if (mode == 0) tc::umma_ss(tmem, tc::umma_desc_sw128(tc::smem_u32(sA) + (ks & 3) * 32), bdesc, idesc, 1u);
+        else tc::umma_ts(tmem, tmem + 256 + ks * 8, bdesc, idesc, 1u);
+      }
+    }
+    const long long t1 = clock64();
+    tc::umma_commit(&bar);
+    tc::mbar_wait(&bar, 0);
+    const long long t2 = clock64();
+    out[0] = t2 - t0;
+    out[1] = t1 - t0;
+    done = 1;
+  } else if (warp >= 4 && warp < 4 + readers) {
+    const uint32_t tb = tmem + ((uint32_t)((warp & 3) * 32) << 16) + 320;
+    uint32_t acc = 0;
+    long long n = 0;
+    while (!done) {
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t r[32];
+        tc::tmem_ld32(tb + c0, r);
+        tc::tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc ^= r[j];
+      }
+      ++n;
+    }
+    if (acc == 0x12345678u) out[3] = acc;
+    if ((tid & 31) == 0 && warp == 4) out[2] = n;
+  }
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<512>(tmem);
+}
+}  // namespace mnf
+
+extern "C" int32_t mnf_selftest_umma_rate(int32_t iters, int32_t N, int32_t mode, int32_t readers, long long* out_dev, void* stream) {
+  using namespace mnf;
+  if (iters <= 0 || N < 16 || N > 256 || N % 16 || mode < 0 || mode > 1 || readers < 0 || readers > 4 || !out_dev) {
+    set_error("mnf_selftest_umma_rate: bad arguments");
+    return MNF_EINVAL;
+  }
+  const size_t smem = 128 * 128 + 256 * 128 + 1024;
+  MNF_CUDA_TRY(cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_rate_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(iters, N, mode, readers, out_dev);
+  MNF_CUDA_TRY(cudaGetLastError());
+  return MNF_OK;
+}

@@ -13,7 +13,6 @@ from __future__ import annotations
 
 import os
 import sys
-import types
 
 import numpy as np
 import torch
@@ -24,55 +23,16 @@ sys.path.insert(0, ROOT)
 REF = os.environ.get("MATCHNERF_REFERENCE", "/root/reference")
 
 
-# ---- import shim: stub the absent third-party modules on the reference's import chain
-class EasyDict(dict):
-    def __init__(self, d=None, **kw):
-        d = dict(d or {})
-        d.update(kw)
-        for k, v in d.items():
-            setattr(self, k, v)
-
-    def __setattr__(self, k, v):
-        if isinstance(v, dict) and not isinstance(v, EasyDict):
-            v = EasyDict(v)
-        elif isinstance(v, (list, tuple)):
-            v = type(v)(EasyDict(x) if isinstance(x, dict) and not isinstance(x, EasyDict) else x for x in v)
-        dict.__setitem__(self, k, v)
-        object.__setattr__(self, k, v)
-
-    __setitem__ = __setattr__
-
-    def update(self, e=None, **f):
-        d = dict(e or {})
-        d.update(f)
-        for k in d:
-            setattr(self, k, d[k])
+# ---- import shim: stubs for the absent third-party modules on the reference's import chain
+from oracle.reference_shim import EasyDict, install_shim as _install_shim, reference_options  # noqa: E402
 
 
 def install_shim():
-    m = types.ModuleType("easydict")
-    m.EasyDict = EasyDict
-    sys.modules["easydict"] = m
-    for name in ["ipdb", "termcolor", "skvideo", "skvideo.io"]:
-        sys.modules[name] = types.ModuleType(name)
-    sys.modules["ipdb"].set_trace = lambda *a, **k: None
-    sys.modules["termcolor"].colored = lambda s, **k: s
-    sys.modules["skvideo"].io = sys.modules["skvideo.io"]
-    if REF not in sys.path:
-        sys.path.insert(0, REF)
+    _install_shim(REF)
 
 
 def ref_options(S: int, **over):
-    opt = EasyDict(yaml.safe_load(open(os.path.join(REF, "configs/base.yaml"))))
-    opt.device = "cpu"
-    opt.nerf.sample_intvs = S
-    for k, v in over.items():
-        node = opt
-        ks = k.split(".")
-        for kk in ks[:-1]:
-            node = getattr(node, kk)
-        setattr(node, ks[-1], v)
-    return opt
+    return reference_options(S, "cpu", REF, **over)
 
 
 def main():
@@ -145,12 +105,17 @@ def main():
                             opacity=out.opacity[0].numpy())
 
     # ------------------------------------------------------------------ small fully-stored render cases (option coverage)
+    IBR = {"decoder.raytrans_act": "ELU", "decoder.density_maskfill": True, "decoder.raytrans_posenc": True}
     small_cases = [
         dict(name="small_base", S=16, over={}, bg=False, stratified=False),
-        dict(name="small_elu_maskfill_posenc_bg", S=24,
-             over={"decoder.raytrans_act": "ELU", "decoder.density_maskfill": True, "decoder.raytrans_posenc": True},
-             bg=True, stratified=False),
+        # ELU + raytrans_posenc + density_maskfill + white background: S = 32 runs on the tcgen05 kernel, S = 24 only on the fp32 one
+        dict(name="small_elu_maskfill_posenc_bg", S=32, over=dict(IBR), bg=True, stratified=False),
+        dict(name="small_s24_elu_maskfill_posenc_bg", S=24, over=dict(IBR), bg=True, stratified=False),
         dict(name="small_wide_baseline", S=32, over={}, bg=False, stratified=False, baseline=35.0),
+        # configs/demo_own.yaml:10-15 (ELU + posenc + maskfill, S = 128) and configs/test_video_own.yaml:10-15 (same, S = 256);
+        # wide baseline so that density_maskfill has samples no view sees
+        dict(name="demo_own_S128", S=128, over=dict(IBR), bg=False, stratified=False, baseline=30.0, n_rays=96, gain=0.5),
+        dict(name="video_own_S256", S=256, over=dict(IBR), bg=False, stratified=False, baseline=30.0, n_rays=48, gain=0.25),
     ]
     for case in small_cases:
         H, W, S = 32, 40, case["S"]
@@ -162,7 +127,7 @@ def main():
         feats, imgs, g = synth.synthetic_scene(H, W, seed=77)
         extr, intr, nf = synth.synthetic_cameras(H, W, baseline_deg=case.get("baseline", 10.0))
         batch = EasyDict(images=None, extrinsics=extr, intrinsics=intr, near_fars=nf)
-        ray_idx = torch.randperm(H * W, generator=g)[:200]
+        ray_idx = torch.randperm(H * W, generator=g)[:case.get("n_rays", 200)]
         tgt, ref = model.extract_poses(batch)
         out = model.render(opt, tgt, ray_idx=ray_idx, mode="test", ref_poses=ref, ref_images=imgs, ref_feats_list=feats)
         # reference intermediate: conditioning vector of the same points

@@ -32,7 +32,11 @@ def test_config1_synthetic_weights(golden_dir, S):
     assert rms(rgb, z["rgb"]) < 1e-6 and rms(depth, z["depth"]) < 3e-6 and rms(op, z["opacity"]) < 1e-6
 
 
-@pytest.mark.parametrize("name", ["small_base", "small_elu_maskfill_posenc_bg", "small_wide_baseline"])
+SMALL_CASES = ["small_base", "small_elu_maskfill_posenc_bg", "small_s24_elu_maskfill_posenc_bg", "small_wide_baseline",
+               "demo_own_S128", "video_own_S256"]
+
+
+@pytest.mark.parametrize("name", SMALL_CASES)
 def test_small_cases_all_options(golden_dir, name):
     z = load_npz(golden_dir, name + ".npz")
     dec = dec_from_npz(z)
@@ -46,8 +50,10 @@ def test_small_cases_all_options(golden_dir, name):
     assert rms(out[3]["cond"], z["cond"]) < 1e-6
     assert rms(out[0], z["rgb"]) < 1e-6 and rms(out[1], z["depth"]) < 3e-6 and rms(out[2], z["opacity"]) < 1e-6
     # the wide-baseline case must exercise out-of-view samples (mask = 0)
-    if name == "small_wide_baseline":
+    if name in ("small_wide_baseline", "demo_own_S128", "video_own_S256"):
         assert float(z["cond"][:, 19:].mean()) < 0.999
+    if bool(z["density_maskfill"]) and name != "small_elu_maskfill_posenc_bg" and name != "small_s24_elu_maskfill_posenc_bg":
+        assert float((z["cond"][:, 19:].sum(1) < 1).mean()) > 0.01     # density_maskfill has samples to act on
 
 
 @pytest.mark.parametrize("name", ["window_attn_8x12_k2_s0", "window_attn_8x12_k2_s1", "window_attn_12x16_k4_s1",
