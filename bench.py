@@ -1,14 +1,26 @@
 #!/usr/bin/env python
 """Benchmark of the MatchNeRF per-ray hot path on B200 (contract: see the task statement / DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--samples S]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--samples S] [--shard images|rays]
 
-A step = one pass of the hot path over one batch of synthetic input: the full forward of ONE target view per rank
-(GMFlow encoder on the 3 source views incl. K-attn, then K-gather + K-mlp-composite over all 512x640 rays, 64 depth
-samples -- BASELINE.json configs[1]) followed, for N > 1, by the single all-gather of the rendered tiles.
-``value`` = rays/s over the whole job with inputs resident in HBM; ``e2e`` = the same through ``MatchNeRF.forward``
-with the batch in pinned HOST memory (H2D of the images/cameras and D2H of rgb/depth/opacity inside the timed
-region).  ``--impl reference`` times the CPU oracle port of the reference path on the host cores.
+A step = one pass of the hot path over one batch of synthetic input: the full forward of ONE 512x640 target view (GMFlow
+encoder on the 3 source views incl. K-attn, then K-gather + K-mlp-composite over all 327,680 rays, 64 depth samples --
+BASELINE.json configs[1]).  With N > 1 ranks:
+  --shard images (default, ``scaling: weak``)  every rank renders its own target view, then ONE all-gather of the tiles;
+  --shard rays   (``scaling: strong``)         ONE target view per step for the whole job: the encoder's 6 window-attention
+                                               batch items and the rays are split over the ranks (MatchNeRF.forward does this
+                                               itself when torch.distributed is initialised), feature maps and rendered tiles
+                                               are all-gathered.
+``value`` = rays/s over the whole job with inputs resident in HBM; ``e2e`` = the same through ``MatchNeRF.forward`` with the
+batch in pinned HOST memory (H2D of the images and D2H of rgb/depth/opacity inside the timed region).
+
+Untimed extras on rank 0 at N = 1: per-kernel CUDA-event timings (``kernels``, ``roofline``), the S = 128 configuration
+(``kernels_s128``), ``parity`` of the TIMED workload (encoder + render at 512x640) against the CPU oracle and against the
+unmodified reference run in fp32 on the same GPU, ``reference_gpu`` (the unmodified reference's own rays/s on this B200: the
+north star's ">= 10x" denominator) and ``cpu_baseline`` (the unmodified reference on the host cores).
+
+``--impl reference`` times the UNMODIFIED reference (baseline/_ref or /root/reference through oracle/reference_shim.py) on
+the host cores; the oracle port is used only if the reference tree is absent.
 """
 from __future__ import annotations
 
@@ -28,6 +40,8 @@ import torch  # noqa: E402
 H_IMG, W_IMG = 512, 640
 FLOP_PER_SAMPLE = {64: 262432, 128: 266528}     # decoder, 2*MAC, unpadded
 GATHER_BYTES_PER_SAMPLE = 12520                 # 3 views x 4 taps x 512 ch x 2 B + colours + 22 floats out
+GATHER_FMA_PER_SAMPLE = 8448                    # 6144 bilinear-blend + 2304 pair-product multiply-adds
+ATTN_FLOP_PER_CALL = 4 * 24 * 1280 * 1280 * 128  # 4 L^2 C per window, 24 windows of L = 1280
 
 
 def peaks():
@@ -40,7 +54,7 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -50,8 +64,9 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.25)              # let the first sample land inside the timed region
         except Exception:
             self.proc = None
 
@@ -84,7 +99,7 @@ class ClockSampler:
         return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
 
 
-def make_opts(S: int, device: str):
+def make_opts(S: int, device: str, rand_rays_test: int = 20480):
     from matchnerf_b200.utils import AttrDict
     return AttrDict(dict(
         device=device, n_src_views=3,
@@ -93,7 +108,7 @@ def make_opts(S: int, device: str):
         decoder=dict(net_width=128, net_depth=6, skip=[4], posenc=dict(L_3D=10, L_view=0), raytrans_posenc=False,
                      density_maskfill=False, raytrans_act="ReLU"),
         nerf=dict(legacy_coord=True, wo_render_interval=True, view_dep=True, depth=dict(param="metric"), sample_intvs=S,
-                  sample_stratified=True, rand_rays_test=20480, rand_rays_train=1024)))
+                  sample_stratified=True, rand_rays_test=rand_rays_test, rand_rays_train=1024)))
 
 
 def synthetic_batch(seed: int):
@@ -104,60 +119,210 @@ def synthetic_batch(seed: int):
     return dict(images=images, extrinsics=extr, intrinsics=intr, near_fars=nf)
 
 
-# ================================================================================================ reference arm
+def workload_name(S):
+    return f"DTU 3-view 512x640 full-image forward (BASELINE configs[1]), S={S}, random-init weights"
+
+
+# ================================================================================================ the unmodified reference
+def load_reference(S: int, device: str, rand_rays_test: int = 20480):
+    """(model, EasyDict, root) of the UNMODIFIED reference with the synthetic weights of this benchmark, or None."""
+    from oracle import reference_shim as RS
+    from oracle import synth
+    ref = RS.reference_root()
+    if ref is None:
+        return None
+    RS.install_shim(ref)
+    from models.matchnerf import MatchNeRF as RefNet              # the reference's own class
+    opt = RS.reference_options(S, device, ref, **{"nerf.rand_rays_test": rand_rays_test})
+    net = RefNet(opt).eval()
+    net.feat_enc.load_state_dict(synth.synthetic_encoder(1), strict=True)
+    net.nerf_dec.load_state_dict(synth.synthetic_decoder(0), strict=True)
+    return net.to(device), RS.EasyDict, ref
+
+
+def pick_threads(fn):
+    """PyTorch's CPU ops do not scale to every core of a large host (128 threads measured 20x slower than 16 on the
+    GPU box): time a small probe at a few thread counts and keep the fastest."""
+    ncpu = os.cpu_count() or 1
+    best, best_t = 1, float("inf")
+    for n in sorted({min(ncpu, c) for c in (8, 16, 32, 64, ncpu)}):
+        torch.set_num_threads(n)
+        fn()
+        t0 = time.perf_counter()
+        fn()
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = n, dt
+    torch.set_num_threads(best)
+    return best
+
+
+def reference_cpu_sample(S: int, n_rays: int, steps: int, warmup: int):
+    """The reference's own CPU implementation of the path on a bounded sample of the benchmark workload: the encoder on the
+    three 512x640 views (timed once) and ``render`` of ``n_rays`` contiguous rays per step.  Returns (rays/s of the whole
+    image, ms per step, description dict).  Falls back to the oracle port when the reference tree is absent."""
+    batch = synthetic_batch(100)
+    hw = H_IMG * W_IMG
+    loaded = load_reference(S, "cpu")
+    with torch.no_grad():
+        if loaded is not None:
+            net, ED, ref_root = loaded
+            b = ED(images=batch["images"], extrinsics=batch["extrinsics"], intrinsics=batch["intrinsics"], near_fars=batch["near_fars"])
+            tgt, ref = net.extract_poses(b)
+            imgs = batch["images"][:, :3]
+            small = [torch.randn(1, 3, 256, 8, 10), torch.randn(1, 3, 256, 16, 20)]
+            pick_threads(lambda: net.render(net.opts, tgt, ray_idx=torch.arange(256), mode="test", ref_poses=ref,
+                                            ref_images=imgs[..., :64, :80].contiguous(), ref_feats_list=small))
+            net.get_img_feat(imgs[..., :64, :96].contiguous())            # warm-up
+            t0 = time.perf_counter()
+            feats = net.get_img_feat(imgs)
+            t_enc = time.perf_counter() - t0
+
+            def step(i):
+                first = (i * 7919 * 640) % (hw - n_rays)
+                net.render(net.opts, tgt, ray_idx=torch.arange(first, first + n_rays), mode="test", ref_poses=ref, ref_images=imgs,
+                           ref_feats_list=feats)
+            kind, what = "reference", f"UNMODIFIED reference ({ref_root}; models/matchnerf.py render + get_img_feat, fp32 torch CPU)"
+        else:
+            from oracle import encoder_oracle as EO
+            from oracle import render_oracle as RO
+            from oracle import synth
+            enc_sd, dec_sd = synth.synthetic_encoder(1), synth.synthetic_decoder(0)
+            imgs3 = batch["images"][0, :3]
+            extr, intr, nf = batch["extrinsics"], batch["intrinsics"], batch["near_fars"]
+            pf, pi, _ = synth.synthetic_scene(64, 80, seed=1)
+            e2, i2, n2 = synth.synthetic_cameras(64, 80)
+            pick_threads(lambda: RO.render_rays(dec_sd, RO.to_channels_last(pf), pi[0].permute(0, 2, 3, 1).contiguous(), e2[0, :3, :3],
+                                                i2[0, :3], n2[0, :3], e2[0, 3, :3], i2[0, 3], n2[0, 3], torch.arange(256), S))
+            EO.encode_views(enc_sd, imgs3[:, :, :64, :96])
+            t0 = time.perf_counter()
+            feats = EO.encode_views(enc_sd, imgs3)
+            t_enc = time.perf_counter() - t0
+            fl = RO.to_channels_last([f[None] for f in feats])
+            img_l = imgs3.permute(0, 2, 3, 1).contiguous()
+
+            def step(i):
+                first = (i * 7919 * 640) % (hw - n_rays)
+                RO.render_rays(dec_sd, fl, img_l, extr[0, :3, :3], intr[0, :3], nf[0, :3], extr[0, 3, :3], intr[0, 3], nf[0, 3],
+                               torch.arange(first, first + n_rays), S)
+            kind, what = "port", "oracle port (the reference tree is absent on this box; fp32 torch CPU)"
+        for i in range(warmup):
+            step(i)
+        t0 = time.perf_counter()
+        for i in range(steps):
+            step(warmup + i)
+        t_s = (time.perf_counter() - t0) / steps
+    value = hw / (t_enc + t_s * hw / n_rays)
+    sample = (f"{what}: {n_rays} contiguous rays x {S} samples x 3 views per step ({steps} steps after {warmup} warm-up, "
+              f"{t_s * 1e3:.0f} ms each), encoder on the three 512x640 views timed once ({t_enc:.2f} s) and amortised over the "
+              f"{hw}-ray image; {torch.get_num_threads()} threads (fastest of 8/16/32/64/all on this host)")
+    return value, t_s * 1e3, dict(value=value, unit="rays/s", cores=torch.get_num_threads(), kind=kind, sample=sample)
+
+
 def run_reference(args):
-    """CPU oracle port of the reference path (oracle/ validated against the unmodified reference, tests/golden/REPORT.txt).
-    Step = render of a bounded sample of rays of the same 512x640x3-view workload; the encoder is timed once and amortised
-    over the image, so value = HW / (t_encoder + t_sample * HW / rays_sample)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    S = args.samples
+    value, ms, cb = reference_cpu_sample(S, args.ref_rays, args.steps, args.warmup)
+    line = dict(impl="reference", metric="rays/sec (DTU 3-view 512x640, %d depth samples, encoder + render)" % S, value=value,
+                unit="rays/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=ms,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=workload_name(S), views=3, samples=S, image=[H_IMG, W_IMG]),
+                cpu_baseline=cb, e2e=dict(value=value, unit="rays/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def reference_on_gpu(dev, S_list, slices):
+    """The unmodified reference's forward(mode='test') on this GPU: fp32 eager with PyTorch's stock defaults, the shipped
+    slice sizes (configs/test.yaml:8 rand_rays_test 20480; 4096 = the README's low-memory advice).  This is the denominator of
+    the north star's ">= 10x the reference's single-GPU PyTorch rays/sec".  Also returns the fp32 image (TF32 off) of the first
+    S for the parity check."""
+    out, images = {}, {}
+    hw = H_IMG * W_IMG
+    batch = synthetic_batch(100)
+    for S in S_list:
+        for rr in slices:
+            loaded = load_reference(S, str(dev), rr)
+            if loaded is None:
+                return None, {}
+            net, ED, ref_root = loaded
+
+            def fwd():
+                b = ED(images=batch["images"].to(dev), extrinsics=batch["extrinsics"].to(dev), intrinsics=batch["intrinsics"].to(dev),
+                       near_fars=batch["near_fars"].to(dev))
+                with torch.no_grad():
+                    return net(b, mode="test")
+            fwd()                                            # warm-up (cuDNN heuristics, allocator)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fwd()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1)
+            out[f"S{S}_slice{rr}"] = dict(ms_per_image=ms, rays_per_s=hw / (ms * 1e-3))
+            if rr == slices[-1]:
+                prev = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+                torch.backends.cuda.matmul.allow_tf32 = False
+                torch.backends.cudnn.allow_tf32 = False
+                r = fwd()
+                torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev
+                images[S] = tuple(r[k][0].float().cpu() for k in ("rgb", "depth", "opacity"))
+            del net
+            torch.cuda.empty_cache()
+    out["how"] = (f"unmodified reference ({ref_root}) MatchNeRF.forward(mode='test') on {torch.cuda.get_device_name(dev)}, fp32 eager, "
+                  "PyTorch default math modes, same synthetic weights / images / cameras as the timed workload, 1 warm-up + 1 timed image "
+                  "per configuration (CUDA events)")
+    return out, images
+
+
+# ================================================================================================ parity of the timed workload
+def psnr_pair(ours, ref, seed=0):
+    """PSNR of both against a common pseudo ground truth = reference + N(0, 0.045^2) (27 dB, the regime where 0.01 dB <=> 2e-3 RMS);
+    misc/metrics.py:35-41 formula."""
+    ours, ref = ours.double(), ref.double()
+    gt = ref + 0.045 * torch.randn(ref.shape, generator=torch.Generator().manual_seed(seed), dtype=torch.float32).double()
+
+    def psnr(a):
+        return -10.0 * float(torch.log10(((a - gt) ** 2).mean()))
+    return psnr(ref), psnr(ours)
+
+
+def rms(a, b):
+    return float(((a.double() - b.double()) ** 2).mean().sqrt())
+
+
+def parity_of_timed_workload(model_out, S, ref_gpu_images):
+    """The workload that is TIMED (encoder + render of the 512x640 target) against (a) the CPU oracle (oracle encoder on the same
+    three images, 512 strided rays) and (b) the unmodified reference run in fp32 on the same GPU (all 327,680 rays)."""
     from oracle import encoder_oracle as EO
     from oracle import render_oracle as RO
     from oracle import synth
-    S = args.samples
+    rgb, depth, opac = (t.float().cpu() for t in model_out)
     batch = synthetic_batch(100)
-    enc_sd, dec_sd = synth.synthetic_encoder(1), synth.synthetic_decoder(0)
-    imgs = batch["images"][0, :3]
+    res = dict(case=f"the timed workload: encoder + render of the 512x640 target view, S={S} (bench synthetic_batch(100))", bar_db=0.01)
     with torch.no_grad():
+        feats = EO.encode_views(synth.synthetic_encoder(1), batch["images"][0, :3])
+        idx = torch.arange(173, H_IMG * W_IMG, 640)[:512]                 # one ray per image row, marching across the columns
         extr, intr, nf = batch["extrinsics"], batch["intrinsics"], batch["near_fars"]
-        probe_f, probe_i, _ = synth.synthetic_scene(H_IMG, W_IMG, seed=1234)
-        pf, pi = RO.to_channels_last(probe_f), probe_i[0].permute(0, 2, 3, 1).contiguous()
-        pick_threads(lambda: RO.render_rays(dec_sd, pf, pi, extr[0, :3, :3], intr[0, :3], nf[0, :3], extr[0, 3, :3], intr[0, 3],
-                                            nf[0, 3], torch.arange(256), S))
-        del probe_f, probe_i, pf, pi
-        EO.encode_views(enc_sd, imgs[:, :, :64, :96])      # warm-up
-        t0 = time.perf_counter()
-        feats = EO.encode_views(enc_sd, imgs)
-        t_enc = time.perf_counter() - t0
-        fl = RO.to_channels_last([f[None] for f in feats])
-        img_l = imgs.permute(0, 2, 3, 1).contiguous()
-        n_sample = args.ref_rays
-
-        def step(i):
-            first = (i * 7919 * 640) % (H_IMG * W_IMG - n_sample)
-            idx = torch.arange(first, first + n_sample)
-            RO.render_rays(dec_sd, fl, img_l, extr[0, :3, :3], intr[0, :3], nf[0, :3], extr[0, 3, :3], intr[0, 3], nf[0, 3], idx, S)
-
-        for i in range(args.warmup):
-            step(i)
-        t0 = time.perf_counter()
-        for i in range(args.steps):
-            step(args.warmup + i)
-        t_s = (time.perf_counter() - t0) / args.steps
-    hw = H_IMG * W_IMG
-    t_img = t_enc + t_s * hw / n_sample
-    value = hw / t_img
-    sample = (f"{n_sample} contiguous rays x {S} samples per step on the CPU oracle port (fp32 torch, {torch.get_num_threads()} threads); "
-              f"encoder timed once ({t_enc:.2f} s) and amortised over the {hw}-ray image")
-    line = dict(impl="reference", metric="rays/sec (DTU 3-view 512x640, %d depth samples, encoder + render)" % S, value=value,
-                unit="rays/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=t_s * 1e3,
-                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload=f"DTU 3-view 512x640 full-image forward, S={S}, random-init weights", views=3, samples=S,
-                            image=[H_IMG, W_IMG]),
-                cpu_baseline=dict(value=value, unit="rays/s", cores=torch.get_num_threads(), kind="port", sample=sample),
-                e2e=dict(value=value, unit="rays/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line), flush=True)
+        o = RO.render_rays(synth.synthetic_decoder(0), RO.to_channels_last([f[None] for f in feats]),
+                           batch["images"][0, :3].permute(0, 2, 3, 1).contiguous(), extr[0, :3, :3], intr[0, :3], nf[0, :3],
+                           extr[0, 3, :3], intr[0, 3], nf[0, 3], idx, S)
+    p_ref, p_ours = psnr_pair(rgb[idx], o[0])
+    res["vs_cpu_oracle"] = dict(rays=int(idx.numel()), rgb_rms=rms(rgb[idx], o[0]), depth_rms=rms(depth[idx], o[1]),
+                                opacity_rms=rms(opac[idx], o[2]), opacity_mean=float(o[2].mean()), psnr_ref_db=p_ref, psnr_ours_db=p_ours,
+                                psnr_delta_db=p_ours - p_ref)
+    if ref_gpu_images and S in ref_gpu_images:
+        r_rgb, r_depth, r_op = ref_gpu_images[S]
+        p_ref, p_ours = psnr_pair(rgb, r_rgb)
+        res["vs_reference_gpu_fp32"] = dict(rays=int(rgb.shape[0]), rgb_rms=rms(rgb, r_rgb), depth_rms=rms(depth, r_depth),
+                                            opacity_rms=rms(opac, r_op), psnr_ref_db=p_ref, psnr_ours_db=p_ours,
+                                            psnr_delta_db=p_ours - p_ref)
+    worst = max(abs(res[k]["psnr_delta_db"]) for k in ("vs_cpu_oracle", "vs_reference_gpu_fp32") if k in res)
+    res["abs_psnr_delta_db_max"] = worst
+    res["within_bar"] = bool(worst <= 0.01)
+    return res
 
 
 # ================================================================================================ our arm
@@ -166,7 +331,7 @@ def run_ours(args):
 
     from matchnerf_b200 import capi
     from matchnerf_b200.matchnerf import MatchNeRF
-    from matchnerf_b200.sharding import gather_tiles
+    from matchnerf_b200.sharding import TileGather
     from matchnerf_b200.utils import AttrDict
     from oracle import synth
 
@@ -180,42 +345,51 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    shard_rays = args.shard == "rays" and world > 1
 
     S = args.samples
-    opt = make_opts(S, str(dev))
-    model = MatchNeRF(opt).eval()
-    model.feat_enc.load_state_dict(synth.synthetic_encoder(1))
-    model.nerf_dec.load_state_dict(synth.synthetic_decoder(0))
-    model.to(dev)
-    if args.chunk:
-        model.render_chunk = args.chunk
-    ctx = capi.get_context(dev)
     hw = H_IMG * W_IMG
 
-    host = synthetic_batch(100 + rank)                      # each rank renders its own target view (image-parallel round)
+    def build_model(S_):
+        m = MatchNeRF(make_opts(S_, str(dev))).eval()
+        m.feat_enc.load_state_dict(synth.synthetic_encoder(1))
+        m.nerf_dec.load_state_dict(synth.synthetic_decoder(0))
+        m.to(dev)
+        m.shard_over_ranks = shard_rays          # MatchNeRF.forward: split encoder + rays over the ranks of the default group
+        if args.chunk:
+            m.render_chunk = args.chunk
+        return m
+
+    model = build_model(S)
+    ctx = capi.get_context(dev)
+
+    # weak: each rank renders its own target view (image-parallel round); strong: every rank holds the SAME batch
+    host = synthetic_batch(100 + (0 if shard_rays else rank))
     host = {k: v.pin_memory() for k, v in host.items()}
     resident = {k: v.to(dev) for k, v in host.items()}
     out_host = torch.empty((hw, 5), dtype=torch.float32).pin_memory()
-    counts = [hw] * world
+    tiles = TileGather(hw, 5, dev) if (world > 1 and not shard_rays) else None
+
+    def render_tile(batch):
+        out = model(batch, mode="test")
+        if tiles is not None:                                   # weak: the single NCCL all-gather of the rendered tiles
+            t = tiles.local_view()
+            t[:, :3].copy_(out.rgb[0]); t[:, 3:4].copy_(out.depth[0]); t[:, 4:5].copy_(out.opacity[0])
+            tiles.all_gather()
+            return t
+        return torch.cat([out.rgb[0], out.depth[0], out.opacity[0]], dim=1)
 
     def step_resident():
         with torch.no_grad():
-            out = model(AttrDict(resident), mode="test")
-            tile = torch.cat([out.rgb[0], out.depth[0], out.opacity[0]], dim=1)
-            if world > 1:
-                tile = gather_tiles(tile, counts)            # the single NCCL all-gather of rendered tiles
-        return tile
+            return render_tile(AttrDict(resident))
 
     def step_e2e():
         with torch.no_grad():
             # images go host -> device every step; the three small camera tensors are consumed on the host (they become the
             # by-value mnf_scene struct), so they stay in the host batch -- MatchNeRF.forward accepts them on either side
             b = AttrDict({k: (v.to(dev, non_blocking=True) if k == "images" else v) for k, v in host.items()})
-            out = model(b, mode="test")
-            tile = torch.cat([out.rgb[0], out.depth[0], out.opacity[0]], dim=1)
+            tile = render_tile(b)
             out_host.copy_(tile, non_blocking=True)
-            if world > 1:
-                gather_tiles(tile, counts)
         return tile
 
     def timed(fn, steps, warmup, sample_clocks=False):
@@ -242,36 +416,25 @@ def run_ours(args):
         return float(ms) / steps, clocks
 
     ms_step, clocks = timed(step_resident, args.steps, max(args.warmup, 3), sample_clocks=True)
-    ms_e2e, _ = timed(step_e2e, args.steps, 1)
-    value = world * hw / (ms_step * 1e-3)
-    e2e_value = world * hw / (ms_e2e * 1e-3)
+    ms_e2e, _ = timed(step_e2e, args.steps, 3)
+    images_per_step = 1 if shard_rays else world
+    value = images_per_step * hw / (ms_step * 1e-3)
+    e2e_value = images_per_step * hw / (ms_e2e * 1e-3)
     h2d = host["images"].numel() * host["images"].element_size()
     d2h = out_host.numel() * out_host.element_size()
 
-    # ---- per-kernel timing (CUDA events on the launching stream) for the roofline of the dominant kernel
-    roofline, kernels, launches = None, {}, None
-    if rank == 0:
+    def kernel_times(model_, S_):
+        """CUDA-event timings of the three kernels groups in isolation (rank 0), on the launching stream."""
         pk = peaks()
         with torch.no_grad():
             b = AttrDict(resident)
-            feats = model.get_img_feat(b["images"][:, :3])
-            tgt, ref = model.extract_poses(b)
-            scene = model._packed_scenes(ref, b["images"][:, :3], feats)[0]
+            feats = model_._get_img_feat_static(b["images"][:, :3])
+            tgt, ref = model_.extract_poses(b)
+            scene = model_._packed_scenes(ref, b["images"][:, :3], feats)[0]
             sc = scene.c_scene(tgt["extrinsics"][0], tgt["intrinsics"][0], tgt["near_fars"][0])
-            cfg = model.nerf_dec.decoder_cfg(opt)
-            chunk = model.render_chunk
-            impl = 2 if _tc_decoder_ok(ctx, sc, cfg) else 1
-
-            def k_gather():
-                return ctx.gather_cossim(sc, S, first_ray=0, n_rays=chunk, want_f32=(impl == 1), want_f16=(impl == 2))
-
-            c32, c16 = k_gather()
-
-            def k_decoder():
-                return ctx.decoder_composite(sc, cfg, cond_f32=c32, cond_f16=c16, first_ray=0, n_rays=chunk, impl=impl)
-
-            def k_encoder():
-                return model.get_img_feat(b["images"][:, :3])
+            cfg = model_.nerf_dec.decoder_cfg(model_.opts)
+            chunk = min(model_.render_chunk, hw)
+            c32, c16 = ctx.gather_cossim(sc, S_, first_ray=0, n_rays=chunk, want_f32=False, want_f16=True)
 
             def ev_time(fn, reps=5):
                 fn()
@@ -284,142 +447,98 @@ def run_ours(args):
                 torch.cuda.synchronize()
                 return e0.elapsed_time(e1) / reps
 
-            t_g, t_d, t_e = ev_time(k_gather), ev_time(k_decoder), ev_time(k_encoder, 3)
-        n_chunks = (hw + chunk - 1) // chunk
-        n_samp = chunk * S
-        gather_gbs = n_samp * GATHER_BYTES_PER_SAMPLE / (t_g * 1e-3) / 1e9
-        dec_tfs = n_samp * FLOP_PER_SAMPLE.get(S, 262432) / (t_d * 1e-3) / 1e12
-        kernels = dict(
-            gather_cossim=dict(ms_per_launch=t_g, rays_per_launch=chunk, launches_per_step=n_chunks, algorithmic_GBps=gather_gbs,
-                               frac_of_hbm_peak=gather_gbs / pk["hbm"]),
-            decoder_composite=dict(ms_per_launch=t_d, rays_per_launch=chunk, launches_per_step=n_chunks, impl=("tcgen05" if impl == 2 else "fp32"),
-                                   algorithmic_TFLOPs=dec_tfs, frac_of_tensor_peak=dec_tfs / pk["tensor"]),
-            encoder=dict(ms_per_call=t_e, note="torch conv/linear + 12 K-attn launches"))
-        traffic = {}
-        tp = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
+            t_g = ev_time(lambda: ctx.gather_cossim(sc, S_, first_ray=0, n_rays=chunk, want_f32=False, want_f16=True))
+            t_d = ev_time(lambda: ctx.decoder_composite(sc, cfg, cond_f16=c16, first_ray=0, n_rays=chunk, impl=2))
+            t_e = ev_time(lambda: model_._get_img_feat_static(b["images"][:, :3]), 3)
+            g = torch.Generator().manual_seed(0)
+            q, k, v = (torch.randn(6, 64 * 80, 128, generator=g).to(dev) for _ in range(3))
+            t_a0 = ev_time(lambda: ctx.window_attn(q, k, v, 64, 80, 2, False), 10)
+            t_a1 = ev_time(lambda: ctx.window_attn(q, k, v, 64, 80, 2, True), 10)
+        n_samp = chunk * S_
+        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        clk = (clocks or {}).get("sm_max_mhz") or 1965.0
+        fma_roof_ms = n_samp * GATHER_FMA_PER_SAMPLE / (n_sm * 128 * clk * 1e6) * 1e3
+        dec_tfs = n_samp * FLOP_PER_SAMPLE.get(S_, 262432) / (t_d * 1e-3) / 1e12
+        att_tfs0, att_tfs1 = (ATTN_FLOP_PER_CALL / (t * 1e-3) / 1e12 for t in (t_a0, t_a1))
+        return dict(
+            gather_cossim=dict(ms_per_launch=t_g, rays_per_launch=chunk, algorithmic_GBps=n_samp * GATHER_BYTES_PER_SAMPLE / (t_g * 1e-3) / 1e9,
+                               bound="CUDA-core FMA / issue (the 39 MB of feature maps are L2-resident: HBM is not the roof)",
+                               fma_roof_ms=fma_roof_ms, frac_of_fma_roof=fma_roof_ms / t_g,
+                               note="fma roof = 8448 multiply-adds per sample at 128 FMA/clk/SM x SMs x max SM clock; ncu L2/L1 shares in profiles/"),
+            decoder_composite=dict(ms_per_launch=t_d, rays_per_launch=chunk, impl="tcgen05", algorithmic_TFLOPs=dec_tfs,
+                                   frac_of_tensor_peak=dec_tfs / pk["tensor"], frac_of_tensor_peak_sustained=dec_tfs / pk["tensor_sustained"]),
+            window_attn=dict(ms_per_call_noshift=t_a0, ms_per_call_shift=t_a1, algorithmic_TFLOPs_noshift=att_tfs0,
+                             algorithmic_TFLOPs_shift=att_tfs1, frac_of_tensor_peak=0.5 * (att_tfs0 + att_tfs1) / pk["tensor"],
+                             calls_per_step=12),
+            encoder=dict(ms_per_call=t_e, note="CUDA graph: backbone / up-sampler convolutions (cuDNN) + this repo's kernels")), pk
+
+    # ---- untimed extras (rank 0): per-kernel timing, S = 128, parity of the timed workload, reference on this GPU / the host
+    roofline, kernels, kernels_s128, parity, ref_gpu, cpu_baseline = None, {}, None, None, None, None
+    n_chunks = (hw + min(model.render_chunk, hw) - 1) // min(model.render_chunk, hw)
+    launches = args.steps * model.launches_per_image(n_chunks) if hasattr(model, "launches_per_image") else None
+    if rank == 0 and not args.quick:
+        kernels, pk = kernel_times(model, S)
+        kd = kernels["decoder_composite"]
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r02_dram_traffic.json")
         if os.path.exists(tp):            # measured once under `ncu --set full`; scaled to this launch size
             tj = json.load(open(tp))
-            for kname in ("gather_cossim_kernel", "decoder_tc_kernel"):
-                traffic[kname] = (tj[kname]["dram_read_bytes"] + tj[kname]["dram_write_bytes"]) * chunk / tj["captured_rays"]
-        if t_g * n_chunks >= t_d * n_chunks:
-            roofline = dict(kernel="gather_cossim_kernel", bound="hbm", achieved=gather_gbs, peak=pk["hbm"], unit="GB/s",
-                            frac=gather_gbs / pk["hbm"], traffic=traffic.get("gather_cossim_kernel"), peak_source=pk["source"],
-                            note="feature maps are L2-resident (39 MB) and a fetched texel cell is reused from registers by the rays of a "
-                                 "quad, so algorithmic bytes exceed DRAM traffic by two orders of magnitude (frac > 1); ncu shows the kernel "
-                                 "bound by the half-rate fp16 FMA pipe and instruction issue (68 %), not by any memory level -- DESIGN.md 4")
-        else:
-            roofline = dict(kernel="decoder_%s_kernel" % ("tc" if impl == 2 else "ref"), bound="tensor", achieved=dec_tfs, peak=pk["tensor"],
-                            unit="TFLOP/s", frac=dec_tfs / pk["tensor"], traffic=traffic.get("decoder_tc_kernel") if impl == 2 else None,
-                            peak_source=pk["source"])
-        launches = args.steps * (n_chunks * 2 + 24 + 3 + 15)  # per step: gather+decoder per chunk, 12 x (K-attn pre-pack + K-attn), 3 pack kernels, 15 instance norms
-
-    parity = None
-    if rank == 0 and world == 1:
-        parity = parity_vs_reference_golden(ctx, S)
-
-    cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_baseline = cpu_baseline_sample(S)
+            if "decoder_tc_kernel" in tj:
+                traffic = (tj["decoder_tc_kernel"]["dram_read_bytes"] + tj["decoder_tc_kernel"]["dram_write_bytes"]) * kd["rays_per_launch"] / tj["captured_rays"]
+        roofline = dict(kernel="decoder_tc_kernel (K-mlp-composite: the kernel the north star sets a roofline target on)", bound="tensor",
+                        achieved=kd["algorithmic_TFLOPs"], peak=pk["tensor"], unit="TFLOP/s", frac=kd["frac_of_tensor_peak"], traffic=traffic,
+                        peak_source=pk["source"] + ", bf16_tflops (burst: the kernel is timed in isolation)",
+                        note="K-gather is reported in `kernels` against the CUDA-core FMA roof: its feature maps are L2-resident, so an HBM "
+                             "fraction would be meaningless")
+    if rank == 0 and world == 1 and not args.quick:
+        with torch.no_grad():
+            out = model(AttrDict(resident), mode="test")
+            ours_img = (out.rgb[0].clone(), out.depth[0].clone(), out.opacity[0].clone())
+        other = 128 if S == 64 else 64
+        m2 = build_model(other)
+        ms2, _ = timed(lambda: m2(AttrDict(resident), mode="test"), 5, 3)
+        k2, _ = kernel_times(m2, other)
+        with torch.no_grad():
+            o2 = m2(AttrDict(resident), mode="test")
+            other_img = (o2.rgb[0].clone(), o2.depth[0].clone(), o2.opacity[0].clone())
+        kernels_s128 = dict(samples=other, ms_per_step=ms2, value=hw / (ms2 * 1e-3), unit="rays/s", kernels=k2,
+                            note=f"same workload at S={other} (configs/base.yaml:48 ships 128; BASELINE's metric is quoted at 64)")
+        del m2
+        torch.cuda.empty_cache()
+        ref_imgs = {}
+        if not args.no_reference_gpu:
+            try:
+                ref_gpu, ref_imgs = reference_on_gpu(dev, (S, other), (4096, 20480))
+            except Exception as e:           # never let the reference's problems take the product line down
+                ref_gpu = dict(error=f"{type(e).__name__}: {e}")
+            if ref_gpu and "error" not in ref_gpu:
+                for key, S_, v_ in ((f"S{S}", S, value), (f"S{other}", other, kernels_s128["value"])):
+                    best = max(ref_gpu[f"{key}_slice{rr}"]["rays_per_s"] for rr in (4096, 20480))
+                    ref_gpu[f"speedup_{key}"] = v_ / best
+        parity = parity_of_timed_workload(ours_img, S, ref_imgs)
+        parity["other_S"] = parity_of_timed_workload(other_img, other, ref_imgs)
+        if not args.no_cpu_baseline:
+            _, _, cpu_baseline = reference_cpu_sample(S, 1024, 2, 1)
 
     if rank == 0:
+        par = "single GPU" if world == 1 else (
+            f"ONE image per step: encoder batch items + rays sharded over {world} ranks, NCCL all-gather of feature maps and tiles"
+            if shard_rays else f"image-parallel x{world} + 1 NCCL all-gather of rendered tiles")
         line = dict(metric="rays/sec (DTU 3-view 512x640, %d depth samples, encoder + render)" % S, value=value, unit="rays/s",
                     n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_step, higher_is_better=True,
-                    scaling="weak", vs_baseline=None, dtype="f16 operands / f32 accumulate (decoder), f16 feature maps, f32 elsewhere",
-                    data="synthetic",
-                    config=dict(workload=f"DTU 3-view 512x640 full-image forward (BASELINE configs[1]), S={S}, random-init weights, "
-                                         "one target view per rank",
-                                views=3, samples=S, image=[H_IMG, W_IMG], rays_per_step=world * hw,
-                                parallelism=("single GPU" if world == 1 else f"image-parallel x{world} + 1 NCCL all-gather of rendered tiles"),
+                    scaling="strong" if shard_rays else "weak", vs_baseline=None,
+                    dtype="f16 operands / f32 accumulate (decoder), f16 feature maps, f32 elsewhere", data="synthetic",
+                    config=dict(workload=workload_name(S) + (", one target view per step" if shard_rays or world == 1 else ", one target view per rank"),
+                                views=3, samples=S, image=[H_IMG, W_IMG], rays_per_step=images_per_step * hw, parallelism=par,
                                 l2="per-step working set (conditioning workspace %.1f GB, activations) exceeds the 126 MB L2; no explicit flush"
                                    % (hw * S * 64 / 1e9)),
                     clocks=clocks,
                     e2e=dict(value=e2e_value, unit="rays/s", ms_per_step=ms_e2e, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
-                    gpu_launches=launches, roofline=roofline, kernels=kernels, cpu_baseline=cpu_baseline, parity=parity)
+                    gpu_launches=launches, roofline=roofline, kernels=kernels, kernels_s128=kernels_s128, cpu_baseline=cpu_baseline,
+                    reference_gpu=ref_gpu, parity=parity)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
-
-
-def parity_vs_reference_golden(ctx, S):
-    """BASELINE configs[0] (1024 rays x S samples x 3 views, random feature maps) through the C ABI against the committed outputs of
-    the UNMODIFIED reference (tests/golden/config1_synth_S*.npz, made by oracle/make_golden.py): rgb RMS and the PSNR delta
-    against a common pseudo ground truth (misc/metrics.py:35-41 formula) -- the north-star bar is 0.01 dB.  Untimed."""
-    import numpy as np
-    from matchnerf_b200 import capi
-    from oracle import synth
-    path = os.path.join(ROOT, "tests", "golden", f"config1_synth_S{S}.npz")
-    if not os.path.exists(path):
-        return None
-    z = np.load(path)
-    feats, imgs, g = synth.synthetic_scene(H_IMG, W_IMG, seed=1234)
-    extr, intr, nf = synth.synthetic_cameras(H_IMG, W_IMG)
-    ray_idx = torch.randperm(H_IMG * W_IMG, generator=g)[:1024]
-    dev = ctx.device
-    ctx.load_decoder(synth.synthetic_decoder(0))
-    packed = ctx.pack_scene([feats[0][0].to(dev), feats[1][0].to(dev)], imgs[0].to(dev), extr[0, :3], intr[0, :3], nf[0, :3])
-    sc = packed.c_scene(extr[0, 3, :3], intr[0, 3], nf[0, 3])
-    cfg = capi.DecoderCfg()
-    cfg.n_samples, cfg.raytrans_act, cfg.raytrans_posenc, cfg.density_maskfill = S, 0, 0, 0
-    rgb = ctx.render_rays(sc, cfg, ray_idx=ray_idx.to(dev))[0].cpu().double()
-    ref = torch.from_numpy(z["rgb"]).double()
-    gt = ref + 0.045 * torch.randn(ref.shape, generator=torch.Generator().manual_seed(0), dtype=torch.float32).double()
-
-    def psnr(a):
-        return -10.0 * float(torch.log10(((a - gt) ** 2).mean()))
-
-    return dict(case=f"BASELINE configs[0]: 1024 rays x {S} samples vs the unmodified reference's fp32 outputs (tests/golden)",
-                rgb_rms=float(((rgb - ref) ** 2).mean().sqrt()), psnr_ref_db=psnr(ref), psnr_ours_db=psnr(rgb),
-                psnr_delta_db=psnr(rgb) - psnr(ref), bar_db=0.01)
-
-
-def _tc_decoder_ok(ctx, sc, cfg) -> bool:
-    try:
-        c16 = torch.zeros((cfg.n_samples, 32), dtype=torch.float16, device=ctx.device)
-        ctx.decoder_composite(sc, cfg, cond_f16=c16, first_ray=0, n_rays=1, impl=2)
-        torch.cuda.synchronize()
-        return True
-    except RuntimeError:
-        return False
-
-
-def pick_threads(fn):
-    """PyTorch's CPU ops do not scale to every core of a large host (128 threads measured 20x slower than 16 on the
-    GPU box): time a small probe at a few thread counts and keep the fastest."""
-    ncpu = os.cpu_count() or 1
-    best, best_t = 1, float("inf")
-    for n in sorted({min(ncpu, c) for c in (8, 16, 32, 64, ncpu)}):
-        torch.set_num_threads(n)
-        fn()
-        t0 = time.perf_counter()
-        fn()
-        dt = time.perf_counter() - t0
-        if dt < best_t:
-            best, best_t = n, dt
-    torch.set_num_threads(best)
-    return best
-
-
-def cpu_baseline_sample(S: int, n_rays: int = 2048):
-    """The oracle port timed on this box's host cores on a bounded sample of the same workload."""
-    from oracle import render_oracle as RO
-    from oracle import synth
-    feats, imgs, _ = synth.synthetic_scene(H_IMG, W_IMG, seed=1234)
-    extr, intr, nf = synth.synthetic_cameras(H_IMG, W_IMG)
-    dec = synth.synthetic_decoder(0)
-    fl = RO.to_channels_last(feats)
-    il = imgs[0].permute(0, 2, 3, 1).contiguous()
-    idx = torch.arange(200 * W_IMG, 200 * W_IMG + n_rays)
-    with torch.no_grad():
-        pick_threads(lambda: RO.render_rays(dec, fl, il, extr[0, :3, :3], intr[0, :3], nf[0, :3], extr[0, 3, :3], intr[0, 3],
-                                            nf[0, 3], idx[:256], S))
-        t0 = time.perf_counter()
-        reps = 3
-        for _ in range(reps):
-            RO.render_rays(dec, fl, il, extr[0, :3, :3], intr[0, :3], nf[0, :3], extr[0, 3, :3], intr[0, 3], nf[0, 3], idx, S)
-        dt = (time.perf_counter() - t0) / reps
-    return dict(value=n_rays / dt, unit="rays/s", cores=torch.get_num_threads(), kind="port",
-                sample=f"render only: {n_rays} contiguous rays x {S} samples x 3 views, random feature maps, oracle port (fp32 torch CPU), "
-                       f"{reps} reps after warm-up")
 
 
 def main():
@@ -429,8 +548,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--samples", type=int, default=64)
-    ap.add_argument("--ref-rays", type=int, default=2048)
+    ap.add_argument("--shard", default="images", choices=["images", "rays"],
+                    help="N > 1: 'images' = one target view per rank (weak scaling), 'rays' = one view per step sharded over the ranks (strong)")
+    ap.add_argument("--ref-rays", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-gpu", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="timed region only (no per-kernel / parity / reference extras)")
     ap.add_argument("--chunk", type=int, default=0, help="rays per render launch (default: MatchNeRF.render_chunk)")
     args = ap.parse_args()
     if args.impl == "reference":

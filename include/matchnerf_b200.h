@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MNF_ABI_VERSION 3
+#define MNF_ABI_VERSION 4
 
 typedef enum mnf_status {
   MNF_OK = 0,
@@ -139,8 +139,10 @@ int32_t mnf_decoder_composite_fwd(mnf_ctx* ctx, const mnf_scene* scene, const mn
                                   float* aux_rgb_sigma, int32_t impl, void* stream);
 
 /* ---- fused per-slice render: MatchNeRF.render (models/matchnerf.py:88-143) ---------------- */
-/* Bytes of caller-provided workspace mnf_render_rays_fwd needs for R rays of S samples. */
-int64_t mnf_render_workspace_bytes(int64_t n_rays, int32_t n_samples);
+/* Bytes of caller-provided workspace mnf_render_rays_fwd needs for R rays of S samples with decoder implementation `impl`
+ * (0 = auto, 1 = fp32 kernel: [N][22] fp32 conditioning rows, 2 = tcgen05 kernel: [N][32] fp16 rows).  `cfg` may be NULL
+ * (then only n_samples is used to resolve impl = 0). */
+int64_t mnf_render_workspace_bytes(int64_t n_rays, int32_t n_samples, int32_t impl);
 int32_t mnf_render_rays_fwd(mnf_ctx* ctx, const mnf_scene* scene, const mnf_rays* rays,
                             const mnf_decoder_cfg* cfg, int32_t setbg_opaque,
                             float* out_rgb, float* out_depth, float* out_opacity,

@@ -15,6 +15,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MNF_LIB_PATH") or os.path.join(_HERE, "libmatchnerf_b200.so")   # override: A/B builds (tools/)
 
+ABI_VERSION = 4
 COND_DIM = 22
 COND_PAD = 32
 FEAT_CH = 256
@@ -78,7 +79,7 @@ def load() -> C.CDLL:
     lib.mnf_decoder_samples_fwd.argtypes = [vp, C.POINTER(DecoderCfg), fp, fp, fp, i64, fp, vp]
     lib.mnf_composite_fwd.argtypes = [vp, fp, fp, fp, i64, i32, i32, fp, fp, fp, fp, vp]
     lib.mnf_instance_norm_fwd.argtypes = [vp, fp, fp, fp, i64, i32, i32, C.c_float, vp]
-    lib.mnf_render_workspace_bytes.argtypes = [i64, i32]
+    lib.mnf_render_workspace_bytes.argtypes = [i64, i32, i32]
     lib.mnf_render_workspace_bytes.restype = i64
     lib.mnf_render_rays_fwd.argtypes = [vp, C.POINTER(Scene), C.POINTER(Rays), C.POINTER(DecoderCfg), i32, fp, fp, fp,
                                         vp, i64, i32, vp]
@@ -91,8 +92,8 @@ def load() -> C.CDLL:
                  "mnf_selftest_umma", "mnf_query_cond_points_fwd", "mnf_decoder_samples_fwd", "mnf_composite_fwd",
                  "mnf_instance_norm_fwd"):
         getattr(lib, name).restype = i32
-    if lib.mnf_abi_version() != 3:
-        raise RuntimeError(f"libmatchnerf_b200.so ABI {lib.mnf_abi_version()} != 3")
+    if lib.mnf_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"libmatchnerf_b200.so ABI {lib.mnf_abi_version()} != {ABI_VERSION}")
     _lib = lib
     return lib
 
@@ -171,6 +172,10 @@ class Context:
         _check(self.lib.mnf_ctx_create(self.device.index, C.byref(h)), "mnf_ctx_create")
         self._h = h
         self.decoder_loaded = False
+        # who loaded the weights currently packed in this context: (id(module), parameter version) for a CondNeRF that
+        # synchronised itself, None after a direct load_decoder(state_dict).  A context is shared by every model on its
+        # device, so a module must reload when ANOTHER owner's weights are resident (two checkpoints, EMA + live model, ...).
+        self.decoder_owner = None
 
     def close(self):
         if getattr(self, "_h", None):
@@ -184,13 +189,14 @@ class Context:
             pass
 
     # ---- weights
-    def load_decoder(self, state_dict: Dict[str, torch.Tensor]) -> None:
+    def load_decoder(self, state_dict: Dict[str, torch.Tensor], owner=None) -> None:
         blob = flatten_decoder_state(state_dict)
         if blob.numel() != self.lib.mnf_decoder_param_count():
             raise ValueError(f"decoder has {blob.numel()} parameters, library expects {self.lib.mnf_decoder_param_count()}")
         with torch.cuda.device(self.device):
             _check(self.lib.mnf_decoder_load_host(self._h, blob.data_ptr(), blob.numel()), "mnf_decoder_load_host")
         self.decoder_loaded = True
+        self.decoder_owner = owner
 
     # ---- packing
     def pack_scene(self, feats: Sequence[torch.Tensor], images: torch.Tensor, src_w2c: torch.Tensor, src_K: torch.Tensor,
@@ -312,7 +318,7 @@ class Context:
             out = (torch.empty((R, 3), dtype=torch.float32, device=self.device),
                    torch.empty((R,), dtype=torch.float32, device=self.device),
                    torch.empty((R,), dtype=torch.float32, device=self.device))
-        need = self.lib.mnf_render_workspace_bytes(R, S)
+        need = self.lib.mnf_render_workspace_bytes(R, S, impl)
         if workspace is None or workspace.numel() < need:
             workspace = torch.empty((max(need, 256),), dtype=torch.uint8, device=self.device)
         _check(self.lib.mnf_render_rays_fwd(self._h, C.byref(scene), C.byref(rays), C.byref(cfg), int(setbg_opaque),

@@ -61,7 +61,6 @@ class CondNeRF(nn.Module):
                 if isinstance(m, nn.Linear):
                     nn.init.kaiming_normal_(m.weight)
                     nn.init.zeros_(m.bias)
-        self._loaded_version = None
 
     # ---- weights -> library
     def _version(self):
@@ -71,10 +70,9 @@ class CondNeRF(nn.Module):
         """(Re)upload the weights into the library context when they changed (load_state_dict, optimiser step)."""
         dev = next(self.parameters()).device
         ctx = ctx or capi.get_context(dev)
-        ver = self._version()
-        if self._loaded_version != (id(ctx), ver) or not ctx.decoder_loaded:
-            ctx.load_decoder(self.state_dict())
-            self._loaded_version = (id(ctx), ver)
+        owner = (id(self), self._version())
+        if ctx.decoder_owner != owner or not ctx.decoder_loaded:      # someone else's (or stale) weights are resident
+            ctx.load_decoder(self.state_dict(), owner=owner)
         return ctx
 
     def decoder_cfg(self, opt) -> "capi.DecoderCfg":

@@ -53,6 +53,20 @@ struct mnf_ctx {
 
 namespace {
 
+// Makes the context's device current for the duration of an ABI call and restores the caller's device afterwards: a
+// model on cuda:1 may be driven by a thread whose current device is 0 (nn.DataParallel, torch.cuda.device scopes).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(const mnf_ctx* ctx);
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+
+DeviceGuard::DeviceGuard(const mnf_ctx* ctx) {
+  if (!ctx) return;
+  if (cudaGetDevice(&prev) == cudaSuccess && prev != ctx->device) switched = cudaSetDevice(ctx->device) == cudaSuccess;
+}
+
 int dev_upload(mnf_ctx* ctx, const std::vector<float>& host, const float** out) {
   void* p = nullptr;
   MNF_CUDA_TRY(cudaMalloc(&p, host.size() * sizeof(float)));
@@ -138,9 +152,11 @@ int32_t mnf_ctx_create(int32_t device, mnf_ctx** out) {
 
 int32_t mnf_ctx_destroy(mnf_ctx* ctx) {
   if (!ctx) return MNF_OK;
-  cudaSetDevice(ctx->device);
-  for (void* p : ctx->allocs) cudaFree(p);
-  if (ctx->wtc) decoder_tc_free(ctx->wtc);
+  {
+    DeviceGuard dev_guard(ctx);
+    for (void* p : ctx->allocs) cudaFree(p);
+    if (ctx->wtc) decoder_tc_free(ctx->wtc);
+  }
   delete ctx;
   return MNF_OK;
 }
@@ -152,7 +168,7 @@ int32_t mnf_decoder_load_host(mnf_ctx* ctx, const float* P, int64_t n_floats) {
     set_error("mnf_decoder_load_host: got %lld floats, the decoder has %lld", (long long)n_floats, (long long)off.total);
     return MNF_EINVAL;
   }
-  MNF_CUDA_TRY(cudaSetDevice(ctx->device));
+  DeviceGuard dev_guard(ctx);
   for (void* p : ctx->allocs) cudaFree(p);
   ctx->allocs.clear();
   if (ctx->wtc) { decoder_tc_free(ctx->wtc); ctx->wtc = nullptr; }
@@ -227,12 +243,14 @@ int64_t mnf_packed_feature_halves(int32_t V, int32_t h, int32_t w) {
 }
 
 int32_t mnf_pack_features(mnf_ctx* ctx, const float* feat_nchw, int32_t V, int32_t h, int32_t w, void* out_packed, void* stream) {
+  DeviceGuard dev_guard(ctx);
   if (!ctx || !feat_nchw || !out_packed || V <= 0 || h <= 0 || w <= 0) { set_error("mnf_pack_features: bad argument"); return MNF_EINVAL; }
   if (((uintptr_t)out_packed & 15) != 0) { set_error("mnf_pack_features: out must be 16-byte aligned"); return MNF_EINVAL; }
   return launch_pack_features(feat_nchw, V, h, w, reinterpret_cast<__half*>(out_packed), (cudaStream_t)stream);
 }
 
 int32_t mnf_pack_images(mnf_ctx* ctx, const float* images_nchw, int32_t V, int32_t H, int32_t W, void* out_packed, void* stream) {
+  DeviceGuard dev_guard(ctx);
   if (!ctx || !images_nchw || !out_packed || V <= 0 || H <= 0 || W <= 0) { set_error("mnf_pack_images: bad argument"); return MNF_EINVAL; }
   if (((uintptr_t)out_packed & 15) != 0) { set_error("mnf_pack_images: out must be 16-byte aligned"); return MNF_EINVAL; }
   return launch_pack_images(images_nchw, V, H, W, reinterpret_cast<float*>(out_packed), (cudaStream_t)stream);
@@ -240,6 +258,7 @@ int32_t mnf_pack_images(mnf_ctx* ctx, const float* images_nchw, int32_t V, int32
 
 int32_t mnf_gather_cossim_fwd(mnf_ctx* ctx, const mnf_scene* scene, const mnf_rays* rays, int32_t n_samples, float* cond_f32,
                               void* cond_f16, void* stream) {
+  DeviceGuard dev_guard(ctx);
   if (!ctx) { set_error("ctx is NULL"); return MNF_EINVAL; }
   DevCams cams;
   DevRays dr{};
@@ -258,6 +277,7 @@ int32_t mnf_gather_cossim_fwd(mnf_ctx* ctx, const mnf_scene* scene, const mnf_ra
 int32_t mnf_decoder_composite_fwd(mnf_ctx* ctx, const mnf_scene* scene, const mnf_rays* rays, const mnf_decoder_cfg* cfg,
                                   const float* cond_f32, const void* cond_f16, int32_t setbg_opaque, float* out_rgb,
                                   float* out_depth, float* out_opacity, float* aux_rgb_sigma, int32_t impl, void* stream) {
+  DeviceGuard dev_guard(ctx);
   if (!ctx) { set_error("ctx is NULL"); return MNF_EINVAL; }
   if (!ctx->loaded) { set_error("decoder weights not loaded (call mnf_decoder_load_host)"); return MNF_ESTATE; }
   DevCams cams;
@@ -283,6 +303,7 @@ int32_t mnf_decoder_composite_fwd(mnf_ctx* ctx, const mnf_scene* scene, const mn
 
 int32_t mnf_query_cond_points_fwd(mnf_ctx* ctx, const mnf_scene* scene, const float* points_world, int64_t n_rays, int32_t n_samples,
                                   float* cond_f32, void* cond_f16, void* stream) {
+  DeviceGuard dev_guard(ctx);
   if (!ctx) { set_error("ctx is NULL"); return MNF_EINVAL; }
   DevCams cams;
   int rc;
@@ -304,6 +325,7 @@ int32_t mnf_query_cond_points_fwd(mnf_ctx* ctx, const mnf_scene* scene, const fl
 
 int32_t mnf_decoder_samples_fwd(mnf_ctx* ctx, const mnf_decoder_cfg* cfg, const float* pts_ndc, const float* ray_unit,
                                 const float* cond_f32, int64_t n_rays, float* out_rgb_sigma, void* stream) {
+  DeviceGuard dev_guard(ctx);
   if (!ctx) { set_error("ctx is NULL"); return MNF_EINVAL; }
   if (!ctx->loaded) { set_error("decoder weights not loaded (call mnf_decoder_load_host)"); return MNF_ESTATE; }
   int rc;
@@ -323,6 +345,7 @@ int32_t mnf_decoder_samples_fwd(mnf_ctx* ctx, const mnf_decoder_cfg* cfg, const 
 int32_t mnf_composite_fwd(mnf_ctx* ctx, const float* rgb, const float* sigma, const float* depth, int64_t n_rays,
                           int32_t n_samples, int32_t setbg_opaque, float* out_rgb, float* out_depth, float* out_opacity,
                           float* out_prob, void* stream) {
+  DeviceGuard dev_guard(ctx);
   if (!ctx) { set_error("ctx is NULL"); return MNF_EINVAL; }
   if (n_rays < 0 || n_samples < 1) { set_error("mnf_composite_fwd: bad shape R=%lld S=%d", (long long)n_rays, n_samples); return MNF_EINVAL; }
   if (n_rays == 0) return MNF_OK;
@@ -331,32 +354,37 @@ int32_t mnf_composite_fwd(mnf_ctx* ctx, const float* rgb, const float* sigma, co
                           (cudaStream_t)stream);
 }
 
-int64_t mnf_render_workspace_bytes(int64_t n_rays, int32_t n_samples) {
+int64_t mnf_render_workspace_bytes(int64_t n_rays, int32_t n_samples, int32_t impl) {
   if (n_rays < 0 || n_samples < 0) return 0;
   const int64_t n = n_rays * (int64_t)n_samples;
-  // fp32 [N][22] then fp16 [N][32], each rounded up to 256 B
-  const int64_t a = ((n * kCond * 4 + 255) / 256) * 256;
-  const int64_t b = ((n * kCondPad * 2 + 255) / 256) * 256;
-  return a + b;
+  if (impl == 0) {
+    mnf_decoder_cfg cfg{};
+    cfg.n_samples = n_samples;
+    impl = decoder_tc_supports(cfg) ? 2 : 1;
+  }
+  // ONE conditioning region, in the layout the selected decoder kernel reads: fp32 [N][22] or fp16 [N][32]
+  const int64_t bytes = impl == 1 ? n * kCond * 4 : n * kCondPad * 2;
+  return ((bytes + 255) / 256) * 256;
 }
 
 int32_t mnf_render_rays_fwd(mnf_ctx* ctx, const mnf_scene* scene, const mnf_rays* rays, const mnf_decoder_cfg* cfg,
                             int32_t setbg_opaque, float* out_rgb, float* out_depth, float* out_opacity, void* workspace,
                             int64_t workspace_bytes, int32_t impl, void* stream) {
+  DeviceGuard dev_guard(ctx);
   if (!ctx || !rays || !cfg) { set_error("NULL argument"); return MNF_EINVAL; }
   int rc;
   if ((rc = check_cfg(cfg))) return rc;
   if (rays->n_rays == 0) return MNF_OK;
-  const int64_t need = mnf_render_workspace_bytes(rays->n_rays, cfg->n_samples);
+  if (impl == 0) impl = decoder_tc_supports(*cfg) ? 2 : 1;
+  if (impl != 1 && impl != 2) { set_error("impl must be 0, 1 or 2"); return MNF_EINVAL; }
+  const int64_t need = mnf_render_workspace_bytes(rays->n_rays, cfg->n_samples, impl);
   if (!workspace || workspace_bytes < need) {
     set_error("workspace too small: %lld < %lld bytes", (long long)workspace_bytes, (long long)need);
     return MNF_ENOMEM;
   }
   if (((uintptr_t)workspace & 255) != 0) { set_error("workspace must be 256-byte aligned"); return MNF_EINVAL; }
-  if (impl == 0) impl = decoder_tc_supports(*cfg) ? 2 : 1;
-  const int64_t n = rays->n_rays * (int64_t)cfg->n_samples;
   float* cond32 = reinterpret_cast<float*>(workspace);
-  void* cond16 = reinterpret_cast<unsigned char*>(workspace) + ((n * kCond * 4 + 255) / 256) * 256;
+  void* cond16 = workspace;
   rc = mnf_gather_cossim_fwd(ctx, scene, rays, cfg->n_samples, impl == 1 ? cond32 : nullptr, impl == 2 ? cond16 : nullptr, stream);
   if (rc) return rc;
   return mnf_decoder_composite_fwd(ctx, scene, rays, cfg, impl == 1 ? cond32 : nullptr, impl == 2 ? cond16 : nullptr, setbg_opaque,
@@ -365,6 +393,7 @@ int32_t mnf_render_rays_fwd(mnf_ctx* ctx, const mnf_scene* scene, const mnf_rays
 
 int32_t mnf_instance_norm_fwd(mnf_ctx* ctx, const float* x, const float* residual, float* y, int64_t n_planes, int32_t hw,
                               int32_t mode, float eps, void* stream) {
+  DeviceGuard dev_guard(ctx);
   if (!ctx || !x || !y) { set_error("mnf_instance_norm_fwd: NULL argument"); return MNF_EINVAL; }
   if (n_planes < 0 || hw <= 0) { set_error("mnf_instance_norm_fwd: bad shape planes=%lld hw=%d", (long long)n_planes, hw); return MNF_EINVAL; }
   if (mode < 0 || mode > 2 || (mode == 2 && !residual)) { set_error("mnf_instance_norm_fwd: mode must be 0, 1 or 2 (2 needs a residual)"); return MNF_EINVAL; }
@@ -378,6 +407,7 @@ int64_t mnf_window_attn_workspace_bytes(int32_t B, int32_t h, int32_t w, int32_t
 int32_t mnf_window_attn_fwd(mnf_ctx* ctx, const float* q, const float* k, const float* v, float* out, int32_t B, int32_t h,
                             int32_t w, int32_t C, int32_t num_splits, int32_t with_shift, int32_t impl, void* workspace,
                             int64_t workspace_bytes, void* stream) {
+  DeviceGuard dev_guard(ctx);
   if (!ctx || !q || !k || !v || !out) { set_error("mnf_window_attn_fwd: NULL argument"); return MNF_EINVAL; }
   if (C != 128) { set_error("mnf_window_attn_fwd: C = %d unsupported (feature_channels is 128)", C); return MNF_EUNSUPPORTED; }
   if (B <= 0 || h <= 0 || w <= 0 || num_splits <= 0 || h % num_splits || w % num_splits) {

@@ -354,7 +354,8 @@ int launch_decoder_ref(const DevCams& cams, const DevRays& rays, const mnf_decod
                        const DecoderWeightsF32& w, const float* cond_f32, int setbg_opaque, float* out_rgb,
                        float* out_depth, float* out_opacity, float* aux, cudaStream_t s) {
   if (rays.n_rays <= 0) return MNF_OK;
-  static bool configured = false;
+  static PerDevice<bool> configured_dev;
+  bool& configured = configured_dev.cur();
   const size_t smem = sizeof(Smem);
   if (!configured) {
     MNF_CUDA_TRY(cudaFuncSetAttribute(decoder_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

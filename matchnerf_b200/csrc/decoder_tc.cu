@@ -25,6 +25,7 @@
 // (DESIGN.md "precision").  Activations are assumed to stay below the fp16 range (65504).
 #include <cuda_fp16.h>
 
+#include <cmath>
 #include <vector>
 
 #include "decoder_weights.cuh"
@@ -186,6 +187,18 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
+}
+// sin / cos of the base angle of the positional encoding.  Two-term Cody-Waite reduction to [-pi, pi] followed by the MUFU
+// approximations (abs error ~1e-6 there): the reference evaluates sin(2^k x) in fp32, whose argument rounding alone is
+// 2^k ulp(x), and the results are rounded to fp16 operands (5e-4), so the accurate sincosf (with its Payne-Hanek slow path:
+// ~100 instructions, a constant-table walk) buys nothing.  |x| beyond ~1e5 (NDC of points far outside view 0) loses the
+// reduction's accuracy -- exactly where the reference's own fp32 sin(512 x) is noise.
+__device__ __forceinline__ void sincos_reduced(float x, float& s, float& c) {
+  const float n = rintf(x * 0.15915494309189535f);
+  float r = fmaf(n, -6.2831854820251465f, x);          // 2 pi = hi + lo
+  r = fmaf(n, 1.7484555e-7f, r);
+  s = __sinf(r);
+  c = __cosf(r);
 }
 __device__ __forceinline__ float rcp_fast(float x) {
   float y;
@@ -370,6 +383,7 @@ __device__ __forceinline__ void ray_transformer_mma(TcSmem& sm, const int slot, 
 struct DecoderWeightsTC {
   unsigned char* packed = nullptr;   // device: kPackedBytes of pre-swizzled fp16 chunks
   TcParams* params = nullptr;        // device
+  float4* posenc = nullptr;          // device: [kMaxSamples][16] sinusoid table of the ray transformer (cond_nerf.py:118-127)
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -377,7 +391,7 @@ template <int kAct>
 __global__ void __launch_bounds__(kThreads, 1)
 decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, const mnf_decoder_cfg cfg,
                   const unsigned char* __restrict__ wpacked, const TcParams* __restrict__ gparams,
-                  const __half* __restrict__ cond, const int setbg_opaque, float* __restrict__ out_rgb,
+                  const float4* __restrict__ posenc_tab, const __half* __restrict__ cond, const int setbg_opaque, float* __restrict__ out_rgb,
                   float* __restrict__ out_depth, float* __restrict__ out_opacity, float* __restrict__ aux) {
   extern __shared__ unsigned char smem_dyn[];
   TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_dyn + ((1024u - (tc::smem_u32(smem_dyn) & 1023u)) & 1023u));
@@ -557,9 +571,11 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
           float p[3];
 #pragma unroll
           for (int i = 0; i < 3; ++i) p[i] = __fadd_rn(o[i], __fmul_rn(d[i], depth_t));
-          project_ndc(cams, 0, p, x[0], x[1], x[2]);
-          const float nrm = fmaxf(sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]), 1e-12f);
-          const float ux = d[0] / nrm, uy = d[1] / nrm, uz = d[2] / nrm;
+          // the NDC point and the unit direction only feed fp16 operands: reciprocal-multiply forms (a few ulp) instead of IEEE
+          // divisions / square root (the gather keeps the exact forms: its mask decisions hang on them)
+          project_ndc_fast(cams, 0, p, x[0], x[1], x[2]);
+          const float inv = rsqrtf(fmaxf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2], 1e-24f));
+          const float ux = d[0] * inv, uy = d[1] * inv, uz = d[2] * inv;
           const float* E = cams.w2c[0];
           dir[0] = ux * E[0] + uy * E[1] + uz * E[2];
           dir[1] = ux * E[4] + uy * E[5] + uz * E[6];
@@ -574,7 +590,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         // encoding order (cond_nerf.py:108-116, :56-57): x, sin(2^k x) k-major, cos(2^k x) k-major, zero pad
         float sn[3], cs[3];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) sincosf(x[i], &sn[i], &cs[i]);
+        for (int i = 0; i < 3; ++i) sincos_reduced(x[i], sn[i], cs[i]);
         TRACE_TRUNK(32);
         uint32_t e[32];
         float prev = 0.f;  // pairs are emitted in index order: idx 0..63
@@ -640,13 +656,21 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
       mbar_wait_sleep(&sm.d_full[slot], 0, 32);
       TRACE_TRUNK(2);
       tc::tc_fence_after_sync();
+      {   // 16-column chunks, the load of chunk c + 1 in flight while chunk c is converted (tcgen05.wait::ld covers all loads issued so far)
+        uint32_t ra[16], rb[16];
+        tc::tmem_ld16(tb + kColD, ra);
+        tc::tmem_wait_ld(ra);
 #pragma unroll
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        uint32_t r[32];
-        tc::tmem_ld32(tb + kColD + c0, r);
-        tc::tmem_wait_ld();
+        for (int c = 0; c < 8; c += 2) {
+          tc::tmem_ld16(tb + kColD + 16 * (c + 1), rb);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) gate[c0 / 2 + j] = pack_h2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+          for (int j = 0; j < 8; ++j) gate[8 * c + j] = pack_h2(__uint_as_float(ra[2 * j]), __uint_as_float(ra[2 * j + 1]));
+          tc::tmem_wait_ld(rb);
+          if (c + 2 < 8) tc::tmem_ld16(tb + kColD + 16 * (c + 2), ra);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) gate[8 * (c + 1) + j] = pack_h2(__uint_as_float(rb[2 * j]), __uint_as_float(rb[2 * j + 1]));
+          if (c + 2 < 8) tc::tmem_wait_ld(ra);
+        }
       }
       tc::tc_fence_before_sync();
       tc::mbar_arrive(&sm.a_ready[slot]);
@@ -658,16 +682,24 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         mbar_wait_sleep(&sm.d_full[slot], (l + 1) & 1, 32);
         TRACE_TRUNK(20 + l);
         tc::tc_fence_after_sync();
+        {   // software-pipelined epilogue: 16 accumulator columns per step, the next step's tcgen05.ld issued before this step's math
+          uint32_t ra[16], rb[16];
+          tc::tmem_ld16(tb + kColD, ra);
+          tc::tmem_wait_ld(ra);
 #pragma unroll
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t r[32];
-          tc::tmem_ld32(tb + kColD + c0, r);
-          tc::tmem_wait_ld();
-          uint32_t o16[16];
+          for (int c = 0; c < 8; c += 2) {
+            uint32_t o8[8];
+            tc::tmem_ld16(tb + kColD + 16 * (c + 1), rb);
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            o16[j] = gate_relu(pack_h2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])), gate[c0 / 2 + j]);
-          tc::tmem_st16(tb + kColH + c0 / 2, o16);
+            for (int j = 0; j < 8; ++j) o8[j] = gate_relu(pack_h2(__uint_as_float(ra[2 * j]), __uint_as_float(ra[2 * j + 1])), gate[8 * c + j]);
+            tc::tmem_st8(tb + kColH + 8 * c, o8);
+            tc::tmem_wait_ld(rb);
+            if (c + 2 < 8) tc::tmem_ld16(tb + kColD + 16 * (c + 2), ra);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o8[j] = gate_relu(pack_h2(__uint_as_float(rb[2 * j]), __uint_as_float(rb[2 * j + 1])), gate[8 * (c + 1) + j]);
+            tc::tmem_st8(tb + kColH + 8 * (c + 1), o8);
+            if (c + 2 < 8) tc::tmem_wait_ld(ra);
+          }
         }
         tc::tmem_wait_st();
         tc::tc_fence_before_sync();
@@ -686,13 +718,13 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         tc::tmem_ld16(tb + kColD, r16);
         tc::tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float v = act_fn<kAct>(__uint_as_float(r16[j]) + sm.p.alpha_b[j]);
-          if (cfg.raytrans_posenc) {   // cond_nerf.py:118-127
-            const float ang = (float)s * exp2f(-(float)(j >> 1) * (13.287712379549449f / 8.f));   // s / 10000^(2*(j/2)/16)
-            v += (j & 1) ? cosf(ang) : sinf(ang);
+        for (int j = 0; j < 16; ++j) xr[j] = act_fn<kAct>(__uint_as_float(r16[j]) + sm.p.alpha_b[j]);
+        if (cfg.raytrans_posenc) {     // cond_nerf.py:118-127: the table is built on the host in float64, as the reference does
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 pe = __ldg(posenc_tab + s * 4 + j);
+            xr[4 * j] += pe.x; xr[4 * j + 1] += pe.y; xr[4 * j + 2] += pe.z; xr[4 * j + 3] += pe.w;
           }
-          xr[j] = v;
         }
         TRACE_TRUNK(40);
         pk2 accrg = pk(sm.p.rgb_b[0], sm.p.rgb_b[1]), accb = pk(sm.p.rgb_b[2], 0.f);
@@ -940,6 +972,16 @@ int decoder_tc_pack(const float* P, const ParamOffsets& off, DecoderWeightsTC** 
   MNF_CUDA_TRY(cudaMemcpy(w->packed, buf.data(), kPackedBytes, cudaMemcpyHostToDevice));
   MNF_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&w->params), sizeof(TcParams)));
   MNF_CUDA_TRY(cudaMemcpy(w->params, &tp, sizeof(TcParams), cudaMemcpyHostToDevice));
+  {
+    std::vector<float> tab((size_t)kMaxSamples * 16);
+    for (int pos = 0; pos < kMaxSamples; ++pos)
+      for (int j = 0; j < 16; ++j) {
+        const double ang = (double)pos / pow(10000.0, 2.0 * (double)(j / 2) / 16.0);
+        tab[(size_t)pos * 16 + j] = (float)((j & 1) ? cos(ang) : sin(ang));
+      }
+    MNF_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&w->posenc), tab.size() * sizeof(float)));
+    MNF_CUDA_TRY(cudaMemcpy(w->posenc, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
   *out = w;
   return MNF_OK;
 }
@@ -948,6 +990,7 @@ void decoder_tc_free(DecoderWeightsTC* w) {
   if (!w) return;
   cudaFree(w->packed);
   cudaFree(w->params);
+  cudaFree(w->posenc);
   delete w;
 }
 
@@ -961,7 +1004,8 @@ int launch_decoder_tc(const DevCams& cams, const DevRays& rays, const mnf_decode
                       float* out_opacity, float* aux, cudaStream_t s) {
   if (rays.n_rays <= 0) return MNF_OK;
   if (!w) { set_error("tcgen05 decoder weights not packed"); return MNF_ESTATE; }
-  static int n_sm = 0;
+  static PerDevice<int> n_sm_dev;
+  int& n_sm = n_sm_dev.cur();
   const size_t smem = sizeof(TcSmem) + 1024;
   if (n_sm == 0) {
     int dev = 0;
@@ -975,10 +1019,10 @@ int launch_decoder_tc(const DevCams& cams, const DevRays& rays, const mnf_decode
   const int64_t n_pairs = (n_tiles + 1) / 2;
   const unsigned grid = (unsigned)(n_pairs < n_sm ? n_pairs : n_sm);
   if (cfg.raytrans_act == 0)
-    decoder_tc_kernel<0><<<grid, kThreads, smem, s>>>(cams, rays, cfg, w->packed, w->params, cond_f16, setbg_opaque, out_rgb,
+    decoder_tc_kernel<0><<<grid, kThreads, smem, s>>>(cams, rays, cfg, w->packed, w->params, w->posenc, cond_f16, setbg_opaque, out_rgb,
                                                       out_depth, out_opacity, aux);
   else
-    decoder_tc_kernel<1><<<grid, kThreads, smem, s>>>(cams, rays, cfg, w->packed, w->params, cond_f16, setbg_opaque, out_rgb,
+    decoder_tc_kernel<1><<<grid, kThreads, smem, s>>>(cams, rays, cfg, w->packed, w->params, w->posenc, cond_f16, setbg_opaque, out_rgb,
                                                       out_depth, out_opacity, aux);
   MNF_CUDA_TRY(cudaGetLastError());
   return MNF_OK;

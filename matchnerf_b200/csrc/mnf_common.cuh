@@ -31,6 +31,20 @@ int cuda_fail(cudaError_t e, const char* what);
     if (_e != cudaSuccess) return ::mnf::cuda_fail(_e, #expr); \
   } while (0)
 
+// Per-device launch state.  cudaFuncSetAttribute and the SM count belong to a DEVICE, not to the process: a library used from
+// one process on several GPUs (nn.DataParallel, one context per device) must configure every device it launches on.
+// The slot of the CURRENT device is returned; the ABI entry points make the context's device current (api.cu DeviceGuard).
+constexpr int kMaxDevices = 64;
+template <typename T>
+struct PerDevice {
+  T v[kMaxDevices] = {};
+  T& cur() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return v[(d >= 0 && d < kMaxDevices) ? d : 0];
+  }
+};
+
 // Camera block handed to kernels by value (constant bank): everything the per-ray geometry needs.
 struct DevCams {
   float w2c[kViews][12];

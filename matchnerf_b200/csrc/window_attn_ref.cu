@@ -190,7 +190,8 @@ int launch_window_attn_ref(const float* q, const float* k, const float* v, float
   g.sh = (with_shift && num_splits > 1) ? g.wh / 2 : 0;
   g.sw = (with_shift && num_splits > 1) ? g.ww / 2 : 0;
   const int Lw = g.wh * g.ww;
-  static bool configured = false;
+  static PerDevice<bool> configured_dev;
+  bool& configured = configured_dev.cur();
   if (!configured) {
     MNF_CUDA_TRY(cudaFuncSetAttribute(window_attn_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttnSmem)));
     configured = true;

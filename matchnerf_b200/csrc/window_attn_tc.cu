@@ -715,7 +715,8 @@ int launch_window_attn_tc(const float* q, const float* k, const float* v, float*
   if (pipe >= 2 && workspace && workspace_bytes >= window_attn_tc_workspace_bytes(B, h, w, num_splits) &&
       ((uintptr_t)workspace & 15) == 0) {
     const size_t smem = sizeof(AttnV4Smem) + 1024;
-    static bool configured = false;
+    static PerDevice<bool> configured_dev;
+    bool& configured = configured_dev.cur();
     if (!configured) {
       MNF_CUDA_TRY(cudaFuncSetAttribute(window_attn_tc_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured = true;
@@ -726,7 +727,8 @@ int launch_window_attn_tc(const float* q, const float* k, const float* v, float*
     window_attn_tc_v4_kernel<<<grid, kV4Threads, smem, s>>>(reinterpret_cast<const unsigned char*>(workspace), out, g);
   } else {              // no workspace: every CTA gathers and converts its own operand tiles (v3)
     const size_t smem = sizeof(AttnPipeSmem) + 1024;
-    static bool configured = false;
+    static PerDevice<bool> configured_dev;
+    bool& configured = configured_dev.cur();
     if (!configured) {
       MNF_CUDA_TRY(cudaFuncSetAttribute(window_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured = true;

@@ -270,11 +270,13 @@ class GMFlow(nn.Module):
     upsampler_memory_format = torch.channels_last
 
     def forward(self, imgs, attn_splits_list: Optional[Sequence[int]] = None, keep_raw_feats: bool = False,
-                wo_self_attn: bool = False, **kwargs):
+                wo_self_attn: bool = False, pair_ids: Optional[Sequence[int]] = None, **kwargs):
+        """``pair_ids`` (not in the reference): encode only these view pairs (indices into the (0,1), (0,2), (1,2) list) -- the
+        multi-GPU encoder split of matchnerf_b200.sharding; the returned tensors then hold len(pair_ids) pairs."""
         with _matmul_precision(self.matmul_precision):
-            return self._forward(imgs, attn_splits_list, keep_raw_feats, wo_self_attn)
+            return self._forward(imgs, attn_splits_list, keep_raw_feats, wo_self_attn, pair_ids)
 
-    def _forward(self, imgs, attn_splits_list, keep_raw_feats, wo_self_attn):
+    def _forward(self, imgs, attn_splits_list, keep_raw_feats, wo_self_attn, pair_ids=None):
         B, V, _, H, W = imgs.shape
         if H == 756 and W == 1008:     # IBRNet setting: pad to a size divisible by 16 (gmflow.py:99-103)
             imgs = F.interpolate(imgs.reshape(B * V, 3, H, W), size=(768, 1024), mode="bilinear",
@@ -284,6 +286,8 @@ class GMFlow(nn.Module):
                              .contiguous(memory_format=self.backbone_memory_format))
         base = base.reshape(B, V, *base.shape[1:])
         pairs = [(a, b) for a in range(V - 1) for b in range(a + 1, V)]
+        if pair_ids is not None:
+            pairs = [pairs[i] for i in pair_ids]
         f0 = torch.stack([base[:, a] for a, _ in pairs], 1).flatten(0, 1)        # [B*P, C, h, w]
         f1 = torch.stack([base[:, b] for _, b in pairs], 1).flatten(0, 1)
         h, w = f0.shape[-2:]

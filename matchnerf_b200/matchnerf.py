@@ -13,6 +13,7 @@ CPU or pure-PyTorch fallback for the per-ray path.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -68,16 +69,35 @@ class MatchNeRF(nn.Module):
 
     def get_img_feat(self, imgs, attn_splits_list=None, cur_n_src_views=3) -> List[torch.Tensor]:
         """[B,V,3,H,W] -> [[B,V,256,H/8,W/8], [B,V,256,H/4,W/4]]: view i holds the features it got as a member of
-        each of its pairs (models/matchnerf.py:183-207)."""
+        each of its pairs (models/matchnerf.py:183-207).  Returns FRESH tensors, as the reference does: the CUDA-graph replay
+        writes into static buffers that the next call overwrites, so the public method hands out copies (78 MB at DTU size,
+        ~25 us); ``forward`` consumes the static buffers directly (they are packed before the next encoder call)."""
+        feats = self._get_img_feat_static(imgs, attn_splits_list, cur_n_src_views)
+        if getattr(self, "_enc_graph", None) is not None and any(f is g for f in feats for g in self._enc_graph[3]):
+            feats = [f.clone() for f in feats]
+        return feats
+
+    def _get_img_feat_static(self, imgs, attn_splits_list=None, cur_n_src_views=3) -> List[torch.Tensor]:
+        """get_img_feat whose result may alias the encoder graph's static output buffers (valid until the next call)."""
         if attn_splits_list is None:
             attn_splits_list = get_opt(self.opts, "encoder.attn_splits_list", [2])
+        world = self._shard_world()
+        if world > 1 and imgs.is_cuda and not torch.is_grad_enabled():
+            return self._get_img_feat_sharded(imgs, attn_splits_list, cur_n_src_views, world)
+        return self._regroup_pairs(self._encode_pairs_static(imgs, attn_splits_list, cur_n_src_views, None), cur_n_src_views)
+
+    def _encode_pairs_static(self, imgs, attn_splits_list, cur_n_src_views, pair_ids):
+        """GMFlow on the listed view pairs (None = all): [(f0, f1) per scale], each [B, P', 128, h, w].  CUDA-graph replay in
+        inference: the result then lives in the graph's static buffers (valid until the next call with the same key)."""
         if not (self.encoder_cuda_graph and imgs.is_cuda and imgs.dtype == torch.float32 and not torch.is_grad_enabled()
                 and not torch.cuda.is_current_stream_capturing()):
-            return self._get_img_feat_eager(imgs, attn_splits_list, cur_n_src_views)
+            return self._encode_pairs(imgs, attn_splits_list, cur_n_src_views, pair_ids)
         enc = self._unwrap(self.feat_enc)
         params = tuple(enc.parameters())
+        from .gmflow import TransformerLayer
         key = (tuple(imgs.shape), imgs.device, tuple(attn_splits_list), cur_n_src_views, enc.matmul_precision,
-               tuple(p.data_ptr() for p in params), sum(p._version for p in params))
+               str(TransformerLayer.ffn_dtype), bool(get_opt(self.opts, "encoder.wo_self_attn", False)),
+               None if pair_ids is None else tuple(pair_ids), tuple(p.data_ptr() for p in params), sum(p._version for p in params))
         hit = getattr(self, "_enc_graph", None)
         if hit is None or hit[0] != key:
             static_in = imgs.detach().clone()
@@ -85,18 +105,18 @@ class MatchNeRF(nn.Module):
             side.wait_stream(torch.cuda.current_stream(imgs.device))
             with torch.cuda.stream(side):                       # warm-up outside the capture: lazy handles, autotuning, caches
                 for _ in range(2):
-                    self._get_img_feat_eager(static_in, attn_splits_list, cur_n_src_views)
+                    self._encode_pairs(static_in, attn_splits_list, cur_n_src_views, pair_ids)
             torch.cuda.current_stream(imgs.device).wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             try:
                 with torch.cuda.graph(graph):
-                    static_out = self._get_img_feat_eager(static_in, attn_splits_list, cur_n_src_views)
+                    static_out = self._encode_pairs(static_in, attn_splits_list, cur_n_src_views, pair_ids)
             except RuntimeError as e:            # an op that cannot be captured on this torch build: stay eager (same kernels)
                 import warnings
                 warnings.warn(f"matchnerf_b200: encoder CUDA-graph capture failed ({e}); running the encoder eagerly")
                 self.encoder_cuda_graph = False
                 torch.cuda.synchronize(imgs.device)
-                return self._get_img_feat_eager(imgs, attn_splits_list, cur_n_src_views)
+                return self._encode_pairs(imgs, attn_splits_list, cur_n_src_views, pair_ids)
             hit = (key, graph, static_in, static_out)
             self._enc_graph = hit
         hit[2].copy_(imgs)
@@ -104,13 +124,20 @@ class MatchNeRF(nn.Module):
         self._feat_epoch = getattr(self, "_feat_epoch", 0) + 1     # static outputs rewritten in place: invalidates packed scenes
         return hit[3]
 
-    def _get_img_feat_eager(self, imgs, attn_splits_list, cur_n_src_views=3) -> List[torch.Tensor]:
+    def _encode_pairs(self, imgs, attn_splits_list, cur_n_src_views=3, pair_ids=None):
         V = cur_n_src_views
+        self._feat_epoch = getattr(self, "_feat_epoch", 0) + 1     # a new set of feature maps: packed scenes of older ones are stale
         out = self.feat_enc(imgs=imgs[:, :V], attn_splits_list=attn_splits_list, keep_raw_feats=True,
-                            wo_self_attn=bool(get_opt(self.opts, "encoder.wo_self_attn", False)))
+                            wo_self_attn=bool(get_opt(self.opts, "encoder.wo_self_attn", False)), pair_ids=pair_ids)
+        return list(zip(out["aug_feat0s"], out["aug_feat1s"]))
+
+    @staticmethod
+    def _regroup_pairs(pair_feats, V=3) -> List[torch.Tensor]:
+        """[(f0, f1) per scale] with all P pairs -> per-view 256-channel maps (models/matchnerf.py:192-205): view i holds the
+        features it got as a member of each of its pairs."""
         pairs = [(a, b) for a in range(V - 1) for b in range(a + 1, V)]
         feats = []
-        for f0, f1 in zip(out["aug_feat0s"], out["aug_feat1s"]):
+        for f0, f1 in pair_feats:
             per_view = [[] for _ in range(V)]
             for p, (i, j) in enumerate(pairs):
                 per_view[i].append(f0[:, p])
@@ -118,10 +145,98 @@ class MatchNeRF(nn.Module):
             feats.append(torch.stack([torch.cat(x, dim=1) for x in per_view], dim=1))
         return feats
 
+    def _get_img_feat_eager(self, imgs, attn_splits_list, cur_n_src_views=3) -> List[torch.Tensor]:
+        return self._regroup_pairs(self._encode_pairs(imgs, attn_splits_list, cur_n_src_views, None), cur_n_src_views)
+
+    # ------------------------------------------------------------------ multi-GPU: one image split over the ranks (SURVEY 8e route B)
+    # Off by default: a model inside an image-parallel job (one target view per rank) must not start collectives of its own.
+    # ``MNF_SHARD_RANKS=1`` or ``model.shard_over_ranks = True`` turns it on for torchrun-launched test.py / bench.py --shard rays.
+    shard_over_ranks = bool(int(os.environ.get("MNF_SHARD_RANKS", "0")))
+
+    def _shard_world(self) -> int:
+        if not self.shard_over_ranks:
+            return 1
+        import torch.distributed as dist
+        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    def _get_img_feat_sharded(self, imgs, attn_splits_list, V, world):
+        """Encoder split over the ranks: the CNN backbone runs replicated (3 views), the transformer + up-sampler of view pair p
+        only on rank ``pair_owner[p]``; the pair's four feature maps travel in ONE broadcast from a contiguous per-pair buffer."""
+        import torch.distributed as dist
+        from .sharding import pair_owner
+        rank = dist.get_rank()
+        n_pairs = V * (V - 1) // 2
+        owner = pair_owner(n_pairs, world)
+        mine = [p for p in range(n_pairs) if owner[p] == rank]
+        B, _, _, H, W = imgs.shape
+        local = self._encode_pairs_static(imgs, attn_splits_list, V, mine) if mine else None
+        key = (tuple(imgs.shape), imgs.device)
+        ex = getattr(self, "_pair_exchange", None)
+        if ex is None or ex[0] != key:
+            if local is not None:
+                shapes = [tuple(f0.shape[2:]) for f0, _ in local]
+            else:                                                  # a rank without pairs: shapes from the encoder geometry
+                hh, ww = (768, 1024) if (H, W) == (756, 1008) else (H, W)
+                up = int(get_opt(self.opts, "encoder.upsample_factor", 2))
+                shapes = [(128, hh // 8, ww // 8), (128, hh // 8 * up, ww // 8 * up)]
+            sizes = [B * c * h * w for c, h, w in shapes]
+            bufs = [torch.empty((2 * sum(sizes),), dtype=torch.float32, device=imgs.device) for _ in range(n_pairs)]
+            ex = (key, bufs, shapes, sizes)
+            self._pair_exchange = ex
+        _, bufs, shapes, sizes = ex
+
+        def views(p):
+            out, off = [], 0
+            for (c, h, w), n in zip(shapes, sizes):
+                out.append((bufs[p][off: off + n].view(B, c, h, w), bufs[p][off + n: off + 2 * n].view(B, c, h, w)))
+                off += 2 * n
+            return out
+        for j, p in enumerate(mine):
+            for (d0, d1), (f0, f1) in zip(views(p), local):
+                d0.copy_(f0[:, j])
+                d1.copy_(f1[:, j])
+        for p in range(n_pairs):
+            dist.broadcast(bufs[p], src=owner[p])
+        self._feat_epoch = getattr(self, "_feat_epoch", 0) + 1
+        per_pair = [views(p) for p in range(n_pairs)]
+        pair_feats = [(torch.stack([per_pair[p][s][0] for p in range(n_pairs)], 1), torch.stack([per_pair[p][s][1] for p in range(n_pairs)], 1))
+                      for s in range(len(shapes))]
+        return self._regroup_pairs(pair_feats, V)
+
+    def _render_image_sharded(self, opt, tgt_pose, mode, ref_poses, ref_images, ref_feats_list):
+        """One full image with its rows split over the ranks: each rank renders its row block straight into its slot of the
+        persistent gather buffers, then rgb / depth / opacity are all-gathered in place (sharding.ImageGather)."""
+        from .sharding import ImageGather
+        B = ref_images.shape[0]
+        H, W = ref_images.shape[-2:]
+        key = (H, W, ref_images.device)
+        hit = getattr(self, "_image_gather", None)
+        if hit is None or hit[0] != key:
+            hit = (key, ImageGather(H, W, ref_images.device))
+            self._image_gather = hit
+        ig = hit[1]
+        outs = []
+        for b in range(B):
+            out = ig.local_out()
+            self._render(opt, tgt_pose, None, ig.first, ig.n, mode, ref_poses, ref_images, ref_feats_list, out=out, only_b=b)
+            ig.all_gather()
+            ig.wait()
+            outs.append((ig.rgb.clone(), ig.depth[:, None].clone(), ig.opacity[:, None].clone()))
+        return AttrDict(rgb=torch.stack([o[0] for o in outs]), depth=torch.stack([o[1] for o in outs]),
+                        opacity=torch.stack([o[2] for o in outs]))
+
+    def launches_per_image(self, n_chunks: int = 1) -> int:
+        """Kernels of THIS library launched per full-image forward (bench.py's gpu_launches): gather + decoder per render chunk,
+        12 x (K-attn operand pre-pack + K-attn), 2 feature-map + 1 image packing kernels, 15 fused instance norms."""
+        return 2 * n_chunks + 24 + 3 + 15
+
     def _packed_scenes(self, ref_poses, ref_images, ref_feats_list):
         """Pack (once per set of feature maps) the per-batch-item scenes the kernels read."""
-        key = (ref_feats_list[0].data_ptr(), ref_feats_list[1].data_ptr(), ref_images.data_ptr(),
-               ref_feats_list[0]._version, ref_images._version, ref_poses["extrinsics"].data_ptr(), getattr(self, "_feat_epoch", 0))
+        # identity AND version of every tensor the packed scene is derived from (feature maps, images, all three camera
+        # tensors), plus the encoder epoch (graph replays rewrite the static feature buffers in place).  The source tensors are
+        # kept alive by the cache entry, so an address cannot be recycled by the allocator while its key is live.
+        src = (ref_feats_list[0], ref_feats_list[1], ref_images, ref_poses["extrinsics"], ref_poses["intrinsics"], ref_poses["near_fars"])
+        key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in src) + (getattr(self, "_feat_epoch", 0),)
         if self._scene_cache is not None and self._scene_cache[0] == key:
             return self._scene_cache[1]
         ctx = self._unwrap(self.nerf_dec).sync_to_library()
@@ -129,7 +244,7 @@ class MatchNeRF(nn.Module):
         for b in range(ref_images.shape[0]):
             scenes.append(ctx.pack_scene([ref_feats_list[0][b], ref_feats_list[1][b]], ref_images[b],
                                          ref_poses["extrinsics"][b], ref_poses["intrinsics"][b], ref_poses["near_fars"][b]))
-        self._scene_cache = (key, scenes)
+        self._scene_cache = (key, scenes, src)
         return scenes
 
     def _host_poses(self, batch):
@@ -147,7 +262,7 @@ class MatchNeRF(nn.Module):
 
     def _c_scene(self, scene, tgt_pose, b):
         """mnf_scene struct of batch item b for one target camera, built once per (scene, pose) and reused by every slice."""
-        key = (id(scene), id(tgt_pose), b, tgt_pose["extrinsics"]._version, tgt_pose["extrinsics"].data_ptr())
+        key = (id(scene), id(tgt_pose), b) + tuple((tgt_pose[k].data_ptr(), tgt_pose[k]._version) for k in ("extrinsics", "intrinsics", "near_fars"))
         hit = getattr(self, "_c_scene_cache", None)
         if hit is not None and hit[0] == key and hit[1] is tgt_pose:
             return hit[2]
@@ -165,8 +280,9 @@ class MatchNeRF(nn.Module):
 
     render_rays = render
 
-    def _render(self, opt, tgt_pose, ray_idx, first_ray, n_rays, mode, ref_poses, ref_images, ref_feats_list):
-        """One kernel-side slice: explicit pixel ids (``ray_idx``) or the contiguous range [first_ray, first_ray+n_rays)."""
+    def _render(self, opt, tgt_pose, ray_idx, first_ray, n_rays, mode, ref_poses, ref_images, ref_feats_list, out=None, only_b=None):
+        """One kernel-side slice: explicit pixel ids (``ray_idx``) or the contiguous range [first_ray, first_ray+n_rays).
+        ``out`` = (rgb [R,3], depth [R], opacity [R]) makes the kernels write into caller buffers (batch item ``only_b``)."""
         if tgt_pose is None:
             raise Exception("Must provide tgt_pose.")
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
@@ -179,11 +295,11 @@ class MatchNeRF(nn.Module):
         scenes = self._packed_scenes(ref_poses, ref_images, ref_feats_list)
         stratified = mode == "train" and bool(get_opt(opt, "nerf.sample_stratified", False))
         outs = []
-        for b in range(B):
+        for b in (range(B) if only_b is None else [only_b]):
             sc = self._c_scene(scenes[b], tgt_pose, b)
             jitter = torch.rand(n_rays, S, device=ctx.device) if stratified else None     # matchnerf.py:168-169
             rgb, depth, opac = ctx.render_rays(sc, cfg, ray_idx=ray_idx, first_ray=first_ray, n_rays=n_rays, jitter=jitter,
-                                               setbg_opaque=self.nerf_setbg_opaque)
+                                               setbg_opaque=self.nerf_setbg_opaque, out=out)
             outs.append((rgb, depth[:, None], opac[:, None]))
         return AttrDict(rgb=torch.stack([o[0] for o in outs]), depth=torch.stack([o[1] for o in outs]),
                         opacity=torch.stack([o[2] for o in outs]))
@@ -255,8 +371,8 @@ class MatchNeRF(nn.Module):
                                                    int(get_opt(self.opts, "nerf.video_n_frames", 30)), batch)
         else:
             frames = [tgt_pose]
-        ref_feats_list = self.get_img_feat(ref_images, attn_splits_list=get_opt(self.opts, "encoder.attn_splits_list", [2]),
-                                           cur_n_src_views=V)
+        ref_feats_list = self._get_img_feat_static(ref_images, attn_splits_list=get_opt(self.opts, "encoder.attn_splits_list", [2]),
+                                                   cur_n_src_views=V)
         B, _, _, H, W = ref_images.shape
         n_rand = int(get_opt(self.opts, f"nerf.rand_rays_{mode}", 0) or 0)
         collected: Dict[str, list] = {}
@@ -265,6 +381,8 @@ class MatchNeRF(nn.Module):
                 batch["ray_idx"] = torch.randperm(H * W, device=ref_images.device)[: n_rand // B]
                 ret = self.render(self.opts, cur_pose, ray_idx=batch["ray_idx"], mode=mode, ref_poses=ref_poses,
                                   ref_images=ref_images, ref_feats_list=ref_feats_list)
+            elif self._shard_world() > 1 and ref_images.is_cuda:
+                ret = self._render_image_sharded(self.opts, cur_pose, mode, ref_poses, ref_images, ref_feats_list)
             elif n_rand:
                 ret = self.render_by_slices(self.opts, cur_pose, mode=mode, ref_poses=ref_poses, ref_images=ref_images,
                                             ref_feats_list=ref_feats_list)

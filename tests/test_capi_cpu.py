@@ -85,7 +85,10 @@ def test_calls_fail_loudly_without_gpu(lib_path):
     assert rc != 0 and len(lib.mnf_last_error()) > 0
     with pytest.raises(RuntimeError):
         capi.Context()
-    assert lib.mnf_render_workspace_bytes(1024, 64) >= 1024 * 64 * (22 * 4 + 32 * 2)
+    assert lib.mnf_render_workspace_bytes(1024, 64, 1) >= 1024 * 64 * 22 * 4          # fp32 rows for the fp32 kernel
+    assert 1024 * 64 * 32 * 2 <= lib.mnf_render_workspace_bytes(1024, 64, 2) < 1024 * 64 * 32 * 2 + 256   # fp16 rows only
+    assert lib.mnf_render_workspace_bytes(1024, 64, 0) == lib.mnf_render_workspace_bytes(1024, 64, 2)       # auto = tcgen05 at S=64
+    assert lib.mnf_render_workspace_bytes(1024, 24, 0) == lib.mnf_render_workspace_bytes(1024, 24, 1)       # S=24: fp32 kernel
 
 
 def test_integration_doc_covers_every_compute_entry_point():
