@@ -496,7 +496,10 @@ def run_ours(args):
             ours_img = (out.rgb[0].clone(), out.depth[0].clone(), out.opacity[0].clone())
         other = 128 if S == 64 else 64
         m2 = build_model(other)
-        ms2, _ = timed(lambda: m2(AttrDict(resident), mode="test"), 5, 3)
+        def step_other():
+            with torch.no_grad():
+                return m2(AttrDict(resident), mode="test")
+        ms2, _ = timed(step_other, 5, 3)
         k2, _ = kernel_times(m2, other)
         with torch.no_grad():
             o2 = m2(AttrDict(resident), mode="test")

@@ -42,6 +42,8 @@ int64_t window_attn_tc_workspace_bytes(int B, int h, int w, int num_splits);
 
 using namespace mnf;
 
+constexpr int kGatherScratchInts = 1 << 16;
+
 struct mnf_ctx {
   int device = 0;
   bool loaded = false;
@@ -49,6 +51,7 @@ struct mnf_ctx {
   DecoderWeightsF32 wf32{};
   HeadParams* head_dev = nullptr;
   DecoderWeightsTC* wtc = nullptr;
+  int* gather_scratch = nullptr;   // device: [0] counter + tile list of the tensor-core gather's fix-up pass (one gather in flight per ctx)
 };
 
 namespace {
@@ -146,6 +149,10 @@ int32_t mnf_ctx_create(int32_t device, mnf_ctx** out) {
   }
   mnf_ctx* c = new mnf_ctx();
   c->device = device;
+  {
+    DeviceGuard dev_guard(c);
+    if (cudaMalloc(reinterpret_cast<void**>(&c->gather_scratch), kGatherScratchInts * sizeof(int)) != cudaSuccess) c->gather_scratch = nullptr;
+  }
   *out = c;
   return MNF_OK;
 }
@@ -156,6 +163,7 @@ int32_t mnf_ctx_destroy(mnf_ctx* ctx) {
     DeviceGuard dev_guard(ctx);
     for (void* p : ctx->allocs) cudaFree(p);
     if (ctx->wtc) decoder_tc_free(ctx->wtc);
+    if (ctx->gather_scratch) cudaFree(ctx->gather_scratch);
   }
   delete ctx;
   return MNF_OK;
@@ -271,7 +279,7 @@ int32_t mnf_gather_cossim_fwd(mnf_ctx* ctx, const mnf_scene* scene, const mnf_ra
   return launch_gather(cams, dr, n_samples, reinterpret_cast<const __half*>(scene->feat0), scene->h0, scene->w0,
                        reinterpret_cast<const __half*>(scene->feat1), scene->h1, scene->w1,
                        reinterpret_cast<const float*>(scene->images), cond_f32, reinterpret_cast<__half*>(cond_f16),
-                       (cudaStream_t)stream);
+                       (cudaStream_t)stream, ctx->gather_scratch, ctx->gather_scratch ? kGatherScratchInts : 0);
 }
 
 int32_t mnf_decoder_composite_fwd(mnf_ctx* ctx, const mnf_scene* scene, const mnf_rays* rays, const mnf_decoder_cfg* cfg,

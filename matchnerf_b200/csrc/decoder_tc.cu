@@ -129,6 +129,13 @@ __device__ unsigned int g_trace_cap = 0;
 
 __device__ __forceinline__ void trunk_barrier(int slot) { asm volatile("bar.sync %0, 128;" ::"r"(slot + 1) : "memory"); }
 __device__ __forceinline__ void ray_barrier(int slot) { asm volatile("bar.sync %0, 128;" ::"r"(slot + 3) : "memory"); }
+// S = 256: a ray spans BOTH slots of a tile pair (slot 0 = samples 0..127, slot 1 = samples 128..255), so the two ray groups
+// share keys / values and the compositing scan: their barriers then span both groups (256 threads, barrier id 5)
+template <bool kBoth>
+__device__ __forceinline__ void ray_barrier_s(int slot) {
+  if constexpr (kBoth) asm volatile("bar.sync 5, 256;" ::: "memory");
+  else ray_barrier(slot);
+}
 using tc::mbar_wait_sleep;
 template <int kRegs> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 template <int kRegs> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
@@ -220,9 +227,12 @@ __device__ __forceinline__ void ray_transformer_mma(TcSmem& sm, const int slot, 
   const bool lo = t < 2;
   const float* hand = &sm.hand[slot][buf][0][0];
   const float* hand_nv = &sm.hand_nv[slot][buf][0];
-  uint32_t qa[2][4];                               // Q as A fragments (fp16 pairs), per m-tile
+  // Both m-tile loops are ROLLED (#pragma unroll 1): the kernel's instruction footprint, not its instruction count, is what
+  // the timeline showed to be expensive -- every phase of every role used to run from a cold instruction cache (~90 KB of
+  // straight-line code per tile against a 32 KB L1.5 I-cache).  Fragments that outlive the loop are kept with selects.
+  uint32_t qa0[4] = {0u, 0u, 0u, 0u}, qa1[4] = {0u, 0u, 0u, 0u};   // Q as A fragments (fp16 pairs), per m-tile
   // ---------------- phase A
-#pragma unroll
+#pragma unroll 1
   for (int mt = 0; mt < 2; ++mt) {
     const int r0 = quarter * 32 + mt * 16 + g;     // fragment rows r0 and r0 + 8
     const float2 x00 = *reinterpret_cast<const float2*>(hand + r0 * kHandRow + 2 * t);
@@ -247,10 +257,15 @@ __device__ __forceinline__ void ray_transformer_mma(TcSmem& sm, const int slot, 
       mma16816(c[j], l0, l1, l2, l3, b0, b1);
       mma16816(c[j], a0, a1, a2, a3, b0, b1);
     }
-    qa[mt][0] = v0 ? pack_h2(c[0][0], c[0][1]) : 0u;
-    qa[mt][1] = v1 ? pack_h2(c[0][2], c[0][3]) : 0u;
-    qa[mt][2] = v0 ? pack_h2(c[1][0], c[1][1]) : 0u;
-    qa[mt][3] = v1 ? pack_h2(c[1][2], c[1][3]) : 0u;
+    {
+      const uint32_t q[4] = {v0 ? pack_h2(c[0][0], c[0][1]) : 0u, v1 ? pack_h2(c[0][2], c[0][3]) : 0u,
+                             v0 ? pack_h2(c[1][0], c[1][1]) : 0u, v1 ? pack_h2(c[1][2], c[1][3]) : 0u};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        qa0[i] = mt == 0 ? q[i] : qa0[i];
+        qa1[i] = mt == 0 ? qa1[i] : q[i];
+      }
+    }
     __half* k0 = &sm.kbuf[slot][r0][0];
     __half* k1 = &sm.kbuf[slot][r0 + 8][0];
     *reinterpret_cast<uint32_t*>(k0 + 2 * t) = pack_h2(c[2][0], c[2][1]);
@@ -266,21 +281,26 @@ __device__ __forceinline__ void ray_transformer_mma(TcSmem& sm, const int slot, 
     *reinterpret_cast<uint32_t*>(v0p + 16) = pack_h2(c[5][0], c[5][1]);
     *reinterpret_cast<uint32_t*>(v1p + 16) = pack_h2(c[5][2], c[5][3]);
   }
-  ray_barrier(slot);                               // a ray's keys / values come from up to four warps
+  ray_barrier_s<(kS > 128)>(slot);                 // a ray's keys / values come from up to four warps (eight when S = 256)
 
   // ---------------- phase B
   const float2 lnw0 = *reinterpret_cast<const float2*>(&sm.p.ln_w[2 * t]), lnw1 = *reinterpret_cast<const float2*>(&sm.p.ln_w[8 + 2 * t]);
   const float2 lnb0 = *reinterpret_cast<const float2*>(&sm.p.ln_b[2 * t]), lnb1 = *reinterpret_cast<const float2*>(&sm.p.ln_b[8 + 2 * t]);
-#pragma unroll
+#pragma unroll 1
   for (int mt = 0; mt < 2; ++mt) {
     const int rbase = quarter * 32 + mt * 16;      // first row of the m-tile; it lies inside one ray (kS >= 16)
-    const int key0 = rbase & ~(kS - 1);            // first key row of that ray
-    // ldmatrix lane addresses.  K (x4): matrices (n-tile 2np, k 0-7), (2np, k 8-15), (2np+1, k 0-7), (2np+1, k 8-15).
-    const uint32_t kaddr = tc::smem_u32(&sm.kbuf[slot][key0 + (lane >> 4) * 8 + (lane & 7)][((lane >> 3) & 1) * 8]);
-    // V (x2, transposed): matrices (keys 16np .. +7), (keys 16np + 8 .. +15), 8 columns of one head
-    const uint32_t vaddr = tc::smem_u32(&sm.vbuf[slot][key0 + ((lane >> 3) & 1) * 8 + (lane & 7)][0]);
-    uint32_t att[4];                               // normalised attention output as the A fragment of fc
+    uint32_t qm[4];
 #pragma unroll
+    for (int i = 0; i < 4; ++i) qm[i] = mt == 0 ? qa0[i] : qa1[i];
+    // first key row of that ray; S = 256: the ray's keys are the 256 rows of kbuf[0] followed by kbuf[1] (contiguous in memory)
+    const int key0 = kS > 128 ? 0 : (rbase & ~(kS - 1));
+    const int kslot = kS > 128 ? 0 : slot;
+    // ldmatrix lane addresses.  K (x4): matrices (n-tile 2np, k 0-7), (2np, k 8-15), (2np+1, k 0-7), (2np+1, k 8-15).
+    const uint32_t kaddr = tc::smem_u32(&sm.kbuf[kslot][key0 + (lane >> 4) * 8 + (lane & 7)][((lane >> 3) & 1) * 8]);
+    // V (x2, transposed): matrices (keys 16np .. +7), (keys 16np + 8 .. +15), 8 columns of one head
+    const uint32_t vaddr = tc::smem_u32(&sm.vbuf[kslot][key0 + ((lane >> 3) & 1) * 8 + (lane & 7)][0]);
+    uint32_t att[4] = {0u, 0u, 0u, 0u};            // normalised attention output as the A fragment of fc
+#pragma unroll 1
     for (int hp = 0; hp < 2; ++hp) {               // head pair (0,1) / (2,3)
       float o[2][4];
 #pragma unroll
@@ -288,10 +308,10 @@ __device__ __forceinline__ void ray_transformer_mma(TcSmem& sm, const int slot, 
         const int h = 2 * hp + hh;
         // Q_h: only the 4 k-columns of head h survive (k 0-3: t<2 of a0/a1; 4-7: t>=2; 8-11: t<2 of a2/a3; 12-15: t>=2)
         const bool mine = (hh == 0) ? lo : !lo;
-        const uint32_t q0 = mine ? qa[mt][2 * hp] : 0u, q1 = mine ? qa[mt][2 * hp + 1] : 0u;
+        const uint32_t q0 = mine ? (hp == 0 ? qm[0] : qm[2]) : 0u, q1 = mine ? (hp == 0 ? qm[1] : qm[3]) : 0u;
         const uint32_t a0 = hp == 0 ? q0 : 0u, a1 = hp == 0 ? q1 : 0u, a2 = hp == 0 ? 0u : q0, a3 = hp == 0 ? 0u : q1;
         float m0 = -INFINITY, m1 = -INFINITY;      // rows g, g + 8
-#pragma unroll
+#pragma unroll(kS / 16 > 4 ? 4 : kS / 16)
         for (int np = 0; np < kS / 16; ++np) {
           uint32_t kf[4];
           ldsm_x4(kf, kaddr + np * 16 * kWRow * 2);
@@ -304,7 +324,7 @@ __device__ __forceinline__ void ray_transformer_mma(TcSmem& sm, const int slot, 
         m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
         m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
         o[hh][0] = o[hh][1] = o[hh][2] = o[hh][3] = 0.f;
-#pragma unroll
+#pragma unroll(kS / 16 > 4 ? 4 : kS / 16)
         for (int np = 0; np < kS / 16; ++np) {
           uint32_t kf[4];
           ldsm_x4(kf, kaddr + np * 16 * kWRow * 2);
@@ -324,8 +344,12 @@ __device__ __forceinline__ void ray_transformer_mma(TcSmem& sm, const int slot, 
       const float den0 = __shfl_sync(0xffffffffu, t == 0 ? o[1][0] : o[0][0], src);
       const float den1 = __shfl_sync(0xffffffffu, t == 0 ? o[1][2] : o[0][2], src);
       const float i0 = rcp_fast(den0), i1 = rcp_fast(den1);
-      att[2 * hp] = pack_h2((lo ? o[0][0] : o[1][0]) * i0, (lo ? o[0][1] : o[1][1]) * i0);
-      att[2 * hp + 1] = pack_h2((lo ? o[0][2] : o[1][2]) * i1, (lo ? o[0][3] : o[1][3]) * i1);
+      {
+        const uint32_t e0 = pack_h2((lo ? o[0][0] : o[1][0]) * i0, (lo ? o[0][1] : o[1][1]) * i0);
+        const uint32_t e1 = pack_h2((lo ? o[0][2] : o[1][2]) * i1, (lo ? o[0][3] : o[1][3]) * i1);
+        att[0] = hp == 0 ? e0 : att[0]; att[1] = hp == 0 ? e1 : att[1];
+        att[2] = hp == 0 ? att[2] : e0; att[3] = hp == 0 ? att[3] : e1;
+      }
     }
     // fc + residual (C layout: y[j] = columns 8j + 2t, 8j + 2t + 1 of rows g | g + 8)
     const int r0 = rbase + g;
@@ -397,8 +421,10 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
   TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_dyn + ((1024u - (tc::smem_u32(smem_dyn) & 1023u)) & 1023u));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = cfg.n_samples;
-  const int rays_per_tile = kTileM / S;
-  const int64_t n_tiles = (rays.n_rays + rays_per_tile - 1) / rays_per_tile;
+  // S <= 128: a 128-sample tile holds 128 / S whole rays.  S = 256: a tile is HALF a ray and the two slots of a pair hold one ray.
+  const bool split_ray = S > kTileM;
+  const int rays_per_tile = split_ray ? 1 : kTileM / S;
+  const int64_t n_tiles = split_ray ? 2 * rays.n_rays : (rays.n_rays + rays_per_tile - 1) / rays_per_tile;
   const int64_t n_pairs = (n_tiles + 1) / 2;
 
   // ---- one-time setup
@@ -545,14 +571,15 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
     const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;             // sample row inside the tile == TMEM lane
     const uint32_t tb = tmem + slot * kSlotCols + ((uint32_t)(quarter * 32) << 16);
-    const int ray_local = row / S, s = row - ray_local * S;
+    const int ray_local = split_ray ? 0 : row / S, s = split_ray ? slot * kTileM + row : row - ray_local * S;
+    const int dir_first = split_ray ? row : s, dir_step = split_ray ? kTileM : S;   // this thread's share of the ray's 64 dirvec entries
     uint32_t it = 0;
     unsigned trace_n = 0;
 
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++it) {
       const int64_t tile = 2 * pair + slot;
       if (tile >= n_tiles) break;
-      const int64_t ray = tile * rays_per_tile + ray_local;
+      const int64_t ray = split_ray ? pair : tile * rays_per_tile + ray_local;
       const bool valid = ray < rays.n_rays;
       const size_t n_glob = valid ? (size_t)ray * S + s : 0;
 
@@ -583,7 +610,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         }
         TRACE_TRUNK(30);
         // direction term of the colour head, one vector per ray (the ray's threads split its 64 outputs)
-        for (int o2 = s; o2 < 64; o2 += S)
+        for (int o2 = dir_first; o2 < 64; o2 += dir_step)
           sm.dirvec[slot][ray_local][o2] = sm.p.views_dir[o2 * 3] * dir[0] + sm.p.views_dir[o2 * 3 + 1] * dir[1] +
                                            sm.p.views_dir[o2 * 3 + 2] * dir[2] + sm.p.views_b[o2];
         TRACE_TRUNK(31);
@@ -728,7 +755,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         }
         TRACE_TRUNK(40);
         pk2 accrg = pk(sm.p.rgb_b[0], sm.p.rgb_b[1]), accb = pk(sm.p.rgb_b[2], 0.f);
-#pragma unroll
+#pragma unroll 1
         for (int c0 = 16; c0 < 80; c0 += 32) {
           uint32_t r[32];
           tc::tmem_ld32(tb + kColD + c0, r);
@@ -778,14 +805,14 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
     const int slot = wg - 3;
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    const int ray_local = row / S, s = row - ray_local * S;
+    const int ray_local = split_ray ? 0 : row / S, s = split_ray ? slot * kTileM + row : row - ray_local * S;
     uint32_t it = 0;
     unsigned trace_n = 0;
 
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++it) {
       const int64_t tile = 2 * pair + slot;
       if (tile >= n_tiles) break;
-      const int64_t ray = tile * rays_per_tile + ray_local;
+      const int64_t ray = split_ray ? pair : tile * rays_per_tile + ray_local;
       const bool valid = ray < rays.n_rays;
       const size_t n_glob = valid ? (size_t)ray * S + s : 0;
       float rgb[3], depth_t, sigma;
@@ -798,7 +825,8 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
           case 16: ray_transformer_mma<kAct, 16>(sm, slot, buf, quarter, lane); break;
           case 32: ray_transformer_mma<kAct, 32>(sm, slot, buf, quarter, lane); break;
           case 64: ray_transformer_mma<kAct, 64>(sm, slot, buf, quarter, lane); break;
-          default: ray_transformer_mma<kAct, 128>(sm, slot, buf, quarter, lane); break;
+          case 128: ray_transformer_mma<kAct, 128>(sm, slot, buf, quarter, lane); break;
+          default: ray_transformer_mma<kAct, 256>(sm, slot, buf, quarter, lane); break;
         }
         TRACE_RAY(5);
         // back to lane = row for the compositing scan
@@ -825,13 +853,15 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
           const float nb = __shfl_up_sync(0xffffffffu, incl, off, 32);
           if ((lane & (seg - 1)) >= off && off < seg) incl += nb;
         }
-        const int wq = quarter;                     // warp index inside the slot == row / 32
+        // warp index inside the ray's scan domain: the slot's 4 warps, or all 8 warps of the pair when the ray spans both slots
+        float (*red)[8] = split_ray ? &sm.red[0][0] : &sm.red[slot][0];
+        const int wq = split_ray ? slot * 4 + quarter : quarter;
         if (S > 32) {
-          if (lane == 31) sm.red[slot][wq][5] = incl;
-          ray_barrier(slot);
+          if (lane == 31) red[wq][5] = incl;
+          if (split_ray) ray_barrier_s<true>(slot); else ray_barrier(slot);
           const int w0 = (ray_local * S) >> 5;      // first warp of this ray
           float base = 0.f;
-          for (int w2 = w0; w2 < wq; ++w2) base += sm.red[slot][w2][5];
+          for (int w2 = w0; w2 < wq; ++w2) base += red[w2][5];
           incl += base;
         }
         const float excl = incl - sigma;
@@ -845,13 +875,13 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         if (S > 32) {
           if (lane == 0)
 #pragma unroll
-            for (int i = 0; i < 5; ++i) sm.red[slot][wq][i] = part[i];
-          ray_barrier(slot);
+            for (int i = 0; i < 5; ++i) red[wq][i] = part[i];
+          if (split_ray) ray_barrier_s<true>(slot); else ray_barrier(slot);
           if (s == 0) {
 #pragma unroll
             for (int i = 0; i < 5; ++i) {
               float t = 0.f;
-              for (int w2 = 0; w2 < S / 32; ++w2) t += sm.red[slot][wq + w2][i];
+              for (int w2 = 0; w2 < S / 32; ++w2) t += red[wq + w2][i];
               part[i] = t;
             }
           }
@@ -864,7 +894,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
           out_depth[ray] = part[3];
           out_opacity[ray] = part[4];
         }
-        ray_barrier(slot);   // kbuf / vbuf / red / dirvec are rewritten by the next tile
+        if (split_ray) ray_barrier_s<true>(slot); else ray_barrier(slot);   // kbuf / vbuf / red are rewritten by the next tile
         TRACE_RAY(7);
       }
     }
@@ -996,7 +1026,7 @@ void decoder_tc_free(DecoderWeightsTC* w) {
 
 bool decoder_tc_supports(const mnf_decoder_cfg& cfg) {
   const int S = cfg.n_samples;
-  return S == 16 || S == 32 || S == 64 || S == 128;
+  return S == 16 || S == 32 || S == 64 || S == 128 || S == 256;
 }
 
 int launch_decoder_tc(const DevCams& cams, const DevRays& rays, const mnf_decoder_cfg& cfg, const DecoderWeightsTC* w,
@@ -1014,8 +1044,9 @@ int launch_decoder_tc(const DevCams& cams, const DevRays& rays, const mnf_decode
     MNF_CUDA_TRY(cudaFuncSetAttribute(decoder_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     MNF_CUDA_TRY(cudaFuncSetAttribute(decoder_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  const int rays_per_tile = kTileM / cfg.n_samples;
-  const int64_t n_tiles = (rays.n_rays + rays_per_tile - 1) / rays_per_tile;
+  const bool split_ray = cfg.n_samples > kTileM;
+  const int rays_per_tile = split_ray ? 1 : kTileM / cfg.n_samples;
+  const int64_t n_tiles = split_ray ? 2 * rays.n_rays : (rays.n_rays + rays_per_tile - 1) / rays_per_tile;
   const int64_t n_pairs = (n_tiles + 1) / 2;
   const unsigned grid = (unsigned)(n_pairs < n_sm ? n_pairs : n_sm);
   if (cfg.raytrans_act == 0)

@@ -170,12 +170,27 @@ gather_cossim_kernel(const __grid_constant__ DevCams cams, const DevRays rays, c
   __shared__ __align__(16) uint4 tp_all[kWarps3][2 * kViews][32];        // per warp: tap parameters [view, scale][sample]
   const uint32_t full = 0xffffffffu;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int64_t quad = (int64_t)blockIdx.x * kWarps3 + wib;
-  const int64_t ray0 = quad * kQuad;
+  int64_t ray0;                    // index (inside the ray list / range) of the quad's first ray; negative rays are not stored
+  int xlimit = kQuad;              // rays of the quad that lie on the image row (tile-list mode)
+  if (rays.tile_list) {
+    // fix-up pass of the tensor-core gather (gather_tc.cu): 8 blocks x 4 warps = the 32 quads of one listed 16 x 8 pixel tile
+    const int slot = blockIdx.x >> 3;
+    if (slot >= *rays.tile_count) return;
+    const int tile = rays.tile_list[slot];
+    const int q = (blockIdx.x & 7) * kWarps3 + wib;
+    const int band = rays.band0 + tile / rays.tiles_x, tx = tile - (tile / rays.tiles_x) * rays.tiles_x;
+    const int y = band * 8 + (q >> 2), x0 = tx * 16 + (q & 3) * 4;
+    if (y >= cams.H || x0 >= cams.W) return;
+    ray0 = (int64_t)y * cams.W + x0 - rays.first_ray;
+    xlimit = min(kQuad, cams.W - x0);
+    if (ray0 + kQuad <= 0) return;
+  } else {
+    ray0 = ((int64_t)blockIdx.x * kWarps3 + wib) * kQuad;
+  }
   if (ray0 >= rays.n_rays) return;
   const int rq = lane >> 3;        // geometry phase: ray of the quad
   const int sj = lane & 7;         // geometry phase: sample inside the chunk
-  const int64_t my_ray = min(ray0 + rq, rays.n_rays - 1);       // rays past the end repeat the last one (not stored)
+  const int64_t my_ray = max((int64_t)0, min(ray0 + rq, rays.n_rays - 1));   // rays outside the range repeat a valid one (not stored)
   const int64_t pix = rays.points ? 0 : (rays.ray_idx ? rays.ray_idx[my_ray] : rays.first_ray + my_ray);
   float o[3], d[3];
   cast_ray(cams, pix, o, d);
@@ -293,7 +308,7 @@ gather_cossim_kernel(const __grid_constant__ DevCams cams, const DevRays rays, c
 #pragma unroll
       for (int i = 0; i < kQuad; ++i) {
         const int sjj = lane >> 2, part = lane & 3;
-        if (ray0 + i < rays.n_rays && sjj < n_it) {
+        if (ray0 + i >= 0 && ray0 + i < rays.n_rays && i < xlimit && sjj < n_it) {
           uint4 pk = make_uint4(0u, 0u, 0u, 0u);
           if (part < 3) {
             const float4 x = *reinterpret_cast<const float4*>(&st[i * 8 + sjj][part * 8]);
@@ -311,7 +326,7 @@ gather_cossim_kernel(const __grid_constant__ DevCams cams, const DevRays rays, c
     if (cond_f32) {
 #pragma unroll
       for (int i = 0; i < kQuad; ++i) {
-        if (ray0 + i < rays.n_rays) {
+        if (ray0 + i >= 0 && ray0 + i < rays.n_rays && i < xlimit) {
           float* dst = cond_f32 + ((size_t)(ray0 + i) * S + s0) * kCond;      // 22 floats per sample: 8-byte aligned rows
 #pragma unroll
           for (int pass = 0; pass < 3; ++pass) {
@@ -335,14 +350,35 @@ int launch_gather_mma(const DevCams& cams, const DevRays& rays, int S, const __h
                       const __half* f1, int h1, int w1, const float* images, float* cond_f32, __half* cond_f16,
                       cudaStream_t s);
 
-int launch_gather(const DevCams& cams, const DevRays& rays, int S, const __half* f0, int h0, int w0,
+// gather_tc.cu: 0 = launched (fix = this kernel's tile-list arguments, fix_blocks = its grid), 1 = not applicable, < 0 = error
+int launch_gather_tc(const DevCams& cams, const DevRays& rays, int S, const __half* f0, int h0, int w0, const __half* f1, int h1, int w1,
+                     const float* images, float* cond_f32, __half* cond_f16, int* scratch, int scratch_ints, cudaStream_t s,
+                     DevRays* fix, int64_t* fix_blocks);
+
+int launch_gather(const DevCams& cams, const DevRays& rays_in, int S, const __half* f0, int h0, int w0,
                   const __half* f1, int h1, int w1, const float* images, float* cond_f32, __half* cond_f16,
-                  cudaStream_t s) {
-  if (rays.n_rays <= 0) return MNF_OK;
+                  cudaStream_t s, int* scratch, int scratch_ints) {
+  if (rays_in.n_rays <= 0) return MNF_OK;
+  DevRays rays = rays_in;
   if (gather_impl() == 4) return launch_gather_mma(cams, rays, S, f0, h0, w0, f1, h1, w1, images, cond_f32, cond_f16, s);
-  const int64_t quads = (rays.n_rays + kQuad - 1) / kQuad;
-  const int64_t blocks = (quads + kWarps3 - 1) / kWarps3;
   if ((int64_t)h0 * w0 >= (1 << 23) || (int64_t)h1 * w1 >= (1 << 23)) { set_error("feature map too large for 32-bit texel offsets"); return MNF_EUNSUPPORTED; }
+  const int64_t quads = (rays.n_rays + kQuad - 1) / kQuad;
+  int64_t blocks = (quads + kWarps3 - 1) / kWarps3;
+  // Contiguous ray ranges (render_by_slices, full images): the tensor-core gather (gather_tc.cu), then THIS kernel in tile-list
+  // mode over the tiles whose footprint did not fit its boxes (none in the common case: those blocks exit at once).
+  // Explicit ray lists / sample points: this kernel directly.  MNF_GATHER_IMPL=3 forces this kernel for A/B runs.
+  static const int tc_on = [] { const char* e = getenv("MNF_GATHER_IMPL"); return e ? atoi(e) != 3 : 1; }();
+  if (tc_on && scratch && !rays.ray_idx && !rays.points && rays.n_rays >= 1024) {
+    DevRays fix{};
+    int64_t fix_blocks = 0;
+    const int rc = launch_gather_tc(cams, rays, S, f0, h0, w0, f1, h1, w1, images, cond_f32, cond_f16, scratch, scratch_ints, s, &fix,
+                                    &fix_blocks);
+    if (rc < 0) return rc;
+    if (rc == 0) {
+      rays = fix;
+      blocks = fix_blocks;
+    }
+  }
   static const int mixed = [] { const char* e = getenv("MNF_GATHER_MIXED"); return e ? atoi(e) : 1; }();   // A/B knob: FHFMA pair products
   static const int occ = [] { const char* e = getenv("MNF_GATHER_OCC"); return e ? atoi(e) : 5; }();   // CTAs (of 4 warps) per SM: 4 -> 2.44 ms, 5 -> 2.35 ms (96 registers, no spills), 6 -> 2.34 ms per 81,920 rays x 64
   if (mixed && occ == 5)

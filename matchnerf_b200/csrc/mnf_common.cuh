@@ -66,6 +66,11 @@ struct DevRays {
   const float* points = nullptr;   // [R*S][3] world-space sample points  (query_cond_info, models/matchnerf.py:209)
   const float* ndc = nullptr;      // [R*S][3] view-0 NDC sample points   (CondNeRF.forward points_3D, cond_nerf.py:52)
   const float* dirs = nullptr;     // [R*S][3] per-sample view direction  (CondNeRF.forward ray_unit)
+  // tile-list mode of the v3 gather (fix-up pass of gather_tc.cu): recompute the 16 x 8 pixel tiles listed in tile_list
+  // (tile = band * tiles_x + tx, band counted from band0) of the contiguous range [first_ray, first_ray + n_rays)
+  const int* tile_list = nullptr;
+  const int* tile_count = nullptr;
+  int tiles_x = 0, band0 = 0;
 };
 
 // ---- per-ray geometry ---------------------------------------------------------------------
@@ -147,9 +152,10 @@ __device__ __forceinline__ float grid_unnormalize(float g, int n) {
 int gather_impl();   // 3 (default) or 4 (MNF_GATHER_IMPL=4, tensor-core experiment): selects the gather kernel AND the feature packing it reads
 int launch_pack_features(const float* nchw, int V, int h, int w, __half* out, cudaStream_t s);
 int launch_pack_images(const float* nchw, int V, int H, int W, float* out, cudaStream_t s);
+// scratch: device ints owned by the context ([0] = counter, [1..] = tile list of the tensor-core gather's fix-up pass), or NULL
 int launch_gather(const DevCams& cams, const DevRays& rays, int S, const __half* f0, int h0, int w0,
                   const __half* f1, int h1, int w1, const float* images, float* cond_f32, __half* cond_f16,
-                  cudaStream_t s);
+                  cudaStream_t s, int* scratch = nullptr, int scratch_ints = 0);
 
 struct DecoderWeightsF32;  // decoder_ref.cu
 int launch_decoder_ref(const DevCams& cams, const DevRays& rays, const mnf_decoder_cfg& cfg,

@@ -190,7 +190,7 @@ extern "C" int32_t mnf_selftest_tmem_bw(int32_t warps, int32_t iters, int32_t co
 // itself took.  mode 0: A and B from shared memory; mode 1: A from tensor memory.  `readers` > 0: that many extra warps
 // (1..4, one per TMEM lane quarter) stream tcgen05.ld over 128 accumulator columns of another region meanwhile.
 namespace mnf {
-__global__ void __launch_bounds__(256, 1) umma_rate_kernel(int iters, int N, int mode, int readers, long long* out) {
+__global__ void __launch_bounds__(256, 1) umma_rate_kernel(int iters, int N, int mode, int readers, int n_acc, long long* out) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   unsigned char* smem = smem_dyn + ((1024u - (tc::smem_u32(smem_dyn) & 1023u)) & 1023u);
   __shared__ uint64_t bar;
@@ -228,8 +228,10 @@ __global__ void __launch_bounds__(256, 1) umma_rate_kernel(int iters, int N, int
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks) {
         const uint64_t bdesc = tc::umma_desc_sw128(tc::smem_u32(sB) + (ks & 3) * 32);
-        if (mode == 0) tc::umma_ss(tmem, tc::umma_desc_sw128(tc::smem_u32(sA) + (ks & 3) * 32), bdesc, idesc, 1u);
-        else tc::umma_ts(tmem, tmem + 256 + ks * 8, bdesc, idesc, 1u);
+        // n_acc independent accumulators (column regions of N) used round-robin: consecutive MMAs then do not depend on each other
+        const uint32_t d = tmem + (uint32_t)((ks % n_acc) * N);
+        if (mode == 0) tc::umma_ss(d, tc::umma_desc_sw128(tc::smem_u32(sA) + (ks & 3) * 32), bdesc, idesc, 1u);
+        else tc::umma_ts(d, tmem + 256 + ks * 8, bdesc, idesc, 1u);
       }
     }
     const long long t1 = clock64();
@@ -262,15 +264,16 @@ __global__ void __launch_bounds__(256, 1) umma_rate_kernel(int iters, int N, int
 }
 }  // namespace mnf
 
-extern "C" int32_t mnf_selftest_umma_rate(int32_t iters, int32_t N, int32_t mode, int32_t readers, long long* out_dev, void* stream) {
+extern "C" int32_t mnf_selftest_umma_rate(int32_t iters, int32_t N, int32_t mode, int32_t readers, int32_t n_acc, long long* out_dev, void* stream) {
   using namespace mnf;
-  if (iters <= 0 || N < 16 || N > 256 || N % 16 || mode < 0 || mode > 1 || readers < 0 || readers > 4 || !out_dev) {
+  if (iters <= 0 || N < 16 || N > 256 || N % 16 || mode < 0 || mode > 1 || readers < 0 || readers > 4 || !out_dev || n_acc < 1 || n_acc > 4 ||
+      n_acc * N > 256) {
     set_error("mnf_selftest_umma_rate: bad arguments");
     return MNF_EINVAL;
   }
   const size_t smem = 128 * 128 + 256 * 128 + 1024;
   MNF_CUDA_TRY(cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  umma_rate_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(iters, N, mode, readers, out_dev);
+  umma_rate_kernel<<<1, 256, smem, (cudaStream_t)stream>>>(iters, N, mode, readers, n_acc, out_dev);
   MNF_CUDA_TRY(cudaGetLastError());
   return MNF_OK;
 }

@@ -152,6 +152,38 @@ def test_gather_borders_ragged(ctx, S, first, n):
     assert torch.equal(b32, c32)
 
 
+@pytest.mark.parametrize("H,W,S,first,n,baseline", [
+    (512, 640, 64, 640 * 96, 640 * 40, 10.0),       # whole 8-row bands of the DTU image
+    (512, 640, 16, 640 * 101 + 37, 640 * 9 + 5, 10.0),   # ragged start / end inside rows, partial bands
+    (40, 56, 13, 0, 40 * 56, 10.0),                  # width not a multiple of the 16-pixel tile, tiny feature maps
+    (64, 96, 8, 96 * 3, 96 * 50, 30.0),              # wide baseline: footprints leave the boxes -> the v3 fix-up pass runs
+    (100, 72, 5, 11, 100 * 72 - 30, 10.0),           # height not a multiple of the 8-row band
+])
+def test_gather_tensor_core_path(ctx, H, W, S, first, n, baseline):
+    """Contiguous ray ranges of >= 1024 rays take the tcgen05 + TMA gather (csrc/gather_tc.cu, with the v3 kernel as its fix-up
+    pass); the same rays given as an explicit list take the v3 kernel.  Both against the CPU oracle: colours and masks to fp32
+    round-off, cosine similarities to the fp16-feature tolerance; and against each other."""
+    g = torch.Generator().manual_seed(H * 7 + S)
+    feats = [torch.randn(1, 3, 256, H // 8, W // 8, generator=g), torch.randn(1, 3, 256, H // 4, W // 4, generator=g)]
+    imgs = torch.rand(1, 3, 3, H, W, generator=g)
+    extr, intr, nf = synth.synthetic_cameras(H, W, baseline_deg=baseline)
+    _, sc = make_scene(ctx, feats, imgs, extr, intr, nf)
+    t32, t16 = ctx.gather_cossim(sc, S, first_ray=first, n_rays=n, want_f32=True, want_f16=True)
+    v32, _ = ctx.gather_cossim(sc, S, ray_idx=torch.arange(first, first + n), want_f32=True)
+    torch.cuda.synchronize()
+    assert t32.shape == (n * S, 22) and t16.shape == (n * S, 32)
+    assert torch.equal(t32[:, 10:], v32[:, 10:])                       # colours and masks: the same arithmetic in both kernels
+    assert rms(t32[:, :10], v32[:, :10]) < 5e-4
+    assert rms(t16[:, :22].float(), t32) < 5e-4 and float(t16[:, 22:].abs().max()) == 0.0
+    sub = torch.arange(first, first + n, max(1, n // 300))              # the oracle on ~300 rays spread over the range
+    aux = oracle_render(synth.synthetic_decoder(0), feats, imgs, extr, intr, nf, sub, S, quantize_feats=True, return_aux=True)[3]
+    rows = ((sub - first)[:, None] * S + torch.arange(S)[None]).reshape(-1)
+    got = t32[rows.to(DEV)]
+    assert frac_above(got[:, 19:], aux["cond"][:, 19:], 0.5) < 5e-3
+    assert rms(got[:, 10:19], aux["cond"][:, 10:19]) < 2e-5
+    assert rms(got[:, :10], aux["cond"][:, :10]) < 5e-4, rms(got[:, :10], aux["cond"][:, :10])
+
+
 # ------------------------------------------------------------------------------------------- K-mlp-composite
 def run_decoder_case(ctx, dec, feats, imgs, extr, intr, nf, ray_idx, S, impl, act="ReLU", posenc=False, maskfill=False, bg=False):
     ctx.load_decoder(dec)

@@ -56,7 +56,7 @@ def main():
     sc = packed.c_scene(extr[0, 3, :3], intr[0, 3], nf[0, 3])
     cfg = capi.DecoderCfg()
     cfg.n_samples, cfg.raytrans_act, cfg.raytrans_posenc, cfg.density_maskfill = S, 0, 0, 0
-    first = 100 * W
+    first = min(100 * W, H * W - args.rays)
     _, c16 = ctx.gather_cossim(sc, S, first_ray=first, n_rays=args.rays, want_f32=False, want_f16=True)
     ctx.decoder_composite(sc, cfg, cond_f16=c16, first_ray=first, n_rays=args.rays, impl=2)      # warm-up
     torch.cuda.synchronize()

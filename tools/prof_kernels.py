@@ -47,7 +47,7 @@ def main():
     cfg = capi.DecoderCfg()
     cfg.n_samples, cfg.raytrans_act, cfg.raytrans_posenc, cfg.density_maskfill = S, 0, 0, 0
     which = args.which.split(",")
-    first = 100 * W
+    first = min(100 * W, H * W - args.rays)
 
     def timeit(name, fn):
         fn()

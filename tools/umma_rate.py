@@ -6,17 +6,17 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from matchnerf_b200 import capi
 lib = capi.load()
-lib.mnf_selftest_umma_rate.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+lib.mnf_selftest_umma_rate.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
 lib.mnf_selftest_umma_rate.restype = C.c_int32
 out = torch.zeros(4, dtype=torch.int64, device="cuda")
 iters = 64
 for mode in (0, 1):
-    for N in (64, 80, 128, 256):
+    for N, n_acc in ((64, 1), (64, 2), (64, 4), (128, 1), (128, 2), (256, 1)):
         for readers in (0, 4):
             out.zero_()
-            rc = lib.mnf_selftest_umma_rate(iters, N, mode, readers, out.data_ptr(), None)
+            rc = lib.mnf_selftest_umma_rate(iters, N, mode, readers, n_acc, out.data_ptr(), None)
             assert rc == 0, capi.load().mnf_last_error()
             torch.cuda.synchronize()
             tot, iss, nrd = int(out[0]), int(out[1]), int(out[2])
-            print(f"{'SS' if mode == 0 else 'TS'} N={N:3d} readers={readers}: {tot / (iters * 8):6.1f} cycles per K=16 step (issue loop {iss / (iters * 8):5.1f}); "
-                  f"reader warp 4 streamed {nrd} x 128 columns", flush=True)
+            print(f"{'SS' if mode == 0 else 'TS'} N={N:3d} accumulators={n_acc} readers={readers}: {tot / (iters * 8):6.1f} cycles per K=16 step "
+                  f"(issue loop {iss / (iters * 8):5.1f}); reader warp 4 streamed {nrd} x 128 columns", flush=True)
