@@ -37,11 +37,12 @@ namespace mnf {
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kNumStages = 6;
+constexpr int kNumStages = 4;                      // weight ring depth (16 KB each); 6 -> 4 pays for the staged-row buffers below
 constexpr int kChunkBytes = 128 * 128;            // [128 rows][64 fp16]
 constexpr int kWRow = 24;                         // halves per row of the small fp16 matrices / of kbuf (48 B)
 constexpr int kVRow = 40;                         // halves per key of vbuf (4 heads x 8 columns + pad = 80 B)
 constexpr int kHandRow = 20;                      // floats per row of the trunk -> ray hand-off (80 B)
+constexpr int kStageRow = 52;                     // 32-bit words per staged sample row: ENC 32 | COND 16 | depth | pad (208 B: conflict-free 16-byte accesses)
 constexpr int kHeadN = 80;                        // 16 alpha + 64 colour-hidden outputs
 constexpr int kHeadChunkBytes = kHeadN * 128;
 constexpr int kNumChunks = 15;                    // gate, L0, 4 x 2, 3 (L5), 2 (heads)
@@ -87,7 +88,8 @@ struct TcSmem {
   alignas(16) __half kbuf[2][kTileM][kWRow];                   // keys, [row][head*4 + dim]
   alignas(16) __half vbuf[2][kTileM][kVRow];                   // values, [row][head][8]: even heads (v0..v3, 1, 0, 0, 0), odd heads (1, 0, 0, 0, v0..v3)
   float sig[2][kTileM];
-  float dirvec[2][kMaxRaysPerTile][64];
+  float dirvec[2][2][kMaxRaysPerTile][64];                     // [slot][tile parity]: direction term of the colour head
+  alignas(16) uint32_t stage[2][kTileM][kStageRow];            // [slot][row]: the NEXT tile's A operands, staged while this tile's MMAs run
   float red[2][4][8];
   alignas(16) float hand[2][2][kTileM][kHandRow];              // trunk -> ray hand-off: [slot][buffer][row][raw alpha 0..15, r, g, b, depth]
   float hand_nv[2][2][kTileM];                     // views that see the sample
@@ -511,9 +513,11 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
             }
             lo[j] = ring_lo + stage[j] * (uint32_t)(kChunkBytes >> 4);
           }
+          // layer 5 (three chunks, a 4-stage ring): only its first chunk is awaited here, the other two right before the K steps
+          // that read them, so that their copies run underneath the first four MMAs
 #pragma unroll
           for (int j = 0; j < 3; ++j)
-            if (j < nch) {
+            if (j < nch && !(ph == 6 && j > 0)) {
               mbar_wait_sleep(&sm.w_full[stage[j]], (full_par >> stage[j]) & 1u, 20);
               full_par ^= 1u << stage[j];
             }
@@ -538,16 +542,28 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) tc::umma_ts(d, tb + kColH + ks * 8, bdesc(lo[ks >> 2] + (ks & 3) * 2), idesc128, ks > 0);
                 tc::umma_ts(d, tb + kColEnc + 3 * 8, bdesc(bias_lo + (ph - 2) * 2), idesc128, 1);
-              } else if (ph == 6) {   // layer 5 on [enc, h]: K = 64 + 128
+              } else if (ph == 6) {   // layer 5 on [enc, h]: K = 64 + 128; the h part follows below (after its chunks have landed)
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) tc::umma_ts(d, tb + kColEnc + ks * 8, bdesc(lo[0] + ks * 2), idesc128, ks > 0);
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks) tc::umma_ts(d, tb + kColH + ks * 8, bdesc(lo[1 + (ks >> 2)] + (ks & 3) * 2), idesc128, 1);
               } else {                // heads: [alpha_linear | views(feature_linear(.))], N = 80, K = 128
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) tc::umma_ts(d, tb + kColH + ks * 8, bdesc(lo[ks >> 2] + (ks & 3) * 2), idesc_head, ks > 0);
               }
-              tc::umma_commit(&sm.d_full[slot]);
+              if (ph != 6) tc::umma_commit(&sm.d_full[slot]);
+            }
+            if (ph == 6) {
+              if (slot == 0) {
+#pragma unroll
+                for (int j = 1; j < 3; ++j) {
+                  mbar_wait_sleep(&sm.w_full[stage[j]], (full_par >> stage[j]) & 1u, 20);
+                  full_par ^= 1u << stage[j];
+                }
+              }
+              if (leader) {
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) tc::umma_ts(d, tb + kColH + ks * 8, bdesc(lo[1 + (ks >> 2)] + (ks & 3) * 2), idesc128, 1);
+                tc::umma_commit(&sm.d_full[slot]);
+              }
             }
             TRACE_MMA(slot, 30 + ph);
             __syncwarp();
@@ -575,6 +591,92 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
     const int dir_first = split_ray ? row : s, dir_step = split_ray ? kTileM : S;   // this thread's share of the ray's 64 dirvec entries
     uint32_t it = 0;
     unsigned trace_n = 0;
+    uint32_t* const srow = &sm.stage[slot][row][0];
+
+    // ---- staging of a sample = its A operands (positional encoding, conditioning row) + depth + the ray's direction term.
+    // It is SOFTWARE-PIPELINED across tiles: the timeline (tools/decoder_trace.py) showed ~5,000 cycles per tile pair in which
+    // both slots staged and the tensor pipe idled.  Now the sample of tile i + 1 is staged inside the windows in which tile i waits
+    // for its accumulators (part A after the gate epilogue, part B after layer 0), into a shared-memory row the SAME thread reads
+    // back at the start of the next tile; the conditioning row travels by cp.async, so it occupies no registers in between.
+    auto stage_geometry = [&](const int64_t pair_n, const uint32_t nb, float (&x)[3]) {
+      const int64_t tile_n = 2 * pair_n + slot;
+      const int64_t ray_n = split_ray ? pair_n : tile_n * rays_per_tile + ray_local;
+      const bool valid_n = ray_n < rays.n_rays;
+      const size_t n_glob_n = valid_n ? (size_t)ray_n * S + s : 0;
+      x[0] = x[1] = x[2] = 0.f;
+      float dir[3] = {0.f, 0.f, 0.f};
+      float depth_n = 0.f;
+      if (valid_n) {
+        const uint32_t dst = tc::smem_u32(srow + 32);
+        const char* src = reinterpret_cast<const char*>(cond + n_glob_n * kCondPad);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * j), "l"(src + 16 * j) : "memory");
+        const int64_t pix = rays.ray_idx ? rays.ray_idx[ray_n] : rays.first_ray + ray_n;
+        float o[3], d[3];
+        cast_ray(cams, pix, o, d);
+        const float u = rays.jitter ? rays.jitter[n_glob_n] : 0.f;
+        depth_n = sample_depth(cams, s, S, u);
+        float p[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) p[i] = __fadd_rn(o[i], __fmul_rn(d[i], depth_n));
+        // the NDC point and the unit direction only feed fp16 operands: reciprocal-multiply forms (a few ulp) instead of IEEE
+        // divisions / square root (the gather keeps the exact forms: its mask decisions hang on them)
+        project_ndc_fast(cams, 0, p, x[0], x[1], x[2]);
+        const float inv = rsqrtf(fmaxf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2], 1e-24f));
+        const float ux = d[0] * inv, uy = d[1] * inv, uz = d[2] * inv;
+        const float* E = cams.w2c[0];
+        dir[0] = ux * E[0] + uy * E[1] + uz * E[2];
+        dir[1] = ux * E[4] + uy * E[5] + uz * E[6];
+        dir[2] = ux * E[8] + uy * E[9] + uz * E[10];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(srow + 32 + 4 * j) = make_uint4(0u, 0u, 0u, 0u);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      srow[48] = __float_as_uint(depth_n);
+      // direction term of the colour head, one vector per ray (the ray's threads split its 64 outputs)
+      for (int o2 = dir_first; o2 < 64; o2 += dir_step)
+        sm.dirvec[slot][nb][ray_local][o2] = sm.p.views_dir[o2 * 3] * dir[0] + sm.p.views_dir[o2 * 3 + 1] * dir[1] +
+                                             sm.p.views_dir[o2 * 3 + 2] * dir[2] + sm.p.views_b[o2];
+    };
+    auto stage_encoding = [&](const float (&x)[3]) {
+      // encoding order (cond_nerf.py:108-116, :56-57): x, sin(2^k x) k-major, cos(2^k x) k-major, pad
+      float sn[3], cs[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) sincos_reduced(x[i], sn[i], cs[i]);
+      uint32_t e[32];
+      float prev = 0.f;  // pairs are emitted in index order: idx 0..63
+      auto put = [&](int idx, float v) {
+        if (idx & 1) e[idx >> 1] = pack_h2(prev, v); else prev = v;
+      };
+      put(0, x[0]); put(1, x[1]); put(2, x[2]);
+      float sk[3] = {sn[0], sn[1], sn[2]}, ck[3] = {cs[0], cs[1], cs[2]};
+      float cosv[30];
+#pragma unroll
+      for (int k = 0; k < kL3D; ++k) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          put(3 + k * 3 + i, sk[i]);
+          cosv[k * 3 + i] = ck[i];
+          const float s2 = 2.f * sk[i] * ck[i];          // double-angle recurrence: 2^k x -> 2^(k+1) x
+          const float c2 = 1.f - 2.f * sk[i] * sk[i];
+          sk[i] = s2; ck[i] = c2;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 30; ++j) put(33 + j, cosv[j]);
+      put(63, 1.f);   // pad column = 1: multiplies the bias column of the layer-0 / layer-5 weights
+#pragma unroll
+      for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(srow + 4 * j) = make_uint4(e[4 * j], e[4 * j + 1], e[4 * j + 2], e[4 * j + 3]);
+    };
+    {   // prologue: the first tile of this CTA is staged up front
+      const int64_t pair0 = blockIdx.x;
+      if (pair0 < n_pairs && 2 * pair0 + slot < n_tiles) {
+        float x0[3];
+        stage_geometry(pair0, 0u, x0);
+        stage_encoding(x0);
+      }
+    }
 
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++it) {
       const int64_t tile = 2 * pair + slot;
@@ -582,86 +684,29 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
       const int64_t ray = split_ray ? pair : tile * rays_per_tile + ray_local;
       const bool valid = ray < rays.n_rays;
       const size_t n_glob = valid ? (size_t)ray * S + s : 0;
+      const uint32_t cb = it & 1u;                                  // dirvec buffer of this tile
+      const int64_t pair_next = pair + gridDim.x;
+      const bool has_next = pair_next < n_pairs && 2 * pair_next + slot < n_tiles;
+      (void)n_glob;
 
       TRACE_TRUNK(0);
-      // ---------------- stage this sample: geometry -> positional encoding -> fp16 A operands in tensor memory
+      // ---------------- this tile's staged row -> fp16 A operands in tensor memory
       float depth_t = 0.f, n_views_seen = 0.f;
       {
-        float x[3] = {0.f, 0.f, 0.f};
-        float dir[3] = {0.f, 0.f, 0.f};
-        if (valid) {
-          const int64_t pix = rays.ray_idx ? rays.ray_idx[ray] : rays.first_ray + ray;
-          float o[3], d[3];
-          cast_ray(cams, pix, o, d);
-          const float u = rays.jitter ? rays.jitter[n_glob] : 0.f;
-          depth_t = sample_depth(cams, s, S, u);
-          float p[3];
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        uint32_t lo[16], hi[16], cnd[16];
 #pragma unroll
-          for (int i = 0; i < 3; ++i) p[i] = __fadd_rn(o[i], __fmul_rn(d[i], depth_t));
-          // the NDC point and the unit direction only feed fp16 operands: reciprocal-multiply forms (a few ulp) instead of IEEE
-          // divisions / square root (the gather keeps the exact forms: its mask decisions hang on them)
-          project_ndc_fast(cams, 0, p, x[0], x[1], x[2]);
-          const float inv = rsqrtf(fmaxf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2], 1e-24f));
-          const float ux = d[0] * inv, uy = d[1] * inv, uz = d[2] * inv;
-          const float* E = cams.w2c[0];
-          dir[0] = ux * E[0] + uy * E[1] + uz * E[2];
-          dir[1] = ux * E[4] + uy * E[5] + uz * E[6];
-          dir[2] = ux * E[8] + uy * E[9] + uz * E[10];
+        for (int j = 0; j < 4; ++j) {
+          const uint4 a4 = *reinterpret_cast<const uint4*>(srow + 4 * j);
+          const uint4 b4 = *reinterpret_cast<const uint4*>(srow + 16 + 4 * j);
+          const uint4 c4 = *reinterpret_cast<const uint4*>(srow + 32 + 4 * j);
+          lo[4 * j] = a4.x; lo[4 * j + 1] = a4.y; lo[4 * j + 2] = a4.z; lo[4 * j + 3] = a4.w;
+          hi[4 * j] = b4.x; hi[4 * j + 1] = b4.y; hi[4 * j + 2] = b4.z; hi[4 * j + 3] = b4.w;
+          cnd[4 * j] = c4.x; cnd[4 * j + 1] = c4.y; cnd[4 * j + 2] = c4.z; cnd[4 * j + 3] = c4.w;
         }
-        TRACE_TRUNK(30);
-        // direction term of the colour head, one vector per ray (the ray's threads split its 64 outputs)
-        for (int o2 = dir_first; o2 < 64; o2 += dir_step)
-          sm.dirvec[slot][ray_local][o2] = sm.p.views_dir[o2 * 3] * dir[0] + sm.p.views_dir[o2 * 3 + 1] * dir[1] +
-                                           sm.p.views_dir[o2 * 3 + 2] * dir[2] + sm.p.views_b[o2];
-        TRACE_TRUNK(31);
-        // encoding order (cond_nerf.py:108-116, :56-57): x, sin(2^k x) k-major, cos(2^k x) k-major, zero pad
-        float sn[3], cs[3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) sincos_reduced(x[i], sn[i], cs[i]);
-        TRACE_TRUNK(32);
-        uint32_t e[32];
-        float prev = 0.f;  // pairs are emitted in index order: idx 0..63
-        auto put = [&](int idx, float v) {
-          if (idx & 1) e[idx >> 1] = pack_h2(prev, v); else prev = v;
-        };
-        put(0, x[0]); put(1, x[1]); put(2, x[2]);
-        float sk[3] = {sn[0], sn[1], sn[2]}, ck[3] = {cs[0], cs[1], cs[2]};
-        float cosv[30];
-#pragma unroll
-        for (int k = 0; k < kL3D; ++k) {
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            put(3 + k * 3 + i, sk[i]);
-            cosv[k * 3 + i] = ck[i];
-            const float s2 = 2.f * sk[i] * ck[i];          // double-angle recurrence: 2^k x -> 2^(k+1) x
-            const float c2 = 1.f - 2.f * sk[i] * sk[i];
-            sk[i] = s2; ck[i] = c2;
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 30; ++j) put(33 + j, cosv[j]);
-        put(63, 1.f);   // pad column = 1: multiplies the bias column of the layer-0 / layer-5 weights
-        {
-          uint32_t lo[16], hi[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) { lo[j] = e[j]; hi[j] = e[16 + j]; }
-          tc::tmem_st16(tb + kColEnc, lo);
-          tc::tmem_st16(tb + kColEnc + 16, hi);
-        }
-        TRACE_TRUNK(33);
-        uint32_t cnd[16];
-        if (valid) {
-          const uint4* src = reinterpret_cast<const uint4*>(cond + n_glob * kCondPad);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 v4 = __ldg(src + j);
-            cnd[4 * j] = v4.x; cnd[4 * j + 1] = v4.y; cnd[4 * j + 2] = v4.z; cnd[4 * j + 3] = v4.w;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) cnd[j] = 0u;
-        }
-        TRACE_TRUNK(34);
+        depth_t = __uint_as_float(srow[48]);
+        tc::tmem_st16(tb + kColEnc, lo);
+        tc::tmem_st16(tb + kColEnc + 16, hi);
         {  // visibility masks live at cond[19..21]
           const __half2 h9 = *reinterpret_cast<const __half2*>(&cnd[9]);
           const __half2 h10 = *reinterpret_cast<const __half2*>(&cnd[10]);
@@ -672,10 +717,11 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         TRACE_TRUNK(35);
         tc::tmem_wait_st();
         tc::tc_fence_before_sync();
-        trunk_barrier(slot);          // dirvec visible to the whole slot before the heads epilogue
+        trunk_barrier(slot);          // this tile's dirvec (written by the whole slot one tile ago) is visible before the heads epilogue
         TRACE_TRUNK(36);
         tc::mbar_arrive(&sm.a_ready[slot]);
       }
+      float xn[3] = {0.f, 0.f, 0.f};                                // NDC point of the NEXT tile's sample (part A -> part B)
 
       // ---------------- gate = pts_bias(cond) (bias folded into the MMA), kept as 64 packed-half registers for all six layers
       uint32_t gate[64];
@@ -701,6 +747,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
       }
       tc::tc_fence_before_sync();
       tc::mbar_arrive(&sm.a_ready[slot]);
+      if (has_next) stage_geometry(pair_next, cb ^ 1u, xn);         // window A: while layer 0 of both slots runs on the tensor pipe
 
       // ---------------- trunk: h = relu(acc * gate), acc = W h + b from the tensor pipe, -> fp16 -> tensor memory (next layer's A operand)
 #pragma unroll 1
@@ -731,6 +778,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         tc::tmem_wait_st();
         tc::tc_fence_before_sync();
         tc::mbar_arrive(&sm.a_ready[slot]);
+        if (l == 0 && has_next) stage_encoding(xn);                 // window B: while layer 1 runs
       }
 
       // ---------------- heads: raw alpha (16) and the colour hidden layer (64)
@@ -763,7 +811,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const int o2 = c0 - 16 + j;
-            const float4 dv = *reinterpret_cast<const float4*>(&sm.dirvec[slot][ray_local][o2]);
+            const float4 dv = *reinterpret_cast<const float4*>(&sm.dirvec[slot][cb][ray_local][o2]);
             const float hv[4] = {fmaxf(__uint_as_float(r[j]) + dv.x, 0.f), fmaxf(__uint_as_float(r[j + 1]) + dv.y, 0.f),
                                  fmaxf(__uint_as_float(r[j + 2]) + dv.z, 0.f), fmaxf(__uint_as_float(r[j + 3]) + dv.w, 0.f)};
 #pragma unroll
@@ -797,7 +845,8 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         tc::mbar_arrive(&sm.ray_full[slot][buf]);       // release semantics: the stores above are visible to the waiter
       }
       TRACE_TRUNK(7);
-      trunk_barrier(slot);   // dirvec is rewritten by the next tile's staging
+      // (no barrier here: dirvec is double-buffered by tile parity, and the barrier at the next tile's start separates this tile's
+      // reads of buffer cb from the writes of window A two tiles later)
     }
   } else {
     // ================================================================== ray group: ray transformer + compositing

@@ -368,7 +368,7 @@ int launch_gather(const DevCams& cams, const DevRays& rays_in, int S, const __ha
   // mode over the tiles whose footprint did not fit its boxes (none in the common case: those blocks exit at once).
   // Explicit ray lists / sample points: this kernel directly.  MNF_GATHER_IMPL=3 forces this kernel for A/B runs.
   static const int tc_on = [] { const char* e = getenv("MNF_GATHER_IMPL"); return e ? atoi(e) != 3 : 1; }();
-  if (tc_on && scratch && !rays.ray_idx && !rays.points && rays.n_rays >= 1024) {
+  if (tc_on && scratch && !rays.ray_idx && !rays.points) {   // every contiguous range, however short: results must not depend on the slicing
     DevRays fix{};
     int64_t fix_blocks = 0;
     const int rc = launch_gather_tc(cams, rays, S, f0, h0, w0, f1, h1, w1, images, cond_f32, cond_f16, scratch, scratch_ints, s, &fix,

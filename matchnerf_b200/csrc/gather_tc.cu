@@ -49,6 +49,7 @@ struct GtSmem {
   alignas(1024) unsigned char Wt[2][2][kWTile];        // [unit slot][tile]; coarse: tile 0 holds views 0,1,2 at k 0,16,32;
                                                        //                     fine: tile 0 views 0,1 at k 0,32, tile 1 view 2 at k 0
   alignas(16) float hand[2][kRays][12];                // geometry -> product threads: colours (9) + masks (3) of a sample
+  alignas(8) float sims[kRays][10];                    // product threads: the 10 cosines of the depth sample in flight (thread-private rows)
   int red[4][24];                                      // per geometry warp: box extents (min x, max x, min y, max y) x 6
   alignas(8) uint64_t t_full[2], t_free[2], w_ready[2], w_free[2], d_full[2], d_free[2], h_full[2], h_free[2];
   uint32_t tmem_base;
@@ -75,13 +76,24 @@ __device__ __forceinline__ float2 ffma2_(const float2 a, const float2 b, const f
   return d;
 }
 
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// orders uses of a tcgen05.ld destination after the (single) tcgen05.wait::ld that precedes this statement; emits no instruction
+__device__ __forceinline__ void tie16(uint32_t (&r)[16]) {
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                    "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :: "memory");
+}
 // mean over the three pairs of <A,B> / (max(|A|,eps) max(|B|,eps))   (models/matchnerf.py:268-271); same form as gather.cu
 __device__ __forceinline__ float mean_cosine9(const float2 (&q)[9]) {
   float acc = 0.f;
 #pragma unroll
   for (int p = 0; p < 3; ++p) {
     const float ab = q[3 * p].x + q[3 * p].y, aa = q[3 * p + 1].x + q[3 * p + 1].y, bb = q[3 * p + 2].x + q[3 * p + 2].y;
-    acc += ab * rsqrtf(fmaxf(aa, 1e-16f)) * rsqrtf(fmaxf(bb, 1e-16f));
+    acc += ab * rsqrt_approx(fmaxf(aa, 1e-16f)) * rsqrt_approx(fmaxf(bb, 1e-16f));   // operands >= 1e-16: no denormal handling needed
   }
   return acc * (1.0f / 3.0f);
 }
@@ -135,11 +147,15 @@ __device__ __forceinline__ void zero_row_chunks(unsigned char* tile, int row, in
   for (int c = 0; c < 4; ++c)
     if (c < n16) *reinterpret_cast<uint4*>(base + ((((c0 + c) ^ (row & 7)) & 7) << 4)) = make_uint4(0u, 0u, 0u, 0u);
 }
-__device__ __forceinline__ void put_weight(unsigned char* tile, int row, int k, unsigned short w) {
-  *reinterpret_cast<unsigned short*>(tile + tc::sw128_offset((uint32_t)row, (uint32_t)k)) = w;
+// row_base = tile + (row >> 3) * 1024 + (row & 7) * 128, r7 = row & 7: one predicated 2-byte store, no branch
+__device__ __forceinline__ void put_weight(unsigned char* row_base, int r7, int k, unsigned short w, bool on) {
+  unsigned char* p = row_base + ((((k >> 3) ^ r7) & 7) << 4) + (k & 7) * 2;
+  if (on) *reinterpret_cast<unsigned short*>(p) = w;
 }
 
 }  // namespace
+
+static_assert(sizeof(GtSmem) + 1024 <= 232448, "gather_tc shared memory exceeds the 227 KB a CTA can have");
 
 struct GatherTcArgs {
   int S, h0, w0, h1, w1;
@@ -259,7 +275,7 @@ gather_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, const
         }
         // ---------------- TMA: the six boxes of this depth sample (one thread), into T slot `slot`
         if (tid == 0) {
-          tc::mbar_wait(&sm.t_free[slot], par ^ 1u);
+          tc::mbar_wait_sleep(&sm.t_free[slot], par ^ 1u, 20);
           tc::mbar_arrive_expect_tx(&sm.t_full[slot], (uint32_t)kTSlot);
 #pragma unroll
           for (int v = 0; v < kViews; ++v) {
@@ -271,7 +287,7 @@ gather_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, const
 #pragma unroll
         for (int sc = 0; sc < 2; ++sc) {
           const uint32_t gu = gs * 2u + (uint32_t)sc, us = gu & 1u, upar = (gu >> 1) & 1u;
-          tc::mbar_wait(&sm.w_free[us], upar ^ 1u);
+          tc::mbar_wait_sleep(&sm.w_free[us], upar ^ 1u, 20);
           const int K = sc ? kK1 : kK0, BX = sc ? kBX1 : kBX0, BY = sc ? kBY1 : kBY0;
 #pragma unroll
           for (int v = 0; v < kViews; ++v) {
@@ -283,16 +299,18 @@ gather_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, const
             const unsigned short w00 = (unsigned short)(tp.w01 & 0xffffu), w01 = (unsigned short)(tp.w01 >> 16);
             const unsigned short w10 = (unsigned short)(tp.w23 & 0xffffu), w11 = (unsigned short)(tp.w23 >> 16);
             const bool in0 = lx < BX && ly < BY, inx = lx + 1 < BX, iny = ly + 1 < BY;   // (lx, ly >= 0 by construction of the box)
-            if (in0) put_weight(tile_w, tid, kbase + ly * BX + lx, w00);
-            if (tp.dx && inx && ly < BY) put_weight(tile_w, tid, kbase + ly * BX + lx + 1, w01);
-            if (tp.dy && iny && lx < BX) put_weight(tile_w, tid, kbase + (ly + 1) * BX + lx, w10);
-            if (tp.dx && tp.dy && inx && iny) put_weight(tile_w, tid, kbase + (ly + 1) * BX + lx + 1, w11);
+            unsigned char* row_base = tile_w + (tid >> 3) * 1024 + (tid & 7) * 128;
+            const int k00 = kbase + ly * BX + lx;
+            put_weight(row_base, tid & 7, k00, w00, in0);
+            put_weight(row_base, tid & 7, k00 + 1, w01, tp.dx && inx && ly < BY);
+            put_weight(row_base, tid & 7, k00 + BX, w10, tp.dy && iny && lx < BX);
+            put_weight(row_base, tid & 7, k00 + BX + 1, w11, tp.dx && tp.dy && inx && iny);
           }
           tc::fence_proxy_async_smem();
           tc::mbar_arrive(&sm.w_ready[us]);
         }
         // ---------------- colours / masks to the product threads
-        tc::mbar_wait(&sm.h_free[slot], par ^ 1u);
+        tc::mbar_wait_sleep(&sm.h_free[slot], par ^ 1u, 20);
         {
           float4* h = reinterpret_cast<float4*>(&sm.hand[slot][tid][0]);
           h[0] = make_float4(colmask[0], colmask[1], colmask[2], colmask[3]);
@@ -305,78 +323,78 @@ gather_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, const
     }
   } else if (warp < 8) {
     // ============================================================================================ product threads (thread = sample)
+    // ONE compact loop over accumulator chunks (64 packed positions x 3 views), four steps of 16 positions each: ~250 instructions
+    // that stay in the instruction cache (the first version unrolled all 32 steps of a depth sample: 36 KB of straight-line code,
+    // and ncu showed `no instruction` as the top stall of these warps).  The tcgen05.ld of step t + 1 -- also across chunk, scale,
+    // sample and tile boundaries -- is in flight while step t is multiplied out.
     const int quarter = warp & 3, row = quarter * 32 + lane;
     const uint32_t tb = tmem + ((uint32_t)(quarter * 32) << 16);
     const int px = row & (kTW - 1), py = row >> 4;
-    for (int tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
-      const int band = args.band0 + tile / args.tiles_x, tx = tile - (tile / args.tiles_x) * args.tiles_x;
-      const int x = tx * kTW + px, y = band * kTH + py;
-      const int64_t rel = (int64_t)y * cams.W + x - rays.first_ray;
-      const bool valid = x < cams.W && y < cams.H && rel >= 0 && rel < rays.n_rays;
-      for (int s = 0; s < S; ++s, ++gs) {
-        const uint32_t slot = gs & 1u, par = (gs >> 1) & 1u;
-        float sims[10];
+    float* const simrow = &sm.sims[row][0];          // this thread's 10 cosines of the current depth sample (thread-private row)
+    const int my_tiles = args.n_tiles > (int)blockIdx.x ? (args.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const uint32_t n_chunks = (uint32_t)my_tiles * (uint32_t)S * 8u;
+    uint32_t ra[2][16], rb[2][16], rc[2][16];
+    float2 q[9];
+    if (n_chunks > 0) {
+      tc::mbar_wait(&sm.d_full[0], 0u);
+      tc::tc_fence_after_sync();
+      tc::tmem_ld16(tb, ra[0]);
+      tc::tmem_ld16(tb + kChunk, rb[0]);
+      tc::tmem_ld16(tb + 2 * kChunk, rc[0]);
+      tc::tmem_wait_ld(ra[0]); tie16(rb[0]); tie16(rc[0]);
+    }
+    int tile = blockIdx.x, s = 0;
+#pragma unroll 1
+    for (uint32_t g = 0; g < n_chunks; ++g) {
+      const uint32_t db = g & 1u;
+      const int sc = (int)((g >> 2) & 1u), c = (int)(g & 3u);
+      const uint32_t d0 = tb + db * kDCols;
 #pragma unroll
-        for (int sc = 0; sc < 2; ++sc) {
-          const uint32_t gu = gs * 2u + (uint32_t)sc;
-          float2 q[9];
-          // 16 steps of 16 packed positions (two runs) x 3 views; the tcgen05.ld of step t + 1 is in flight while step t is
-          // multiplied out (tcgen05.wait::ld covers every load issued so far, so the wait comes AFTER the math).  A chunk
-          // boundary (every 4 steps) first releases the accumulator buffer, then waits for the next chunk's MMAs.
-          uint32_t ra[2][16], rb[2][16], rc[2][16];
-          {
-            const uint32_t g = gu * 4u, db = g & 1u, dpar = (g >> 1) & 1u;
-            tc::mbar_wait(&sm.d_full[db], dpar);
-            tc::tc_fence_after_sync();
-            const uint32_t d0 = tb + db * kDCols;
-            tc::tmem_ld16(d0, ra[0]);
-            tc::tmem_ld16(d0 + kChunk, rb[0]);
-            tc::tmem_ld16(d0 + 2 * kChunk, rc[0]);
-            tc::tmem_wait_ld(ra[0]); tc::tmem_wait_ld(rb[0]); tc::tmem_wait_ld(rc[0]);
-          }
-#pragma unroll
-          for (int t = 0; t < 16; ++t) {
-            const int c = t >> 2, j = t & 3, cur = t & 1, nxt = cur ^ 1;
-            const uint32_t g = gu * 4u + (uint32_t)c, db = g & 1u;
-            if (j != 3) {                             // next step lies in the same chunk: prefetch it
-              const uint32_t d0 = tb + db * kDCols + 16 * (j + 1);
-              tc::tmem_ld16(d0, ra[nxt]);
-              tc::tmem_ld16(d0 + kChunk, rb[nxt]);
-              tc::tmem_ld16(d0 + 2 * kChunk, rc[nxt]);
-            }
-            if (j % 2 == 0 && (sc == 1 || (c % 2 == 0 && j == 0))) {   // a new cosine group starts: fine = 32 positions, coarse = 128
-#pragma unroll
-              for (int i = 0; i < 9; ++i) q[i] = make_float2(0.f, 0.f);
-            }
-            run_products(ra[cur], rb[cur], rc[cur], q);
-            run_products(ra[cur] + 8, rb[cur] + 8, rc[cur] + 8, q);
-            if (sc == 1 && j % 2 == 1) sims[2 + c * 2 + j / 2] = mean_cosine9(q);
-            if (sc == 0 && c % 2 == 1 && j == 3) sims[c / 2] = mean_cosine9(q);
-            if (j != 3) {
-              tc::tmem_wait_ld(ra[nxt]); tc::tmem_wait_ld(rb[nxt]); tc::tmem_wait_ld(rc[nxt]);
-            } else {
-              tc::tc_fence_before_sync();
-              tc::mbar_arrive(&sm.d_free[db]);        // every load of this chunk has completed (waited in the previous step)
-              if (t + 1 < 16) {
-                const uint32_t g2 = g + 1u, db2 = g2 & 1u, dpar2 = (g2 >> 1) & 1u;
-                tc::mbar_wait(&sm.d_full[db2], dpar2);
-                tc::tc_fence_after_sync();
-                const uint32_t d0 = tb + db2 * kDCols;
-                tc::tmem_ld16(d0, ra[nxt]);
-                tc::tmem_ld16(d0 + kChunk, rb[nxt]);
-                tc::tmem_ld16(d0 + 2 * kChunk, rc[nxt]);
-                tc::tmem_wait_ld(ra[nxt]); tc::tmem_wait_ld(rb[nxt]); tc::tmem_wait_ld(rc[nxt]);
-              }
-            }
-          }
+      for (int j = 0; j < 4; ++j) {
+        const int cur = j & 1, nxt = cur ^ 1;
+        if (j != 3) {                                 // next step lies in the same chunk
+          tc::tmem_ld16(d0 + 16 * (j + 1), ra[nxt]);
+          tc::tmem_ld16(d0 + kChunk + 16 * (j + 1), rb[nxt]);
+          tc::tmem_ld16(d0 + 2 * kChunk + 16 * (j + 1), rc[nxt]);
+        } else if (g + 1 < n_chunks) {                // first step of the next chunk (its MMAs were issued a chunk ago)
+          const uint32_t g2 = g + 1u, db2 = g2 & 1u;
+          tc::mbar_wait_sleep(&sm.d_full[db2], (g2 >> 1) & 1u, 20);
+          tc::tc_fence_after_sync();
+          const uint32_t d2 = tb + db2 * kDCols;
+          tc::tmem_ld16(d2, ra[nxt]);
+          tc::tmem_ld16(d2 + kChunk, rb[nxt]);
+          tc::tmem_ld16(d2 + 2 * kChunk, rc[nxt]);
         }
+        if (j % 2 == 0 && (sc == 1 || (c % 2 == 0 && j == 0))) {   // a new cosine group starts: fine = 32 positions, coarse = 128
+#pragma unroll
+          for (int i = 0; i < 9; ++i) q[i] = make_float2(0.f, 0.f);
+        }
+        run_products(ra[cur], rb[cur], rc[cur], q);
+        run_products(ra[cur] + 8, rb[cur] + 8, rc[cur] + 8, q);
+        if (j % 2 == 1) {
+          if (sc == 1) simrow[2 + c * 2 + j / 2] = mean_cosine9(q);
+          else if (j == 3 && c % 2 == 1) simrow[c / 2] = mean_cosine9(q);
+        }
+        tc::tmem_wait_ld(ra[nxt]); tie16(rb[nxt]); tie16(rc[nxt]);
+      }
+      tc::tc_fence_before_sync();
+      tc::mbar_arrive(&sm.d_free[db]);                // every load of this chunk completed a step ago
+      if (sc == 1 && c == 3) {
         // ---------------- assemble the conditioning row: feat_info[10], color_info[9], mask_info[3] (cond_nerf.py:59)
-        tc::mbar_wait(&sm.h_full[slot], par);
+        const uint32_t gsl = g >> 3, slot = gsl & 1u, par = (gsl >> 1) & 1u;
+        const int band = args.band0 + tile / args.tiles_x, tx = tile - (tile / args.tiles_x) * args.tiles_x;
+        const int x = tx * kTW + px, y = band * kTH + py;
+        const int64_t rel = (int64_t)y * cams.W + x - rays.first_ray;
+        const bool valid = x < cams.W && y < cams.H && rel >= 0 && rel < rays.n_rays;
+        tc::mbar_wait_sleep(&sm.h_full[slot], par, 20);
         const float4* h = reinterpret_cast<const float4*>(&sm.hand[slot][row][0]);
         const float4 h0 = h[0], h1 = h[1], h2 = h[2];
         tc::mbar_arrive(&sm.h_free[slot]);
         if (valid) {
-          const float vals[24] = {sims[0], sims[1], sims[2], sims[3], sims[4], sims[5], sims[6], sims[7], sims[8], sims[9],
+          const float2 s0 = *reinterpret_cast<const float2*>(simrow), s1 = *reinterpret_cast<const float2*>(simrow + 2);
+          const float2 s2 = *reinterpret_cast<const float2*>(simrow + 4), s3 = *reinterpret_cast<const float2*>(simrow + 6);
+          const float2 s4 = *reinterpret_cast<const float2*>(simrow + 8);
+          const float vals[24] = {s0.x, s0.y, s1.x, s1.y, s2.x, s2.y, s3.x, s3.y, s4.x, s4.y,
                                   h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w, h2.x, h2.y, h2.z, h2.w, 0.f, 0.f};
           const size_t n = (size_t)rel * S + s;
           if (cond_f16) {
@@ -397,6 +415,7 @@ gather_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, const
             for (int i = 0; i < 11; ++i) dst[i] = make_float2(vals[2 * i], vals[2 * i + 1]);
           }
         }
+        if (++s == S) { s = 0; tile += gridDim.x; }
       }
     }
   } else {
@@ -406,11 +425,11 @@ gather_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, const
     for (int tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
       for (int s = 0; s < S; ++s, ++gs) {
         const uint32_t slot = gs & 1u, par = (gs >> 1) & 1u;
-        tc::mbar_wait(&sm.t_full[slot], par);
+        tc::mbar_wait_sleep(&sm.t_full[slot], par, 20);
 #pragma unroll
         for (int sc = 0; sc < 2; ++sc) {
           const uint32_t gu = gs * 2u + (uint32_t)sc, us = gu & 1u, upar = (gu >> 1) & 1u;
-          tc::mbar_wait(&sm.w_ready[us], upar);
+          tc::mbar_wait_sleep(&sm.w_ready[us], upar, 20);
           tc::tc_fence_after_sync();
           const int K = sc ? kK1 : kK0;
           const uint32_t tview = sc ? kT1 : kT0;
@@ -418,7 +437,7 @@ gather_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, const
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const uint32_t g = gu * 4u + (uint32_t)c, db = g & 1u, dpar = (g >> 1) & 1u;
-            tc::mbar_wait(&sm.d_free[db], dpar ^ 1u);
+            tc::mbar_wait_sleep(&sm.d_free[db], dpar ^ 1u, 20);
             tc::tc_fence_after_sync();
             if (leader) {
 #pragma unroll

@@ -226,9 +226,10 @@ class MatchNeRF(nn.Module):
                         opacity=torch.stack([o[2] for o in outs]))
 
     def launches_per_image(self, n_chunks: int = 1) -> int:
-        """Kernels of THIS library launched per full-image forward (bench.py's gpu_launches): gather + decoder per render chunk,
-        12 x (K-attn operand pre-pack + K-attn), 2 feature-map + 1 image packing kernels, 15 fused instance norms."""
-        return 2 * n_chunks + 24 + 3 + 15
+        """Kernels of THIS library launched per full-image forward (bench.py's gpu_launches): tensor-core gather + its v3 fix-up pass
+        + decoder per render chunk, 12 x (K-attn operand pre-pack + K-attn), 2 feature-map + 1 image packing kernels, 15 fused
+        instance norms."""
+        return 3 * n_chunks + 24 + 3 + 15
 
     def _packed_scenes(self, ref_poses, ref_images, ref_feats_list):
         """Pack (once per set of feature maps) the per-batch-item scenes the kernels read."""
