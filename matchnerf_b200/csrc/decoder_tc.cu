@@ -53,6 +53,13 @@ constexpr int kThreads = 640;                     // 5 warpgroups: control | tru
 constexpr int kRegsCtrl = 32, kRegsTrunk = 136, kRegsRay = 88;
 constexpr int kColD = 0, kColH = 128, kColEnc = 192, kColCond = 224, kSlotCols = 256;
 constexpr int kMaxRaysPerTile = 8;                // S >= 16
+#ifndef MNF_STAGE_GEOM_LAYER
+#define MNF_STAGE_GEOM_LAYER 1
+#endif
+#ifndef MNF_STAGE_ENC_LAYER
+#define MNF_STAGE_ENC_LAYER 2
+#endif
+constexpr int kStageGeomLayer = MNF_STAGE_GEOM_LAYER, kStageEncLayer = MNF_STAGE_ENC_LAYER;   // trunk layers after whose epilogue the next tile is staged
 
 __host__ __device__ constexpr int chunk_bytes(int c) { return c < 13 ? kChunkBytes : kHeadChunkBytes; }
 __host__ __device__ constexpr int chunk_offset(int c) { return c <= 13 ? c * kChunkBytes : 13 * kChunkBytes + (c - 13) * kHeadChunkBytes; }   // c = 15: the bias tile
@@ -90,7 +97,7 @@ struct TcSmem {
   float sig[2][kTileM];
   float dirvec[2][2][kMaxRaysPerTile][64];                     // [slot][tile parity]: direction term of the colour head
   alignas(16) uint32_t stage[2][kTileM][kStageRow];            // [slot][row]: the NEXT tile's A operands, staged while this tile's MMAs run
-  float red[2][4][8];
+  alignas(16) float red[2][2][4][8];                           // [tile parity][slot][warp]: compositing partials of a ray segment (5 sums, optical depth)
   alignas(16) float hand[2][2][kTileM][kHandRow];              // trunk -> ray hand-off: [slot][buffer][row][raw alpha 0..15, r, g, b, depth]
   float hand_nv[2][2][kTileM];                     // views that see the sample
   alignas(8) uint64_t w_full[kNumStages];
@@ -137,6 +144,11 @@ template <bool kBoth>
 __device__ __forceinline__ void ray_barrier_s(int slot) {
   if constexpr (kBoth) asm volatile("bar.sync 5, 256;" ::: "memory");
   else ray_barrier(slot);
+}
+// S = 64: a ray is exactly two warps of a ray group, so its keys / values / scan partials only need a 64-thread barrier
+// (ids 6..9 = slot * 2 + warp pair): the two rays of a tile no longer wait for each other
+__device__ __forceinline__ void ray_pair_barrier(int slot, int quarter) {
+  asm volatile("bar.sync %0, 64;" ::"r"(6 + slot * 2 + (quarter >> 1)) : "memory");
 }
 using tc::mbar_wait_sleep;
 template <int kRegs> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
@@ -224,7 +236,8 @@ __device__ __forceinline__ float rcp_fast(float x) {
 // V_h carries a column of ones: the softmax denominator drops out of the same MMA.  fc (+ residual), LayerNorm,
 // out_alpha_linear.0 are two more MMAs on C-layout registers; sigma is written to sm.sig for the compositing scan.
 template <int kAct, int kS>
-__device__ __forceinline__ void ray_transformer_mma(TcSmem& sm, const int slot, const uint32_t buf, const int quarter, const int lane) {
+__device__ __forceinline__ void ray_transformer_mma(TcSmem& sm, const int slot, const uint32_t buf, const int quarter, const int lane,
+                                                    [[maybe_unused]] const unsigned it, [[maybe_unused]] unsigned& trace_n) {
   const int g = lane >> 2, t = lane & 3;
   const bool lo = t < 2;
   const float* hand = &sm.hand[slot][buf][0][0];
@@ -283,8 +296,11 @@ __device__ __forceinline__ void ray_transformer_mma(TcSmem& sm, const int slot, 
     *reinterpret_cast<uint32_t*>(v0p + 16) = pack_h2(c[5][0], c[5][1]);
     *reinterpret_cast<uint32_t*>(v1p + 16) = pack_h2(c[5][2], c[5][3]);
   }
-  ray_barrier_s<(kS > 128)>(slot);                 // a ray's keys / values come from up to four warps (eight when S = 256)
+  TRACE_RAY(2);
+  if constexpr (kS == 64) ray_pair_barrier(slot, quarter);   // a ray's keys / values come from two warps,
+  else ray_barrier_s<(kS > 128)>(slot);                       // ... from up to four (eight when S = 256)
 
+  TRACE_RAY(3);
   // ---------------- phase B
   const float2 lnw0 = *reinterpret_cast<const float2*>(&sm.p.ln_w[2 * t]), lnw1 = *reinterpret_cast<const float2*>(&sm.p.ln_w[8 + 2 * t]);
   const float2 lnb0 = *reinterpret_cast<const float2*>(&sm.p.ln_b[2 * t]), lnb1 = *reinterpret_cast<const float2*>(&sm.p.ln_b[8 + 2 * t]);
@@ -313,31 +329,60 @@ __device__ __forceinline__ void ray_transformer_mma(TcSmem& sm, const int slot, 
         const uint32_t q0 = mine ? (hp == 0 ? qm[0] : qm[2]) : 0u, q1 = mine ? (hp == 0 ? qm[1] : qm[3]) : 0u;
         const uint32_t a0 = hp == 0 ? q0 : 0u, a1 = hp == 0 ? q1 : 0u, a2 = hp == 0 ? 0u : q0, a3 = hp == 0 ? 0u : q1;
         float m0 = -INFINITY, m1 = -INFINITY;      // rows g, g + 8
-#pragma unroll(kS / 16 > 4 ? 4 : kS / 16)
-        for (int np = 0; np < kS / 16; ++np) {
-          uint32_t kf[4];
-          ldsm_x4(kf, kaddr + np * 16 * kWRow * 2);
-          float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
-          mma16816(c0, a0, a1, a2, a3, kf[0], kf[1]);
-          mma16816(c1, a0, a1, a2, a3, kf[2], kf[3]);
-          m0 = fmax3(m0, c0[0], c0[1]); m0 = fmax3(m0, c1[0], c1[1]);
-          m1 = fmax3(m1, c0[2], c0[3]); m1 = fmax3(m1, c1[2], c1[3]);
-        }
-        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
         o[hh][0] = o[hh][1] = o[hh][2] = o[hh][3] = 0.f;
-#pragma unroll(kS / 16 > 4 ? 4 : kS / 16)
-        for (int np = 0; np < kS / 16; ++np) {
-          uint32_t kf[4];
-          ldsm_x4(kf, kaddr + np * 16 * kWRow * 2);
-          float c0[4] = {-m0, -m0, -m1, -m1}, c1[4] = {-m0, -m0, -m1, -m1};
-          mma16816(c0, a0, a1, a2, a3, kf[0], kf[1]);
-          mma16816(c1, a0, a1, a2, a3, kf[2], kf[3]);
-          const uint32_t p0 = pack_h2(ex2_fast(c0[0]), ex2_fast(c0[1])), p1 = pack_h2(ex2_fast(c0[2]), ex2_fast(c0[3]));
-          const uint32_t p2 = pack_h2(ex2_fast(c1[0]), ex2_fast(c1[1])), p3 = pack_h2(ex2_fast(c1[2]), ex2_fast(c1[3]));
-          uint32_t vf0, vf1;
-          ldsm_x2_trans(vf0, vf1, vaddr + np * 16 * kVRow * 2 + h * 16);
-          mma16816(o[hh], p0, p1, p2, p3, vf0, vf1);
+        if constexpr (kS <= 64) {
+          // S <= 64: the head's scores of this m-tile (16 rows x S keys = S / 2 registers per lane) stay in registers between the
+          // row-maximum pass and the exponentials -- ONE score product instead of two.  The legacy mma.sync pipe is what bounds the
+          // ray groups on this part (~27 cycles per m16n8k16 per SM sub-partition, ncu: `math pipe throttle` is their top stall).
+          float sc[kS / 16][8];
+#pragma unroll
+          for (int np = 0; np < kS / 16; ++np) {
+            uint32_t kf[4];
+            ldsm_x4(kf, kaddr + np * 16 * kWRow * 2);
+            float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+            mma16816(c0, a0, a1, a2, a3, kf[0], kf[1]);
+            mma16816(c1, a0, a1, a2, a3, kf[2], kf[3]);
+            m0 = fmax3(m0, c0[0], c0[1]); m0 = fmax3(m0, c1[0], c1[1]);
+            m1 = fmax3(m1, c0[2], c0[3]); m1 = fmax3(m1, c1[2], c1[3]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { sc[np][i] = c0[i]; sc[np][4 + i] = c1[i]; }
+          }
+          m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+          m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+#pragma unroll
+          for (int np = 0; np < kS / 16; ++np) {
+            const uint32_t p0 = pack_h2(ex2_fast(sc[np][0] - m0), ex2_fast(sc[np][1] - m0)), p1 = pack_h2(ex2_fast(sc[np][2] - m1), ex2_fast(sc[np][3] - m1));
+            const uint32_t p2 = pack_h2(ex2_fast(sc[np][4] - m0), ex2_fast(sc[np][5] - m0)), p3 = pack_h2(ex2_fast(sc[np][6] - m1), ex2_fast(sc[np][7] - m1));
+            uint32_t vf0, vf1;
+            ldsm_x2_trans(vf0, vf1, vaddr + np * 16 * kVRow * 2 + h * 16);
+            mma16816(o[hh], p0, p1, p2, p3, vf0, vf1);
+          }
+        } else {
+#pragma unroll 4
+          for (int np = 0; np < kS / 16; ++np) {
+            uint32_t kf[4];
+            ldsm_x4(kf, kaddr + np * 16 * kWRow * 2);
+            float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+            mma16816(c0, a0, a1, a2, a3, kf[0], kf[1]);
+            mma16816(c1, a0, a1, a2, a3, kf[2], kf[3]);
+            m0 = fmax3(m0, c0[0], c0[1]); m0 = fmax3(m0, c1[0], c1[1]);
+            m1 = fmax3(m1, c0[2], c0[3]); m1 = fmax3(m1, c1[2], c1[3]);
+          }
+          m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+          m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+#pragma unroll 4
+          for (int np = 0; np < kS / 16; ++np) {
+            uint32_t kf[4];
+            ldsm_x4(kf, kaddr + np * 16 * kWRow * 2);
+            float c0[4] = {-m0, -m0, -m1, -m1}, c1[4] = {-m0, -m0, -m1, -m1};
+            mma16816(c0, a0, a1, a2, a3, kf[0], kf[1]);
+            mma16816(c1, a0, a1, a2, a3, kf[2], kf[3]);
+            const uint32_t p0 = pack_h2(ex2_fast(c0[0]), ex2_fast(c0[1])), p1 = pack_h2(ex2_fast(c0[2]), ex2_fast(c0[3]));
+            const uint32_t p2 = pack_h2(ex2_fast(c1[0]), ex2_fast(c1[1])), p3 = pack_h2(ex2_fast(c1[2]), ex2_fast(c1[3]));
+            uint32_t vf0, vf1;
+            ldsm_x2_trans(vf0, vf1, vaddr + np * 16 * kVRow * 2 + h * 16);
+            mma16816(o[hh], p0, p1, p2, p3, vf0, vf1);
+          }
         }
       }
       // even head: (o0,o1 | o2,o3 | den,0 | 0,0) over t = 0..3; odd head: (den,0 | 0,0 | o0,o1 | o2,o3).  fc wants
@@ -353,6 +398,7 @@ __device__ __forceinline__ void ray_transformer_mma(TcSmem& sm, const int slot, 
         att[2] = hp == 0 ? att[2] : e0; att[3] = hp == 0 ? att[3] : e1;
       }
     }
+    TRACE_RAY(4);
     // fc + residual (C layout: y[j] = columns 8j + 2t, 8j + 2t + 1 of rows g | g + 8)
     const int r0 = rbase + g;
     float y[2][4];
@@ -396,12 +442,91 @@ __device__ __forceinline__ void ray_transformer_mma(TcSmem& sm, const int slot, 
     }
     d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
     d1 += __shfl_xor_sync(0xffffffffu, d1, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
+    TRACE_RAY(8);
     if (t == 0) {
       sm.sig[slot][r0] = fmaxf(d0 + sm.p.oa2_b, 0.f);
       sm.sig[slot][r0 + 8] = fmaxf(d1 + sm.p.oa2_b, 0.f);
     }
   }
   __syncwarp();
+}
+
+
+// ---- alpha compositing of the rows of one warp (nerf.py:101-124 with wo_render_interval: alpha = 1 - exp(-sigma),
+// T_i = exp(-sum_{j<i} sigma_j), out = sum_i T_i alpha_i x_i for x = r, g, b, depth, 1).
+// Each warp composites ITS segment of the ray with a transmittance that starts at 1 (shuffle scan + a butterfly that reduces the five
+// sums with 9 shuffles instead of 25), and publishes (five partial sums, its optical depth).  Segments combine as
+// out = sum_w exp(-sum_{w' < w} tau_w') part_w, evaluated by the ray's first lane after ONE barrier per tile (the same barrier also
+// orders this tile's key / value reads before the next tile's writes; `red` is double-buffered by tile parity).
+// Returns true in the lane that holds the ray's result.
+template <int kS>
+__device__ __forceinline__ bool composite_rows(TcSmem& sm, const int slot, const int quarter, const int lane, const unsigned it,
+                                               const float sigma, const bool valid, const float (&x)[5], float (&out)[5]) {
+  constexpr int kSeg = kS < 32 ? kS : 32;          // rows of one ray inside a warp
+  constexpr int kWarps = kS < 32 ? 1 : kS / 32;    // warps per ray
+  float incl = sigma;
+#pragma unroll
+  for (int off = 1; off < kSeg; off <<= 1) {
+    const float nb = __shfl_up_sync(0xffffffffu, incl, off, 32);
+    if ((lane & (kSeg - 1)) >= off) incl += nb;
+  }
+  const float wgt = valid ? __expf(sigma - incl) * (1.f - __expf(-sigma)) : 0.f;
+  float v[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) v[i] = wgt * x[i];
+  if constexpr (kSeg < 32) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+      for (int off = kSeg / 2; off >= 1; off >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) out[i] = v[i];
+    return (lane & (kSeg - 1)) == 0;
+  } else {
+    // butterfly: after the xor-16 / 8 / 4 steps lane l holds value index ((l >> 4) & 1) * 4 + ((l >> 3) & 1) * 2 + ((l >> 2) & 1)
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+    float a4[4];
+    a4[0] = (b4 ? v[4] : v[0]) + __shfl_xor_sync(0xffffffffu, b4 ? v[0] : v[4], 16);
+#pragma unroll
+    for (int i = 1; i < 4; ++i) a4[i] = (b4 ? 0.f : v[i]) + __shfl_xor_sync(0xffffffffu, b4 ? v[i] : 0.f, 16);
+    float a2[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) a2[i] = (b3 ? a4[i + 2] : a4[i]) + __shfl_xor_sync(0xffffffffu, b3 ? a4[i] : a4[i + 2], 8);
+    float a1 = (b2 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? a2[0] : a2[1], 4);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+    const float tau = __shfl_sync(0xffffffffu, incl, 31);        // optical depth of this warp's segment
+    if constexpr (kWarps == 1) {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) out[i] = __shfl_sync(0xffffffffu, a1, (i & 4) * 4 + (i & 2) * 4 + (i & 1) * 4);
+      return lane == 0;
+    } else {
+      constexpr bool kBoth = kS > 128;                            // S = 256: the ray spans both ray groups
+      const int wq = kBoth ? slot * 4 + quarter : quarter;        // warp index inside the scan domain
+      float (*red)[8] = kBoth ? &sm.red[it & 1][0][0] : &sm.red[it & 1][slot][0];
+      if ((lane & 3) == 0 && lane < 20) red[wq][(lane >> 4) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = a1;
+      if (lane == 31) red[wq][5] = tau;
+      if constexpr (kBoth) ray_barrier_s<true>(slot);
+      else if constexpr (kS == 64) ray_pair_barrier(slot, quarter);
+      else ray_barrier(slot);
+      const int w0 = wq & ~(kWarps - 1);                          // first warp of this ray
+      const bool writer = lane == 0 && wq == w0;
+      if (writer) {
+        float T = 1.f;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) out[i] = 0.f;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+          const float4 p = *reinterpret_cast<const float4*>(&red[w0 + w][0]);
+          const float2 q = *reinterpret_cast<const float2*>(&red[w0 + w][4]);
+          out[0] = fmaf(T, p.x, out[0]); out[1] = fmaf(T, p.y, out[1]); out[2] = fmaf(T, p.z, out[2]); out[3] = fmaf(T, p.w, out[3]);
+          out[4] = fmaf(T, q.x, out[4]);
+          T *= __expf(-q.y);
+        }
+      }
+      return writer;
+    }
+  }
 }
 
 }  // namespace
@@ -669,12 +794,53 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
 #pragma unroll
       for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(srow + 4 * j) = make_uint4(e[4 * j], e[4 * j + 1], e[4 * j + 2], e[4 * j + 3]);
     };
+    // ---- a staged row -> fp16 A operands in tensor memory (positional encoding, conditioning), then "operands ready" to the MMA issuer.
+    // Runs in the prologue for the CTA's first tile and, for every later tile, at the END of the previous tile right after the heads
+    // accumulator has been read into registers: the gate MMA of tile i + 1 then runs underneath the colour-head arithmetic of tile i.
+    auto stage_to_tmem = [&](float& depth_o, float& nvs_o) {
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      // three 16-register groups, one after the other (the call at the end of a tile runs while the 80 head values are live)
+      auto load16 = [&](uint32_t (&r)[16], const int word0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 a4 = *reinterpret_cast<const uint4*>(srow + word0 + 4 * j);
+          r[4 * j] = a4.x; r[4 * j + 1] = a4.y; r[4 * j + 2] = a4.z; r[4 * j + 3] = a4.w;
+        }
+      };
+      {
+        uint32_t e[16];
+        load16(e, 0);
+        tc::tmem_st16(tb + kColEnc, e);
+      }
+      {
+        uint32_t e[16];
+        load16(e, 16);
+        tc::tmem_st16(tb + kColEnc + 16, e);
+      }
+      {
+        uint32_t cnd[16];
+        load16(cnd, 32);
+        // visibility masks live at cond[19..21]
+        const __half2 h9 = *reinterpret_cast<const __half2*>(&cnd[9]);
+        const __half2 h10 = *reinterpret_cast<const __half2*>(&cnd[10]);
+        nvs_o = __high2float(h9) + __low2float(h10) + __high2float(h10);
+        cnd[11] = (cnd[11] & 0xffff0000u) | 0x3c00u;   // pad column 22 = 1.0: multiplies the gate's bias column
+        tc::tmem_st16(tb + kColCond, cnd);
+      }
+      depth_o = __uint_as_float(srow[48]);
+      tc::tmem_wait_st();
+      tc::tc_fence_before_sync();
+      trunk_barrier(slot);          // the tile's dirvec (written by the whole slot during the previous tile) is visible before its heads epilogue
+      tc::mbar_arrive(&sm.a_ready[slot]);
+    };
+    float depth_t = 0.f, n_views_seen = 0.f;        // of the tile whose operands are in tensor memory
     {   // prologue: the first tile of this CTA is staged up front
       const int64_t pair0 = blockIdx.x;
       if (pair0 < n_pairs && 2 * pair0 + slot < n_tiles) {
         float x0[3];
         stage_geometry(pair0, 0u, x0);
         stage_encoding(x0);
+        stage_to_tmem(depth_t, n_views_seen);
       }
     }
 
@@ -690,37 +856,6 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
       (void)n_glob;
 
       TRACE_TRUNK(0);
-      // ---------------- this tile's staged row -> fp16 A operands in tensor memory
-      float depth_t = 0.f, n_views_seen = 0.f;
-      {
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        uint32_t lo[16], hi[16], cnd[16];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint4 a4 = *reinterpret_cast<const uint4*>(srow + 4 * j);
-          const uint4 b4 = *reinterpret_cast<const uint4*>(srow + 16 + 4 * j);
-          const uint4 c4 = *reinterpret_cast<const uint4*>(srow + 32 + 4 * j);
-          lo[4 * j] = a4.x; lo[4 * j + 1] = a4.y; lo[4 * j + 2] = a4.z; lo[4 * j + 3] = a4.w;
-          hi[4 * j] = b4.x; hi[4 * j + 1] = b4.y; hi[4 * j + 2] = b4.z; hi[4 * j + 3] = b4.w;
-          cnd[4 * j] = c4.x; cnd[4 * j + 1] = c4.y; cnd[4 * j + 2] = c4.z; cnd[4 * j + 3] = c4.w;
-        }
-        depth_t = __uint_as_float(srow[48]);
-        tc::tmem_st16(tb + kColEnc, lo);
-        tc::tmem_st16(tb + kColEnc + 16, hi);
-        {  // visibility masks live at cond[19..21]
-          const __half2 h9 = *reinterpret_cast<const __half2*>(&cnd[9]);
-          const __half2 h10 = *reinterpret_cast<const __half2*>(&cnd[10]);
-          n_views_seen = __high2float(h9) + __low2float(h10) + __high2float(h10);
-        }
-        cnd[11] = (cnd[11] & 0xffff0000u) | 0x3c00u;   // pad column 22 = 1.0: multiplies the gate's bias column
-        tc::tmem_st16(tb + kColCond, cnd);
-        TRACE_TRUNK(35);
-        tc::tmem_wait_st();
-        tc::tc_fence_before_sync();
-        trunk_barrier(slot);          // this tile's dirvec (written by the whole slot one tile ago) is visible before the heads epilogue
-        TRACE_TRUNK(36);
-        tc::mbar_arrive(&sm.a_ready[slot]);
-      }
       float xn[3] = {0.f, 0.f, 0.f};                                // NDC point of the NEXT tile's sample (part A -> part B)
 
       // ---------------- gate = pts_bias(cond) (bias folded into the MMA), kept as 64 packed-half registers for all six layers
@@ -747,7 +882,6 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
       }
       tc::tc_fence_before_sync();
       tc::mbar_arrive(&sm.a_ready[slot]);
-      if (has_next) stage_geometry(pair_next, cb ^ 1u, xn);         // window A: while layer 0 of both slots runs on the tensor pipe
 
       // ---------------- trunk: h = relu(acc * gate), acc = W h + b from the tensor pipe, -> fp16 -> tensor memory (next layer's A operand)
 #pragma unroll 1
@@ -778,7 +912,10 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         tc::tmem_wait_st();
         tc::tc_fence_before_sync();
         tc::mbar_arrive(&sm.a_ready[slot]);
-        if (l == 0 && has_next) stage_encoding(xn);                 // window B: while layer 1 runs
+        // the NEXT tile's sample is staged inside the two longest accumulator waits of this tile (dirvec[cb ^ 1] is free: every thread of
+        // the slot finished the previous tile's heads arithmetic before this tile's layer-0 MMA could start)
+        if (l == kStageGeomLayer && has_next) stage_geometry(pair_next, cb ^ 1u, xn);
+        if (l == kStageEncLayer && has_next) stage_encoding(xn);
       }
 
       // ---------------- heads: raw alpha (16) and the colour hidden layer (64)
@@ -788,10 +925,17 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
       mbar_wait_sleep(&sm.d_full[slot], 1, 32);
       TRACE_TRUNK(4);
       tc::tc_fence_after_sync();
+      const float depth_cur = depth_t, nvs_cur = n_views_seen;
       {
-        uint32_t r16[16];
+        // the whole heads accumulator (16 + 64 columns) moves to registers at once (the gate registers are dead by now), which frees
+        // the accumulator columns: the NEXT tile's operands go to tensor memory right away and its gate MMA runs underneath the
+        // colour-head arithmetic below
+        uint32_t r16[16], rc0[32], rc1[32];
         tc::tmem_ld16(tb + kColD, r16);
+        tc::tmem_ld32(tb + kColD + 16, rc0);
+        tc::tmem_ld32(tb + kColD + 48, rc1);
         tc::tmem_wait_ld();
+        if (has_next) stage_to_tmem(depth_t, n_views_seen);
 #pragma unroll
         for (int j = 0; j < 16; ++j) xr[j] = act_fn<kAct>(__uint_as_float(r16[j]) + sm.p.alpha_b[j]);
         if (cfg.raytrans_posenc) {     // cond_nerf.py:118-127: the table is built on the host in float64, as the reference does
@@ -803,14 +947,10 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         }
         TRACE_TRUNK(40);
         pk2 accrg = pk(sm.p.rgb_b[0], sm.p.rgb_b[1]), accb = pk(sm.p.rgb_b[2], 0.f);
-#pragma unroll 1
-        for (int c0 = 16; c0 < 80; c0 += 32) {
-          uint32_t r[32];
-          tc::tmem_ld32(tb + kColD + c0, r);
-          tc::tmem_wait_ld();
+        auto colour_half = [&](const uint32_t (&r)[32], const int base) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const int o2 = c0 - 16 + j;
+            const int o2 = base + j;
             const float4 dv = *reinterpret_cast<const float4*>(&sm.dirvec[slot][cb][ray_local][o2]);
             const float hv[4] = {fmaxf(__uint_as_float(r[j]) + dv.x, 0.f), fmaxf(__uint_as_float(r[j + 1]) + dv.y, 0.f),
                                  fmaxf(__uint_as_float(r[j + 2]) + dv.z, 0.f), fmaxf(__uint_as_float(r[j + 3]) + dv.w, 0.f)};
@@ -822,7 +962,9 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
               accb = pk_fma(hh, w4.y, accb);
             }
           }
-        }
+        };
+        colour_half(rc0, 0);
+        colour_half(rc1, 32);
         TRACE_TRUNK(41);
         rgb[0] = 1.f / (1.f + __expf(-pk_lo(accrg)));
         rgb[1] = 1.f / (1.f + __expf(-pk_hi(accrg)));
@@ -840,8 +982,8 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         h[1] = make_float4(xr[4], xr[5], xr[6], xr[7]);
         h[2] = make_float4(xr[8], xr[9], xr[10], xr[11]);
         h[3] = make_float4(xr[12], xr[13], xr[14], xr[15]);
-        h[4] = make_float4(rgb[0], rgb[1], rgb[2], depth_t);
-        sm.hand_nv[slot][buf][row] = n_views_seen;
+        h[4] = make_float4(rgb[0], rgb[1], rgb[2], depth_cur);
+        sm.hand_nv[slot][buf][row] = nvs_cur;
         tc::mbar_arrive(&sm.ray_full[slot][buf]);       // release semantics: the stores above are visible to the waiter
       }
       TRACE_TRUNK(7);
@@ -871,11 +1013,11 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         mbar_wait_sleep(&sm.ray_full[slot][buf], (it >> 1) & 1, 64);
         TRACE_RAY(1);
         switch (S) {
-          case 16: ray_transformer_mma<kAct, 16>(sm, slot, buf, quarter, lane); break;
-          case 32: ray_transformer_mma<kAct, 32>(sm, slot, buf, quarter, lane); break;
-          case 64: ray_transformer_mma<kAct, 64>(sm, slot, buf, quarter, lane); break;
-          case 128: ray_transformer_mma<kAct, 128>(sm, slot, buf, quarter, lane); break;
-          default: ray_transformer_mma<kAct, 256>(sm, slot, buf, quarter, lane); break;
+          case 16: ray_transformer_mma<kAct, 16>(sm, slot, buf, quarter, lane, it, trace_n); break;
+          case 32: ray_transformer_mma<kAct, 32>(sm, slot, buf, quarter, lane, it, trace_n); break;
+          case 64: ray_transformer_mma<kAct, 64>(sm, slot, buf, quarter, lane, it, trace_n); break;
+          case 128: ray_transformer_mma<kAct, 128>(sm, slot, buf, quarter, lane, it, trace_n); break;
+          default: ray_transformer_mma<kAct, 256>(sm, slot, buf, quarter, lane, it, trace_n); break;
         }
         TRACE_RAY(5);
         // back to lane = row for the compositing scan
@@ -895,55 +1037,24 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
 
       // ---------------- alpha compositing along the ray (nerf.py:101-124, wo_render_interval)
       {
-        const int seg = S < 32 ? S : 32;            // rows of one ray inside a warp
-        float incl = sigma;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-          const float nb = __shfl_up_sync(0xffffffffu, incl, off, 32);
-          if ((lane & (seg - 1)) >= off && off < seg) incl += nb;
+        const float part_in[5] = {rgb[0], rgb[1], rgb[2], depth_t, 1.f};
+        float outv[5];
+        bool writer;
+        switch (S) {
+          case 16: writer = composite_rows<16>(sm, slot, quarter, lane, it, sigma, valid, part_in, outv); break;
+          case 32: writer = composite_rows<32>(sm, slot, quarter, lane, it, sigma, valid, part_in, outv); break;
+          case 64: writer = composite_rows<64>(sm, slot, quarter, lane, it, sigma, valid, part_in, outv); break;
+          case 128: writer = composite_rows<128>(sm, slot, quarter, lane, it, sigma, valid, part_in, outv); break;
+          default: writer = composite_rows<256>(sm, slot, quarter, lane, it, sigma, valid, part_in, outv); break;
         }
-        // warp index inside the ray's scan domain: the slot's 4 warps, or all 8 warps of the pair when the ray spans both slots
-        float (*red)[8] = split_ray ? &sm.red[0][0] : &sm.red[slot][0];
-        const int wq = split_ray ? slot * 4 + quarter : quarter;
-        if (S > 32) {
-          if (lane == 31) red[wq][5] = incl;
-          if (split_ray) ray_barrier_s<true>(slot); else ray_barrier(slot);
-          const int w0 = (ray_local * S) >> 5;      // first warp of this ray
-          float base = 0.f;
-          for (int w2 = w0; w2 < wq; ++w2) base += red[w2][5];
-          incl += base;
+        if (writer && valid) {
+          const float bg = setbg_opaque ? 1.f - outv[4] : 0.f;
+          out_rgb[ray * 3 + 0] = outv[0] + bg;
+          out_rgb[ray * 3 + 1] = outv[1] + bg;
+          out_rgb[ray * 3 + 2] = outv[2] + bg;
+          out_depth[ray] = outv[3];
+          out_opacity[ray] = outv[4];
         }
-        const float excl = incl - sigma;
-        const float wgt = valid ? __expf(-excl) * (1.f - __expf(-sigma)) : 0.f;
-        float part[5] = {wgt * rgb[0], wgt * rgb[1], wgt * rgb[2], wgt * depth_t, wgt};
-#pragma unroll
-        for (int i = 0; i < 5; ++i)
-#pragma unroll
-          for (int off = 16; off >= 1; off >>= 1)
-            if (off < seg) part[i] += __shfl_xor_sync(0xffffffffu, part[i], off);
-        if (S > 32) {
-          if (lane == 0)
-#pragma unroll
-            for (int i = 0; i < 5; ++i) red[wq][i] = part[i];
-          if (split_ray) ray_barrier_s<true>(slot); else ray_barrier(slot);
-          if (s == 0) {
-#pragma unroll
-            for (int i = 0; i < 5; ++i) {
-              float t = 0.f;
-              for (int w2 = 0; w2 < S / 32; ++w2) t += red[wq + w2][i];
-              part[i] = t;
-            }
-          }
-        }
-        if (s == 0 && valid) {
-          const float bg = setbg_opaque ? 1.f - part[4] : 0.f;
-          out_rgb[ray * 3 + 0] = part[0] + bg;
-          out_rgb[ray * 3 + 1] = part[1] + bg;
-          out_rgb[ray * 3 + 2] = part[2] + bg;
-          out_depth[ray] = part[3];
-          out_opacity[ray] = part[4];
-        }
-        if (split_ray) ray_barrier_s<true>(slot); else ray_barrier(slot);   // kbuf / vbuf / red are rewritten by the next tile
         TRACE_RAY(7);
       }
     }

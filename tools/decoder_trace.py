@@ -26,7 +26,7 @@ MMA.update({50 + p: f"ph{p}: weights resident" for p in range(8)})
 MMA.update({10 + p: f"ph{p}: slot A operand ready" for p in range(8)})
 MMA.update({30 + p: f"ph{p}: MMAs issued + committed" for p in range(8)})
 MMA.update({60 + p: f"ph{p}: weight stages released" for p in range(8)})
-RAY = {0: "wait hand-off", 1: "hand-off received", 5: "ray transformer (mma.sync) done", 6: "sigma read back, buffer released",
+RAY = {0: "wait hand-off", 1: "hand-off received", 2: "q/k/v projected (phase A)", 3: "keys / values of the ray visible", 4: "attention of an m-tile done", 8: "fc + LN + sigma head of an m-tile done", 5: "ray transformer (mma.sync) done", 6: "sigma read back, buffer released",
        7: "composite + tile end"}
 
 
@@ -34,6 +34,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rays", type=int, default=40960)
     ap.add_argument("--samples", type=int, default=64)
+    ap.add_argument("--quarters", action="store_true", help="also summarise warps 1..3 of every ray group (drift between the warps of a group)")
     ap.add_argument("--timeline", type=int, default=-1, help="also print the merged event timeline of this tile iteration of CTA 0")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
@@ -75,6 +76,8 @@ def main():
     for clk, role, slot, e, it in ev:
         if role == 0 or (slot >> 2) == 0:
             per[(role, slot & 3)].append((clk - t0, e, it))
+        elif args.quarters and role == 2:
+            per[(role, (slot & 3) + 10 * (slot >> 2))].append((clk - t0, e, it))   # key 10 q + slot: the other warps of a ray group
     if args.timeline >= 0:
         starts = sorted(c for c, e, it in per[(1, 0)] if e == 0 and it in (args.timeline, args.timeline + 1))
         if len(starts) == 2:
