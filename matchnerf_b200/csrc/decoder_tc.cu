@@ -96,6 +96,7 @@ struct TcSmem {
   alignas(16) __half vbuf[2][kTileM][kVRow];                   // values, [row][head][8]: even heads (v0..v3, 1, 0, 0, 0), odd heads (1, 0, 0, 0, v0..v3)
   float sig[2][kTileM];
   float dirvec[2][2][kMaxRaysPerTile][64];                     // [slot][tile parity]: direction term of the colour head
+  alignas(16) float4 rayrec[2][2][kMaxRaysPerTile];            // [slot][tile parity][ray]: d(q)/d(depth) of the view-0 projection (x, y, z), valid flag
   alignas(16) uint32_t stage[2][kTileM][kStageRow];            // [slot][row]: the NEXT tile's A operands, staged while this tile's MMAs run
   alignas(16) float red[2][2][4][8];                           // [tile parity][slot][warp]: compositing partials of a ray segment (5 sums, optical depth)
   alignas(16) float hand[2][2][kTileM][kHandRow];              // trunk -> ray hand-off: [slot][buffer][row][raw alpha 0..15, r, g, b, depth]
@@ -107,6 +108,8 @@ struct TcSmem {
   uint64_t d_full[2];
   uint64_t ray_full[2][2];
   uint64_t ray_empty[2][2];
+  uint64_t geo_full[2][2];                         // [slot][tile parity]: ray records + dirvec of a tile written (geometry warp -> trunk slot)
+  uint64_t geo_empty[2][2];                        // ... and consumed (trunk slot -> geometry warp)
   uint32_t tmem_base;
   TraceCtl trace;
 };
@@ -136,7 +139,7 @@ __device__ unsigned int g_trace_cap = 0;
 #define TRACE_MMA(sl, ev) do { } while (0)
 #endif
 
-__device__ __forceinline__ void trunk_barrier(int slot) { asm volatile("bar.sync %0, 128;" ::"r"(slot + 1) : "memory"); }
+[[maybe_unused]] __device__ __forceinline__ void trunk_barrier(int slot) { asm volatile("bar.sync %0, 128;" ::"r"(slot + 1) : "memory"); }
 __device__ __forceinline__ void ray_barrier(int slot) { asm volatile("bar.sync %0, 128;" ::"r"(slot + 3) : "memory"); }
 // S = 256: a ray spans BOTH slots of a tile pair (slot 0 = samples 0..127, slot 1 = samples 128..255), so the two ray groups
 // share keys / values and the compositing scan: their barriers then span both groups (256 threads, barrier id 5)
@@ -196,6 +199,12 @@ __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1
   asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// m16n8k8: A: a0 (row g, k 2t..2t+1), a1 (row g+8, same k);  B: b0 (k 2t..2t+1, n g);  C as above
+__device__ __forceinline__ void mma1688(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(b0));
 }
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -327,62 +336,58 @@ __device__ __forceinline__ void ray_transformer_mma(TcSmem& sm, const int slot, 
         // Q_h: only the 4 k-columns of head h survive (k 0-3: t<2 of a0/a1; 4-7: t>=2; 8-11: t<2 of a2/a3; 12-15: t>=2)
         const bool mine = (hh == 0) ? lo : !lo;
         const uint32_t q0 = mine ? (hp == 0 ? qm[0] : qm[2]) : 0u, q1 = mine ? (hp == 0 ? qm[1] : qm[3]) : 0u;
-        const uint32_t a0 = hp == 0 ? q0 : 0u, a1 = hp == 0 ? q1 : 0u, a2 = hp == 0 ? 0u : q0, a3 = hp == 0 ? 0u : q1;
-        float m0 = -INFINITY, m1 = -INFINITY;      // rows g, g + 8
+        // The keys are walked in blocks of <= 64.  Inside a block the head's scores of this m-tile (16 rows x 64 keys = 32 registers
+        // per lane) stay in registers between the row-maximum pass and the exponentials -- ONE score product per key instead of the two
+        // of a two-pass softmax -- and blocks are merged flash-attention style (exact: both partial results are rescaled to the common
+        // maximum; the softmax denominator rides in the ones-column of V and is rescaled with it).  The legacy mma.sync pipe is what
+        // bounds the ray groups on this part (~27 cycles per m16n8k16 per SM sub-partition; ncu: `math pipe throttle` is their top stall).
+        constexpr int kBlk = kS < 64 ? kS : 64;
+        float m0 = -INFINITY, m1 = -INFINITY;      // running maxima of rows g, g + 8
         o[hh][0] = o[hh][1] = o[hh][2] = o[hh][3] = 0.f;
-        if constexpr (kS <= 64) {
-          // S <= 64: the head's scores of this m-tile (16 rows x S keys = S / 2 registers per lane) stay in registers between the
-          // row-maximum pass and the exponentials -- ONE score product instead of two.  The legacy mma.sync pipe is what bounds the
-          // ray groups on this part (~27 cycles per m16n8k16 per SM sub-partition, ncu: `math pipe throttle` is their top stall).
-          float sc[kS / 16][8];
+        auto do_block = [&](const int blk) {
+          const uint32_t kblk = kaddr + blk * kBlk * kWRow * 2, vblk = vaddr + blk * kBlk * kVRow * 2 + h * 16;
+          float sc[kBlk / 16][8];
+          float b0 = -INFINITY, b1 = -INFINITY;
 #pragma unroll
-          for (int np = 0; np < kS / 16; ++np) {
+          for (int np = 0; np < kBlk / 16; ++np) {
             uint32_t kf[4];
-            ldsm_x4(kf, kaddr + np * 16 * kWRow * 2);
+            ldsm_x4(kf, kblk + np * 16 * kWRow * 2);
             float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
-            mma16816(c0, a0, a1, a2, a3, kf[0], kf[1]);
-            mma16816(c1, a0, a1, a2, a3, kf[2], kf[3]);
-            m0 = fmax3(m0, c0[0], c0[1]); m0 = fmax3(m0, c1[0], c1[1]);
-            m1 = fmax3(m1, c0[2], c0[3]); m1 = fmax3(m1, c1[2], c1[3]);
+            // K = 8 products: only the k-half that holds this head pair's dimensions is multiplied (the other half of Q_h is zero)
+            mma1688(c0, q0, q1, hp == 0 ? kf[0] : kf[1]);
+            mma1688(c1, q0, q1, hp == 0 ? kf[2] : kf[3]);
+            b0 = fmax3(b0, c0[0], c0[1]); b0 = fmax3(b0, c1[0], c1[1]);
+            b1 = fmax3(b1, c0[2], c0[3]); b1 = fmax3(b1, c1[2], c1[3]);
 #pragma unroll
             for (int i = 0; i < 4; ++i) { sc[np][i] = c0[i]; sc[np][4 + i] = c1[i]; }
           }
-          m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-          m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+          b0 = fmaxf(b0, __shfl_xor_sync(0xffffffffu, b0, 1)); b0 = fmaxf(b0, __shfl_xor_sync(0xffffffffu, b0, 2));
+          b1 = fmaxf(b1, __shfl_xor_sync(0xffffffffu, b1, 1)); b1 = fmaxf(b1, __shfl_xor_sync(0xffffffffu, b1, 2));
+          float ob[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int np = 0; np < kS / 16; ++np) {
-            const uint32_t p0 = pack_h2(ex2_fast(sc[np][0] - m0), ex2_fast(sc[np][1] - m0)), p1 = pack_h2(ex2_fast(sc[np][2] - m1), ex2_fast(sc[np][3] - m1));
-            const uint32_t p2 = pack_h2(ex2_fast(sc[np][4] - m0), ex2_fast(sc[np][5] - m0)), p3 = pack_h2(ex2_fast(sc[np][6] - m1), ex2_fast(sc[np][7] - m1));
+          for (int np = 0; np < kBlk / 16; ++np) {
+            const uint32_t p0 = pack_h2(ex2_fast(sc[np][0] - b0), ex2_fast(sc[np][1] - b0)), p1 = pack_h2(ex2_fast(sc[np][2] - b1), ex2_fast(sc[np][3] - b1));
+            const uint32_t p2 = pack_h2(ex2_fast(sc[np][4] - b0), ex2_fast(sc[np][5] - b0)), p3 = pack_h2(ex2_fast(sc[np][6] - b1), ex2_fast(sc[np][7] - b1));
             uint32_t vf0, vf1;
-            ldsm_x2_trans(vf0, vf1, vaddr + np * 16 * kVRow * 2 + h * 16);
-            mma16816(o[hh], p0, p1, p2, p3, vf0, vf1);
+            ldsm_x2_trans(vf0, vf1, vblk + np * 16 * kVRow * 2);
+            mma16816(ob, p0, p1, p2, p3, vf0, vf1);
           }
+          if constexpr (kS / kBlk == 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[hh][i] = ob[i];
+          } else {
+            const float n0 = fmaxf(m0, b0), n1 = fmaxf(m1, b1);
+            const float r0 = ex2_fast(m0 - n0), r1 = ex2_fast(m1 - n1), s0 = ex2_fast(b0 - n0), s1 = ex2_fast(b1 - n1);   // first block: ex2(-inf) = 0
+            o[hh][0] = o[hh][0] * r0 + ob[0] * s0; o[hh][1] = o[hh][1] * r0 + ob[1] * s0;
+            o[hh][2] = o[hh][2] * r1 + ob[2] * s1; o[hh][3] = o[hh][3] * r1 + ob[3] * s1;
+            m0 = n0; m1 = n1;
+          }
+        };
+        if constexpr (kS / kBlk == 1) {
+          do_block(0);
         } else {
-#pragma unroll 4
-          for (int np = 0; np < kS / 16; ++np) {
-            uint32_t kf[4];
-            ldsm_x4(kf, kaddr + np * 16 * kWRow * 2);
-            float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
-            mma16816(c0, a0, a1, a2, a3, kf[0], kf[1]);
-            mma16816(c1, a0, a1, a2, a3, kf[2], kf[3]);
-            m0 = fmax3(m0, c0[0], c0[1]); m0 = fmax3(m0, c1[0], c1[1]);
-            m1 = fmax3(m1, c0[2], c0[3]); m1 = fmax3(m1, c1[2], c1[3]);
-          }
-          m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-          m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-#pragma unroll 4
-          for (int np = 0; np < kS / 16; ++np) {
-            uint32_t kf[4];
-            ldsm_x4(kf, kaddr + np * 16 * kWRow * 2);
-            float c0[4] = {-m0, -m0, -m1, -m1}, c1[4] = {-m0, -m0, -m1, -m1};
-            mma16816(c0, a0, a1, a2, a3, kf[0], kf[1]);
-            mma16816(c1, a0, a1, a2, a3, kf[2], kf[3]);
-            const uint32_t p0 = pack_h2(ex2_fast(c0[0]), ex2_fast(c0[1])), p1 = pack_h2(ex2_fast(c0[2]), ex2_fast(c0[3]));
-            const uint32_t p2 = pack_h2(ex2_fast(c1[0]), ex2_fast(c1[1])), p3 = pack_h2(ex2_fast(c1[2]), ex2_fast(c1[3]));
-            uint32_t vf0, vf1;
-            ldsm_x2_trans(vf0, vf1, vaddr + np * 16 * kVRow * 2 + h * 16);
-            mma16816(o[hh], p0, p1, p2, p3, vf0, vf1);
-          }
+#pragma unroll 1
+          for (int blk = 0; blk < kS / kBlk; ++blk) do_block(blk);
         }
       }
       // even head: (o0,o1 | o2,o3 | den,0 | 0,0) over t = 0..3; odd head: (den,0 | 0,0 | o0,o1 | o2,o3).  fc wants
@@ -576,6 +581,8 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
       for (int j = 0; j < 2; ++j) {
         tc::mbar_init(&sm.ray_full[i][j], kTileM);
         tc::mbar_init(&sm.ray_empty[i][j], kTileM);
+        tc::mbar_init(&sm.geo_full[i][j], 1);
+        tc::mbar_init(&sm.geo_empty[i][j], kTileM);
       }
     }
     tc::fence_mbar_init();
@@ -704,6 +711,54 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         }
       }
       (void)n; (void)trace_m;
+    } else {
+      // ================================================================== ray geometry (warp 2 -> trunk slot 0, warp 3 -> slot 1)
+      // Everything a tile needs PER RAY is computed here, once, one tile ahead of the trunk slot: the ray direction (misc/camera.py:
+      // 255-278), the slope of the view-0 projection along the ray, q(t) = K0 (R0 (o + t d) + T0) = q_o + t K0 R0 d (camera.py:351-379 is
+      // linear in the depth before its perspective division), and the direction term of the colour head (64 values per ray).  The
+      // trunk threads used to derive all of it per SAMPLE -- ~250 instructions on the critical path of every tile -- and are left
+      // with one fused multiply-add per coordinate.
+      const int slot = warp - 2;
+      const float* E = cams.w2c[0];
+      const float* K = cams.K[0];
+      uint32_t n = 0;
+      for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x, ++n) {
+        const int64_t tile = 2 * pair + slot;
+        if (tile >= n_tiles) break;
+        const uint32_t nb = n & 1u;
+        if (n >= 2) mbar_wait_sleep(&sm.geo_empty[slot][nb], ((n >> 1) - 1u) & 1u, 64);
+        float dir[3] = {0.f, 0.f, 0.f};
+        if (lane < rays_per_tile) {
+          const int64_t ray_n = split_ray ? pair : tile * rays_per_tile + lane;
+          float4 rec = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ray_n < rays.n_rays) {
+            const int64_t pix = rays.ray_idx ? rays.ray_idx[ray_n] : rays.first_ray + ray_n;
+            float o[3], d[3];
+            cast_ray(cams, pix, o, d);
+            float rd[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) rd[i] = fmaf(d[2], E[i * 4 + 2], fmaf(d[1], E[i * 4 + 1], d[0] * E[i * 4 + 0]));
+            rec.x = fmaf(rd[2], K[2], fmaf(rd[1], K[1], rd[0] * K[0]));
+            rec.y = fmaf(rd[2], K[5], fmaf(rd[1], K[4], rd[0] * K[3]));
+            rec.z = fmaf(rd[2], K[8], fmaf(rd[1], K[7], rd[0] * K[6]));
+            rec.w = 1.f;
+            const float inv = rsqrtf(fmaxf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2], 1e-24f));
+#pragma unroll
+            for (int i = 0; i < 3; ++i) dir[i] = rd[i] * inv;                  // unit direction in the frame of source view 0 (matchnerf.py:129-134)
+          }
+          sm.rayrec[slot][nb][lane] = rec;
+        }
+        for (int rl = 0; rl < rays_per_tile; ++rl) {
+          const float dx = __shfl_sync(0xffffffffu, dir[0], rl), dy = __shfl_sync(0xffffffffu, dir[1], rl), dz = __shfl_sync(0xffffffffu, dir[2], rl);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int o2 = lane + 32 * h;
+            sm.dirvec[slot][nb][rl][o2] = sm.p.views_dir[o2 * 3] * dx + sm.p.views_dir[o2 * 3 + 1] * dy + sm.p.views_dir[o2 * 3 + 2] * dz + sm.p.views_b[o2];
+          }
+        }
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&sm.geo_full[slot][nb]);
+      }
     }
   } else if (wg <= 2) {
     // ================================================================== trunk slot: staging, epilogues, heads
@@ -713,7 +768,6 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
     const int row = quarter * 32 + lane;             // sample row inside the tile == TMEM lane
     const uint32_t tb = tmem + slot * kSlotCols + ((uint32_t)(quarter * 32) << 16);
     const int ray_local = split_ray ? 0 : row / S, s = split_ray ? slot * kTileM + row : row - ray_local * S;
-    const int dir_first = split_ray ? row : s, dir_step = split_ray ? kTileM : S;   // this thread's share of the ray's 64 dirvec entries
     uint32_t it = 0;
     unsigned trace_n = 0;
     uint32_t* const srow = &sm.stage[slot][row][0];
@@ -723,46 +777,56 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
     // both slots staged and the tensor pipe idled.  Now the sample of tile i + 1 is staged inside the windows in which tile i waits
     // for its accumulators (part A after the gate epilogue, part B after layer 0), into a shared-memory row the SAME thread reads
     // back at the start of the next tile; the conditioning row travels by cp.async, so it occupies no registers in between.
-    auto stage_geometry = [&](const int64_t pair_n, const uint32_t nb, float (&x)[3]) {
+    // q_o = K0 (R0 o + T0): the view-0 projection of the target camera centre (every ray starts there)
+    float qo[3];
+    {
+      const float* E = cams.w2c[0];
+      const float* K = cams.K[0];
+      const float o[3] = {cams.c2w[3], cams.c2w[7], cams.c2w[11]};
+      float c[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) c[i] = fmaf(o[2], E[i * 4 + 2], fmaf(o[1], E[i * 4 + 1], fmaf(o[0], E[i * 4 + 0], E[i * 4 + 3])));
+#pragma unroll
+      for (int i = 0; i < 3; ++i) qo[i] = fmaf(c[2], K[i * 3 + 2], fmaf(c[1], K[i * 3 + 1], c[0] * K[i * 3 + 0]));
+    }
+    const float rW1 = __frcp_rn((float)(cams.W - 1)), rH1 = __frcp_rn((float)(cams.H - 1));
+    const float rS1 = (cams.tfar - cams.tnear) * __frcp_rn((float)(S - 1)), rNF = __frcp_rn(cams.nf[0][1] - cams.nf[0][0]);
+    // `n_it` = index of the tile among this CTA's tiles (selects the parity of its ray-record buffer)
+    auto stage_geometry = [&](const int64_t pair_n, const uint32_t n_it, float (&x)[3]) {
+      const uint32_t nb = n_it & 1u;
       const int64_t tile_n = 2 * pair_n + slot;
       const int64_t ray_n = split_ray ? pair_n : tile_n * rays_per_tile + ray_local;
       const bool valid_n = ray_n < rays.n_rays;
       const size_t n_glob_n = valid_n ? (size_t)ray_n * S + s : 0;
       x[0] = x[1] = x[2] = 0.f;
-      float dir[3] = {0.f, 0.f, 0.f};
       float depth_n = 0.f;
       if (valid_n) {
         const uint32_t dst = tc::smem_u32(srow + 32);
         const char* src = reinterpret_cast<const char*>(cond + n_glob_n * kCondPad);
 #pragma unroll
         for (int j = 0; j < 4; ++j) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * j), "l"(src + 16 * j) : "memory");
-        const int64_t pix = rays.ray_idx ? rays.ray_idx[ray_n] : rays.first_ray + ray_n;
-        float o[3], d[3];
-        cast_ray(cams, pix, o, d);
-        const float u = rays.jitter ? rays.jitter[n_glob_n] : 0.f;
-        depth_n = sample_depth(cams, s, S, u);
-        float p[3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) p[i] = __fadd_rn(o[i], __fmul_rn(d[i], depth_n));
-        // the NDC point and the unit direction only feed fp16 operands: reciprocal-multiply forms (a few ulp) instead of IEEE
-        // divisions / square root (the gather keeps the exact forms: its mask decisions hang on them)
-        project_ndc_fast(cams, 0, p, x[0], x[1], x[2]);
-        const float inv = rsqrtf(fmaxf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2], 1e-24f));
-        const float ux = d[0] * inv, uy = d[1] * inv, uz = d[2] * inv;
-        const float* E = cams.w2c[0];
-        dir[0] = ux * E[0] + uy * E[1] + uz * E[2];
-        dir[1] = ux * E[4] + uy * E[5] + uz * E[6];
-        dir[2] = ux * E[8] + uy * E[9] + uz * E[10];
       } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(srow + 32 + 4 * j) = make_uint4(0u, 0u, 0u, 0u);
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
+      TRACE_TRUNK(30);
+      mbar_wait_sleep(&sm.geo_full[slot][nb], (n_it >> 1) & 1u, 32);      // the tile's ray records and dirvec (written a tile ahead)
+      TRACE_TRUNK(31);
+      if (valid_n) {
+        const float4 rec = sm.rayrec[slot][nb][ray_local];
+        const float u = rays.jitter ? rays.jitter[n_glob_n] : 0.f;
+        // matchnerf.py:163-181 (legacy): t = near + (i + u) / (S - 1) (far - near); the decoder's copy only feeds fp16 operands and the
+        // depth output, so the reciprocal-multiply form (<= 1 ulp) replaces the IEEE division the gather keeps for its mask decisions
+        depth_n = fmaf((float)s + u, rS1, cams.tnear);
+        const float q0 = fmaf(depth_n, rec.x, qo[0]), q1 = fmaf(depth_n, rec.y, qo[1]), q2 = fmaf(depth_n, rec.z, qo[2]);
+        const float rz = rcp_fast(q2);                                  // feeds fp16 operands only
+        x[0] = q0 * rz * rW1;
+        x[1] = q1 * rz * rH1;
+        x[2] = (q2 - cams.nf[0][0]) * rNF;
+      }
+      TRACE_TRUNK(34);
       srow[48] = __float_as_uint(depth_n);
-      // direction term of the colour head, one vector per ray (the ray's threads split its 64 outputs)
-      for (int o2 = dir_first; o2 < 64; o2 += dir_step)
-        sm.dirvec[slot][nb][ray_local][o2] = sm.p.views_dir[o2 * 3] * dir[0] + sm.p.views_dir[o2 * 3 + 1] * dir[1] +
-                                             sm.p.views_dir[o2 * 3 + 2] * dir[2] + sm.p.views_b[o2];
     };
     auto stage_encoding = [&](const float (&x)[3]) {
       // encoding order (cond_nerf.py:108-116, :56-57): x, sin(2^k x) k-major, cos(2^k x) k-major, pad
@@ -830,7 +894,6 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
       depth_o = __uint_as_float(srow[48]);
       tc::tmem_wait_st();
       tc::tc_fence_before_sync();
-      trunk_barrier(slot);          // the tile's dirvec (written by the whole slot during the previous tile) is visible before its heads epilogue
       tc::mbar_arrive(&sm.a_ready[slot]);
     };
     float depth_t = 0.f, n_views_seen = 0.f;        // of the tile whose operands are in tensor memory
@@ -914,7 +977,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         tc::mbar_arrive(&sm.a_ready[slot]);
         // the NEXT tile's sample is staged inside the two longest accumulator waits of this tile (dirvec[cb ^ 1] is free: every thread of
         // the slot finished the previous tile's heads arithmetic before this tile's layer-0 MMA could start)
-        if (l == kStageGeomLayer && has_next) stage_geometry(pair_next, cb ^ 1u, xn);
+        if (l == kStageGeomLayer && has_next) stage_geometry(pair_next, it + 1u, xn);
         if (l == kStageEncLayer && has_next) stage_encoding(xn);
       }
 
@@ -966,6 +1029,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
         colour_half(rc0, 0);
         colour_half(rc1, 32);
         TRACE_TRUNK(41);
+        tc::mbar_arrive(&sm.geo_empty[slot][cb]);        // this tile's dirvec / ray records may be overwritten (geometry warp, two tiles on)
         rgb[0] = 1.f / (1.f + __expf(-pk_lo(accrg)));
         rgb[1] = 1.f / (1.f + __expf(-pk_hi(accrg)));
         rgb[2] = 1.f / (1.f + __expf(-pk_lo(accb)));

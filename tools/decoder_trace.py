@@ -19,6 +19,7 @@ from oracle import synth  # noqa: E402
 
 TRUNK = {0: "tile start", 1: "staged (A operands written)", 2: "gate acc ready", 3: "trunk done, wait heads acc", 4: "heads acc ready",
          5: "heads epilogue done", 6: "hand-off buffer free", 7: "tile end"}
+TRUNK.update({30: "staging: cp.async issued", 31: "staging: ray cast", 32: "staging: sample point", 33: "staging: NDC projected", 34: "staging: direction done"})
 TRUNK.update({10 + l: f"L{l}: gate/prev epilogue done -> wait acc" for l in range(6)})
 TRUNK.update({20 + l: f"L{l}: acc ready" for l in range(6)})
 MMA = {}

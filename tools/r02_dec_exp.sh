@@ -9,6 +9,6 @@ L=gpurun_out/${1:-r02_dec_exp}.log
  python tools/prof_kernels.py --rays 327680 --samples 128 --which decoder --impl 2 --reps 3
  python tools/prof_kernels.py --rays 81920 --samples 256 --which decoder --impl 2 --reps 3
  if [ "${2:-}" = "trace" ]; then
-   MNF_LIB_PATH=matchnerf_b200/variants/lib_trace.so python tools/decoder_trace.py --quarters
+   MNF_LIB_PATH=matchnerf_b200/variants/lib_trace.so python tools/decoder_trace.py --samples ${3:-64}
  fi) >> $L 2>&1
 tail -4 $L | cut -c1-200
