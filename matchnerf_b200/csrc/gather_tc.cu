@@ -42,7 +42,9 @@ constexpr int kTSlot = kViews * (kT0 + kT1);           // all boxes of one depth
 constexpr int kWTile = kRays * 128;                    // one [128 rows][64 fp16] SWIZZLE_128B tile: 16 KB
 constexpr int kChunk = 64;                             // channel positions per accumulator chunk
 constexpr int kDCols = kViews * kChunk;                // 192 TMEM columns per accumulator buffer
-constexpr int kThreadsTc = 288;                        // warps 0-3 geometry, 4-7 products, 8 MMA / TMA issue
+constexpr int kThreadsTc = 416;                        // warps 0-3 geometry, 4-7 / 8-11 products (even / odd accumulator chunks), 12 MMA issue
+constexpr int kMmaWarp = 12;
+constexpr int kColX = 2 * kDCols;                      // 32 spare TMEM columns: coarse-group partial sums handed from product set A to set B
 
 struct GtSmem {
   alignas(1024) unsigned char T[2][kTSlot];            // [depth slot]: coarse v0 v1 v2, then fine v0 v1 v2
@@ -186,7 +188,7 @@ gather_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, const
     }
     tc::fence_mbar_init();
   }
-  if (warp == 8) tc::tmem_alloc<512>(&sm.tmem_base);
+  if (warp == kMmaWarp) tc::tmem_alloc<512>(&sm.tmem_base);
   tc::tc_fence_before_sync();
   __syncthreads();
   tc::tc_fence_after_sync();
@@ -321,34 +323,42 @@ gather_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, const
       }
       if (tid == 0 && overflow) args.overflow_list[atomicAdd(args.overflow_count, 1)] = tile;   // every thread holds the same flag
     }
-  } else if (warp < 8) {
+  } else if (warp < kMmaWarp) {
     // ============================================================================================ product threads (thread = sample)
     // ONE compact loop over accumulator chunks (64 packed positions x 3 views), four steps of 16 positions each: ~250 instructions
     // that stay in the instruction cache (the first version unrolled all 32 steps of a depth sample: 36 KB of straight-line code,
     // and ncu showed `no instruction` as the top stall of these warps).  The tcgen05.ld of step t + 1 -- also across chunk, scale,
     // sample and tile boundaries -- is in flight while step t is multiplied out.
+    // TWO sets of 128 product threads share the work by accumulator buffer: set A (warps 4-7) multiplies out the even chunks
+    // (buffer 0), set B (warps 8-11) the odd ones (buffer 1) -- a single warp per SM sub-partition ran this loop at ~0.19 IPC (ncu:
+    // fixed-latency `wait` stalls between dependent FFMA2s and tcgen05.ld round trips), so a second warp per sub-partition nearly
+    // doubles the rate.  A fine cosine group (32 positions) lies inside a chunk; a coarse group (128 positions) spans an even and
+    // an odd chunk: set A hands its nine partial sums to set B through 16 spare tensor-memory columns (same lane = same sample)
+    // and a 64-thread named barrier per lane quarter.  Set B assembles and writes the conditioning row.
     const int quarter = warp & 3, row = quarter * 32 + lane;
+    const uint32_t set = (uint32_t)(warp >> 2) - 1u;                  // 0: even chunks, 1: odd chunks
     const uint32_t tb = tmem + ((uint32_t)(quarter * 32) << 16);
     const int px = row & (kTW - 1), py = row >> 4;
-    float* const simrow = &sm.sims[row][0];          // this thread's 10 cosines of the current depth sample (thread-private row)
+    float* const simrow = &sm.sims[row][0];          // the 10 cosines of the depth sample in flight (one row per sample, written by both sets)
     const int my_tiles = args.n_tiles > (int)blockIdx.x ? (args.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const uint32_t n_chunks = (uint32_t)my_tiles * (uint32_t)S * 8u;
+    const uint32_t d0 = tb + set * kDCols;           // this set's accumulator buffer
+    auto pair_arrive = [&](int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); };
+    auto pair_sync = [&](int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); };
     uint32_t ra[2][16], rb[2][16], rc[2][16];
     float2 q[9];
     if (n_chunks > 0) {
-      tc::mbar_wait(&sm.d_full[0], 0u);
+      tc::mbar_wait(&sm.d_full[set], 0u);
       tc::tc_fence_after_sync();
-      tc::tmem_ld16(tb, ra[0]);
-      tc::tmem_ld16(tb + kChunk, rb[0]);
-      tc::tmem_ld16(tb + 2 * kChunk, rc[0]);
+      tc::tmem_ld16(d0, ra[0]);
+      tc::tmem_ld16(d0 + kChunk, rb[0]);
+      tc::tmem_ld16(d0 + 2 * kChunk, rc[0]);
       tc::tmem_wait_ld(ra[0]); tie16(rb[0]); tie16(rc[0]);
     }
     int tile = blockIdx.x, s = 0;
 #pragma unroll 1
-    for (uint32_t g = 0; g < n_chunks; ++g) {
-      const uint32_t db = g & 1u;
+    for (uint32_t g = set; g < n_chunks; g += 2u) {
       const int sc = (int)((g >> 2) & 1u), c = (int)(g & 3u);
-      const uint32_t d0 = tb + db * kDCols;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int cur = j & 1, nxt = cur ^ 1;
@@ -356,31 +366,60 @@ gather_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, const
           tc::tmem_ld16(d0 + 16 * (j + 1), ra[nxt]);
           tc::tmem_ld16(d0 + kChunk + 16 * (j + 1), rb[nxt]);
           tc::tmem_ld16(d0 + 2 * kChunk + 16 * (j + 1), rc[nxt]);
-        } else if (g + 1 < n_chunks) {                // first step of the next chunk (its MMAs were issued a chunk ago)
-          const uint32_t g2 = g + 1u, db2 = g2 & 1u;
-          tc::mbar_wait_sleep(&sm.d_full[db2], (g2 >> 1) & 1u, 20);
-          tc::tc_fence_after_sync();
-          const uint32_t d2 = tb + db2 * kDCols;
-          tc::tmem_ld16(d2, ra[nxt]);
-          tc::tmem_ld16(d2 + kChunk, rb[nxt]);
-          tc::tmem_ld16(d2 + 2 * kChunk, rc[nxt]);
+        } else {
+          // every load of this chunk completed a step ago: hand the buffer back, then look at this set's next chunk
+          tc::tc_fence_before_sync();
+          tc::mbar_arrive(&sm.d_free[set]);
+          if (g + 2u < n_chunks) {
+            const uint32_t g2 = g + 2u;
+            tc::mbar_wait_sleep(&sm.d_full[set], (g2 >> 1) & 1u, 20);
+            tc::tc_fence_after_sync();
+            tc::tmem_ld16(d0, ra[nxt]);
+            tc::tmem_ld16(d0 + kChunk, rb[nxt]);
+            tc::tmem_ld16(d0 + 2 * kChunk, rc[nxt]);
+          }
         }
-        if (j % 2 == 0 && (sc == 1 || (c % 2 == 0 && j == 0))) {   // a new cosine group starts: fine = 32 positions, coarse = 128
+        if (j % 2 == 0 && (sc == 1 || j == 0)) {      // a new cosine (partial) group starts: fine = 32 positions, coarse = this chunk's 64
 #pragma unroll
           for (int i = 0; i < 9; ++i) q[i] = make_float2(0.f, 0.f);
         }
         run_products(ra[cur], rb[cur], rc[cur], q);
         run_products(ra[cur] + 8, rb[cur] + 8, rc[cur] + 8, q);
         if (j % 2 == 1) {
-          if (sc == 1) simrow[2 + c * 2 + j / 2] = mean_cosine9(q);
-          else if (j == 3 && c % 2 == 1) simrow[c / 2] = mean_cosine9(q);
+          if (sc == 1) {
+            simrow[2 + c * 2 + j / 2] = mean_cosine9(q);
+          } else if (j == 3) {
+            const uint32_t xcol = tb + kColX + (uint32_t)(c >> 1) * 16u;
+            const int bar_id = 2 + quarter * 2 + (c >> 1);
+            if (set == 0u) {                          // first half of a coarse group: nine sums -> tensor memory -> set B
+              uint32_t x[16];
+#pragma unroll
+              for (int i = 0; i < 9; ++i) x[i] = __float_as_uint(q[i].x + q[i].y);
+#pragma unroll
+              for (int i = 9; i < 16; ++i) x[i] = 0u;
+              tc::tmem_wait_ld(ra[nxt]); tie16(rb[nxt]); tie16(rc[nxt]);    // (the prefetch shares the wait below with nothing else)
+              tc::tmem_st16(xcol, x);
+              tc::tmem_wait_st();
+              tc::tc_fence_before_sync();
+              pair_arrive(bar_id);
+            } else {                                  // second half: add set A's sums, then the cosine
+              pair_sync(bar_id);
+              tc::tc_fence_after_sync();
+              uint32_t x[16];
+              tc::tmem_ld16(xcol, x);
+              tc::tmem_wait_ld(x); tie16(ra[nxt]); tie16(rb[nxt]); tie16(rc[nxt]);
+#pragma unroll
+              for (int i = 0; i < 9; ++i) q[i] = make_float2(q[i].x + q[i].y, __uint_as_float(x[i]));
+              simrow[c >> 1] = mean_cosine9(q);
+            }
+          }
         }
         tc::tmem_wait_ld(ra[nxt]); tie16(rb[nxt]); tie16(rc[nxt]);
       }
-      tc::tc_fence_before_sync();
-      tc::mbar_arrive(&sm.d_free[db]);                // every load of this chunk completed a step ago
+      if (sc == 1 && c == 2) pair_arrive(10 + quarter);        // set A: its fine cosines of this depth sample are in simrow
       if (sc == 1 && c == 3) {
-        // ---------------- assemble the conditioning row: feat_info[10], color_info[9], mask_info[3] (cond_nerf.py:59)
+        // ---------------- assemble the conditioning row: feat_info[10], color_info[9], mask_info[3] (cond_nerf.py:59)   (set B)
+        pair_sync(10 + quarter);
         const uint32_t gsl = g >> 3, slot = gsl & 1u, par = (gsl >> 1) & 1u;
         const int band = args.band0 + tile / args.tiles_x, tx = tile - (tile / args.tiles_x) * args.tiles_x;
         const int x = tx * kTW + px, y = band * kTH + py;
@@ -469,7 +508,7 @@ gather_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, const
   }
   tc::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 8) tc::tmem_dealloc<512>(tmem);
+  if (warp == kMmaWarp) tc::tmem_dealloc<512>(tmem);
 }
 
 // ------------------------------------------------------------------------------------------------------------------ host side
