@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MNF_ABI_VERSION 4
+#define MNF_ABI_VERSION 5
 
 typedef enum mnf_status {
   MNF_OK = 0,
@@ -170,6 +170,16 @@ int32_t mnf_composite_fwd(mnf_ctx* ctx, const float* rgb, const float* sigma, co
  *   mode 0: y = IN(x);  mode 1: y = relu(IN(x));  mode 2: y = relu(residual + relu(IN(x)))   (backbone.py:28-36) */
 int32_t mnf_instance_norm_fwd(mnf_ctx* ctx, const float* x, const float* residual, float* y, int64_t n_planes,
                               int32_t hw, int32_t mode, float eps, void* stream);
+
+/* ---- encoder helper: token LayerNorm of TransformerLayer.forward fused with what follows it -- */
+/* x: [n_tokens][128], fp32 or (x_is_f16) fp16; gamma / beta: fp32 [128]; nn.LayerNorm semantics (biased variance, eps inside the
+ * square root).  Exactly one output:
+ *   out_f32 [n_tokens][128] = (residual ? residual : 0) + LN(x)      `source + message`, models/gmflow/transformer.py:176 and :183-185
+ *   out_f16 [n_tokens][prefix ? 256 : 128] = half([prefix | LN(x)])  `cat([source, message])` as the FFN operand, :181
+ * residual, prefix: fp32 [n_tokens][128] or NULL.  All pointers 16-byte aligned. */
+int32_t mnf_token_layernorm_fwd(mnf_ctx* ctx, const void* x, int32_t x_is_f16, const float* gamma, const float* beta, float eps,
+                                const float* residual, const float* prefix, float* out_f32, void* out_f16, int64_t n_tokens,
+                                int32_t channels, void* stream);
 
 /* ---- K-attn: GMFlow split-window single-head attention ----------------------------------- */
 /* Replaces single_head_split_window_attention / single_head_full_attention

@@ -15,7 +15,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MNF_LIB_PATH") or os.path.join(_HERE, "libmatchnerf_b200.so")   # override: A/B builds (tools/)
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 COND_DIM = 22
 COND_PAD = 32
 FEAT_CH = 256
@@ -79,6 +79,7 @@ def load() -> C.CDLL:
     lib.mnf_decoder_samples_fwd.argtypes = [vp, C.POINTER(DecoderCfg), fp, fp, fp, i64, fp, vp]
     lib.mnf_composite_fwd.argtypes = [vp, fp, fp, fp, i64, i32, i32, fp, fp, fp, fp, vp]
     lib.mnf_instance_norm_fwd.argtypes = [vp, fp, fp, fp, i64, i32, i32, C.c_float, vp]
+    lib.mnf_token_layernorm_fwd.argtypes = [vp, vp, i32, fp, fp, C.c_float, fp, fp, fp, vp, i64, i32, vp]
     lib.mnf_render_workspace_bytes.argtypes = [i64, i32, i32]
     lib.mnf_render_workspace_bytes.restype = i64
     lib.mnf_render_rays_fwd.argtypes = [vp, C.POINTER(Scene), C.POINTER(Rays), C.POINTER(DecoderCfg), i32, fp, fp, fp,
@@ -90,7 +91,7 @@ def load() -> C.CDLL:
     for name in ("mnf_ctx_create", "mnf_ctx_destroy", "mnf_decoder_load_host", "mnf_pack_features", "mnf_pack_images",
                  "mnf_gather_cossim_fwd", "mnf_decoder_composite_fwd", "mnf_render_rays_fwd", "mnf_window_attn_fwd",
                  "mnf_selftest_umma", "mnf_query_cond_points_fwd", "mnf_decoder_samples_fwd", "mnf_composite_fwd",
-                 "mnf_instance_norm_fwd"):
+                 "mnf_instance_norm_fwd", "mnf_token_layernorm_fwd"):
         getattr(lib, name).restype = i32
     if lib.mnf_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libmatchnerf_b200.so ABI {lib.mnf_abi_version()} != {ABI_VERSION}")
@@ -337,6 +338,34 @@ class Context:
         _check(self.lib.mnf_instance_norm_fwd(self._h, xc.data_ptr(), _ptr(rc), y.data_ptr(), N * Cc, H * W, mode, eps,
                                               _stream(self.device)), "mnf_instance_norm_fwd")
         return y
+
+    def token_layernorm(self, x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5,
+                        residual: Optional[torch.Tensor] = None, prefix: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """LayerNorm over the last (128-wide) axis of x (fp32 or fp16) fused with what follows it in TransformerLayer.forward:
+        ``residual + LN(x)`` (fp32) or, with ``prefix``, ``cat([prefix, LN(x)], -1)`` in fp16; see mnf_token_layernorm_fwd."""
+        if x.dtype not in (torch.float32, torch.float16) or not x.is_cuda or x.device != self.device:
+            raise ValueError("x must be an fp32 / fp16 tensor on this context's device")
+        xc = x.contiguous()
+        if xc.shape[-1] != 128:
+            raise ValueError("token_layernorm is built for 128 channels")
+        n = xc.numel() // 128
+        w, b = _dev_f32(weight, self.device, "weight"), _dev_f32(bias, self.device, "bias")
+        rc = _dev_f32(residual, self.device, "residual") if residual is not None else None
+        pc = _dev_f32(prefix, self.device, "prefix") if prefix is not None else None
+        for t, nm in ((rc, "residual"), (pc, "prefix")):
+            if t is not None and t.shape != xc.shape:
+                raise ValueError(f"{nm} {tuple(t.shape)} != x {tuple(xc.shape)}")
+        if pc is not None and rc is not None:
+            raise ValueError("residual and prefix are exclusive")
+        if pc is not None:
+            out = torch.empty(xc.shape[:-1] + (256,), dtype=torch.float16, device=self.device)
+            o32, o16 = None, out.data_ptr()
+        else:
+            out = torch.empty(xc.shape, dtype=torch.float32, device=self.device)
+            o32, o16 = out.data_ptr(), None
+        _check(self.lib.mnf_token_layernorm_fwd(self._h, xc.data_ptr(), int(xc.dtype == torch.float16), w.data_ptr(), b.data_ptr(), eps,
+                                                _ptr(rc), _ptr(pc), o32, o16, n, 128, _stream(self.device)), "mnf_token_layernorm_fwd")
+        return out
 
     def window_attn(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, h: int, w: int, num_splits: int,
                     with_shift: bool, impl: int = 0, use_workspace: bool = True) -> torch.Tensor:

@@ -408,6 +408,22 @@ int32_t mnf_instance_norm_fwd(mnf_ctx* ctx, const float* x, const float* residua
   return launch_instance_norm(x, mode == 2 ? residual : nullptr, y, n_planes, hw, mode, eps, (cudaStream_t)stream);
 }
 
+int32_t mnf_token_layernorm_fwd(mnf_ctx* ctx, const void* x, int32_t x_is_f16, const float* gamma, const float* beta, float eps,
+                                const float* residual, const float* prefix, float* out_f32, void* out_f16, int64_t n_tokens,
+                                int32_t channels, void* stream) {
+  DeviceGuard dev_guard(ctx);
+  if (!ctx || !x || !gamma || !beta) { set_error("mnf_token_layernorm_fwd: NULL argument"); return MNF_EINVAL; }
+  if (channels != 128 || n_tokens < 0) { set_error("mnf_token_layernorm_fwd: %d channels / %lld tokens (the kernel is built for 128 channels)", channels, (long long)n_tokens); return MNF_EUNSUPPORTED; }
+  if ((out_f32 != nullptr) == (out_f16 != nullptr)) { set_error("mnf_token_layernorm_fwd: exactly one of out_f32 / out_f16"); return MNF_EINVAL; }
+  if ((out_f32 && prefix) || (out_f16 && residual)) { set_error("mnf_token_layernorm_fwd: residual goes with out_f32, prefix with out_f16"); return MNF_EINVAL; }
+  if ((((uintptr_t)x | (uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)residual | (uintptr_t)prefix | (uintptr_t)out_f32 | (uintptr_t)out_f16) & 15) != 0) {
+    set_error("mnf_token_layernorm_fwd: pointers must be 16-byte aligned");
+    return MNF_EINVAL;
+  }
+  return launch_token_layernorm(x, x_is_f16, gamma, beta, eps, residual, prefix, out_f32, reinterpret_cast<__half*>(out_f16), n_tokens,
+                                (cudaStream_t)stream);
+}
+
 int64_t mnf_window_attn_workspace_bytes(int32_t B, int32_t h, int32_t w, int32_t num_splits) {
   return window_attn_tc_workspace_bytes(B, h, w, num_splits);
 }

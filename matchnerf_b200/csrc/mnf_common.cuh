@@ -166,6 +166,8 @@ int launch_composite(const float* rgb, const float* sigma, const float* depth, i
                      float* out_rgb, float* out_depth, float* out_opacity, float* out_prob, cudaStream_t s);
 
 int launch_instance_norm(const float* x, const float* res, float* y, int64_t planes, int hw, int mode, float eps, cudaStream_t s);
+int launch_token_layernorm(const void* x, int x_is_f16, const float* gamma, const float* beta, float eps, const float* residual,
+                           const float* prefix, float* out_f32, __half* out_f16, int64_t rows, cudaStream_t s);
 
 int launch_window_attn_ref(const float* q, const float* k, const float* v, float* out, int B, int h, int w, int C,
                            int num_splits, int with_shift, cudaStream_t s);

@@ -112,15 +112,31 @@ class TransformerLayer(nn.Module):
         shift = self.with_shift and attn_num_splits > 1
         msg = window_attention(self.q_proj(source), self.k_proj(target), self.v_proj(target), height, width,
                                attn_num_splits, shift)
-        msg = self.norm1(self.merge(msg))
-        if not self.no_ffn:
-            msg = self.norm2(self._ffn(torch.cat([source, msg], dim=-1)))
-        return source + msg
+        msg = self.merge(msg)
+        if not self._fused_norms(msg):                       # CPU tensors / autograd: the PyTorch ops the reference uses
+            msg = self.norm1(msg)
+            if not self.no_ffn:
+                msg = self.norm2(self._ffn(torch.cat([source, msg], dim=-1)))
+            return source + msg
+        # inference on the GPU: every LayerNorm is one kernel of this repo's library together with the add / cat / dtype conversion
+        # around it (mnf_token_layernorm_fwd)
+        ctx = capi.get_context(msg.device)
+        if self.no_ffn:
+            return ctx.token_layernorm(msg, self.norm1.weight, self.norm1.bias, self.norm1.eps, residual=source)       # source + LN1(.)
+        dt = self.ffn_dtype
+        w1, w2 = self._ffn_weights(dt)
+        x16 = ctx.token_layernorm(msg, self.norm1.weight, self.norm1.bias, self.norm1.eps, prefix=source)             # half(cat[source, LN1(.)])
+        hid = F.linear(F.gelu(F.linear(x16, w1)), w2)                                                                # fp16, fp32 accumulation
+        return ctx.token_layernorm(hid, self.norm2.weight, self.norm2.bias, self.norm2.eps, residual=source)         # source + LN2(.)
 
     # dtype of the FFN's operands and 1024-wide hidden tensor.  The TF32 path (None) already rounds every GEMM operand to a
     # 10-bit mantissa; storing the hidden activations as fp16 (same mantissa, fp32 accumulation in both GEMMs, GELU
     # evaluated in fp32 inside the kernel) halves the 126 MB-per-layer hidden round trips.  Inference only.
     ffn_dtype = torch.float16
+
+    def _fused_norms(self, x) -> bool:
+        return (x.is_cuda and x.dtype == torch.float32 and x.shape[-1] == 128 and self.ffn_dtype == torch.float16
+                and not (torch.is_grad_enabled() and x.requires_grad))
 
     def _ffn(self, x):
         dt = self.ffn_dtype

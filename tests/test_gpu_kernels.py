@@ -399,3 +399,27 @@ def test_window_attn_blender_llff_shapes(ctx, h, w, splits, shift):
     assert rms(got[:1], oracle) < 2e-3 * float(oracle.std()) and rms(nows[:1], oracle) < 2e-3 * float(oracle.std())
     assert max_abs(got[:1], oracle) < 2e-2
     assert rms(got, ref) < 2e-3 * float(ref.std()) and rms(nows, ref) < 2e-3 * float(ref.std())
+
+
+@pytest.mark.parametrize("rows", [1, 37, 5120 * 6])
+def test_token_layernorm_fused_modes(ctx, rows):
+    """mnf_token_layernorm_fwd vs nn.LayerNorm + the add / cat that follow it in TransformerLayer.forward
+    (models/gmflow/transformer.py:173-185): fp32 arithmetic, tolerance 2e-5 (fp16 outputs: one fp16 rounding)."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(rows)
+    dev = ctx.device
+    x = (torch.randn(rows, 128, generator=g) * 3 + 0.7).to(dev)
+    src = torch.randn(rows, 128, generator=g).to(dev)
+    w = (1 + 0.1 * torch.randn(128, generator=g)).to(dev)
+    b = (0.1 * torch.randn(128, generator=g)).to(dev)
+    ref = F.layer_norm(x.double(), (128,), w.double(), b.double(), 1e-5)
+    assert max_abs(ctx.token_layernorm(x, w, b, 1e-5), ref.float()) < 2e-5
+    assert max_abs(ctx.token_layernorm(x, w, b, 1e-5, residual=src), (src.double() + ref).float()) < 2e-5
+    cat = ctx.token_layernorm(x, w, b, 1e-5, prefix=src)
+    assert cat.dtype == torch.float16 and cat.shape == (rows, 256)
+    assert torch.equal(cat[:, :128], src.half()) and max_abs(cat[:, 128:].float(), ref.float()) < 4e-3
+    xh = x.half()                                        # fp16 input (the FFN output)
+    refh = F.layer_norm(xh.double(), (128,), w.double(), b.double(), 1e-5)
+    assert max_abs(ctx.token_layernorm(xh, w, b, 1e-5, residual=src), (src.double() + refh).float()) < 2e-5
+    with pytest.raises(ValueError):
+        ctx.token_layernorm(x, w, b, 1e-5, residual=src, prefix=src)
