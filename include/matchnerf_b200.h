@@ -122,6 +122,14 @@ int32_t mnf_pack_images(mnf_ctx* ctx, const float* images_nchw, int32_t V, int32
  *   cond_f32: [N][22] fp32 or NULL;  cond_f16: [N][32] fp16 (cols 22..31 zero) or NULL. */
 int32_t mnf_gather_cossim_fwd(mnf_ctx* ctx, const mnf_scene* scene, const mnf_rays* rays, int32_t n_samples,
                               float* cond_f32, void* cond_f16, void* stream);
+/* Backward of the above for the training step (coach.py:215-243: loss.backward() through query_cond_info): dcond_f32 [N][22] =
+ * d(loss)/d(conditioning row) -- only columns 0..9 (the cosine similarities) reach parameters: F.grid_sample backward of
+ * models/gmflow/utils.py:134 + nn.CosineSimilarity backward of models/matchnerf.py:268-271 -- is scattered (ADDED: the caller
+ * zero-fills once per step) into fp32 gradient maps laid out like the packed feature maps, [V][h][w][256] channels-last in the
+ * packed channel order of mnf_pack_features (position 8*l + e <-> channel (e < 4 ? 0 : 128) + 4*l + (e & 3)).  Same `scene` /
+ * `rays` (incl. jitter) as the forward call. */
+int32_t mnf_gather_cossim_bwd(mnf_ctx* ctx, const mnf_scene* scene, const mnf_rays* rays, int32_t n_samples,
+                              const float* dcond_f32, float* grad_feat0_packed, float* grad_feat1_packed, void* stream);
 
 /* ---- K-mlp-composite: conditional MLP + ray transformer + alpha compositing -------------- */
 /* Replaces CondNeRF.forward (models/rfdecoder/cond_nerf.py:52-100), MultiHeadAttention.forward

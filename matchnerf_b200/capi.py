@@ -79,6 +79,7 @@ def load() -> C.CDLL:
     lib.mnf_decoder_samples_fwd.argtypes = [vp, C.POINTER(DecoderCfg), fp, fp, fp, i64, fp, vp]
     lib.mnf_composite_fwd.argtypes = [vp, fp, fp, fp, i64, i32, i32, fp, fp, fp, fp, vp]
     lib.mnf_instance_norm_fwd.argtypes = [vp, fp, fp, fp, i64, i32, i32, C.c_float, vp]
+    lib.mnf_gather_cossim_bwd.argtypes = [vp, C.POINTER(Scene), C.POINTER(Rays), i32, fp, fp, fp, vp]
     lib.mnf_token_layernorm_fwd.argtypes = [vp, vp, i32, fp, fp, C.c_float, fp, fp, fp, vp, i64, i32, vp]
     lib.mnf_render_workspace_bytes.argtypes = [i64, i32, i32]
     lib.mnf_render_workspace_bytes.restype = i64
@@ -91,7 +92,7 @@ def load() -> C.CDLL:
     for name in ("mnf_ctx_create", "mnf_ctx_destroy", "mnf_decoder_load_host", "mnf_pack_features", "mnf_pack_images",
                  "mnf_gather_cossim_fwd", "mnf_decoder_composite_fwd", "mnf_render_rays_fwd", "mnf_window_attn_fwd",
                  "mnf_selftest_umma", "mnf_query_cond_points_fwd", "mnf_decoder_samples_fwd", "mnf_composite_fwd",
-                 "mnf_instance_norm_fwd", "mnf_token_layernorm_fwd"):
+                 "mnf_instance_norm_fwd", "mnf_token_layernorm_fwd", "mnf_gather_cossim_bwd"):
         getattr(lib, name).restype = i32
     if lib.mnf_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libmatchnerf_b200.so ABI {lib.mnf_abi_version()} != {ABI_VERSION}")
@@ -254,6 +255,29 @@ class Context:
         _check(self.lib.mnf_gather_cossim_fwd(self._h, C.byref(scene), C.byref(rays), S, _ptr(c32), _ptr(c16),
                                               _stream(self.device)), "mnf_gather_cossim_fwd")
         return c32, c16
+
+    def gather_cossim_bwd(self, scene: Scene, S: int, dcond: torch.Tensor, ray_idx=None, first_ray=0, n_rays=0, jitter=None):
+        """d(loss)/d(cond) [R*S,22] -> gradients of the two feature maps, [V,256,h,w] fp32 each (NCHW, the layout the encoder
+        produced them in); see mnf_gather_cossim_bwd.  Same scene / rays / jitter as the forward call."""
+        rays, R, keep = self._rays(n_rays, ray_idx, first_ray, jitter, S)
+        dc = _dev_f32(dcond, self.device, "dcond")
+        if dc.shape != (R * S, COND_DIM):
+            raise ValueError(f"dcond {tuple(dc.shape)} != {(R * S, COND_DIM)}")
+        V = 3
+        g0 = torch.zeros((V, scene.h0, scene.w0, FEAT_CH), dtype=torch.float32, device=self.device)
+        g1 = torch.zeros((V, scene.h1, scene.w1, FEAT_CH), dtype=torch.float32, device=self.device)
+        _check(self.lib.mnf_gather_cossim_bwd(self._h, C.byref(scene), C.byref(rays), S, dc.data_ptr(), g0.data_ptr(), g1.data_ptr(),
+                                              _stream(self.device)), "mnf_gather_cossim_bwd")
+        perm = self._unpack_perm()
+        return (g0.index_select(3, perm).permute(0, 3, 1, 2).contiguous(), g1.index_select(3, perm).permute(0, 3, 1, 2).contiguous())
+
+    def _unpack_perm(self) -> torch.Tensor:
+        """perm[c] = packed position of channel c (mnf_pack_features: position 8 l + e <-> channel (e < 4 ? 0 : 128) + 4 l + (e & 3))."""
+        if getattr(self, "_perm", None) is None:
+            c = torch.arange(FEAT_CH)
+            half, within = c // 128, c % 128
+            self._perm = (8 * (within // 4) + 4 * half + within % 4).to(self.device)
+        return self._perm
 
     def decoder_composite(self, scene: Scene, cfg: DecoderCfg, cond_f32=None, cond_f16=None, ray_idx=None, first_ray=0,
                           n_rays=0, jitter=None, setbg_opaque=False, impl=0, want_aux=False):

@@ -282,6 +282,24 @@ int32_t mnf_gather_cossim_fwd(mnf_ctx* ctx, const mnf_scene* scene, const mnf_ra
                        (cudaStream_t)stream, ctx->gather_scratch, ctx->gather_scratch ? kGatherScratchInts : 0);
 }
 
+int32_t mnf_gather_cossim_bwd(mnf_ctx* ctx, const mnf_scene* scene, const mnf_rays* rays, int32_t n_samples, const float* dcond_f32,
+                              float* grad_feat0_packed, float* grad_feat1_packed, void* stream) {
+  DeviceGuard dev_guard(ctx);
+  if (!ctx) { set_error("ctx is NULL"); return MNF_EINVAL; }
+  DevCams cams;
+  DevRays dr{};
+  int rc;
+  if ((rc = fill_cams(scene, &cams))) return rc;
+  if ((rc = fill_rays(scene, rays, &dr))) return rc;
+  if (n_samples < 2 || n_samples > kMaxSamples) { set_error("n_samples = %d outside [2, %d]", n_samples, kMaxSamples); return MNF_EUNSUPPORTED; }
+  if (!scene->feat0 || !scene->feat1) { set_error("scene feature maps missing"); return MNF_EINVAL; }
+  if (!dcond_f32 || !grad_feat0_packed || !grad_feat1_packed) { set_error("mnf_gather_cossim_bwd: NULL gradient buffer"); return MNF_EINVAL; }
+  if ((((uintptr_t)grad_feat0_packed | (uintptr_t)grad_feat1_packed) & 15) != 0) { set_error("gradient maps must be 16-byte aligned"); return MNF_EINVAL; }
+  return launch_gather_bwd(cams, dr, n_samples, reinterpret_cast<const __half*>(scene->feat0), scene->h0, scene->w0,
+                           reinterpret_cast<const __half*>(scene->feat1), scene->h1, scene->w1, dcond_f32, grad_feat0_packed,
+                           grad_feat1_packed, (cudaStream_t)stream);
+}
+
 int32_t mnf_decoder_composite_fwd(mnf_ctx* ctx, const mnf_scene* scene, const mnf_rays* rays, const mnf_decoder_cfg* cfg,
                                   const float* cond_f32, const void* cond_f16, int32_t setbg_opaque, float* out_rgb,
                                   float* out_depth, float* out_opacity, float* aux_rgb_sigma, int32_t impl, void* stream) {

@@ -157,6 +157,9 @@ int launch_gather(const DevCams& cams, const DevRays& rays, int S, const __half*
                   const __half* f1, int h1, int w1, const float* images, float* cond_f32, __half* cond_f16,
                   cudaStream_t s, int* scratch = nullptr, int scratch_ints = 0);
 
+int launch_gather_bwd(const DevCams& cams, const DevRays& rays, int S, const __half* f0, int h0, int w0, const __half* f1, int h1,
+                      int w1, const float* dcond, float* g0, float* g1, cudaStream_t s);
+
 struct DecoderWeightsF32;  // decoder_ref.cu
 int launch_decoder_ref(const DevCams& cams, const DevRays& rays, const mnf_decoder_cfg& cfg,
                        const DecoderWeightsF32& w, const float* cond_f32, int setbg_opaque, float* out_rgb,

@@ -87,7 +87,8 @@ def window_attention(q, k, v, h: int, w: int, num_splits: int, with_shift: bool,
     if not q.is_cuda:
         raise RuntimeError("matchnerf_b200: split-window attention only exists as a CUDA kernel (no CPU path)")
     if torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad):
-        raise NotImplementedError("matchnerf_b200: backward of the attention kernel is not built yet; run under torch.no_grad()")
+        from .train_path import window_attention_autograd        # training step: index-gathered batched GEMMs + autograd
+        return window_attention_autograd(q, k, v, h, w, num_splits, with_shift)
     return capi.get_context(q.device).window_attn(q, k, v, h, w, num_splits, with_shift, impl)
 
 

@@ -287,7 +287,17 @@ class MatchNeRF(nn.Module):
         if tgt_pose is None:
             raise Exception("Must provide tgt_pose.")
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("matchnerf_b200: the backward kernels are not built yet; call under torch.no_grad()")
+            # training step (coach.py:215-243): K-gather forward / backward kernels behind an autograd Function, the MLP / ray
+            # transformer / compositing as library GEMMs under autograd (train_path.py)
+            from .train_path import render_rays_train
+            if not ref_images.is_cuda:
+                raise RuntimeError("matchnerf_b200: the render path only exists as CUDA kernels (no CPU path)")
+            idx = ray_idx if ray_idx is not None else torch.arange(first_ray, first_ray + n_rays, device=ref_images.device)
+            strat = mode == "train" and bool(get_opt(opt, "nerf.sample_stratified", False))
+            res = [render_rays_train(self, opt, tgt_pose, idx, ref_poses, ref_images, ref_feats_list, b, strat)
+                   for b in (range(ref_images.shape[0]) if only_b is None else [only_b])]
+            return AttrDict(rgb=torch.stack([r[0] for r in res]), depth=torch.stack([r[1] for r in res]),
+                            opacity=torch.stack([r[2] for r in res]))
         dec = self._unwrap(self.nerf_dec)
         ctx = dec.sync_to_library()
         cfg = dec.decoder_cfg(opt)

@@ -1,0 +1,115 @@
+"""GPU (B200): the training step (BASELINE configs[4]; reference coach.py:215-243).  K-gather backward kernel against the
+oracle's autograd, and forward(mode='train') + loss.backward() + AdamW for a few steps against the same steps taken by the oracle
+(a differentiable fp32 restatement of the reference) from the same weights, rays and jitter."""
+import copy
+
+import pytest
+import torch
+
+from oracle import encoder_oracle as EO
+from oracle import render_oracle as RO
+from oracle import synth
+from tests.helpers import half_round
+from tests.test_gpu_kernels import make_scene
+from tests.test_host_cpu import make_opts
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("S,n_rays", [(16, 96), (64, 40)])
+def test_gather_backward_vs_oracle_autograd(ctx, S, n_rays):
+    """mnf_gather_cossim_bwd: d(sum(cond[:, :10] * w)) / d(feature maps) vs autograd through the oracle's query_cond on the same
+    (fp16-rounded) maps.  The kernel blends in fp32; tolerance 1e-3 of the gradient scale."""
+    H, W = 64, 80
+    feats, imgs, g = synth.synthetic_scene(H, W, seed=7)
+    extr, intr, nf = synth.synthetic_cameras(H, W)
+    _, sc = make_scene(ctx, feats, imgs, extr, intr, nf)
+    ray_idx = torch.randperm(H * W, generator=g)[:n_rays]
+    jit = torch.rand(n_rays, S, generator=g)
+    wgt = torch.randn(n_rays * S, 10, generator=g)
+    dcond = torch.zeros(n_rays * S, 22)
+    dcond[:, :10] = wgt
+    g8, g4 = ctx.gather_cossim_bwd(sc, S, dcond.to(DEV), ray_idx=ray_idx, jitter=jit.to(DEV))
+    fl = [half_round(f)[0].permute(0, 2, 3, 1).contiguous().requires_grad_(True) for f in feats]        # [V,h,w,C]
+    centre, ray = RO.cast_rays(H, W, extr[0, 3, :3], intr[0, 3], ray_idx)
+    t = RO.sample_depths(float(nf[0, 3, 0]), float(nf[0, 3, 1]), S, jit)
+    pts = (centre[None, None] + ray[:, None] * t[..., None]).reshape(-1, 3)
+    cond = RO.query_cond(pts, fl, imgs[0].permute(0, 2, 3, 1).contiguous(), extr[0, :3, :3], intr[0, :3], nf[0, :3], (2, 8))
+    (cond[:, :10] * wgt).sum().backward()
+    for got, ref in ((g8, fl[0].grad), (g4, fl[1].grad)):
+        ref = ref.permute(0, 3, 1, 2)
+        scale = float(ref.abs().max())
+        assert scale > 0 and float((got.cpu() - ref).abs().max()) < 1e-3 * scale, (float((got.cpu() - ref).abs().max()), scale)
+    # the forward the Function pairs with it: same rays / jitter
+    c32, _ = ctx.gather_cossim(sc, S, ray_idx=ray_idx, jitter=jit.to(DEV))
+    assert float((c32[:, :10].cpu() - cond[:, :10].detach()).abs().max()) < 5e-3
+
+
+def test_train_steps_follow_the_oracle():
+    """Three AdamW steps of forward(mode='train') + MSE + backward on a 64x96 scene vs the same three steps through the oracle
+    (encoder + render restatement under autograd): losses within 2 %, parameter updates aligned (cosine > 0.98)."""
+    from matchnerf_b200.matchnerf import MatchNeRF
+    from matchnerf_b200.utils import AttrDict
+    H, W, S, R = 64, 96, 16, 256
+    opt = make_opts(**{"nerf.sample_intvs": S, "nerf.rand_rays_train": R, "nerf.sample_stratified": True})
+    opt.device = DEV
+    torch.manual_seed(0)
+    model = MatchNeRF(opt).train()
+    enc_sd, dec_sd = synth.synthetic_encoder(1), synth.synthetic_decoder(0)
+    model.feat_enc.load_state_dict(enc_sd)
+    model.nerf_dec.load_state_dict(dec_sd)
+    model.to(DEV)
+    g = torch.Generator().manual_seed(11)
+    images = torch.rand(1, 4, 3, H, W, generator=g)
+    extr, intr, nf = synth.synthetic_cameras(H, W)
+    batch = dict(images=images.to(DEV), extrinsics=extr.to(DEV), intrinsics=intr.to(DEV), near_fars=nf.to(DEV))
+    optim = torch.optim.AdamW(model.parameters(), lr=5e-4, weight_decay=1e-4)
+    # oracle side: parameters as leaf tensors, same optimiser
+    o_enc = {k: v.clone().requires_grad_(True) for k, v in enc_sd.items()}
+    o_dec = {k: v.clone().requires_grad_(True) for k, v in dec_sd.items()}
+    o_optim = torch.optim.AdamW(list(o_enc.values()) + list(o_dec.values()), lr=5e-4, weight_decay=1e-4)
+    losses, o_losses = [], []
+    import matchnerf_b200.train_path as TP
+    for step in range(3):
+        # fix the random choices of the step so that both sides see the same rays and jitter
+        ray_idx = torch.randperm(H * W, generator=g)[:R]
+        jit = torch.rand(R, S, generator=g)
+        real_randperm, real_rand = torch.randperm, torch.rand
+        torch.randperm = lambda n, device=None, **kw: ray_idx.to(device) if device is not None else ray_idx
+        torch.rand = lambda *a, device=None, **kw: jit.to(device) if device is not None else jit
+        try:
+            out = model(AttrDict(batch), mode="train")
+        finally:
+            torch.randperm, torch.rand = real_randperm, real_rand
+        assert torch.equal(out["ray_idx"].cpu(), ray_idx)
+        gt = images[0, 3].permute(1, 2, 0).reshape(-1, 3)[ray_idx].to(DEV)
+        loss = ((out["rgb"][0] - gt) ** 2).mean()
+        optim.zero_grad()
+        loss.backward()
+        if step == 0:
+            grads = {"dec": {k: p.grad.detach().cpu().clone() for k, p in model.nerf_dec.named_parameters()},
+                     "enc": {k: p.grad.detach().cpu().clone() for k, p in model.feat_enc.named_parameters()}}
+        optim.step()
+        losses.append(float(loss.detach()))
+        feats = EO.encode_views(o_enc, images[0, :3])
+        o = RO.render_rays(o_dec, RO.to_channels_last([f[None] for f in feats]), images[0, :3].permute(0, 2, 3, 1).contiguous(),
+                           extr[0, :3, :3], intr[0, :3], nf[0, :3], extr[0, 3, :3], intr[0, 3], nf[0, 3], ray_idx, S, jitter=jit)
+        o_loss = ((o[0] - gt.cpu()) ** 2).mean()
+        o_optim.zero_grad()
+        o_loss.backward()
+        if step == 0:
+            o_grads = {"dec": {k: v.grad.clone() for k, v in o_dec.items()}, "enc": {k: v.grad.clone() for k, v in o_enc.items() if v.grad is not None}}
+        o_optim.step()
+        o_losses.append(float(o_loss.detach()))
+    for a, b in zip(losses, o_losses):
+        assert abs(a - b) < 0.02 * b + 1e-6, (losses, o_losses)
+    # the gradients of the first step point the same way (decoder: fp32 GEMMs; encoder: TF32 GEMMs + fp16-rounded feature maps
+    # in the gather, so a little looser)
+    for part, bar in (("dec", 0.999), ("enc", 0.99)):
+        keys = [k for k in o_grads[part] if k in grads[part]]
+        ga = torch.cat([grads[part][k].reshape(-1).float() for k in keys])
+        gb = torch.cat([o_grads[part][k].reshape(-1) for k in keys])
+        cos = float((ga * gb).sum() / (ga.norm() * gb.norm()).clamp_min(1e-30))
+        assert float(gb.norm()) > 0 and cos > bar, (part, cos)
+        assert abs(float(ga.norm()) / float(gb.norm()) - 1.0) < 0.05, (part, float(ga.norm()), float(gb.norm()))
