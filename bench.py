@@ -27,6 +27,8 @@ from __future__ import annotations
 import argparse
 import json
 import os
+
+os.environ.setdefault("TQDM_DISABLE", "1")          # the reference wraps its slice loop in tqdm (stderr noise in the logs)
 import subprocess
 import sys
 import time
@@ -277,6 +279,67 @@ def reference_on_gpu(dev, S_list, slices):
     return out, images
 
 
+def train_step_times(dev, S=128, n_rays=1024, steps=5, warmup=2):
+    """BASELINE configs[4] (configs/train.yaml: one 512x640 triplet per rank, rand_rays_train 1024 random rays, S = 128 stratified,
+    MSE, AdamW wd 1e-4, clip_grad_norm 1.0 on the encoder -- coach.py:215-243): ms per training step (forward + backward +
+    optimiser) of this repo and of the unmodified reference, both on this GPU from the same weights and batch."""
+    from matchnerf_b200.matchnerf import MatchNeRF
+    from matchnerf_b200.utils import AttrDict
+    from oracle import synth
+    host = synthetic_batch(100)
+
+    def loop(net, make_batch):
+        net.train()
+        enc_params = list(net.feat_enc.parameters())
+        optim = torch.optim.AdamW(net.parameters(), lr=5e-4, weight_decay=1e-4)
+        gt_all = host["images"][0, 3].permute(1, 2, 0).reshape(-1, 3).to(dev)
+
+        def step():
+            out = net(make_batch(), mode="train")
+            loss = ((out["rgb"][0] - gt_all[out["ray_idx"]]) ** 2).mean()
+            optim.zero_grad()
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(enc_params, 1.0)
+            optim.step()
+            return loss
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = step()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / steps, float(loss.detach())
+
+    res = dict(config=f"configs/train.yaml shape: 1 x (3 + 1) x 512x640 images, {n_rays} random rays x S={S} stratified, MSE + AdamW + "
+                      f"clip_grad_norm(encoder, 1.0); {steps} steps after {warmup} warm-up, CUDA events")
+    opt = make_opts(S, str(dev))
+    opt.nerf.rand_rays_train = n_rays
+    m = MatchNeRF(opt)
+    m.feat_enc.load_state_dict(synth.synthetic_encoder(1))
+    m.nerf_dec.load_state_dict(synth.synthetic_decoder(0))
+    m.to(dev)
+    res["ours_ms_per_step"], res["ours_last_loss"] = loop(m, lambda: AttrDict({k: v.to(dev) for k, v in host.items()}))
+    res["ours_path"] = ("K-gather forward + backward: this repo's CUDA kernels behind an autograd Function; decoder / ray transformer / "
+                        "compositing / encoder: library GEMMs + cuDNN under autograd (matchnerf_b200/train_path.py)")
+    del m
+    torch.cuda.empty_cache()
+    try:
+        loaded = load_reference(S, str(dev))
+        if loaded is not None:
+            net, ED, _ = loaded
+            net.opts.nerf.rand_rays_train = n_rays
+            res["reference_gpu_ms_per_step"], res["reference_last_loss"] = loop(net, lambda: ED(**{k: v.to(dev) for k, v in host.items()}))
+            res["speedup"] = res["reference_gpu_ms_per_step"] / res["ours_ms_per_step"]
+            del net
+    except Exception as e:
+        res["reference_error"] = f"{type(e).__name__}: {e}"
+    torch.cuda.empty_cache()
+    return res
+
+
 # ================================================================================================ parity of the timed workload
 def psnr_pair(ours, ref, seed=0):
     """PSNR of both against a common pseudo ground truth = reference + N(0, 0.045^2) (27 dB, the regime where 0.01 dB <=> 2e-3 RMS);
@@ -473,7 +536,7 @@ def run_ours(args):
             encoder=dict(ms_per_call=t_e, note="CUDA graph: backbone / up-sampler convolutions (cuDNN) + this repo's kernels")), pk
 
     # ---- untimed extras (rank 0): per-kernel timing, S = 128, parity of the timed workload, reference on this GPU / the host
-    roofline, kernels, kernels_s128, parity, ref_gpu, cpu_baseline = None, {}, None, None, None, None
+    roofline, kernels, kernels_s128, parity, ref_gpu, cpu_baseline, train_step = None, {}, None, None, None, None, None
     n_chunks = (hw + min(model.render_chunk, hw) - 1) // min(model.render_chunk, hw)
     launches = args.steps * model.launches_per_image(n_chunks) if hasattr(model, "launches_per_image") else None
     if rank == 0 and not args.quick:
@@ -522,6 +585,11 @@ def run_ours(args):
         parity["other_S"] = parity_of_timed_workload(other_img, other, ref_imgs)
         if not args.no_cpu_baseline:
             _, _, cpu_baseline = reference_cpu_sample(S, 1024, 2, 1)
+        if not args.no_train_step:
+            try:
+                train_step = train_step_times(dev)
+            except Exception as e:               # an extra: never take the headline line down
+                train_step = dict(error=f"{type(e).__name__}: {e}")
 
     if rank == 0:
         par = "single GPU" if world == 1 else (
@@ -538,7 +606,7 @@ def run_ours(args):
                     clocks=clocks,
                     e2e=dict(value=e2e_value, unit="rays/s", ms_per_step=ms_e2e, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
                     gpu_launches=launches, roofline=roofline, kernels=kernels, kernels_s128=kernels_s128, cpu_baseline=cpu_baseline,
-                    reference_gpu=ref_gpu, parity=parity)
+                    reference_gpu=ref_gpu, parity=parity, train_step=train_step)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -556,6 +624,7 @@ def main():
     ap.add_argument("--ref-rays", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-gpu", action="store_true")
+    ap.add_argument("--no-train-step", action="store_true")
     ap.add_argument("--quick", action="store_true", help="timed region only (no per-kernel / parity / reference extras)")
     ap.add_argument("--chunk", type=int, default=0, help="rays per render launch (default: MatchNeRF.render_chunk)")
     args = ap.parse_args()

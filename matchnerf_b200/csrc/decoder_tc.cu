@@ -581,7 +581,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
       for (int j = 0; j < 2; ++j) {
         tc::mbar_init(&sm.ray_full[i][j], kTileM);
         tc::mbar_init(&sm.ray_empty[i][j], kTileM);
-        tc::mbar_init(&sm.geo_full[i][j], 1);
+        tc::mbar_init(&sm.geo_full[i][j], 32);
         tc::mbar_init(&sm.geo_empty[i][j], kTileM);
       }
     }
@@ -756,8 +756,7 @@ decoder_tc_kernel(const __grid_constant__ DevCams cams, const DevRays rays, cons
             sm.dirvec[slot][nb][rl][o2] = sm.p.views_dir[o2 * 3] * dx + sm.p.views_dir[o2 * 3 + 1] * dy + sm.p.views_dir[o2 * 3 + 2] * dz + sm.p.views_b[o2];
           }
         }
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&sm.geo_full[slot][nb]);
+        tc::mbar_arrive(&sm.geo_full[slot][nb]);             // every lane releases its own writes (count 32)
       }
     }
   } else if (wg <= 2) {
