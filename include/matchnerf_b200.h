@@ -179,6 +179,13 @@ int32_t mnf_composite_fwd(mnf_ctx* ctx, const float* rgb, const float* sigma, co
 int32_t mnf_instance_norm_fwd(mnf_ctx* ctx, const float* x, const float* residual, float* y, int64_t n_planes,
                               int32_t hw, int32_t mode, float eps, void* stream);
 
+/* Same three modes on channels-last activations: x, y, residual = fp32 or (is_f16) fp16 [n_images][hw][channels] (the memory of a
+ * torch.channels_last NCHW tensor), channels a multiple of 8 (<= 256), n_images <= 64.  Used when the backbone runs
+ * its cuDNN convolutions in NHWC (no layout-conversion kernels around them).  Two kernels (statistics in a fixed summation order: bit-reproducible;
+ * normalise) over a context-owned scratch: one call in flight per context. */
+int32_t mnf_instance_norm_nhwc_fwd(mnf_ctx* ctx, const void* x, const void* residual, void* y, int32_t is_f16, int32_t n_images,
+                                   int32_t hw, int32_t channels, int32_t mode, float eps, void* stream);
+
 /* ---- encoder helper: token LayerNorm of TransformerLayer.forward fused with what follows it -- */
 /* x: [n_tokens][128], fp32 or (x_is_f16) fp16; gamma / beta: fp32 [128]; nn.LayerNorm semantics (biased variance, eps inside the
  * square root).  Exactly one output:

@@ -79,6 +79,7 @@ def load() -> C.CDLL:
     lib.mnf_decoder_samples_fwd.argtypes = [vp, C.POINTER(DecoderCfg), fp, fp, fp, i64, fp, vp]
     lib.mnf_composite_fwd.argtypes = [vp, fp, fp, fp, i64, i32, i32, fp, fp, fp, fp, vp]
     lib.mnf_instance_norm_fwd.argtypes = [vp, fp, fp, fp, i64, i32, i32, C.c_float, vp]
+    lib.mnf_instance_norm_nhwc_fwd.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, C.c_float, vp]
     lib.mnf_gather_cossim_bwd.argtypes = [vp, C.POINTER(Scene), C.POINTER(Rays), i32, fp, fp, fp, vp]
     lib.mnf_token_layernorm_fwd.argtypes = [vp, vp, i32, fp, fp, C.c_float, fp, fp, fp, vp, i64, i32, vp]
     lib.mnf_render_workspace_bytes.argtypes = [i64, i32, i32]
@@ -92,7 +93,8 @@ def load() -> C.CDLL:
     for name in ("mnf_ctx_create", "mnf_ctx_destroy", "mnf_decoder_load_host", "mnf_pack_features", "mnf_pack_images",
                  "mnf_gather_cossim_fwd", "mnf_decoder_composite_fwd", "mnf_render_rays_fwd", "mnf_window_attn_fwd",
                  "mnf_selftest_umma", "mnf_query_cond_points_fwd", "mnf_decoder_samples_fwd", "mnf_composite_fwd",
-                 "mnf_instance_norm_fwd", "mnf_token_layernorm_fwd", "mnf_gather_cossim_bwd"):
+                 "mnf_instance_norm_fwd", "mnf_token_layernorm_fwd", "mnf_gather_cossim_bwd",
+                 "mnf_instance_norm_nhwc_fwd"):
         getattr(lib, name).restype = i32
     if lib.mnf_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libmatchnerf_b200.so ABI {lib.mnf_abi_version()} != {ABI_VERSION}")
@@ -361,6 +363,23 @@ class Context:
         y = torch.empty_like(xc)
         _check(self.lib.mnf_instance_norm_fwd(self._h, xc.data_ptr(), _ptr(rc), y.data_ptr(), N * Cc, H * W, mode, eps,
                                               _stream(self.device)), "mnf_instance_norm_fwd")
+        return y
+
+    def instance_norm_nhwc(self, x: torch.Tensor, mode: int = 1, residual: Optional[torch.Tensor] = None, eps: float = 1e-5):
+        """Fused InstanceNorm2d(+ReLU)(+residual, ReLU) on an fp32 / fp16 [N,C,H,W] tensor in torch.channels_last memory format; see
+        mnf_instance_norm_nhwc_fwd.  Returns a channels_last tensor of the same dtype."""
+        for t, nm in ((x, "x"), (residual, "residual")):
+            if t is None:
+                continue
+            if t.dtype != x.dtype or x.dtype not in (torch.float16, torch.float32) or t.device != self.device or t.dim() != 4 \
+                    or not t.is_contiguous(memory_format=torch.channels_last):
+                raise ValueError(f"{nm} must be an fp32 / fp16 channels_last [N,C,H,W] tensor on {self.device}")
+        if residual is not None and residual.shape != x.shape:
+            raise ValueError(f"residual {tuple(residual.shape)} != x {tuple(x.shape)}")
+        N, Cc, H, W = x.shape
+        y = torch.empty_like(x, memory_format=torch.channels_last)
+        _check(self.lib.mnf_instance_norm_nhwc_fwd(self._h, x.data_ptr(), _ptr(residual), y.data_ptr(), int(x.dtype == torch.float16), N, H * W,
+                                                   Cc, mode, eps, _stream(self.device)), "mnf_instance_norm_nhwc_fwd")
         return y
 
     def token_layernorm(self, x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5,

@@ -43,6 +43,7 @@ int64_t window_attn_tc_workspace_bytes(int B, int h, int w, int num_splits);
 using namespace mnf;
 
 constexpr int kGatherScratchInts = 1 << 16;
+constexpr int64_t kInScratchFloats = 1 << 20;  // context scratch of the NHWC instance norm: counters, statistics, per-CTA partial sums (4 MB)
 
 struct mnf_ctx {
   int device = 0;
@@ -51,6 +52,7 @@ struct mnf_ctx {
   DecoderWeightsF32 wf32{};
   HeadParams* head_dev = nullptr;
   DecoderWeightsTC* wtc = nullptr;
+  float* in_stats = nullptr;       // device: [N][C][2] sum / sum-of-squares scratch of the NHWC instance norm (one in flight per ctx)
   int* gather_scratch = nullptr;   // device: [0] counter + tile list of the tensor-core gather's fix-up pass (one gather in flight per ctx)
 };
 
@@ -152,6 +154,8 @@ int32_t mnf_ctx_create(int32_t device, mnf_ctx** out) {
   {
     DeviceGuard dev_guard(c);
     if (cudaMalloc(reinterpret_cast<void**>(&c->gather_scratch), kGatherScratchInts * sizeof(int)) != cudaSuccess) c->gather_scratch = nullptr;
+    if (cudaMalloc(reinterpret_cast<void**>(&c->in_stats), kInScratchFloats * sizeof(float)) != cudaSuccess) c->in_stats = nullptr;
+    else cudaMemset(c->in_stats, 0, 64 * sizeof(float));      // the per-image CTA counters start (and are left) at zero
   }
   *out = c;
   return MNF_OK;
@@ -164,6 +168,7 @@ int32_t mnf_ctx_destroy(mnf_ctx* ctx) {
     for (void* p : ctx->allocs) cudaFree(p);
     if (ctx->wtc) decoder_tc_free(ctx->wtc);
     if (ctx->gather_scratch) cudaFree(ctx->gather_scratch);
+    if (ctx->in_stats) cudaFree(ctx->in_stats);
   }
   delete ctx;
   return MNF_OK;
@@ -424,6 +429,18 @@ int32_t mnf_instance_norm_fwd(mnf_ctx* ctx, const float* x, const float* residua
   if (n_planes < 0 || hw <= 0) { set_error("mnf_instance_norm_fwd: bad shape planes=%lld hw=%d", (long long)n_planes, hw); return MNF_EINVAL; }
   if (mode < 0 || mode > 2 || (mode == 2 && !residual)) { set_error("mnf_instance_norm_fwd: mode must be 0, 1 or 2 (2 needs a residual)"); return MNF_EINVAL; }
   return launch_instance_norm(x, mode == 2 ? residual : nullptr, y, n_planes, hw, mode, eps, (cudaStream_t)stream);
+}
+
+int32_t mnf_instance_norm_nhwc_fwd(mnf_ctx* ctx, const void* x, const void* residual, void* y, int32_t is_f16, int32_t n_images,
+                                   int32_t hw, int32_t channels, int32_t mode, float eps, void* stream) {
+  DeviceGuard dev_guard(ctx);
+  if (!ctx || !x || !y) { set_error("mnf_instance_norm_nhwc_fwd: NULL argument"); return MNF_EINVAL; }
+  if (n_images < 0 || hw <= 0 || channels <= 0) { set_error("mnf_instance_norm_nhwc_fwd: bad shape"); return MNF_EINVAL; }
+  if (mode < 0 || mode > 2 || (mode == 2 && !residual)) { set_error("mnf_instance_norm_nhwc_fwd: mode must be 0, 1 or 2 (2 needs a residual)"); return MNF_EINVAL; }
+  if (!ctx->in_stats) { set_error("mnf_instance_norm_nhwc_fwd: the context has no scratch buffer"); return MNF_ESTATE; }
+  if ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)residual) & 15) != 0) { set_error("mnf_instance_norm_nhwc_fwd: pointers must be 16-byte aligned"); return MNF_EINVAL; }
+  return launch_instance_norm_nhwc(x, mode == 2 ? residual : nullptr, y, is_f16, ctx->in_stats, kInScratchFloats, n_images, hw, channels, mode,
+                                   eps, (cudaStream_t)stream);
 }
 
 int32_t mnf_token_layernorm_fwd(mnf_ctx* ctx, const void* x, int32_t x_is_f16, const float* gamma, const float* beta, float eps,

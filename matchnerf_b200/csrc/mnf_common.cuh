@@ -169,6 +169,8 @@ int launch_composite(const float* rgb, const float* sigma, const float* depth, i
                      float* out_rgb, float* out_depth, float* out_opacity, float* out_prob, cudaStream_t s);
 
 int launch_instance_norm(const float* x, const float* res, float* y, int64_t planes, int hw, int mode, float eps, cudaStream_t s);
+int launch_instance_norm_nhwc(const void* x, const void* res, void* y, int is_f16, float* scratch, int64_t scratch_floats, int N, int hw,
+                              int C, int mode, float eps, cudaStream_t s);
 int launch_token_layernorm(const void* x, int x_is_f16, const float* gamma, const float* beta, float eps, const float* residual,
                            const float* prefix, float* out_f32, __half* out_f16, int64_t rows, cudaStream_t s);
 

@@ -423,3 +423,22 @@ def test_token_layernorm_fused_modes(ctx, rows):
     assert max_abs(ctx.token_layernorm(xh, w, b, 1e-5, residual=src), (src.double() + refh).float()) < 2e-5
     with pytest.raises(ValueError):
         ctx.token_layernorm(x, w, b, 1e-5, residual=src, prefix=src)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("shape", [(3, 64, 32, 40), (2, 96, 7, 9), (1, 8, 1, 3), (3, 128, 64, 80), (3, 64, 256, 320)])
+def test_instance_norm_nhwc_modes(ctx, shape, dtype):
+    """mnf_instance_norm_nhwc_fwd (channels-last activations of the backbone, fp32 or fp16) vs the PyTorch ops of the reference
+    backbone (models/gmflow/backbone.py:28-36) in float64 on the same inputs: fp32 2e-5, fp16 one rounding of the output."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(sum(shape))
+    x = (torch.randn(*shape, generator=g) * 2.5 + 0.3).to(dtype).to(ctx.device).contiguous(memory_format=torch.channels_last)
+    res = torch.randn(*shape, generator=g).to(dtype).to(ctx.device).contiguous(memory_format=torch.channels_last)
+    ref0 = F.instance_norm(x.double())
+    rel = 1.5e-3 if dtype == torch.float16 else 2e-5
+    for mode, ref in ((0, ref0), (1, F.relu(ref0)), (2, F.relu(res.double() + F.relu(ref0)))):
+        y = ctx.instance_norm_nhwc(x, mode, res if mode == 2 else None)
+        assert y.dtype == dtype and y.shape == x.shape and y.is_contiguous(memory_format=torch.channels_last)
+        assert max_abs(y.float(), ref.float()) < rel * max(1.0, float(ref.abs().max())), (mode, max_abs(y.float(), ref.float()))
+    with pytest.raises(ValueError):
+        ctx.instance_norm_nhwc(x.contiguous(), 0)           # not channels_last
