@@ -1,0 +1,65 @@
+"""GPU (B200): the drop-in on REAL data.  The reference's own COLMAP dataset class reads its shipped demo scene
+(docs/demo_data/printer: 3 photographs + poses_bounds.npy), its DataLoader collates the batch (coach.py:368-392 does the same),
+and ``model(var, mode="test")`` runs through this repo's model and through the UNMODIFIED reference model on the same GPU in
+fp32 from the same seeded weights: the full 256 x 160 image must agree to the north-star tolerance.
+Needs the reference tree (/root/reference in the dev container, baseline/_ref on the GPU box); skipped without it."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_shim as RS
+from oracle import synth
+from tests.helpers import psnr, rms
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(RS.reference_root() is None, reason="reference tree (baseline/_ref) not present")]
+DEV = "cuda:0"
+
+
+def test_reference_dataset_and_model_call_on_the_demo_scene():
+    import os
+    ref = RS.install_shim()
+    from datasets import datas_dict                                   # the reference's dataset registry
+    from models.matchnerf import MatchNeRF as RefNet                  # the reference's model
+    from matchnerf_b200.matchnerf import MatchNeRF
+    S = 128                                                           # configs/base.yaml:48
+    ds = datas_dict["colmap"](os.path.join(ref, "docs/demo_data"), "test", n_views=3, img_wh=[256, 160], max_len=-1, scene_list=["printer"],
+                              test_views_method="fixed", nf_mode="minmax")
+    batch = next(iter(torch.utils.data.DataLoader(ds, batch_size=1, shuffle=False)))
+    assert batch["images"].shape == (1, 4, 3, 160, 256)
+    enc_sd, dec_sd = synth.synthetic_encoder(1), synth.synthetic_decoder(0)
+    outs = {}
+    for name, cls in (("ours", MatchNeRF), ("reference", RefNet)):
+        opt = RS.reference_options(S, DEV, ref, **{"nerf.rand_rays_test": 20480})
+        net = cls(opt).eval()
+        net.feat_enc.load_state_dict(enc_sd, strict=True)
+        net.nerf_dec.load_state_dict(dec_sd, strict=True)
+        net.to(DEV)
+        var = RS.EasyDict({k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in batch.items()})
+        prev = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+        if name == "reference":                                       # the comparison target is true fp32
+            torch.backends.cuda.matmul.allow_tf32 = False
+            torch.backends.cudnn.allow_tf32 = False
+        try:
+            with torch.no_grad():
+                out = net(var, mode="test")
+        finally:
+            torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev
+        outs[name] = tuple(out[k][0].float().cpu() for k in ("rgb", "depth", "opacity"))
+        del net
+    (rgb, depth, opac), (r_rgb, r_depth, r_opac) = outs["ours"], outs["reference"]
+    assert rgb.shape == (160 * 256, 3) == r_rgb.shape
+    assert 0.01 < float(r_opac.mean()) < 0.99, float(r_opac.mean())   # a non-degenerate render (SURVEY 8c warning)
+    # In this demo batch the target photograph is ALSO source view 2 (view_ids [2, 1, 0, 0]), so every target ray projects onto its
+    # own pixel there and the image's outermost rows / columns land EXACTLY on the visibility-mask boundary g = +-1
+    # (models/matchnerf.py:248-250 is a strict inequality): on those 832 pixels the mask is decided by the last bit of the
+    # projection, and the reference itself disagrees between its CPU and GPU runs there (tools/r02_demo_debug.py).  They are
+    # compared separately with a loose bound; the interior carries the parity claim.
+    H, W = 160, 256
+    inner = torch.zeros(H, W, dtype=torch.bool)
+    inner[1:-1, 1:-1] = True
+    inner = inner.view(-1)
+    assert rms(rgb[inner], r_rgb[inner]) < 2e-3 and rms(opac[inner], r_opac[inner]) < 4e-3, (rms(rgb[inner], r_rgb[inner]), rms(opac[inner], r_opac[inner]))
+    assert rms(depth[inner], r_depth[inner]) < 2e-2
+    assert rms(rgb[~inner], r_rgb[~inner]) < 0.15
+    gt = batch["images"][0, -1].permute(1, 2, 0).reshape(-1, 3)
+    assert abs(psnr(rgb[inner], gt[inner]) - psnr(r_rgb[inner], gt[inner])) < 0.01      # PSNR against the real photograph (misc/metrics.py:35-41)
