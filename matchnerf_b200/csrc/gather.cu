@@ -342,8 +342,12 @@ gather_cossim_kernel(const __grid_constant__ DevCams cams, const DevRays rays, c
 }
 
 int gather_impl() {
-  static const int impl = [] { const char* e = getenv("MNF_GATHER_IMPL"); return e ? atoi(e) : 3; }();   // 3 = v3 (default), 4 = tensor-core blend experiment (gather_mma.cu)
+#ifdef MNF_EXPERIMENTS      // -DMNF_EXPERIMENTS builds the mma.sync blend experiment (gather_mma.cu, packing v4); not part of the product library
+  static const int impl = [] { const char* e = getenv("MNF_GATHER_IMPL"); return e ? atoi(e) : 3; }();
   return impl == 4 ? 4 : 3;
+#else
+  return 3;
+#endif
 }
 
 int launch_gather_mma(const DevCams& cams, const DevRays& rays, int S, const __half* f0, int h0, int w0,
@@ -360,7 +364,9 @@ int launch_gather(const DevCams& cams, const DevRays& rays_in, int S, const __ha
                   cudaStream_t s, int* scratch, int scratch_ints) {
   if (rays_in.n_rays <= 0) return MNF_OK;
   DevRays rays = rays_in;
+#ifdef MNF_EXPERIMENTS
   if (gather_impl() == 4) return launch_gather_mma(cams, rays, S, f0, h0, w0, f1, h1, w1, images, cond_f32, cond_f16, s);
+#endif
   if ((int64_t)h0 * w0 >= (1 << 23) || (int64_t)h1 * w1 >= (1 << 23)) { set_error("feature map too large for 32-bit texel offsets"); return MNF_EUNSUPPORTED; }
   const int64_t quads = (rays.n_rays + kQuad - 1) / kQuad;
   int64_t blocks = (quads + kWarps3 - 1) / kWarps3;

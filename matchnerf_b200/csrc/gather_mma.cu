@@ -1,3 +1,4 @@
+#ifdef MNF_EXPERIMENTS   // experiment (slower than v3): compiled only with -DMNF_EXPERIMENTS, never part of the product library
 // K-gather v5: the bilinear blend as a tensor-core product.
 //
 // Same function as gather.cu (MatchNeRF.query_cond_info, models/matchnerf.py:209-293, fused with ray casting / depth
@@ -417,3 +418,5 @@ int launch_gather_mma(const DevCams& cams, const DevRays& rays, int S, const __h
 }
 
 }  // namespace mnf
+
+#endif  // MNF_EXPERIMENTS

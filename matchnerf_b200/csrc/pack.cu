@@ -46,6 +46,7 @@ __global__ void pack_features_kernel(const float* __restrict__ in, __half* __res
 
 // v4: tile = 32 consecutive pixels (row-major) x 256 channels; a thread writes one channel of one pixel (or of an
 // x-pair when the width is even, so that pairs never straddle rows)
+#ifdef MNF_EXPERIMENTS
 __global__ void pack_features_v4_kernel(const float* __restrict__ in, __half* __restrict__ out, int h, int w, int wp) {
   __shared__ float tile[kFeatCh][33];
   const int hw = h * w;
@@ -78,6 +79,7 @@ __global__ void pack_features_v4_kernel(const float* __restrict__ in, __half* __
     }
   }
 }
+#endif
 
 __global__ void pack_images_kernel(const float* __restrict__ in, float4* __restrict__ out, int hw, int total) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -90,6 +92,7 @@ __global__ void pack_images_kernel(const float* __restrict__ in, float4* __restr
 int launch_pack_features(const float* nchw, int V, int h, int w, __half* out, cudaStream_t s) {
   const int hw = h * w;
   dim3 grid((hw + 31) / 32, V);
+#ifdef MNF_EXPERIMENTS
   if (gather_impl() == 4) {
     const int wp = (w + 1) / 2;
     const size_t body = (size_t)V * h * wp * 2 * kFeatCh;
@@ -101,6 +104,7 @@ int launch_pack_features(const float* nchw, int V, int h, int w, __half* out, cu
     MNF_CUDA_TRY(cudaGetLastError());
     return MNF_OK;
   }
+#endif
   pack_features_kernel<<<grid, 256, 0, s>>>(nchw, out, hw);
   MNF_CUDA_TRY(cudaGetLastError());
   // zero tail of (w + 1) texels: the zero-weight taps of samples on the last row / column stay in bounds (gather v3)

@@ -140,6 +140,7 @@ extern "C" int32_t mnf_selftest_umma(const void* a_f16, const void* b_f16, float
   return MNF_OK;
 }
 
+#ifdef MNF_MICROBENCH   // tensor-memory / UMMA rate micro-benchmarks (tools/tmem_bw.py, tools/umma_rate.py): built only with -DMNF_MICROBENCH
 // ---- micro-benchmark: tensor-memory read (tcgen05.ld) throughput of one SM ------------------------------------------
 // `warps` warps (4 or 8; two warps share a lane quarter when 8) each read `cols` columns `iters` times; out[0] = cycles.
 namespace mnf {
@@ -277,3 +278,4 @@ extern "C" int32_t mnf_selftest_umma_rate(int32_t iters, int32_t N, int32_t mode
   MNF_CUDA_TRY(cudaGetLastError());
   return MNF_OK;
 }
+#endif  // MNF_MICROBENCH

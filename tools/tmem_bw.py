@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Tensor-memory read throughput micro-benchmark (tcgen05.ld 32x32b.x32), one CTA on one SM."""
+"""[needs a library built with -DMNF_MICROBENCH:  NVCC_EXTRA=-DMNF_MICROBENCH tools/build_variants.sh bench=WORK; MNF_LIB_PATH=matchnerf_b200/variants/lib_bench.so python tools/tmem_bw.py]
+Tensor-memory read throughput micro-benchmark (tcgen05.ld 32x32b.x32), one CTA on one SM."""
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

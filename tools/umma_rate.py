@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""tcgen05.mma rate micro-benchmark (one CTA on one SM): cycles per M=128 x N x K=16 step, A from shared memory (SS) or
+"""[needs a library built with -DMNF_MICROBENCH:  NVCC_EXTRA=-DMNF_MICROBENCH tools/build_variants.sh bench=WORK; MNF_LIB_PATH=matchnerf_b200/variants/lib_bench.so python tools/umma_rate.py]
+tcgen05.mma rate micro-benchmark (one CTA on one SM): cycles per M=128 x N x K=16 step, A from shared memory (SS) or
 from tensor memory (TS), with 0..4 warps streaming tcgen05.ld meanwhile."""
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
