@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MNF_ABI_VERSION 5
+#define MNF_ABI_VERSION 6
 
 typedef enum mnf_status {
   MNF_OK = 0,
@@ -74,6 +74,11 @@ typedef struct mnf_scene {
   float tgt_c2w[12];        /* camera->world [3x4] of the target = float64 inverse of its w2c (misc/camera.py:231-240) */
   float tgt_Kinv[9];        /* inverse target intrinsics (misc/camera.py:221) */
   float tgt_near_far[2];
+  /* encoder.feature_sample_local_radius / _dilation (models/gmflow/utils.py:136-162): 0 = plain bilinear samples (every shipped
+   * config); r in 1..8 = each feature sample is the mean of the (2r+1)^2 bilinear samples at offsets {-r..r} * dilation around
+   * it, positions scaled exactly as the reference does.  Forward only (mnf_gather_cossim_bwd rejects r > 0). */
+  int32_t sample_local_radius;
+  int32_t sample_local_dilation;
 } mnf_scene;
 
 /* Which rays to render: either an explicit pixel-id list or a contiguous row-major range. */

@@ -15,7 +15,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MNF_LIB_PATH") or os.path.join(_HERE, "libmatchnerf_b200.so")   # override: A/B builds (tools/)
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 COND_DIM = 22
 COND_PAD = 32
 FEAT_CH = 256
@@ -42,7 +42,8 @@ class Scene(C.Structure):
                 ("h0", C.c_int32), ("w0", C.c_int32), ("h1", C.c_int32), ("w1", C.c_int32),
                 ("feat0", C.c_void_p), ("feat1", C.c_void_p), ("images", C.c_void_p),
                 ("src_w2c", (C.c_float * 12) * 3), ("src_K", (C.c_float * 9) * 3), ("src_near_far", (C.c_float * 2) * 3),
-                ("tgt_c2w", C.c_float * 12), ("tgt_Kinv", C.c_float * 9), ("tgt_near_far", C.c_float * 2)]
+                ("tgt_c2w", C.c_float * 12), ("tgt_Kinv", C.c_float * 9), ("tgt_near_far", C.c_float * 2),
+                ("sample_local_radius", C.c_int32), ("sample_local_dilation", C.c_int32)]
 
 
 class Rays(C.Structure):
@@ -135,8 +136,9 @@ def flatten_decoder_state(sd: Dict[str, torch.Tensor]) -> torch.Tensor:
 class PackedScene:
     """Device-resident packed feature maps / images of one encoded source-view triplet plus its cameras."""
 
-    def __init__(self, feat0, feat1, images, H, W, h0, w0, h1, w1, src_w2c, src_K, src_nf):
+    def __init__(self, feat0, feat1, images, H, W, h0, w0, h1, w1, src_w2c, src_K, src_nf, local_radius=0, local_dilation=1):
         self.feat0, self.feat1, self.images = feat0, feat1, images
+        self.local_radius, self.local_dilation = int(local_radius), int(local_dilation)   # encoder.feature_sample_local_*
         self.H, self.W, self.h0, self.w0, self.h1, self.w1 = H, W, h0, w0, h1, w1
         self.src_w2c, self.src_K, self.src_nf = src_w2c, src_K, src_nf   # CPU float32 [3,3,4], [3,3,3], [3,2]
 
@@ -159,6 +161,7 @@ class PackedScene:
         sc.tgt_c2w[:] = c2w.reshape(-1).tolist()
         sc.tgt_Kinv[:] = kinv.reshape(-1).tolist()
         sc.tgt_near_far[:] = tgt_nf.detach().to("cpu", torch.float32).tolist()
+        sc.sample_local_radius, sc.sample_local_dilation = self.local_radius, self.local_dilation
         return sc
 
 
@@ -204,7 +207,7 @@ class Context:
 
     # ---- packing
     def pack_scene(self, feats: Sequence[torch.Tensor], images: torch.Tensor, src_w2c: torch.Tensor, src_K: torch.Tensor,
-                   src_nf: torch.Tensor) -> PackedScene:
+                   src_nf: torch.Tensor, local_radius: int = 0, local_dilation: int = 1) -> PackedScene:
         """feats: [feat_coarse [V,256,h0,w0], feat_fine [V,256,h1,w1]] fp32 NCHW on device (get_img_feat layout
         without the batch dim); images [V,3,H,W] fp32 in [0,1]; cameras [V,3,4], [V,3,3], [V,2]."""
         f0 = _dev_f32(feats[0], self.device, "feat0")
@@ -226,7 +229,7 @@ class Context:
         return PackedScene(p0, p1, pi, H, W, h0, w0, h1, w1,
                            src_w2c.detach().to("cpu", torch.float32)[:, :3, :4].contiguous(),
                            src_K.detach().to("cpu", torch.float32).contiguous(),
-                           src_nf.detach().to("cpu", torch.float32).contiguous())
+                           src_nf.detach().to("cpu", torch.float32).contiguous(), local_radius, local_dilation)
 
     # ---- rays helper
     def _rays(self, n_rays: int, ray_idx: Optional[torch.Tensor], first_ray: int, jitter: Optional[torch.Tensor], S: int):

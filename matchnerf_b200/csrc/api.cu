@@ -102,7 +102,12 @@ int fill_cams(const mnf_scene* sc, DevCams* c) {
   c->tfar = sc->tgt_near_far[1];
   c->W = sc->W;
   c->H = sc->H;
-  c->inv_w1 = c->inv_h1 = 0.f;
+  if (sc->sample_local_radius < 0 || sc->sample_local_radius > 8 || (sc->sample_local_radius > 0 && sc->sample_local_dilation < 1)) {
+    set_error("sample_local_radius = %d / sample_local_dilation = %d unsupported (radius 0..8, dilation >= 1)", sc->sample_local_radius, sc->sample_local_dilation);
+    return MNF_EUNSUPPORTED;
+  }
+  c->local_radius = sc->sample_local_radius;
+  c->local_dilation = sc->sample_local_radius > 0 ? sc->sample_local_dilation : 1;
   return MNF_OK;
 }
 
@@ -298,6 +303,7 @@ int32_t mnf_gather_cossim_bwd(mnf_ctx* ctx, const mnf_scene* scene, const mnf_ra
   if ((rc = fill_rays(scene, rays, &dr))) return rc;
   if (n_samples < 2 || n_samples > kMaxSamples) { set_error("n_samples = %d outside [2, %d]", n_samples, kMaxSamples); return MNF_EUNSUPPORTED; }
   if (!scene->feat0 || !scene->feat1) { set_error("scene feature maps missing"); return MNF_EINVAL; }
+  if (cams.local_radius > 0) { set_error("mnf_gather_cossim_bwd: sample_local_radius > 0 has no backward kernel"); return MNF_EUNSUPPORTED; }
   if (!dcond_f32 || !grad_feat0_packed || !grad_feat1_packed) { set_error("mnf_gather_cossim_bwd: NULL gradient buffer"); return MNF_EINVAL; }
   if ((((uintptr_t)grad_feat0_packed | (uintptr_t)grad_feat1_packed) & 15) != 0) { set_error("gradient maps must be 16-byte aligned"); return MNF_EINVAL; }
   return launch_gather_bwd(cams, dr, n_samples, reinterpret_cast<const __half*>(scene->feat0), scene->h0, scene->w0,

@@ -364,6 +364,8 @@ int launch_gather(const DevCams& cams, const DevRays& rays_in, int S, const __ha
                   cudaStream_t s, int* scratch, int scratch_ints) {
   if (rays_in.n_rays <= 0) return MNF_OK;
   DevRays rays = rays_in;
+  if (cams.local_radius > 0)     // encoder.feature_sample_local_radius > 0: its own (simple) kernel, every kind of ray input
+    return launch_gather_local(cams, rays, S, f0, h0, w0, f1, h1, w1, images, cond_f32, cond_f16, s);
 #ifdef MNF_EXPERIMENTS
   if (gather_impl() == 4) return launch_gather_mma(cams, rays, S, f0, h0, w0, f1, h1, w1, images, cond_f32, cond_f16, s);
 #endif

@@ -50,7 +50,7 @@ struct DevCams {
   float w2c[kViews][12];
   float K[kViews][9];
   float nf[kViews][2];
-  float inv_w1, inv_h1;      // unused placeholders kept for alignment
+  int local_radius, local_dilation;   // encoder.feature_sample_local_radius / _dilation (0 / 1 in every shipped config; > 0: gather_local.cu)
   float c2w[12];             // target camera->world
   float Kinv[9];             // target inverse intrinsics
   float tnear, tfar;
@@ -156,6 +156,10 @@ int launch_pack_images(const float* nchw, int V, int H, int W, float* out, cudaS
 int launch_gather(const DevCams& cams, const DevRays& rays, int S, const __half* f0, int h0, int w0,
                   const __half* f1, int h1, int w1, const float* images, float* cond_f32, __half* cond_f16,
                   cudaStream_t s, int* scratch = nullptr, int scratch_ints = 0);
+
+// encoder.feature_sample_local_radius > 0 (gather_local.cu): mean over the (2r+1)^2 dilated bilinear samples
+int launch_gather_local(const DevCams& cams, const DevRays& rays, int S, const __half* f0, int h0, int w0, const __half* f1, int h1,
+                        int w1, const float* images, float* cond_f32, __half* cond_f16, cudaStream_t s);
 
 int launch_gather_bwd(const DevCams& cams, const DevRays& rays, int S, const __half* f0, int h0, int w0, const __half* f1, int h1,
                       int w1, const float* dcond, float* g0, float* g1, cudaStream_t s);

@@ -43,8 +43,11 @@ class MatchNeRF(nn.Module):
                                num_transformer_layers=int(get_opt(opts, "encoder.num_transformer_layers", 6)),
                                device=dev).to(dev)
         self.nerf_dec = CondNeRF(opts).to(dev)
-        if int(get_opt(opts, "encoder.feature_sample_local_radius", 0)) > 0:
-            raise NotImplementedError("feature_sample_local_radius > 0 is not built (no shipped config uses it)")
+        # encoder.feature_sample_local_radius > 0 (models/gmflow/utils.py:136-162): mean over (2r+1)^2 dilated samples, forward only
+        self.local_radius = int(get_opt(opts, "encoder.feature_sample_local_radius", 0))
+        self.local_dilation = int(get_opt(opts, "encoder.feature_sample_local_dilation", 1))
+        if not 0 <= self.local_radius <= 8 or (self.local_radius > 0 and self.local_dilation < 1):
+            raise NotImplementedError("feature_sample_local_radius outside 0..8 (dilation >= 1) is not built")
         if not get_opt(opts, "nerf.legacy_coord", True) or get_opt(opts, "nerf.depth.param", "metric") != "metric":
             raise NotImplementedError("only legacy_coord=True with metric depth (all shipped configs) is built")
         self._scene_cache = None
@@ -244,7 +247,8 @@ class MatchNeRF(nn.Module):
         scenes = []
         for b in range(ref_images.shape[0]):
             scenes.append(ctx.pack_scene([ref_feats_list[0][b], ref_feats_list[1][b]], ref_images[b],
-                                         ref_poses["extrinsics"][b], ref_poses["intrinsics"][b], ref_poses["near_fars"][b]))
+                                         ref_poses["extrinsics"][b], ref_poses["intrinsics"][b], ref_poses["near_fars"][b],
+                                         self.local_radius, self.local_dilation))
         self._scene_cache = (key, scenes, src)
         return scenes
 

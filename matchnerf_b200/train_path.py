@@ -131,6 +131,8 @@ def render_rays_train(model, opt, tgt_pose, ray_idx, ref_poses, ref_images, ref_
     feature maps) and to the decoder parameters."""
     dec = model._unwrap(model.nerf_dec)
     dev = ref_images.device
+    if getattr(model, "local_radius", 0) > 0:
+        raise NotImplementedError("feature_sample_local_radius > 0 has no backward kernel (forward / inference only)")
     lib_ctx = capi.get_context(dev)
     S = int(get_opt(opt, "nerf.sample_intvs", 128))
     R = int(ray_idx.numel())

@@ -116,6 +116,9 @@ def main():
         # wide baseline so that density_maskfill has samples no view sees
         dict(name="demo_own_S128", S=128, over=dict(IBR), bg=False, stratified=False, baseline=30.0, n_rays=96, gain=0.5),
         dict(name="video_own_S256", S=256, over=dict(IBR), bg=False, stratified=False, baseline=30.0, n_rays=48, gain=0.25),
+        # encoder.feature_sample_local_radius > 0 (models/gmflow/utils.py:136-162; no shipped config): mean over 3 x 3 dilated taps
+        dict(name="small_local_radius1", S=16, over={"encoder.feature_sample_local_radius": 1, "encoder.feature_sample_local_dilation": 2},
+             bg=False, stratified=False),
     ]
     for case in small_cases:
         H, W, S = 32, 40, case["S"]
@@ -136,7 +139,8 @@ def main():
                            extr[0, :3, :3], intr[0, :3], nf[0, :3], extr[0, 3, :3], intr[0, 3], nf[0, 3], ray_idx, S,
                            setbg_opaque=case["bg"], raytrans_act=opt.decoder.raytrans_act,
                            raytrans_posenc=opt.decoder.raytrans_posenc, density_maskfill=opt.decoder.density_maskfill,
-                           return_aux=True)
+                           return_aux=True, local_radius=int(opt.encoder.feature_sample_local_radius),
+                           local_dilation=int(opt.encoder.feature_sample_local_dilation))
         cond_ref = model.query_cond_info(o[3]["pts"].reshape(1, -1, S, 3), ref, imgs, feats)
         cond_ref = torch.cat([cond_ref["feat_info"], cond_ref["color_info"], cond_ref["mask_info"]], -1)[0].reshape(-1, 22)
         e = (rms(o[0], out.rgb[0]), rms(o[1], out.depth[0]), rms(o[2], out.opacity[0]), rms(o[3]["cond"], cond_ref))
@@ -147,6 +151,7 @@ def main():
                             H=H, W=W, S=S, setbg_opaque=case["bg"],
                             raytrans_act=str(opt.decoder.raytrans_act), raytrans_posenc=bool(opt.decoder.raytrans_posenc),
                             density_maskfill=bool(opt.decoder.density_maskfill),
+                            local_radius=int(opt.encoder.feature_sample_local_radius), local_dilation=int(opt.encoder.feature_sample_local_dilation),
                             feat8=feats[0].numpy(), feat4=feats[1].numpy(), images=imgs.numpy(),
                             extrinsics=extr.numpy(), intrinsics=intr.numpy(), near_fars=nf.numpy(),
                             ray_idx=ray_idx.numpy(), cond=cond_ref.numpy(),

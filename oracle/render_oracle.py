@@ -113,6 +113,29 @@ def bilinear_border(fmap: Tensor, gx: Tensor, gy: Tensor) -> Tensor:
     return (t00 * (1 - fx) * (1 - fy) + t01 * fx * (1 - fy) + t10 * (1 - fx) * fy + t11 * fx * fy)
 
 
+def bilinear_border_local(fmap: Tensor, gx: Tensor, gy: Tensor, radius: int, dilation: int) -> Tensor:
+    """``sample_features_by_grid`` with ``local_radius > 0`` (models/gmflow/utils.py:136-162): the mean of the bilinear samples
+    at the (2r+1)^2 dilated offsets around the un-normalised coordinate.  The reference re-normalises the offset coordinates with
+    ``c = (size + (2r+1)*dilation - 1) / 2`` before handing them to ``F.grid_sample(align_corners=True)``, which un-normalises
+    with ``(size - 1) / 2`` -- so every sample position is SCALED by (size - 1) / (size + (2r+1)*dilation - 1).  Reproduced as
+    is (same operation order), including that shrink towards the origin.
+    """
+    h, w, _ = fmap.shape
+    cx, cy = (w - 1) / 2.0, (h - 1) / 2.0
+    ux = gx * cx + cx                                   # utils.py:141-142 (not clipped)
+    uy = gy * cy + cy
+    k = 2 * radius + 1
+    c2x, c2y = (w + k * dilation - 1) / 2.0, (h + k * dilation - 1) / 2.0       # utils.py:153-154
+    acc = None
+    for oy in range(-radius, radius + 1):               # generate_window_grid: [2r+1 (y), 2r+1 (x), (x, y)]
+        for ox in range(-radius, radius + 1):
+            nx = ((ux + float(ox * dilation)) - c2x) / c2x                        # utils.py:155
+            ny = ((uy + float(oy * dilation)) - c2y) / c2y
+            t = bilinear_border(fmap, nx, ny)
+            acc = t if acc is None else acc + t
+    return acc / float(k * k)                           # adaptive_avg_pool2d over the window (utils.py:160)
+
+
 def grouped_cosine(a: Tensor, b: Tensor, groups: int, eps: float = 1e-8) -> Tensor:
     """[N,C] x [N,C] -> [N,groups]: cosine similarity inside each contiguous channel group.
 
@@ -128,7 +151,7 @@ def grouped_cosine(a: Tensor, b: Tensor, groups: int, eps: float = 1e-8) -> Tens
 
 
 def query_cond(pts: Tensor, feats: Sequence[Tensor], images: Tensor, w2c: Tensor, K: Tensor,
-               near_far: Tensor, cos_n_group: Sequence[int]) -> Tensor:
+               near_far: Tensor, cos_n_group: Sequence[int], local_radius: int = 0, local_dilation: int = 1) -> Tensor:
     """World points [N,3] -> conditioning vector [N, sum(G)+3V+V] = (cos-sim, colours, masks).
 
     models/matchnerf.py:209-293.  Per view: project, ``grid = uv*2-1``, gather
@@ -147,7 +170,8 @@ def query_cond(pts: Tensor, feats: Sequence[Tensor], images: Tensor, w2c: Tensor
         gx = ndc[:, 0] * 2.0 - 1.0
         gy = ndc[:, 1] * 2.0 - 1.0
         for s, fm in enumerate(feats):
-            sampled[s].append(bilinear_border(fm[v], gx, gy))
+            sampled[s].append(bilinear_border(fm[v], gx, gy) if local_radius <= 0 else
+                              bilinear_border_local(fm[v], gx, gy, local_radius, local_dilation))
         colours.append(bilinear_border(images[v], gx, gy))
         inside = (gx > -1.0) & (gx < 1.0) & (gy > -1.0) & (gy < 1.0)
         masks.append(inside.to(torch.float32)[:, None])
@@ -282,7 +306,7 @@ def render_rays(dec: Dict[str, Tensor], feats: Sequence[Tensor], images: Tensor,
                 ray_idx: Tensor, S: int, *, cos_n_group: Sequence[int] = (2, 8),
                 jitter: Optional[Tensor] = None, setbg_opaque: bool = False,
                 raytrans_act: str = "ReLU", raytrans_posenc: bool = False,
-                density_maskfill: bool = False, return_aux: bool = False):
+                density_maskfill: bool = False, return_aux: bool = False, local_radius: int = 0, local_dilation: int = 1):
     """models/matchnerf.py:88-143 (``MatchNeRF.render``) for batch size 1.
 
     Returns rgb [R,3], depth [R,1], opacity [R,1] (and, with ``return_aux``, the
@@ -294,7 +318,7 @@ def render_rays(dec: Dict[str, Tensor], feats: Sequence[Tensor], images: Tensor,
     t = sample_depths(float(nf_tgt[0]), float(nf_tgt[1]), S, jitter)
     t = t[None, :].expand(R, S) if t.dim() == 1 else t
     pts = (centre[None, None, :] + ray[:, None, :] * t[..., None]).reshape(R * S, 3)   # camera.py:281-286
-    cond = query_cond(pts, feats, images, w2c_src, K_src, nf_src, cos_n_group)
+    cond = query_cond(pts, feats, images, w2c_src, K_src, nf_src, cos_n_group, local_radius, local_dilation)
     ndc0 = project_ndc(pts, w2c_src[0], K_src[0], W, H, float(nf_src[0, 0]), float(nf_src[0, 1]))
     unit = ray / ray.norm(dim=-1, keepdim=True).clamp_min(1e-12)                        # matchnerf.py:130
     dir_ref = unit @ w2c_src[0, :, :3].T                                               # matchnerf.py:131

@@ -43,6 +43,7 @@ int main(void) {
   printf("%zu %zu %zu\n", sizeof(mnf_decoder_cfg), sizeof(mnf_scene), sizeof(mnf_rays));
   printf("%zu %zu %zu %zu %zu %zu\n", offsetof(mnf_scene, feat0), offsetof(mnf_scene, images), offsetof(mnf_scene, src_w2c),
          offsetof(mnf_scene, src_K), offsetof(mnf_scene, tgt_c2w), offsetof(mnf_scene, tgt_near_far));
+  printf("%zu %zu\n", offsetof(mnf_scene, sample_local_radius), offsetof(mnf_scene, sample_local_dilation));
   printf("%zu %zu %zu\n", offsetof(mnf_rays, ray_idx), offsetof(mnf_rays, first_ray), offsetof(mnf_rays, jitter));
   return 0;
 }''')
@@ -53,6 +54,7 @@ int main(void) {
     S, R = capi.Scene, capi.Rays
     exp = [C.sizeof(capi.DecoderCfg), C.sizeof(S), C.sizeof(R),
            S.feat0.offset, S.images.offset, S.src_w2c.offset, S.src_K.offset, S.tgt_c2w.offset, S.tgt_near_far.offset,
+           S.sample_local_radius.offset, S.sample_local_dilation.offset,
            R.ray_idx.offset, R.first_ray.offset, R.jitter.offset]
     assert got == exp
 

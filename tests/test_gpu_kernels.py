@@ -23,8 +23,9 @@ DEV = "cuda:0"
 GATHER_IMPL_DEFAULT = 3       # csrc/gather.cu gather_impl()
 
 
-def make_scene(ctx, feats, imgs, extr, intr, nf):
-    packed = ctx.pack_scene([feats[0][0].to(DEV), feats[1][0].to(DEV)], imgs[0].to(DEV), extr[0, :3], intr[0, :3], nf[0, :3])
+def make_scene(ctx, feats, imgs, extr, intr, nf, local_radius=0, local_dilation=1):
+    packed = ctx.pack_scene([feats[0][0].to(DEV), feats[1][0].to(DEV)], imgs[0].to(DEV), extr[0, :3], intr[0, :3], nf[0, :3],
+                            local_radius, local_dilation)
     return packed, packed.c_scene(extr[0, 3, :3], intr[0, 3], nf[0, 3])
 
 
@@ -109,6 +110,43 @@ def test_gather_small_golden(ctx, golden_dir, name):
     assert rms(c32[:, :10], cond_q[:, :10]) < 5e-4, rms(c32[:, :10], cond_q[:, :10])   # taps blended in packed fp16
     assert rms(c32[:, :10], z["cond"][:, :10]) < 1e-3                   # vs the reference on fp32 features
     assert rms(c16[:, :22].float(), c32) < 5e-4 and float(c16[:, 22:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("radius,dilation", [(1, 2), (2, 1)])
+def test_gather_local_radius(ctx, golden_dir, radius, dilation):
+    """encoder.feature_sample_local_radius > 0 (models/gmflow/utils.py:136-162): mean over (2r+1)^2 dilated bilinear samples, with
+    the reference's re-normalisation.  (1, 2) = the golden of the unmodified reference; every ray-input kind (explicit ids,
+    contiguous range, explicit points) goes through the same kernel; the fused render agrees with the reference's rgb."""
+    z = load_npz(golden_dir, "small_local_radius1.npz")
+    S = int(z["S"])
+    feats = [torch.from_numpy(z["feat8"]), torch.from_numpy(z["feat4"])]
+    imgs, extr, intr, nf = (torch.from_numpy(z[k]) for k in ("images", "extrinsics", "intrinsics", "near_fars"))
+    ray_idx = torch.from_numpy(z["ray_idx"])
+    _, sc = make_scene(ctx, feats, imgs, extr, intr, nf, radius, dilation)
+    c32, c16 = ctx.gather_cossim(sc, S, ray_idx=ray_idx, want_f32=True, want_f16=True)
+    torch.cuda.synchronize()
+    dec = dec_from_npz(z)
+    o = oracle_render(dec, feats, imgs, extr, intr, nf, ray_idx, S, quantize_feats=True, return_aux=True,
+                      local_radius=radius, local_dilation=dilation)
+    cond_q = o[3]["cond"]
+    assert frac_above(c32[:, 19:], cond_q[:, 19:], 0.5) < 2e-3 and rms(c32[:, 10:19], cond_q[:, 10:19]) < 2e-5
+    assert rms(c32[:, :10], cond_q[:, :10]) < 2e-5, rms(c32[:, :10], cond_q[:, :10])      # fp32 blend: round-off only
+    assert rms(c16[:, :22].float(), c32) < 5e-4 and float(c16[:, 22:].abs().max()) == 0.0
+    plain = oracle_render(dec, feats, imgs, extr, intr, nf, ray_idx, S, quantize_feats=True, return_aux=True)[3]["cond"]
+    assert rms(cond_q[:, :10], plain[:, :10]) > 1e-2                                    # the option changes the answer
+    if (radius, dilation) == (int(z["local_radius"]), int(z["local_dilation"])):
+        assert rms(c32[:, :10], z["cond"][:, :10]) < 1e-3                               # vs the reference on fp32 features
+        ctx.load_decoder(dec)
+        rgb, depth, op = ctx.render_rays(sc, make_cfg(S), ray_idx=ray_idx, impl=2)
+        assert rms(rgb, z["rgb"]) < 2e-3 and rms(op, z["opacity"][:, 0]) < 2e-3
+    # contiguous range and explicit points: the same kernel, identical bits
+    first = 40 * 7 + 3
+    a, _ = ctx.gather_cossim(sc, S, first_ray=first, n_rays=50)
+    b, _ = ctx.gather_cossim(sc, S, ray_idx=torch.arange(first, first + 50))
+    assert torch.equal(a, b)
+    pts = o[3]["pts"].reshape(-1, S, 3)[:64].contiguous()
+    cpts, _ = ctx.query_cond_points(sc, pts.to(DEV))
+    assert torch.equal(cpts, c32[: 64 * S])
 
 
 def test_gather_config1_and_ray_range(ctx):

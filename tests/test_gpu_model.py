@@ -41,10 +41,12 @@ def test_encoder_matches_reference_golden(golden_dir):
     assert rms(f4[0][:, ::8], z["feat4_ch0mod8"]) < 2.5e-3 * scale
 
 
-def test_forward_small_image_vs_oracle():
-    """forward(mode='test') on a 64x96 triplet: encoder + full-image render, vs the CPU oracle chain."""
+@pytest.mark.parametrize("local", [(0, 1), (1, 2)])
+def test_forward_small_image_vs_oracle(local):
+    """forward(mode='test') on a 64x96 triplet: encoder + full-image render, vs the CPU oracle chain; also with
+    encoder.feature_sample_local_radius / _dilation = (1, 2) (models/gmflow/utils.py:136-162)."""
     H, W, S = 64, 96, 32
-    m, opt = build_model(S)
+    m, opt = build_model(S, **{"encoder.feature_sample_local_radius": local[0], "encoder.feature_sample_local_dilation": local[1]})
     g = torch.Generator().manual_seed(4)
     images = torch.rand(1, 4, 3, H, W, generator=g)
     extr, intr, nf = synth.synthetic_cameras(H, W)
@@ -54,7 +56,8 @@ def test_forward_small_image_vs_oracle():
     assert out.rgb.shape == (1, H * W, 3) and out.depth.shape == (1, H * W, 1) and out.opacity.shape == (1, H * W, 1)
     feats = EO.encode_views(synth.synthetic_encoder(1), images[0, :3])
     idx = torch.arange(0, H * W, 7)
-    o = oracle_render(synth.synthetic_decoder(0), [f[None] for f in feats], images[:, :3], extr, intr, nf, idx, S)
+    o = oracle_render(synth.synthetic_decoder(0), [f[None] for f in feats], images[:, :3], extr, intr, nf, idx, S,
+                      local_radius=local[0], local_dilation=local[1])
     e = (rms(out.rgb[0, idx], o[0]), rms(out.depth[0, idx], o[1]), rms(out.opacity[0, idx], o[2]))
     assert e[0] < 2e-3 and e[2] < 4e-3, e
     assert 0.02 < float(out.opacity.mean()) < 0.98

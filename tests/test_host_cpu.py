@@ -67,7 +67,7 @@ def test_unsupported_architectures_are_rejected():
     with pytest.raises(NotImplementedError):
         MatchNeRF(make_opts(**{"decoder.net_width": 256}))
     with pytest.raises(NotImplementedError):
-        MatchNeRF(make_opts(**{"encoder.feature_sample_local_radius": 1}))
+        MatchNeRF(make_opts(**{"encoder.feature_sample_local_radius": 9}))
     with pytest.raises(NotImplementedError):
         MatchNeRF(make_opts(**{"nerf.legacy_coord": False}))
 

@@ -33,7 +33,7 @@ def test_config1_synthetic_weights(golden_dir, S):
 
 
 SMALL_CASES = ["small_base", "small_elu_maskfill_posenc_bg", "small_s24_elu_maskfill_posenc_bg", "small_wide_baseline",
-               "demo_own_S128", "video_own_S256"]
+               "demo_own_S128", "video_own_S256", "small_local_radius1"]
 
 
 @pytest.mark.parametrize("name", SMALL_CASES)
@@ -46,7 +46,8 @@ def test_small_cases_all_options(golden_dir, name):
                         torch.from_numpy(z["intrinsics"]), torch.from_numpy(z["near_fars"]),
                         torch.from_numpy(z["ray_idx"]), S, setbg_opaque=bool(z["setbg_opaque"]),
                         raytrans_act=str(z["raytrans_act"]), raytrans_posenc=bool(z["raytrans_posenc"]),
-                        density_maskfill=bool(z["density_maskfill"]), return_aux=True)
+                        density_maskfill=bool(z["density_maskfill"]), return_aux=True,
+                        local_radius=int(z["local_radius"]), local_dilation=int(z["local_dilation"]))
     assert rms(out[3]["cond"], z["cond"]) < 1e-6
     assert rms(out[0], z["rgb"]) < 1e-6 and rms(out[1], z["depth"]) < 3e-6 and rms(out[2], z["opacity"]) < 1e-6
     # the wide-baseline case must exercise out-of-view samples (mask = 0)
