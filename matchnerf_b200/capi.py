@@ -162,6 +162,7 @@ class PackedScene:
         sc.tgt_Kinv[:] = kinv.reshape(-1).tolist()
         sc.tgt_near_far[:] = tgt_nf.detach().to("cpu", torch.float32).tolist()
         sc.sample_local_radius, sc.sample_local_dilation = self.local_radius, self.local_dilation
+        sc._owner = self        # the struct holds raw device pointers: keep the packed buffers alive as long as it is
         return sc
 
 

@@ -99,7 +99,7 @@ def test_gather_small_golden(ctx, golden_dir, name):
     feats = [torch.from_numpy(z["feat8"]), torch.from_numpy(z["feat4"])]
     imgs, extr, intr, nf = (torch.from_numpy(z[k]) for k in ("images", "extrinsics", "intrinsics", "near_fars"))
     ray_idx = torch.from_numpy(z["ray_idx"])
-    _, sc = make_scene(ctx, feats, imgs, extr, intr, nf)
+    packed, sc = make_scene(ctx, feats, imgs, extr, intr, nf)
     c32, c16 = ctx.gather_cossim(sc, S, ray_idx=ray_idx, want_f32=True, want_f16=True)
     torch.cuda.synchronize()
     aux = oracle_render(dec_from_npz(z), feats, imgs, extr, intr, nf, ray_idx, S, quantize_feats=True, return_aux=True)[3]
@@ -122,7 +122,7 @@ def test_gather_local_radius(ctx, golden_dir, radius, dilation):
     feats = [torch.from_numpy(z["feat8"]), torch.from_numpy(z["feat4"])]
     imgs, extr, intr, nf = (torch.from_numpy(z[k]) for k in ("images", "extrinsics", "intrinsics", "near_fars"))
     ray_idx = torch.from_numpy(z["ray_idx"])
-    _, sc = make_scene(ctx, feats, imgs, extr, intr, nf, radius, dilation)
+    packed, sc = make_scene(ctx, feats, imgs, extr, intr, nf, radius, dilation)
     c32, c16 = ctx.gather_cossim(sc, S, ray_idx=ray_idx, want_f32=True, want_f16=True)
     torch.cuda.synchronize()
     dec = dec_from_npz(z)
@@ -151,7 +151,7 @@ def test_gather_local_radius(ctx, golden_dir, radius, dilation):
 
 def test_gather_config1_and_ray_range(ctx):
     feats, imgs, extr, intr, nf, ray_idx = config1_inputs()
-    _, sc = make_scene(ctx, feats, imgs, extr, intr, nf)
+    packed, sc = make_scene(ctx, feats, imgs, extr, intr, nf)
     S = 64
     sub = ray_idx[:128]
     c32, _ = ctx.gather_cossim(sc, S, ray_idx=sub)
@@ -178,7 +178,7 @@ def test_gather_borders_ragged(ctx, S, first, n):
     feats = [torch.randn(1, 3, 256, H // 8, W // 8, generator=g), torch.randn(1, 3, 256, H // 4, W // 4, generator=g)]
     imgs = torch.rand(1, 3, 3, H, W, generator=g)
     extr, intr, nf = synth.synthetic_cameras(H, W, baseline_deg=25.0)
-    _, sc = make_scene(ctx, feats, imgs, extr, intr, nf)
+    packed, sc = make_scene(ctx, feats, imgs, extr, intr, nf)
     c32, c16 = ctx.gather_cossim(sc, S, first_ray=first, n_rays=n, want_f32=True, want_f16=True)
     torch.cuda.synchronize()
     ray_idx = torch.arange(first, first + n)
@@ -210,7 +210,7 @@ def test_gather_tensor_core_path(ctx, H, W, S, first, n, baseline):
     feats = [torch.randn(1, 3, 256, H // 8, W // 8, generator=g), torch.randn(1, 3, 256, H // 4, W // 4, generator=g)]
     imgs = torch.rand(1, 3, 3, H, W, generator=g)
     extr, intr, nf = synth.synthetic_cameras(H, W, baseline_deg=baseline)
-    _, sc = make_scene(ctx, feats, imgs, extr, intr, nf)
+    packed, sc = make_scene(ctx, feats, imgs, extr, intr, nf)
     t32, t16 = ctx.gather_cossim(sc, S, first_ray=first, n_rays=n, want_f32=True, want_f16=True)
     v32, _ = ctx.gather_cossim(sc, S, ray_idx=torch.arange(first, first + n), want_f32=True)
     torch.cuda.synchronize()
@@ -230,7 +230,7 @@ def test_gather_tensor_core_path(ctx, H, W, S, first, n, baseline):
 # ------------------------------------------------------------------------------------------- K-mlp-composite
 def run_decoder_case(ctx, dec, feats, imgs, extr, intr, nf, ray_idx, S, impl, act="ReLU", posenc=False, maskfill=False, bg=False):
     ctx.load_decoder(dec)
-    _, sc = make_scene(ctx, feats, imgs, extr, intr, nf)
+    packed, sc = make_scene(ctx, feats, imgs, extr, intr, nf)
     cfg = make_cfg(S, act, posenc, maskfill)
     o = oracle_render(dec, feats, imgs, extr, intr, nf, ray_idx, S, quantize_feats=True, return_aux=True, setbg_opaque=bg,
                       raytrans_act=act, raytrans_posenc=posenc, density_maskfill=maskfill)
@@ -308,7 +308,7 @@ def test_render_options_vs_reference_golden(ctx, golden_dir, name, impl):
     feats = [torch.from_numpy(z["feat8"]), torch.from_numpy(z["feat4"])]
     imgs, extr, intr, nf = (torch.from_numpy(z[k]) for k in ("images", "extrinsics", "intrinsics", "near_fars"))
     ctx.load_decoder(dec_from_npz(z))
-    _, sc = make_scene(ctx, feats, imgs, extr, intr, nf)
+    packed, sc = make_scene(ctx, feats, imgs, extr, intr, nf)
     cfg = make_cfg(int(z["S"]), str(z["raytrans_act"]), bool(z["raytrans_posenc"]), bool(z["density_maskfill"]))
     rgb, depth, op = ctx.render_rays(sc, cfg, ray_idx=torch.from_numpy(z["ray_idx"]), setbg_opaque=bool(z["setbg_opaque"]), impl=impl)
     torch.cuda.synchronize()
@@ -324,7 +324,7 @@ def test_render_config1_vs_reference_golden(ctx, golden_dir, S, impl):
     z = load_npz(golden_dir, f"config1_synth_S{S}.npz")
     feats, imgs, extr, intr, nf, ray_idx = config1_inputs()
     ctx.load_decoder(synth.synthetic_decoder(0))
-    _, sc = make_scene(ctx, feats, imgs, extr, intr, nf)
+    packed, sc = make_scene(ctx, feats, imgs, extr, intr, nf)
     rgb, depth, op = ctx.render_rays(sc, make_cfg(S), ray_idx=ray_idx, impl=impl)
     torch.cuda.synchronize()
     e = (rms(rgb, z["rgb"]), rms(depth, z["depth"][:, 0]), rms(op, z["opacity"][:, 0]))
@@ -339,7 +339,7 @@ def test_render_known_answer_reference_init(ctx, golden_dir):
     z = load_npz(golden_dir, "config1_refinit_S64.npz")
     feats, imgs, extr, intr, nf, ray_idx = config1_inputs()
     ctx.load_decoder(dec_from_npz(z))
-    _, sc = make_scene(ctx, feats, imgs, extr, intr, nf)
+    packed, sc = make_scene(ctx, feats, imgs, extr, intr, nf)
     rgb, depth, op = ctx.render_rays(sc, make_cfg(64), ray_idx=ray_idx, impl=1)
     assert abs(float(rgb.mean()) - 0.1042879) < 2e-4 and rms(rgb, z["rgb"]) < 1e-3
 
@@ -347,7 +347,7 @@ def test_render_known_answer_reference_init(ctx, golden_dir):
 def test_render_edge_cases(ctx):
     feats, imgs, extr, intr, nf, ray_idx = config1_inputs()
     ctx.load_decoder(synth.synthetic_decoder(0))
-    _, sc = make_scene(ctx, feats, imgs, extr, intr, nf)
+    packed, sc = make_scene(ctx, feats, imgs, extr, intr, nf)
     # empty ray set
     rgb, depth, op = ctx.render_rays(sc, make_cfg(64), first_ray=0, n_rays=0, impl=1)
     assert rgb.shape == (0, 3)

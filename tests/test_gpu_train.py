@@ -24,7 +24,7 @@ def test_gather_backward_vs_oracle_autograd(ctx, S, n_rays):
     H, W = 64, 80
     feats, imgs, g = synth.synthetic_scene(H, W, seed=7)
     extr, intr, nf = synth.synthetic_cameras(H, W)
-    _, sc = make_scene(ctx, feats, imgs, extr, intr, nf)
+    packed, sc = make_scene(ctx, feats, imgs, extr, intr, nf)
     ray_idx = torch.randperm(H * W, generator=g)[:n_rays]
     jit = torch.rand(n_rays, S, generator=g)
     wgt = torch.randn(n_rays * S, 10, generator=g)
