@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MNF_ABI_VERSION 6
+#define MNF_ABI_VERSION 8
 
 typedef enum mnf_status {
   MNF_OK = 0,
@@ -201,6 +201,22 @@ int32_t mnf_token_layernorm_fwd(mnf_ctx* ctx, const void* x, int32_t x_is_f16, c
                                 const float* residual, const float* prefix, float* out_f32, void* out_f16, int64_t n_tokens,
                                 int32_t channels, void* stream);
 
+/* ---- K-block: everything of TransformerLayer.forward after the attention, one tcgen05 kernel ---- */
+/* Replaces models/gmflow/transformer.py:173-185 for d_model 128, ffn_dim_expansion 4:
+ *     out = source + LN1(merge(attn_out))                                               (self-attention layer, no_ffn)
+ *     out = source + LN2(mlp2(GELU(mlp0(cat[source, LN1(merge(attn_out))]))))             (cross-attention + FFN layer)
+ * attn_out, source, out: [n_tokens][128] fp32 (out must not alias the inputs).  fp16 operands, fp32 accumulation; LayerNorm
+ * (biased variance, eps inside the square root), erf-form GELU and the residual in fp32; the 1024-wide hidden tensor stays on chip.
+ * The layer's parameters are packed once (fp16 operand tiles in streaming order + the LayerNorm vectors) by
+ * mnf_token_block_pack_weights into mnf_token_block_weight_bytes(with_ffn) bytes of device memory, 16-byte aligned:
+ *   merge_w [128][128], norm1_w / norm1_b [128]; with an FFN: mlp0_w [1024][256], mlp2_w [128][1024], norm2_w / norm2_b [128]
+ *   (fp32, device, nn.Linear / nn.LayerNorm layouts); mlp0_w == NULL packs a no_ffn layer. */
+int64_t mnf_token_block_weight_bytes(int32_t with_ffn);
+int32_t mnf_token_block_pack_weights(mnf_ctx* ctx, const float* merge_w, const float* norm1_w, const float* norm1_b, const float* mlp0_w,
+                                     const float* mlp2_w, const float* norm2_w, const float* norm2_b, void* out_packed, void* stream);
+int32_t mnf_token_block_fwd(mnf_ctx* ctx, const float* attn_out, const float* source, const void* weights_packed, int32_t with_ffn,
+                            float eps, float* out, int64_t n_tokens, int32_t channels, void* stream);
+
 /* ---- K-attn: GMFlow split-window single-head attention ----------------------------------- */
 /* Replaces single_head_split_window_attention / single_head_full_attention
  * (models/gmflow/transformer.py:46-105 / :8-16) including the roll, the window partition and the
@@ -215,6 +231,21 @@ int64_t mnf_window_attn_workspace_bytes(int32_t B, int32_t h, int32_t w, int32_t
 int32_t mnf_window_attn_fwd(mnf_ctx* ctx, const float* q, const float* k, const float* v, float* out,
                             int32_t B, int32_t h, int32_t w, int32_t C, int32_t num_splits, int32_t with_shift,
                             int32_t impl, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* The same attention with the layer's projections fused in front of it (TransformerLayer.forward, models/gmflow/transformer.py:158-171):
+ *     out = attention(q_proj(source), k_proj(target), v_proj(target))
+ * source, target, out: [B][h*w][128] fp32.  One kernel gathers each window tile from source / target, multiplies it by the fp16
+ * projection weight on the tensor cores and writes the attention kernel's operand images directly (no fp32 q / k / v tensors, no
+ * pre-pack pass); then the tcgen05 attention kernel runs.  fp16 operands, fp32 accumulation.
+ *   proj_weights_packed: mnf_window_attn_proj_weight_bytes() bytes written by mnf_window_attn_pack_proj_weights from the three
+ *     nn.Linear weights [128][128] fp32 (device), once per parameter state;
+ *   workspace: mnf_window_attn_workspace_bytes(B, h, w, num_splits) bytes, 16-byte aligned (required). */
+int64_t mnf_window_attn_proj_weight_bytes(void);
+int32_t mnf_window_attn_pack_proj_weights(mnf_ctx* ctx, const float* q_proj_w, const float* k_proj_w, const float* v_proj_w,
+                                          void* out_packed, void* stream);
+int32_t mnf_window_attn_proj_fwd(mnf_ctx* ctx, const float* source, const float* target, const void* proj_weights_packed, float* out,
+                                 int32_t B, int32_t h, int32_t w, int32_t C, int32_t num_splits, int32_t with_shift, void* workspace,
+                                 int64_t workspace_bytes, void* stream);
 
 /* ---- self tests of the tcgen05 building blocks (used by tests/ on the GPU box) ------------- */
 /* D[128][N] = A[128][K] * B[N][K]^T with fp16 operands, fp32 accumulate, one CTA.

@@ -15,7 +15,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MNF_LIB_PATH") or os.path.join(_HERE, "libmatchnerf_b200.so")   # override: A/B builds (tools/)
 
-ABI_VERSION = 6
+ABI_VERSION = 8
 COND_DIM = 22
 COND_PAD = 32
 FEAT_CH = 256
@@ -83,6 +83,10 @@ def load() -> C.CDLL:
     lib.mnf_instance_norm_nhwc_fwd.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, C.c_float, vp]
     lib.mnf_gather_cossim_bwd.argtypes = [vp, C.POINTER(Scene), C.POINTER(Rays), i32, fp, fp, fp, vp]
     lib.mnf_token_layernorm_fwd.argtypes = [vp, vp, i32, fp, fp, C.c_float, fp, fp, fp, vp, i64, i32, vp]
+    lib.mnf_token_block_weight_bytes.argtypes = [i32]
+    lib.mnf_token_block_weight_bytes.restype = i64
+    lib.mnf_token_block_pack_weights.argtypes = [vp, fp, fp, fp, fp, fp, fp, fp, vp, vp]
+    lib.mnf_token_block_fwd.argtypes = [vp, fp, fp, vp, i32, C.c_float, fp, i64, i32, vp]
     lib.mnf_render_workspace_bytes.argtypes = [i64, i32, i32]
     lib.mnf_render_workspace_bytes.restype = i64
     lib.mnf_render_rays_fwd.argtypes = [vp, C.POINTER(Scene), C.POINTER(Rays), C.POINTER(DecoderCfg), i32, fp, fp, fp,
@@ -90,12 +94,16 @@ def load() -> C.CDLL:
     lib.mnf_window_attn_workspace_bytes.argtypes = [i32, i32, i32, i32]
     lib.mnf_window_attn_workspace_bytes.restype = i64
     lib.mnf_window_attn_fwd.argtypes = [vp, fp, fp, fp, fp, i32, i32, i32, i32, i32, i32, i32, vp, i64, vp]
+    lib.mnf_window_attn_proj_weight_bytes.restype = i64
+    lib.mnf_window_attn_pack_proj_weights.argtypes = [vp, fp, fp, fp, vp, vp]
+    lib.mnf_window_attn_proj_fwd.argtypes = [vp, fp, fp, vp, fp, i32, i32, i32, i32, i32, i32, vp, i64, vp]
     lib.mnf_selftest_umma.argtypes = [vp, vp, fp, i32, i32, i32, vp]
     for name in ("mnf_ctx_create", "mnf_ctx_destroy", "mnf_decoder_load_host", "mnf_pack_features", "mnf_pack_images",
                  "mnf_gather_cossim_fwd", "mnf_decoder_composite_fwd", "mnf_render_rays_fwd", "mnf_window_attn_fwd",
                  "mnf_selftest_umma", "mnf_query_cond_points_fwd", "mnf_decoder_samples_fwd", "mnf_composite_fwd",
                  "mnf_instance_norm_fwd", "mnf_token_layernorm_fwd", "mnf_gather_cossim_bwd",
-                 "mnf_instance_norm_nhwc_fwd"):
+                 "mnf_instance_norm_nhwc_fwd", "mnf_token_block_pack_weights", "mnf_token_block_fwd",
+                 "mnf_window_attn_pack_proj_weights", "mnf_window_attn_proj_fwd"):
         getattr(lib, name).restype = i32
     if lib.mnf_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libmatchnerf_b200.so ABI {lib.mnf_abi_version()} != {ABI_VERSION}")
@@ -414,6 +422,33 @@ class Context:
                                                 _ptr(rc), _ptr(pc), o32, o16, n, 128, _stream(self.device)), "mnf_token_layernorm_fwd")
         return out
 
+    def token_block_pack(self, merge_w, norm1_w, norm1_b, mlp0_w=None, mlp2_w=None, norm2_w=None, norm2_b=None) -> torch.Tensor:
+        """Pack one TransformerLayer's post-attention parameters for ``token_block`` (mnf_token_block_pack_weights): fp16 operand
+        tiles in streaming order + the LayerNorm vectors.  ``mlp0_w is None`` packs a no_ffn (self-attention) layer."""
+        with_ffn = mlp0_w is not None
+        ts = [_dev_f32(t.detach(), self.device, nm) if t is not None else None
+              for t, nm in ((merge_w, "merge_w"), (norm1_w, "norm1_w"), (norm1_b, "norm1_b"), (mlp0_w, "mlp0_w"), (mlp2_w, "mlp2_w"),
+                            (norm2_w, "norm2_w"), (norm2_b, "norm2_b"))]
+        if ts[0].shape != (128, 128) or (with_ffn and (ts[3].shape != (1024, 256) or ts[4].shape != (128, 1024))):
+            raise ValueError("token_block is built for d_model 128 with ffn_dim_expansion 4")
+        blob = torch.empty(self.lib.mnf_token_block_weight_bytes(int(with_ffn)), dtype=torch.uint8, device=self.device)
+        _check(self.lib.mnf_token_block_pack_weights(self._h, *[_ptr(t) for t in ts], blob.data_ptr(), _stream(self.device)),
+               "mnf_token_block_pack_weights")
+        return blob
+
+    def token_block(self, attn_out: torch.Tensor, source: torch.Tensor, blob: torch.Tensor, with_ffn: bool, eps: float = 1e-5) -> torch.Tensor:
+        """``source + LN1(merge(attn_out))`` or ``source + LN2(mlp(cat[source, LN1(merge(attn_out))]))`` (models/gmflow/transformer.py:173-185)
+        in one tcgen05 kernel; attn_out / source [..., 128] fp32 on this device; see mnf_token_block_fwd."""
+        a, s = _dev_f32(attn_out, self.device, "attn_out"), _dev_f32(source, self.device, "source")
+        if a.shape != s.shape or a.shape[-1] != 128:
+            raise ValueError(f"attn_out {tuple(a.shape)} / source {tuple(s.shape)}: expected equal [..., 128] shapes")
+        if blob.numel() != self.lib.mnf_token_block_weight_bytes(int(with_ffn)):
+            raise ValueError("packed weights do not match with_ffn")
+        out = torch.empty_like(s)
+        _check(self.lib.mnf_token_block_fwd(self._h, a.data_ptr(), s.data_ptr(), blob.data_ptr(), int(with_ffn), eps, out.data_ptr(),
+                                            a.numel() // 128, 128, _stream(self.device)), "mnf_token_block_fwd")
+        return out
+
     def window_attn(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, h: int, w: int, num_splits: int,
                     with_shift: bool, impl: int = 0, use_workspace: bool = True) -> torch.Tensor:
         q = _dev_f32(q, self.device, "q")
@@ -430,6 +465,32 @@ class Context:
         _check(self.lib.mnf_window_attn_fwd(self._h, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, h, w, Cc,
                                             num_splits, int(with_shift), impl, _ptr(ws), ws.numel() if ws is not None else 0,
                                             _stream(self.device)), "mnf_window_attn_fwd")
+        return out
+
+    def window_attn_pack_proj(self, wq: torch.Tensor, wk: torch.Tensor, wv: torch.Tensor) -> torch.Tensor:
+        """q_proj / k_proj / v_proj weights ([128,128] fp32, nn.Linear layout) -> packed operand images for ``window_attn_proj``."""
+        ws = [_dev_f32(t.detach(), self.device, nm) for t, nm in ((wq, "q_proj"), (wk, "k_proj"), (wv, "v_proj"))]
+        if any(t.shape != (128, 128) for t in ws):
+            raise ValueError("projection weights must be [128, 128]")
+        blob = torch.empty(self.lib.mnf_window_attn_proj_weight_bytes(), dtype=torch.uint8, device=self.device)
+        _check(self.lib.mnf_window_attn_pack_proj_weights(self._h, ws[0].data_ptr(), ws[1].data_ptr(), ws[2].data_ptr(), blob.data_ptr(),
+                                                          _stream(self.device)), "mnf_window_attn_pack_proj_weights")
+        return blob
+
+    def window_attn_proj(self, source: torch.Tensor, target: torch.Tensor, blob: torch.Tensor, h: int, w: int, num_splits: int,
+                         with_shift: bool) -> torch.Tensor:
+        """``attention(q_proj(source), k_proj(target), v_proj(target))`` (models/gmflow/transformer.py:158-171): projections fused
+        into the operand-packing kernel, then the tcgen05 attention kernel; see mnf_window_attn_proj_fwd."""
+        s_, t_ = _dev_f32(source, self.device, "source"), _dev_f32(target, self.device, "target")
+        B, L, Cc = s_.shape
+        if L != h * w or t_.shape != s_.shape:
+            raise ValueError("source / target must be [B, h*w, 128] with equal shapes")
+        out = torch.empty_like(s_)
+        need = self.lib.mnf_window_attn_workspace_bytes(B, h, w, num_splits)
+        ws = torch.empty((max(need, 16),), dtype=torch.uint8, device=self.device)
+        _check(self.lib.mnf_window_attn_proj_fwd(self._h, s_.data_ptr(), t_.data_ptr(), blob.data_ptr(), out.data_ptr(), B, h, w, Cc,
+                                                 num_splits, int(with_shift), ws.data_ptr(), ws.numel(), _stream(self.device)),
+               "mnf_window_attn_proj_fwd")
         return out
 
     def selftest_umma(self, a: torch.Tensor, b: torch.Tensor, mode: int) -> torch.Tensor:

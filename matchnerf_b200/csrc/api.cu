@@ -37,6 +37,10 @@ bool window_attn_tc_supports(int B, int h, int w, int C, int num_splits);
 int launch_window_attn_tc(const float* q, const float* k, const float* v, float* out, int B, int h, int w, int C,
                           int num_splits, int with_shift, void* workspace, int64_t workspace_bytes, cudaStream_t s);
 int64_t window_attn_tc_workspace_bytes(int B, int h, int w, int num_splits);
+int64_t window_attn_proj_weight_bytes();
+int launch_window_attn_pack_proj_weights(const float* wq, const float* wk, const float* wv, void* out, cudaStream_t s);
+int launch_window_attn_proj_tc(const float* source, const float* target, const void* proj_weights, float* out, int B, int h, int w,
+                               int num_splits, int with_shift, void* workspace, int64_t workspace_bytes, cudaStream_t s);
 
 }  // namespace mnf
 
@@ -465,8 +469,66 @@ int32_t mnf_token_layernorm_fwd(mnf_ctx* ctx, const void* x, int32_t x_is_f16, c
                                 (cudaStream_t)stream);
 }
 
+int64_t mnf_token_block_weight_bytes(int32_t with_ffn) { return token_block_weight_bytes(with_ffn); }
+
+int32_t mnf_token_block_pack_weights(mnf_ctx* ctx, const float* merge_w, const float* norm1_w, const float* norm1_b, const float* mlp0_w,
+                                     const float* mlp2_w, const float* norm2_w, const float* norm2_b, void* out_packed, void* stream) {
+  DeviceGuard dev_guard(ctx);
+  if (!ctx || !merge_w || !norm1_w || !norm1_b || !out_packed) { set_error("mnf_token_block_pack_weights: NULL argument"); return MNF_EINVAL; }
+  const int with_ffn = mlp0_w != nullptr;
+  if (with_ffn && (!mlp2_w || !norm2_w || !norm2_b)) { set_error("mnf_token_block_pack_weights: mlp0_w given without mlp2_w / norm2"); return MNF_EINVAL; }
+  if ((((uintptr_t)merge_w | (uintptr_t)mlp0_w | (uintptr_t)mlp2_w | (uintptr_t)out_packed) & 15) != 0) {
+    set_error("mnf_token_block_pack_weights: pointers must be 16-byte aligned");
+    return MNF_EINVAL;
+  }
+  return launch_token_block_pack(merge_w, norm1_w, norm1_b, mlp0_w, mlp2_w, norm2_w, norm2_b, out_packed, with_ffn, (cudaStream_t)stream);
+}
+
+int32_t mnf_token_block_fwd(mnf_ctx* ctx, const float* attn_out, const float* source, const void* weights_packed, int32_t with_ffn,
+                            float eps, float* out, int64_t n_tokens, int32_t channels, void* stream) {
+  DeviceGuard dev_guard(ctx);
+  if (!ctx || !attn_out || !source || !weights_packed || !out) { set_error("mnf_token_block_fwd: NULL argument"); return MNF_EINVAL; }
+  if (channels != 128 || n_tokens < 0) { set_error("mnf_token_block_fwd: %d channels / %lld tokens (the kernel is built for d_model 128, ffn expansion 4)", channels, (long long)n_tokens); return MNF_EUNSUPPORTED; }
+  if ((((uintptr_t)attn_out | (uintptr_t)source | (uintptr_t)weights_packed | (uintptr_t)out) & 15) != 0) {
+    set_error("mnf_token_block_fwd: pointers must be 16-byte aligned");
+    return MNF_EINVAL;
+  }
+  return launch_token_block(attn_out, source, weights_packed, with_ffn != 0, eps, out, n_tokens, (cudaStream_t)stream);
+}
+
 int64_t mnf_window_attn_workspace_bytes(int32_t B, int32_t h, int32_t w, int32_t num_splits) {
   return window_attn_tc_workspace_bytes(B, h, w, num_splits);
+}
+
+int64_t mnf_window_attn_proj_weight_bytes(void) { return window_attn_proj_weight_bytes(); }
+
+int32_t mnf_window_attn_pack_proj_weights(mnf_ctx* ctx, const float* q_proj_w, const float* k_proj_w, const float* v_proj_w, void* out_packed,
+                                          void* stream) {
+  DeviceGuard dev_guard(ctx);
+  if (!ctx || !q_proj_w || !k_proj_w || !v_proj_w || !out_packed) { set_error("mnf_window_attn_pack_proj_weights: NULL argument"); return MNF_EINVAL; }
+  if ((((uintptr_t)q_proj_w | (uintptr_t)k_proj_w | (uintptr_t)v_proj_w | (uintptr_t)out_packed) & 15) != 0) {
+    set_error("mnf_window_attn_pack_proj_weights: pointers must be 16-byte aligned");
+    return MNF_EINVAL;
+  }
+  return launch_window_attn_pack_proj_weights(q_proj_w, k_proj_w, v_proj_w, out_packed, (cudaStream_t)stream);
+}
+
+int32_t mnf_window_attn_proj_fwd(mnf_ctx* ctx, const float* source, const float* target, const void* proj_weights_packed, float* out,
+                                 int32_t B, int32_t h, int32_t w, int32_t C, int32_t num_splits, int32_t with_shift, void* workspace,
+                                 int64_t workspace_bytes, void* stream) {
+  DeviceGuard dev_guard(ctx);
+  if (!ctx || !source || !target || !proj_weights_packed || !out) { set_error("mnf_window_attn_proj_fwd: NULL argument"); return MNF_EINVAL; }
+  if (C != 128) { set_error("mnf_window_attn_proj_fwd: C = %d unsupported (feature_channels is 128)", C); return MNF_EUNSUPPORTED; }
+  if (B <= 0 || h <= 0 || w <= 0 || num_splits <= 0 || h % num_splits || w % num_splits) {
+    set_error("mnf_window_attn_proj_fwd: bad shape B=%d h=%d w=%d splits=%d", B, h, w, num_splits);
+    return MNF_EINVAL;
+  }
+  if ((((uintptr_t)source | (uintptr_t)target | (uintptr_t)proj_weights_packed | (uintptr_t)out) & 15) != 0) {
+    set_error("mnf_window_attn_proj_fwd: pointers must be 16-byte aligned");
+    return MNF_EINVAL;
+  }
+  return launch_window_attn_proj_tc(source, target, proj_weights_packed, out, B, h, w, num_splits, with_shift, workspace, workspace_bytes,
+                                    (cudaStream_t)stream);
 }
 
 int32_t mnf_window_attn_fwd(mnf_ctx* ctx, const float* q, const float* k, const float* v, float* out, int32_t B, int32_t h,

@@ -178,6 +178,13 @@ int launch_instance_norm_nhwc(const void* x, const void* res, void* y, int is_f1
 int launch_token_layernorm(const void* x, int x_is_f16, const float* gamma, const float* beta, float eps, const float* residual,
                            const float* prefix, float* out_f32, __half* out_f16, int64_t rows, cudaStream_t s);
 
+// token_block.cu: merge + LayerNorm (+ FFN + LayerNorm) + residual of a TransformerLayer, one tcgen05 kernel
+int64_t token_block_weight_bytes(int with_ffn);
+int launch_token_block_pack(const float* merge_w, const float* g1, const float* b1, const float* w1, const float* w2, const float* g2,
+                            const float* b2, void* out, int with_ffn, cudaStream_t s);
+int launch_token_block(const float* attn, const float* source, const void* weights, int with_ffn, float eps, float* out, int64_t T,
+                       cudaStream_t s);
+
 int launch_window_attn_ref(const float* q, const float* k, const float* v, float* out, int B, int h, int w, int C,
                            int num_splits, int with_shift, cudaStream_t s);
 

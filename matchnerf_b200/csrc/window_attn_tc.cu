@@ -691,6 +691,116 @@ window_attn_tc_v4_kernel(const unsigned char* __restrict__ ws, float* __restrict
   if (warp == 9) tc::tmem_dealloc<256>(tmem);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Fused q / k / v projection + operand packing (TransformerLayer.forward, models/gmflow/transformer.py:158-163: query =
+// q_proj(source), key = k_proj(target), value = v_proj(target)).  Before: three cuBLAS TF32 GEMMs wrote q / k / v as fp32
+// [B, L, 128] tensors (47 MB per call at DTU size) and attn_pack_tiles_kernel re-read them to build the operand images.  Here a
+// CTA = one operand image (b, window, tile, matrix): it gathers the 128 token rows of the tile from the layer's INPUT (roll /
+// window partition by index arithmetic, rows past the window end zero), converts them to the fp16 swizzled A operand in shared
+// memory, multiplies by the matrix' pre-swizzled fp16 weight (one 32 KB bulk copy) with 8 tcgen05.mma steps into 128 TMEM columns,
+// and the epilogue writes the image (Q pre-scaled into the exp2 domain) straight into the workspace the attention kernel reads.
+// fp16 operands / fp32 accumulation (the TF32 GEMMs rounded their operands to the same 10-bit mantissa).
+constexpr int kProjThreads = 256;
+
+struct ProjSmem {
+  alignas(1024) unsigned char a[2][kBlockBytes];
+  unsigned char w[2][kBlockBytes];
+  int tok[kTile];
+  alignas(8) uint64_t w_full;
+  uint64_t d_full;
+  uint32_t tmem_base;
+};
+
+// grid (n_tiles, B * n_windows, 3)
+__global__ void __launch_bounds__(kProjThreads, 2)
+attn_project_pack_kernel(const float* __restrict__ source, const float* __restrict__ target, const unsigned char* __restrict__ wpk,
+                         unsigned char* __restrict__ ws, const WinGeomTc g) {
+  extern __shared__ unsigned char smem_dyn[];
+  ProjSmem& sm = *reinterpret_cast<ProjSmem*>(smem_dyn + ((1024u - (tc::smem_u32(smem_dyn) & 1023u)) & 1023u));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Lw = g.wh * g.ww;
+  const int n_tiles = gridDim.x;
+  const int win = blockIdx.y % (g.splits * g.splits), b = blockIdx.y / (g.splits * g.splits);
+  const int wy = win / g.splits, wx = win - wy * g.splits;
+  const int mat = blockIdx.z;
+  const float* x = (mat == 0 ? source : target) + (size_t)b * g.h * g.w * kC;
+  if (tid == 0) {
+    tc::mbar_init(&sm.w_full, 1);
+    tc::mbar_init(&sm.d_full, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 1) tc::tmem_alloc<128>(&sm.tmem_base);
+  if (tid < kTile) {
+    int tok = -1, reg = 0;
+    if (blockIdx.x * kTile + tid < Lw) window_token(g, wy, wx, blockIdx.x * kTile + tid, tok, reg);
+    sm.tok[tid] = tok;
+  }
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  tc::tc_fence_after_sync();
+  const uint32_t tmem = sm.tmem_base;
+  if (tid == 0) {
+    tc::mbar_arrive_expect_tx(&sm.w_full, kImageBytes);
+    tc::bulk_g2s(&sm.w[0][0], wpk + (size_t)mat * kImageBytes, kImageBytes, &sm.w_full);
+  }
+  load_rows_swizzled(x, sm.tok, &sm.a[0][0], 1.0f, tid);
+  tc::fence_proxy_async_smem();
+  __syncthreads();
+  if (warp == 0) {
+    tc::mbar_wait(&sm.w_full, 0);
+    tc::tc_fence_after_sync();
+    if (tc::elect_one()) {
+      const uint32_t idesc = tc::umma_idesc_f16(128, 128);
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          tc::umma_ss(tmem, tc::umma_desc_sw128(tc::smem_u32(&sm.a[kb][0]) + ks * 32), tc::umma_desc_sw128(tc::smem_u32(&sm.w[kb][0]) + ks * 32),
+                      idesc, (kb | ks) ? 1u : 0u);
+      tc::umma_commit(&sm.d_full);
+    }
+    __syncwarp();
+  }
+  tc::mbar_wait(&sm.d_full, 0);
+  tc::tc_fence_after_sync();
+  {
+    const int q4 = warp & 3, hf = warp >> 2, row = q4 * 32 + lane;
+    const float scale = mat == 0 ? rsqrtf((float)kC) * 1.4426950408889634f : 1.0f;   // scores in the exp2 domain, as attn_pack_tiles_kernel
+    unsigned char* img = ws + (((size_t)blockIdx.y * n_tiles + blockIdx.x) * 3 + mat) * kImageBytes + (size_t)hf * kBlockBytes;
+    const uint32_t acc = tmem + ((uint32_t)(q4 * 32) << 16) + hf * 64;
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4) {
+      uint32_t r[16];
+      tc::tmem_ld16(acc + c4 * 16, r);
+      tc::tmem_wait_ld(r);
+#pragma unroll
+      for (int h8 = 0; h8 < 2; ++h8) {
+        uint4 o;
+        o.x = pack_h2f(__uint_as_float(r[h8 * 8 + 0]) * scale, __uint_as_float(r[h8 * 8 + 1]) * scale);
+        o.y = pack_h2f(__uint_as_float(r[h8 * 8 + 2]) * scale, __uint_as_float(r[h8 * 8 + 3]) * scale);
+        o.z = pack_h2f(__uint_as_float(r[h8 * 8 + 4]) * scale, __uint_as_float(r[h8 * 8 + 5]) * scale);
+        o.w = pack_h2f(__uint_as_float(r[h8 * 8 + 6]) * scale, __uint_as_float(r[h8 * 8 + 7]) * scale);
+        *reinterpret_cast<uint4*>(img + tc::sw128_offset(row, c4 * 16 + h8 * 8)) = o;
+      }
+    }
+  }
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc<128>(tmem);
+}
+
+// q_proj / k_proj / v_proj weights [128][128] fp32 (nn.Linear layout: [out][in]) -> three pre-swizzled fp16 operand images
+__global__ void attn_pack_proj_weights_kernel(const float* __restrict__ wq, const float* __restrict__ wk, const float* __restrict__ wv,
+                                              unsigned char* __restrict__ outp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;      // one 16-byte chunk each: 3 matrices x 2 K-blocks x 128 rows x 8 chunks
+  if (i >= 3 * 2 * 128 * 8) return;
+  const int mat = i >> 11, kb = (i >> 10) & 1, r = (i >> 3) & 127, c8 = i & 7;
+  const float* src = (mat == 0 ? wq : (mat == 1 ? wk : wv)) + (size_t)r * kC + kb * 64 + c8 * 8;
+  const float4 lo = __ldg(reinterpret_cast<const float4*>(src)), hi = __ldg(reinterpret_cast<const float4*>(src) + 1);
+  *reinterpret_cast<uint4*>(outp + (size_t)mat * kImageBytes + (size_t)kb * kBlockBytes + tc::sw128_offset(r, c8 * 8)) =
+      make_uint4(pack_h2f(lo.x, lo.y), pack_h2f(lo.z, lo.w), pack_h2f(hi.x, hi.y), pack_h2f(hi.z, hi.w));
+}
+
 int64_t window_attn_tc_workspace_bytes(int B, int h, int w, int num_splits) {
   if (B <= 0 || h <= 0 || w <= 0 || num_splits <= 0 || h % num_splits || w % num_splits) return 0;
   const int64_t Lw = (int64_t)(h / num_splits) * (w / num_splits);
@@ -735,6 +845,45 @@ int launch_window_attn_tc(const float* q, const float* k, const float* v, float*
     }
     window_attn_tc_kernel<<<grid, kPipeThreads, smem, s>>>(q, k, v, out, g);
   }
+  MNF_CUDA_TRY(cudaGetLastError());
+  return MNF_OK;
+}
+
+int64_t window_attn_proj_weight_bytes() { return 3 * (int64_t)kImageBytes; }
+
+int launch_window_attn_pack_proj_weights(const float* wq, const float* wk, const float* wv, void* out, cudaStream_t s) {
+  attn_pack_proj_weights_kernel<<<(3 * 2 * 128 * 8 + 255) / 256, 256, 0, s>>>(wq, wk, wv, reinterpret_cast<unsigned char*>(out));
+  MNF_CUDA_TRY(cudaGetLastError());
+  return MNF_OK;
+}
+
+// attention(q_proj(source), k_proj(target), v_proj(target)): projection + operand packing kernel, then the v4 attention kernel
+int launch_window_attn_proj_tc(const float* source, const float* target, const void* proj_weights, float* out, int B, int h, int w,
+                               int num_splits, int with_shift, void* workspace, int64_t workspace_bytes, cudaStream_t s) {
+  WinGeomTc g;
+  g.h = h; g.w = w; g.splits = num_splits;
+  g.wh = h / num_splits; g.ww = w / num_splits;
+  g.sh = (with_shift && num_splits > 1) ? g.wh / 2 : 0;
+  g.sw = (with_shift && num_splits > 1) ? g.ww / 2 : 0;
+  const int Lw = g.wh * g.ww;
+  if (!workspace || workspace_bytes < window_attn_tc_workspace_bytes(B, h, w, num_splits) || ((uintptr_t)workspace & 15) != 0) {
+    set_error("mnf_window_attn_proj_fwd: workspace missing, misaligned or smaller than mnf_window_attn_workspace_bytes");
+    return MNF_ENOMEM;
+  }
+  dim3 grid((Lw + kTile - 1) / kTile, B * num_splits * num_splits);
+  const size_t smem = sizeof(AttnV4Smem) + 1024, psmem = sizeof(ProjSmem) + 1024;
+  static PerDevice<bool> configured_dev;
+  bool& configured = configured_dev.cur();
+  if (!configured) {
+    MNF_CUDA_TRY(cudaFuncSetAttribute(window_attn_tc_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MNF_CUDA_TRY(cudaFuncSetAttribute(attn_project_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+    configured = true;
+  }
+  dim3 pgrid(grid.x, grid.y, 3);
+  attn_project_pack_kernel<<<pgrid, kProjThreads, psmem, s>>>(source, target, reinterpret_cast<const unsigned char*>(proj_weights),
+                                                              reinterpret_cast<unsigned char*>(workspace), g);
+  MNF_CUDA_TRY(cudaGetLastError());
+  window_attn_tc_v4_kernel<<<grid, kV4Threads, smem, s>>>(reinterpret_cast<const unsigned char*>(workspace), out, g);
   MNF_CUDA_TRY(cudaGetLastError());
   return MNF_OK;
 }

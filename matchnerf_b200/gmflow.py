@@ -11,6 +11,7 @@ There is no CPU execution path for the attention: off-GPU the forward raises.
 from __future__ import annotations
 
 import math
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -150,8 +151,19 @@ class TransformerLayer(nn.Module):
 
     def forward(self, source, target, height: int, width: int, attn_num_splits: int):
         shift = self.with_shift and attn_num_splits > 1
-        msg = window_attention(self.q_proj(source), self.k_proj(target), self.v_proj(target), height, width,
-                               attn_num_splits, shift)
+        if self.fused_proj and self._fused_norms(source):
+            # inference on the GPU: the three projections run inside the kernel that builds the attention operands
+            # (mnf_window_attn_proj_fwd): no fp32 q / k / v tensors, no pre-pack pass
+            ctx = capi.get_context(source.device)
+            msg = ctx.window_attn_proj(source, target, self._proj_weights(ctx), height, width, attn_num_splits, shift)
+        else:
+            msg = window_attention(self.q_proj(source), self.k_proj(target), self.v_proj(target), height, width,
+                                   attn_num_splits, shift)
+        if self.fused_block and self._fused_norms(msg):
+            # inference on the GPU: merge + LayerNorm (+ FFN + LayerNorm) + residual = ONE tcgen05 kernel of this repo's library
+            # (mnf_token_block_fwd); the 1024-wide hidden tensor never leaves the SM
+            ctx = capi.get_context(msg.device)
+            return ctx.token_block(msg, source, self._block_weights(ctx), not self.no_ffn, self.norm1.eps)
         msg = self.merge(msg)
         if not self._fused_norms(msg):                       # CPU tensors / autograd: the PyTorch ops the reference uses
             msg = self.norm1(msg)
@@ -173,6 +185,28 @@ class TransformerLayer(nn.Module):
     # 10-bit mantissa; storing the hidden activations as fp16 (same mantissa, fp32 accumulation in both GEMMs, GELU
     # evaluated in fp32 inside the kernel) halves the 126 MB-per-layer hidden round trips.  Inference only.
     ffn_dtype = torch.float16
+    # merge / LayerNorm / FFN / residual as one kernel (csrc/token_block.cu); False = the library-GEMM + token_layernorm path (A/B runs)
+    fused_block = os.environ.get("MNF_FUSED_BLOCK", "1") != "0"
+
+    fused_proj = os.environ.get("MNF_FUSED_PROJ", "1") != "0"     # q / k / v projections inside the attention operand-packing kernel
+
+    def _proj_weights(self, ctx):
+        ps = [self.q_proj.weight, self.k_proj.weight, self.v_proj.weight]
+        key = (ctx.device,) + tuple((p.data_ptr(), p._version) for p in ps)
+        if getattr(self, "_proj_cache", None) is None or self._proj_cache[0] != key:
+            self._proj_cache = (key, ctx.window_attn_pack_proj(*ps))
+        return self._proj_cache[1]
+
+    def _block_weights(self, ctx):
+        ps = [self.merge.weight, self.norm1.weight, self.norm1.bias]
+        if not self.no_ffn:
+            ps += [self.mlp[0].weight, self.mlp[2].weight, self.norm2.weight, self.norm2.bias]
+        key = (ctx.device,) + tuple((p.data_ptr(), p._version) for p in ps)
+        if getattr(self, "_block_cache", None) is None or self._block_cache[0] != key:
+            if not self.no_ffn and self.norm2.eps != self.norm1.eps:
+                raise NotImplementedError("token_block assumes one LayerNorm eps per layer")
+            self._block_cache = (key, ctx.token_block_pack(*ps))
+        return self._block_cache[1]
 
     def _fused_norms(self, x) -> bool:
         return (x.is_cuda and x.dtype == torch.float32 and x.shape[-1] == 128 and self.ffn_dtype == torch.float16

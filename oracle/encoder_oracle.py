@@ -73,6 +73,18 @@ def _ln(x: Tensor, w: Tensor, b: Tensor, eps: float = 1e-5) -> Tensor:
     return (x - mu) / torch.sqrt(var + eps) * w + b
 
 
+def post_attention(sd: Dict[str, Tensor], pfx: str, src: Tensor, msg: Tensor, ffn: bool, quant=None) -> Tensor:
+    """models/gmflow/transformer.py:173-185: merge, norm1, (mlp on cat[source, message], norm2), residual.  ``quant`` (tests of
+    the fp16-operand kernel): a function applied to every GEMM operand (activations and weights) before the product."""
+    qz = quant if quant is not None else (lambda t: t)
+    msg = _ln(qz(msg) @ qz(sd[pfx + "merge.weight"]).T, sd[pfx + "norm1.weight"], sd[pfx + "norm1.bias"])
+    if ffn:
+        x = qz(torch.cat([src, msg], dim=-1)) @ qz(sd[pfx + "mlp.0.weight"]).T
+        x = 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))          # exact GELU
+        msg = _ln(qz(x) @ qz(sd[pfx + "mlp.2.weight"]).T, sd[pfx + "norm2.weight"], sd[pfx + "norm2.bias"])
+    return src + msg
+
+
 def transformer_layer(sd: Dict[str, Tensor], pfx: str, src: Tensor, tgt: Tensor, h: int, w: int,
                       num_splits: int, with_shift: bool, ffn: bool) -> Tensor:
     """models/gmflow/transformer.py:147-185."""
@@ -80,12 +92,7 @@ def transformer_layer(sd: Dict[str, Tensor], pfx: str, src: Tensor, tgt: Tensor,
     k = tgt @ sd[pfx + "k_proj.weight"].T
     v = tgt @ sd[pfx + "v_proj.weight"].T
     msg = window_attention(q, k, v, h, w, num_splits, with_shift)
-    msg = _ln(msg @ sd[pfx + "merge.weight"].T, sd[pfx + "norm1.weight"], sd[pfx + "norm1.bias"])
-    if ffn:
-        x = torch.cat([src, msg], dim=-1) @ sd[pfx + "mlp.0.weight"].T
-        x = 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))          # exact GELU
-        msg = _ln(x @ sd[pfx + "mlp.2.weight"].T, sd[pfx + "norm2.weight"], sd[pfx + "norm2.bias"])
-    return src + msg
+    return post_attention(sd, pfx, src, msg, ffn)
 
 
 def feature_transformer(sd: Dict[str, Tensor], f0: Tensor, f1: Tensor, num_splits: int, n_layers: int,

@@ -439,6 +439,30 @@ def test_window_attn_blender_llff_shapes(ctx, h, w, splits, shift):
     assert rms(got, ref) < 2e-3 * float(ref.std()) and rms(nows, ref) < 2e-3 * float(ref.std())
 
 
+@pytest.mark.parametrize("h,w,splits,shift,cross", [(64, 80, 2, False, False), (64, 80, 2, True, True), (100, 100, 2, True, True),
+                                                    (8, 12, 2, True, True), (6, 10, 1, False, True), (80, 120, 4, True, False)])
+def test_window_attn_fused_projection(ctx, h, w, splits, shift, cross):
+    """mnf_window_attn_proj_fwd = attention(q_proj(source), k_proj(target), v_proj(target)) (models/gmflow/transformer.py:158-171)
+    with the projections inside the operand-packing kernel: vs the CPU oracle (projections in fp32, oracle attention) on batch item
+    0, and vs the unfused path of this library (fp32 projections by torch, then mnf_window_attn_fwd) on the whole batch.  Self
+    (source is target) and cross attention; DTU, Blender (partial tiles), tiny, full-attention and 4 x 4 window shapes."""
+    g = torch.Generator().manual_seed(h * w + splits)
+    B = 2
+    src = torch.randn(B, h * w, 128, generator=g)
+    tgt = torch.randn(B, h * w, 128, generator=g) if cross else src
+    wq, wk, wv = (torch.randn(128, 128, generator=g) / 128 ** 0.5 * gain for gain in (1.6, 1.6, 1.0))
+    blob = ctx.window_attn_pack_proj(wq.to(DEV), wk.to(DEV), wv.to(DEV))
+    got = ctx.window_attn_proj(src.to(DEV), tgt.to(DEV), blob, h, w, splits, shift)
+    got2 = ctx.window_attn_proj(src.to(DEV), tgt.to(DEV), blob, h, w, splits, shift)
+    torch.cuda.synchronize()
+    assert torch.equal(got, got2)
+    oracle = EO.window_attention(src[:1] @ wq.T, tgt[:1] @ wk.T, tgt[:1] @ wv.T, h, w, splits, shift)
+    sd = float(oracle.std())
+    assert rms(got[:1], oracle) < 3e-3 * sd and max_abs(got[:1], oracle) < 3e-2 * max(1.0, sd), (rms(got[:1], oracle), sd)
+    unfused = ctx.window_attn(src.to(DEV) @ wq.to(DEV).T, tgt.to(DEV) @ wk.to(DEV).T, tgt.to(DEV) @ wv.to(DEV).T, h, w, splits, shift, impl=2)
+    assert rms(got, unfused) < 3e-3 * float(unfused.std())
+
+
 @pytest.mark.parametrize("rows", [1, 37, 5120 * 6])
 def test_token_layernorm_fused_modes(ctx, rows):
     """mnf_token_layernorm_fwd vs nn.LayerNorm + the add / cat that follow it in TransformerLayer.forward
@@ -461,6 +485,38 @@ def test_token_layernorm_fused_modes(ctx, rows):
     assert max_abs(ctx.token_layernorm(xh, w, b, 1e-5, residual=src), (src.double() + refh).float()) < 2e-5
     with pytest.raises(ValueError):
         ctx.token_layernorm(x, w, b, 1e-5, residual=src, prefix=src)
+
+
+@pytest.mark.parametrize("ffn", [False, True])
+@pytest.mark.parametrize("rows", [1, 37, 128, 300, 148 * 128 + 5, 5120 * 6])
+def test_token_block(ctx, rows, ffn):
+    """mnf_token_block_fwd (merge + LayerNorm [+ FFN + LayerNorm] + residual in one tcgen05 kernel) vs the oracle's restatement of
+    models/gmflow/transformer.py:173-185 on the same inputs.  Two references: the oracle with every GEMM operand rounded to fp16
+    where the kernel rounds it (sharp: 3e-4 RMS -- accumulation order, the GELU fit, rsqrt) and the plain fp32 oracle (the
+    mixed-precision budget: 3e-3 RMS of O(1) outputs).  Ragged token counts, more tiles than SMs, DTU size (6 x 64 x 80 tokens)."""
+    g = torch.Generator().manual_seed(rows + int(ffn))
+    sd = {"merge.weight": torch.randn(128, 128, generator=g) / 128 ** 0.5,
+          "norm1.weight": 1 + 0.2 * torch.randn(128, generator=g), "norm1.bias": 0.2 * torch.randn(128, generator=g),
+          "mlp.0.weight": torch.randn(1024, 256, generator=g) / 256 ** 0.5 * 1.5,
+          "mlp.2.weight": torch.randn(128, 1024, generator=g) / 1024 ** 0.5,
+          "norm2.weight": 1 + 0.2 * torch.randn(128, generator=g), "norm2.bias": 0.2 * torch.randn(128, generator=g)}
+    attn = torch.randn(rows, 128, generator=g) * 1.3
+    src = torch.randn(rows, 128, generator=g)
+    dev = ctx.device
+    blob = ctx.token_block_pack(sd["merge.weight"].to(dev), sd["norm1.weight"].to(dev), sd["norm1.bias"].to(dev),
+                                *([sd[k].to(dev) for k in ("mlp.0.weight", "mlp.2.weight", "norm2.weight", "norm2.bias")] if ffn else []))
+    out = ctx.token_block(attn.to(dev), src.to(dev), blob, ffn)
+    out2 = ctx.token_block(attn.to(dev), src.to(dev), blob, ffn)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)                                         # deterministic
+    sub = slice(None) if rows <= 4096 else torch.randperm(rows, generator=g)[:4096]
+    sd64 = {k: v.double() for k, v in sd.items()}
+    ref_q = EO.post_attention(sd64, "", src[sub].double(), attn[sub].double(), ffn, quant=lambda t: t.half().double())
+    ref = EO.post_attention(sd64, "", src[sub].double(), attn[sub].double(), ffn)
+    got = out.cpu()[sub].double()
+    assert bool(torch.isfinite(got).all())
+    assert rms(got, ref_q) < 3e-4 and max_abs(got, ref_q) < 1e-2, (rms(got, ref_q), max_abs(got, ref_q))
+    assert rms(got, ref) < 3e-3, rms(got, ref)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float16])

@@ -1,0 +1,13 @@
+#!/bin/bash
+# token_block bring-up: kernel parity, timing, encoder / model tests, bench A/B
+set -u
+mkdir -p gpurun_out
+L=gpurun_out/${1:-r02_call12}.log
+: > $L
+run() { echo "=== $*" >> $L; local t0=$SECONDS; ( "$@" ) >> $L 2>&1; echo "--- exit $? after $((SECONDS - t0)) s" >> $L; }
+run timeout 300 python -m pytest tests/test_gpu_kernels.py -q -m gpu -x -k "token_block or local_radius"
+run timeout 120 python tools/time_token_block.py
+run timeout 600 python -m pytest tests/test_gpu_model.py tests/test_gpu_dropin_demo.py -q -m gpu
+run timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-train-step --no-reference-gpu
+MNF_FUSED_BLOCK=0 run timeout 600 python bench.py --steps 10 --warmup 3 --quick
+grep -n "^===\|^--- exit\|passed\|failed\|token_block rows\|Error\|error\|assert" $L | cut -c1-260 | head -60
