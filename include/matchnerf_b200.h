@@ -239,13 +239,15 @@ int32_t mnf_window_attn_fwd(mnf_ctx* ctx, const float* q, const float* k, const 
  * pre-pack pass); then the tcgen05 attention kernel runs.  fp16 operands, fp32 accumulation.
  *   proj_weights_packed: mnf_window_attn_proj_weight_bytes() bytes written by mnf_window_attn_pack_proj_weights from the three
  *     nn.Linear weights [128][128] fp32 (device), once per parameter state;
+ *   target_batch_roll r: keys / values of batch item b are taken from target[(b + r) mod B] -- FeatureTransformer.forward pairs every
+ *     view with "the other view" through torch.cat([x[b:], x[:b]]) (transformer.py:331); r = B/2 on the un-rolled tensor is the same;
  *   workspace: mnf_window_attn_workspace_bytes(B, h, w, num_splits) bytes, 16-byte aligned (required). */
 int64_t mnf_window_attn_proj_weight_bytes(void);
 int32_t mnf_window_attn_pack_proj_weights(mnf_ctx* ctx, const float* q_proj_w, const float* k_proj_w, const float* v_proj_w,
                                           void* out_packed, void* stream);
 int32_t mnf_window_attn_proj_fwd(mnf_ctx* ctx, const float* source, const float* target, const void* proj_weights_packed, float* out,
-                                 int32_t B, int32_t h, int32_t w, int32_t C, int32_t num_splits, int32_t with_shift, void* workspace,
-                                 int64_t workspace_bytes, void* stream);
+                                 int32_t B, int32_t h, int32_t w, int32_t C, int32_t num_splits, int32_t with_shift, int32_t target_batch_roll,
+                                 void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- self tests of the tcgen05 building blocks (used by tests/ on the GPU box) ------------- */
 /* D[128][N] = A[128][K] * B[N][K]^T with fp16 operands, fp32 accumulate, one CTA.

@@ -96,7 +96,7 @@ def load() -> C.CDLL:
     lib.mnf_window_attn_fwd.argtypes = [vp, fp, fp, fp, fp, i32, i32, i32, i32, i32, i32, i32, vp, i64, vp]
     lib.mnf_window_attn_proj_weight_bytes.restype = i64
     lib.mnf_window_attn_pack_proj_weights.argtypes = [vp, fp, fp, fp, vp, vp]
-    lib.mnf_window_attn_proj_fwd.argtypes = [vp, fp, fp, vp, fp, i32, i32, i32, i32, i32, i32, vp, i64, vp]
+    lib.mnf_window_attn_proj_fwd.argtypes = [vp, fp, fp, vp, fp, i32, i32, i32, i32, i32, i32, i32, vp, i64, vp]
     lib.mnf_selftest_umma.argtypes = [vp, vp, fp, i32, i32, i32, vp]
     for name in ("mnf_ctx_create", "mnf_ctx_destroy", "mnf_decoder_load_host", "mnf_pack_features", "mnf_pack_images",
                  "mnf_gather_cossim_fwd", "mnf_decoder_composite_fwd", "mnf_render_rays_fwd", "mnf_window_attn_fwd",
@@ -478,9 +478,10 @@ class Context:
         return blob
 
     def window_attn_proj(self, source: torch.Tensor, target: torch.Tensor, blob: torch.Tensor, h: int, w: int, num_splits: int,
-                         with_shift: bool) -> torch.Tensor:
+                         with_shift: bool, target_roll: int = 0) -> torch.Tensor:
         """``attention(q_proj(source), k_proj(target), v_proj(target))`` (models/gmflow/transformer.py:158-171): projections fused
-        into the operand-packing kernel, then the tcgen05 attention kernel; see mnf_window_attn_proj_fwd."""
+        into the operand-packing kernel, then the tcgen05 attention kernel; see mnf_window_attn_proj_fwd.  ``target_roll`` r: keys /
+        values of batch item b come from ``target[(b + r) % B]``."""
         s_, t_ = _dev_f32(source, self.device, "source"), _dev_f32(target, self.device, "target")
         B, L, Cc = s_.shape
         if L != h * w or t_.shape != s_.shape:
@@ -489,7 +490,8 @@ class Context:
         need = self.lib.mnf_window_attn_workspace_bytes(B, h, w, num_splits)
         ws = torch.empty((max(need, 16),), dtype=torch.uint8, device=self.device)
         _check(self.lib.mnf_window_attn_proj_fwd(self._h, s_.data_ptr(), t_.data_ptr(), blob.data_ptr(), out.data_ptr(), B, h, w, Cc,
-                                                 num_splits, int(with_shift), ws.data_ptr(), ws.numel(), _stream(self.device)),
+                                                 num_splits, int(with_shift), int(target_roll), ws.data_ptr(), ws.numel(),
+                                                 _stream(self.device)),
                "mnf_window_attn_proj_fwd")
         return out
 

@@ -40,7 +40,7 @@ int64_t window_attn_tc_workspace_bytes(int B, int h, int w, int num_splits);
 int64_t window_attn_proj_weight_bytes();
 int launch_window_attn_pack_proj_weights(const float* wq, const float* wk, const float* wv, void* out, cudaStream_t s);
 int launch_window_attn_proj_tc(const float* source, const float* target, const void* proj_weights, float* out, int B, int h, int w,
-                               int num_splits, int with_shift, void* workspace, int64_t workspace_bytes, cudaStream_t s);
+                               int num_splits, int with_shift, int target_roll, void* workspace, int64_t workspace_bytes, cudaStream_t s);
 
 }  // namespace mnf
 
@@ -514,8 +514,8 @@ int32_t mnf_window_attn_pack_proj_weights(mnf_ctx* ctx, const float* q_proj_w, c
 }
 
 int32_t mnf_window_attn_proj_fwd(mnf_ctx* ctx, const float* source, const float* target, const void* proj_weights_packed, float* out,
-                                 int32_t B, int32_t h, int32_t w, int32_t C, int32_t num_splits, int32_t with_shift, void* workspace,
-                                 int64_t workspace_bytes, void* stream) {
+                                 int32_t B, int32_t h, int32_t w, int32_t C, int32_t num_splits, int32_t with_shift, int32_t target_batch_roll,
+                                 void* workspace, int64_t workspace_bytes, void* stream) {
   DeviceGuard dev_guard(ctx);
   if (!ctx || !source || !target || !proj_weights_packed || !out) { set_error("mnf_window_attn_proj_fwd: NULL argument"); return MNF_EINVAL; }
   if (C != 128) { set_error("mnf_window_attn_proj_fwd: C = %d unsupported (feature_channels is 128)", C); return MNF_EUNSUPPORTED; }
@@ -527,7 +527,7 @@ int32_t mnf_window_attn_proj_fwd(mnf_ctx* ctx, const float* source, const float*
     set_error("mnf_window_attn_proj_fwd: pointers must be 16-byte aligned");
     return MNF_EINVAL;
   }
-  return launch_window_attn_proj_tc(source, target, proj_weights_packed, out, B, h, w, num_splits, with_shift, workspace, workspace_bytes,
+  return launch_window_attn_proj_tc(source, target, proj_weights_packed, out, B, h, w, num_splits, with_shift, target_batch_roll, workspace, workspace_bytes,
                                     (cudaStream_t)stream);
 }
 

@@ -714,7 +714,7 @@ struct ProjSmem {
 // grid (n_tiles, B * n_windows, 3)
 __global__ void __launch_bounds__(kProjThreads, 2)
 attn_project_pack_kernel(const float* __restrict__ source, const float* __restrict__ target, const unsigned char* __restrict__ wpk,
-                         unsigned char* __restrict__ ws, const WinGeomTc g) {
+                         unsigned char* __restrict__ ws, const WinGeomTc g, const int target_roll) {
   extern __shared__ unsigned char smem_dyn[];
   ProjSmem& sm = *reinterpret_cast<ProjSmem*>(smem_dyn + ((1024u - (tc::smem_u32(smem_dyn) & 1023u)) & 1023u));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -723,7 +723,10 @@ attn_project_pack_kernel(const float* __restrict__ source, const float* __restri
   const int win = blockIdx.y % (g.splits * g.splits), b = blockIdx.y / (g.splits * g.splits);
   const int wy = win / g.splits, wx = win - wy * g.splits;
   const int mat = blockIdx.z;
-  const float* x = (mat == 0 ? source : target) + (size_t)b * g.h * g.w * kC;
+  // keys / values of batch item b come from target[(b + target_roll) % B]: FeatureTransformer's "the other view of the pair"
+  // (torch.cat([x[b:], x[:b]]), transformer.py:331) without materialising the concatenation
+  const int n_batch = gridDim.y / (g.splits * g.splits);
+  const float* x = mat == 0 ? source + (size_t)b * g.h * g.w * kC : target + (size_t)((b + target_roll) % n_batch) * g.h * g.w * kC;
   if (tid == 0) {
     tc::mbar_init(&sm.w_full, 1);
     tc::mbar_init(&sm.d_full, 1);
@@ -859,7 +862,7 @@ int launch_window_attn_pack_proj_weights(const float* wq, const float* wk, const
 
 // attention(q_proj(source), k_proj(target), v_proj(target)): projection + operand packing kernel, then the v4 attention kernel
 int launch_window_attn_proj_tc(const float* source, const float* target, const void* proj_weights, float* out, int B, int h, int w,
-                               int num_splits, int with_shift, void* workspace, int64_t workspace_bytes, cudaStream_t s) {
+                               int num_splits, int with_shift, int target_roll, void* workspace, int64_t workspace_bytes, cudaStream_t s) {
   WinGeomTc g;
   g.h = h; g.w = w; g.splits = num_splits;
   g.wh = h / num_splits; g.ww = w / num_splits;
@@ -881,7 +884,7 @@ int launch_window_attn_proj_tc(const float* source, const float* target, const v
   }
   dim3 pgrid(grid.x, grid.y, 3);
   attn_project_pack_kernel<<<pgrid, kProjThreads, psmem, s>>>(source, target, reinterpret_cast<const unsigned char*>(proj_weights),
-                                                              reinterpret_cast<unsigned char*>(workspace), g);
+                                                              reinterpret_cast<unsigned char*>(workspace), g, ((target_roll % B) + B) % B);
   MNF_CUDA_TRY(cudaGetLastError());
   window_attn_tc_v4_kernel<<<grid, kV4Threads, smem, s>>>(reinterpret_cast<const unsigned char*>(workspace), out, g);
   MNF_CUDA_TRY(cudaGetLastError());

@@ -98,7 +98,7 @@ class CNNEncoder(nn.Module):
             self._f16_cache = (key, conv)
         return self._f16_cache[1]
 
-    def _forward_nhwc(self, x):
+    def _forward_nhwc(self, x, keep_nhwc: bool = False):
         ctx = capi.get_context(x.device)
         P = self._nhwc_params()
 
@@ -115,7 +115,8 @@ class CNNEncoder(nn.Module):
                 if (pre + ".downsample.0") in P:
                     h = ctx.instance_norm_nhwc(conv(h, pre + ".downsample.0"), 0)
                 h = ctx.instance_norm_nhwc(y2, 2, h)             # relu(x + relu(IN(conv2(y))))
-        return conv(h, "conv2").float().contiguous()
+        out = conv(h, "conv2").float()
+        return out if keep_nhwc else out.contiguous()      # keep_nhwc: channels_last strides (the token layout of the transformer)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -149,13 +150,17 @@ class TransformerLayer(nn.Module):
                                      nn.Linear(c * ffn_dim_expansion, d_model, bias=False))
             self.norm2 = nn.LayerNorm(d_model)
 
-    def forward(self, source, target, height: int, width: int, attn_num_splits: int):
+    def forward(self, source, target, height: int, width: int, attn_num_splits: int, target_roll: int = 0):
+        """``target_roll`` r (not in the reference): keys / values of batch item b come from ``target[(b + r) % B]`` -- lets
+        FeatureTransformer pair every view with the other one without materialising ``cat([x[b:], x[:b]])``."""
         shift = self.with_shift and attn_num_splits > 1
+        if target_roll and not (self.fused_proj and self._fused_norms(source)):
+            target, target_roll = torch.roll(target, -target_roll, 0), 0
         if self.fused_proj and self._fused_norms(source):
             # inference on the GPU: the three projections run inside the kernel that builds the attention operands
             # (mnf_window_attn_proj_fwd): no fp32 q / k / v tensors, no pre-pack pass
             ctx = capi.get_context(source.device)
-            msg = ctx.window_attn_proj(source, target, self._proj_weights(ctx), height, width, attn_num_splits, shift)
+            msg = ctx.window_attn_proj(source, target, self._proj_weights(ctx), height, width, attn_num_splits, shift, target_roll)
         else:
             msg = window_attention(self.q_proj(source), self.k_proj(target), self.v_proj(target), height, width,
                                    attn_num_splits, shift)
@@ -234,10 +239,10 @@ class TransformerBlock(nn.Module):
         self.self_attn = TransformerLayer(d_model, True, ffn_dim_expansion, with_shift)
         self.cross_attn_ffn = TransformerLayer(d_model, False, ffn_dim_expansion, with_shift)
 
-    def forward(self, source, target, height, width, attn_num_splits, wo_self_attn=False):
+    def forward(self, source, target, height, width, attn_num_splits, wo_self_attn=False, target_roll: int = 0):
         if not wo_self_attn:
             source = self.self_attn(source, source, height, width, attn_num_splits)
-        return self.cross_attn_ffn(source, target, height, width, attn_num_splits)
+        return self.cross_attn_ffn(source, target, height, width, attn_num_splits, target_roll)
 
 
 class FeatureTransformer(nn.Module):
@@ -260,6 +265,13 @@ class FeatureTransformer(nn.Module):
             x = layer(x, y, h, w, attn_num_splits, wo_self_attn)
         x = x.transpose(1, 2).reshape(2 * b, c, h, w)
         return x[:b].contiguous(), x[b:].contiguous()
+
+    def forward_tokens(self, x, b: int, h: int, w: int, attn_num_splits: int, wo_self_attn: bool = False):
+        """The same layers on tokens: x [2b, h*w, C] (first b items = feature0 of the pairs, last b = feature1) -> [2b, h*w, C].
+        The other view's tokens from before the block (:331) are addressed by a batch roll inside the attention kernel."""
+        for layer in self.layers:
+            x = layer(x, x, h, w, attn_num_splits, wo_self_attn, target_roll=b)
+        return x
 
 
 def sine_position(hw: int, ww: int, channels: int, device, dtype=torch.float32):
@@ -366,27 +378,75 @@ class GMFlow(nn.Module):
         with _matmul_precision(self.matmul_precision):
             return self._forward(imgs, attn_splits_list, keep_raw_feats, wo_self_attn, pair_ids)
 
+    def _position(self, h, w, splits, device):
+        pkey = (h, w, splits, device)
+        if getattr(self, "_pos_cache", None) is None or self._pos_cache[0] != pkey:
+            pos = sine_position(h // splits, w // splits, self.feature_channels, device).repeat(1, splits, splits)
+            self._pos_cache = (pkey, pos, pos.permute(1, 2, 0).reshape(h * w, self.feature_channels).contiguous())
+        return self._pos_cache[1]
+
+    # Inference on the GPU keeps the activations in ONE layout from the backbone's last convolution to the up-sampler's first:
+    # channels-last == tokens [image, h*w, C].  The reference-shaped path around the transformer (stack the pairs in NCHW, add the
+    # position, cat + transpose to tokens, per-block cat of the swapped halves, transpose back, cat + convert for the up-sampler)
+    # was ~25 copy / add kernels per encoder call; here: one add (position, V images), one gather (pairs), views.
+    token_path = os.environ.get("MNF_TOKEN_PATH", "1") != "0"
+
+    def _token_path_ok(self, imgs) -> bool:
+        return (self.token_path and imgs.is_cuda and imgs.dtype == torch.float32 and not torch.is_grad_enabled()
+                and self.backbone.fast_dtype is not None and TransformerLayer.fused_proj and TransformerLayer.fused_block
+                and TransformerLayer.ffn_dtype == torch.float16 and self.feature_channels == 128)
+
+    def _forward_tokens(self, imgs, B, V, pairs, splits, keep_raw_feats, wo_self_attn):
+        C = self.feature_channels
+        base = self.backbone._forward_nhwc(self.normalize_images(imgs).reshape(B * V, 3, *imgs.shape[-2:]), keep_nhwc=True)
+        h, w = base.shape[-2:]
+        if h % splits or w % splits:
+            raise ValueError(f"feature map {h}x{w} not divisible by attn_splits {splits}")
+        tok = base.permute(0, 2, 3, 1).reshape(B * V, h * w, C)              # a view of the channels-last convolution output
+        self._position(h, w, splits, base.device)
+        tok = tok + self._pos_cache[2]
+        P = len(pairs)
+        ikey = (B, V, tuple(pairs), base.device)
+        if getattr(self, "_pair_index", None) is None or self._pair_index[0] != ikey:
+            idx = [b * V + a for b in range(B) for a, _ in pairs] + [b * V + c for b in range(B) for _, c in pairs]
+            self._pair_index = (ikey, torch.tensor(idx, dtype=torch.long, device=base.device))
+        x = tok.index_select(0, self._pair_index[1])                         # [2BP, hw, C]: feature0 of every pair, then feature1
+        x = self.transformer.forward_tokens(x, B * P, h, w, splits, wo_self_attn)
+        xv = x.view(2 * B * P, h, w, C).permute(0, 3, 1, 2)                  # [2BP, C, h, w] with channels-last strides (no copy)
+        out0, out1 = [], []
+        if keep_raw_feats:
+            raw = xv.contiguous()                                            # NCHW, as the reference-shaped path returns them
+            out0.append(raw[: B * P].reshape(B, P, C, h, w))
+            out1.append(raw[B * P:].reshape(B, P, C, h, w))
+        if self.feature_upsampler == "network":
+            up = self.featup_net(xv.contiguous(memory_format=self.upsampler_memory_format))   # already channels-last: no copy
+            f0, f1 = up[: B * P], up[B * P:]
+        else:
+            f0, f1 = xv[: B * P], xv[B * P:]
+        out0.append(f0.reshape(B, P, *f0.shape[1:]))
+        out1.append(f1.reshape(B, P, *f1.shape[1:]))
+        return {"aug_feat0s": out0, "aug_feat1s": out1}
+
     def _forward(self, imgs, attn_splits_list, keep_raw_feats, wo_self_attn, pair_ids=None):
         B, V, _, H, W = imgs.shape
         if H == 756 and W == 1008:     # IBRNet setting: pad to a size divisible by 16 (gmflow.py:99-103)
             imgs = F.interpolate(imgs.reshape(B * V, 3, H, W), size=(768, 1024), mode="bilinear",
                                  align_corners=True).reshape(B, V, 3, 768, 1024)
         splits = int((attn_splits_list or [2])[0])
-        base = self.backbone(self.normalize_images(imgs).reshape(B * V, 3, *imgs.shape[-2:])
-                             .contiguous(memory_format=self.backbone_memory_format))
-        base = base.reshape(B, V, *base.shape[1:])
         pairs = [(a, b) for a in range(V - 1) for b in range(a + 1, V)]
         if pair_ids is not None:
             pairs = [pairs[i] for i in pair_ids]
+        if self._token_path_ok(imgs):
+            return self._forward_tokens(imgs, B, V, pairs, splits, keep_raw_feats, wo_self_attn)
+        base = self.backbone(self.normalize_images(imgs).reshape(B * V, 3, *imgs.shape[-2:])
+                             .contiguous(memory_format=self.backbone_memory_format))
+        base = base.reshape(B, V, *base.shape[1:])
         f0 = torch.stack([base[:, a] for a, _ in pairs], 1).flatten(0, 1)        # [B*P, C, h, w]
         f1 = torch.stack([base[:, b] for _, b in pairs], 1).flatten(0, 1)
         h, w = f0.shape[-2:]
         if h % splits or w % splits:
             raise ValueError(f"feature map {h}x{w} not divisible by attn_splits {splits}")
-        pkey = (h, w, splits, f0.device)
-        if getattr(self, "_pos_cache", None) is None or self._pos_cache[0] != pkey:
-            self._pos_cache = (pkey, sine_position(h // splits, w // splits, self.feature_channels, f0.device).repeat(1, splits, splits))
-        pos = self._pos_cache[1]
+        pos = self._position(h, w, splits, f0.device)
         f0, f1 = self.transformer(f0 + pos, f1 + pos, splits, wo_self_attn)
         P = len(pairs)
         out0, out1 = [], []

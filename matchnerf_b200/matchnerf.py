@@ -99,7 +99,7 @@ class MatchNeRF(nn.Module):
         params = tuple(enc.parameters())
         from .gmflow import TransformerLayer
         key = (tuple(imgs.shape), imgs.device, tuple(attn_splits_list), cur_n_src_views, enc.matmul_precision,
-               str(TransformerLayer.ffn_dtype), bool(TransformerLayer.fused_block), bool(TransformerLayer.fused_proj), str(getattr(enc.backbone, "fast_dtype", None)), bool(get_opt(self.opts, "encoder.wo_self_attn", False)),
+               str(TransformerLayer.ffn_dtype), bool(TransformerLayer.fused_block), bool(TransformerLayer.fused_proj), bool(getattr(enc, 'token_path', False)), str(getattr(enc.backbone, "fast_dtype", None)), bool(get_opt(self.opts, "encoder.wo_self_attn", False)),
                None if pair_ids is None else tuple(pair_ids), tuple(p.data_ptr() for p in params), sum(p._version for p in params))
         hit = getattr(self, "_enc_graph", None)
         if hit is None or hit[0] != key:

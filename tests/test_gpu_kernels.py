@@ -461,6 +461,10 @@ def test_window_attn_fused_projection(ctx, h, w, splits, shift, cross):
     assert rms(got[:1], oracle) < 3e-3 * sd and max_abs(got[:1], oracle) < 3e-2 * max(1.0, sd), (rms(got[:1], oracle), sd)
     unfused = ctx.window_attn(src.to(DEV) @ wq.to(DEV).T, tgt.to(DEV) @ wk.to(DEV).T, tgt.to(DEV) @ wv.to(DEV).T, h, w, splits, shift, impl=2)
     assert rms(got, unfused) < 3e-3 * float(unfused.std())
+    # target_batch_roll: keys / values of item b from target[(b + 1) % B] == the same call on the rolled tensor, bit for bit
+    rolled = ctx.window_attn_proj(src.to(DEV), tgt.to(DEV), blob, h, w, splits, shift, target_roll=1)
+    explicit = ctx.window_attn_proj(src.to(DEV), torch.roll(tgt, -1, 0).to(DEV), blob, h, w, splits, shift)
+    assert torch.equal(rolled, explicit) and (not cross or not torch.equal(rolled, got))
 
 
 @pytest.mark.parametrize("rows", [1, 37, 5120 * 6])

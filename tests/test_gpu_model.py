@@ -41,6 +41,30 @@ def test_encoder_matches_reference_golden(golden_dir):
     assert rms(f4[0][:, ::8], z["feat4_ch0mod8"]) < 2.5e-3 * scale
 
 
+def test_encoder_token_path_equals_reference_shaped_path():
+    """GMFlow._forward_tokens (activations kept in the token / channels-last layout, the other view addressed by a batch roll inside
+    the attention kernel) vs the reference-shaped glue around the same kernels (NCHW stacks, cat + transpose, per-block cat of the
+    swapped halves): identical bits, for all pairs and for a pair subset (the multi-GPU encoder split)."""
+    from matchnerf_b200.gmflow import GMFlow
+    m, opt = build_model(16)
+    m.encoder_cuda_graph = False
+    imgs = torch.rand(2, 3, 3, 64, 96, generator=torch.Generator().manual_seed(9)).to(DEV)
+    enc = m.feat_enc
+    with torch.no_grad():
+        for pair_ids in (None, [2, 0]):
+            assert enc._token_path_ok(imgs)
+            a = enc(imgs=imgs, attn_splits_list=[2], keep_raw_feats=True, pair_ids=pair_ids)
+            GMFlow.token_path = False
+            try:
+                b = enc(imgs=imgs, attn_splits_list=[2], keep_raw_feats=True, pair_ids=pair_ids)
+            finally:
+                GMFlow.token_path = True
+            for k in ("aug_feat0s", "aug_feat1s"):
+                assert len(a[k]) == len(b[k]) == 2
+                for x, y in zip(a[k], b[k]):
+                    assert x.shape == y.shape and torch.equal(x, y)
+
+
 @pytest.mark.parametrize("local", [(0, 1), (1, 2)])
 def test_forward_small_image_vs_oracle(local):
     """forward(mode='test') on a 64x96 triplet: encoder + full-image render, vs the CPU oracle chain; also with
