@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MNF_ABI_VERSION 8
+#define MNF_ABI_VERSION 9
 
 typedef enum mnf_status {
   MNF_OK = 0,
@@ -248,6 +248,20 @@ int32_t mnf_window_attn_pack_proj_weights(mnf_ctx* ctx, const float* q_proj_w, c
 int32_t mnf_window_attn_proj_fwd(mnf_ctx* ctx, const float* source, const float* target, const void* proj_weights_packed, float* out,
                                  int32_t B, int32_t h, int32_t w, int32_t C, int32_t num_splits, int32_t with_shift, int32_t target_batch_roll,
                                  void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- evaluation metrics of a rendered view: PSNR and SSIM sums ------------------------------ */
+/* Replaces EvalTools.set_inputs / get_psnr / get_ssim (misc/metrics.py:19-46; SSIM = scikit-image 0.19.2 structural_similarity with
+ * its defaults: 7 x 7 uniform window, sample covariance, K1 0.01, K2 0.03, 3-pixel border cropped) without copying the images to the
+ * host.  pred_hwc, gt_hwc: [H][W][3] fp32; mask_hw: [H][W] bytes (non-zero = masked OUT, e.g. DTU depth == 0) or NULL.
+ * The metrics are evaluated on the region rows [y0, y0 + region_h) x columns [x0, x0 + region_w) (whole image, or the reference's
+ * 80 % centre crop); masked pixels count as 0 in both images for SSIM and are left out of the PSNR mean.  data_range: the reference
+ * gets 2.0 (skimage's range for float images).  out_sums4 (device, 4 doubles, overwritten):
+ *   [0] sum of squared differences over unmasked region pixels x 3 channels   [1] their element count
+ *   [2] sum of the SSIM map over interior pixels x 3 channels                 [3] its element count
+ * PSNR = -10 log10([0] / [1]),  SSIM = [2] / [3]. */
+int32_t mnf_image_metrics_fwd(mnf_ctx* ctx, const float* pred_hwc, const float* gt_hwc, const uint8_t* mask_hw, int32_t H, int32_t W,
+                              int32_t y0, int32_t x0, int32_t region_h, int32_t region_w, float data_range, double* out_sums4,
+                              void* stream);
 
 /* ---- self tests of the tcgen05 building blocks (used by tests/ on the GPU box) ------------- */
 /* D[128][N] = A[128][K] * B[N][K]^T with fp16 operands, fp32 accumulate, one CTA.

@@ -15,7 +15,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MNF_LIB_PATH") or os.path.join(_HERE, "libmatchnerf_b200.so")   # override: A/B builds (tools/)
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 COND_DIM = 22
 COND_PAD = 32
 FEAT_CH = 256
@@ -97,13 +97,14 @@ def load() -> C.CDLL:
     lib.mnf_window_attn_proj_weight_bytes.restype = i64
     lib.mnf_window_attn_pack_proj_weights.argtypes = [vp, fp, fp, fp, vp, vp]
     lib.mnf_window_attn_proj_fwd.argtypes = [vp, fp, fp, vp, fp, i32, i32, i32, i32, i32, i32, i32, vp, i64, vp]
+    lib.mnf_image_metrics_fwd.argtypes = [vp, fp, fp, vp, i32, i32, i32, i32, i32, i32, C.c_float, vp, vp]
     lib.mnf_selftest_umma.argtypes = [vp, vp, fp, i32, i32, i32, vp]
     for name in ("mnf_ctx_create", "mnf_ctx_destroy", "mnf_decoder_load_host", "mnf_pack_features", "mnf_pack_images",
                  "mnf_gather_cossim_fwd", "mnf_decoder_composite_fwd", "mnf_render_rays_fwd", "mnf_window_attn_fwd",
                  "mnf_selftest_umma", "mnf_query_cond_points_fwd", "mnf_decoder_samples_fwd", "mnf_composite_fwd",
                  "mnf_instance_norm_fwd", "mnf_token_layernorm_fwd", "mnf_gather_cossim_bwd",
                  "mnf_instance_norm_nhwc_fwd", "mnf_token_block_pack_weights", "mnf_token_block_fwd",
-                 "mnf_window_attn_pack_proj_weights", "mnf_window_attn_proj_fwd"):
+                 "mnf_window_attn_pack_proj_weights", "mnf_window_attn_proj_fwd", "mnf_image_metrics_fwd"):
         getattr(lib, name).restype = i32
     if lib.mnf_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libmatchnerf_b200.so ABI {lib.mnf_abi_version()} != {ABI_VERSION}")
@@ -493,6 +494,26 @@ class Context:
                                                  num_splits, int(with_shift), int(target_roll), ws.data_ptr(), ws.numel(),
                                                  _stream(self.device)),
                "mnf_window_attn_proj_fwd")
+        return out
+
+    def image_metrics(self, pred: torch.Tensor, gt: torch.Tensor, mask: Optional[torch.Tensor] = None, region=None,
+                      data_range: float = 2.0) -> torch.Tensor:
+        """PSNR / SSIM sums of a rendered view (mnf_image_metrics_fwd): pred, gt [H,W,3] fp32 on this device, mask [H,W] bool / uint8
+        (True = masked out) or None, region = (y0, x0, h, w) or None (whole image).  Returns 4 doubles ON THE DEVICE:
+        (squared-error sum, element count, SSIM-map sum, element count)."""
+        p, g = _dev_f32(pred, self.device, "pred"), _dev_f32(gt, self.device, "gt")
+        if p.dim() != 3 or p.shape[-1] != 3 or g.shape != p.shape:
+            raise ValueError(f"pred {tuple(p.shape)} / gt {tuple(g.shape)}: expected equal [H, W, 3] shapes")
+        H, W = int(p.shape[0]), int(p.shape[1])
+        m = None
+        if mask is not None:
+            if mask.device != self.device or tuple(mask.shape) != (H, W):
+                raise ValueError("mask must be [H, W] on the context's device")
+            m = mask.to(torch.uint8).contiguous()
+        y0, x0, rh, rw = (0, 0, H, W) if region is None else (int(v) for v in region)
+        out = torch.empty(4, dtype=torch.float64, device=self.device)
+        _check(self.lib.mnf_image_metrics_fwd(self._h, p.data_ptr(), g.data_ptr(), _ptr(m), H, W, y0, x0, rh, rw, float(data_range),
+                                              out.data_ptr(), _stream(self.device)), "mnf_image_metrics_fwd")
         return out
 
     def selftest_umma(self, a: torch.Tensor, b: torch.Tensor, mode: int) -> torch.Tensor:

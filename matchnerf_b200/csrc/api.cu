@@ -469,6 +469,19 @@ int32_t mnf_token_layernorm_fwd(mnf_ctx* ctx, const void* x, int32_t x_is_f16, c
                                 (cudaStream_t)stream);
 }
 
+int32_t mnf_image_metrics_fwd(mnf_ctx* ctx, const float* pred_hwc, const float* gt_hwc, const uint8_t* mask_hw, int32_t H, int32_t W,
+                              int32_t y0, int32_t x0, int32_t region_h, int32_t region_w, float data_range, double* out_sums4, void* stream) {
+  DeviceGuard dev_guard(ctx);
+  if (!ctx || !pred_hwc || !gt_hwc || !out_sums4) { set_error("mnf_image_metrics_fwd: NULL argument"); return MNF_EINVAL; }
+  if (H <= 0 || W <= 0 || y0 < 0 || x0 < 0 || region_h < 0 || region_w < 0 || y0 + region_h > H || x0 + region_w > W) {
+    set_error("mnf_image_metrics_fwd: region [%d, %d) x [%d, %d) outside the %d x %d image", y0, y0 + region_h, x0, x0 + region_w, H, W);
+    return MNF_EINVAL;
+  }
+  if (!(data_range > 0.f)) { set_error("mnf_image_metrics_fwd: data_range must be positive"); return MNF_EINVAL; }
+  if (((uintptr_t)out_sums4 & 7) != 0) { set_error("mnf_image_metrics_fwd: out_sums4 must be 8-byte aligned"); return MNF_EINVAL; }
+  return launch_image_metrics(pred_hwc, gt_hwc, mask_hw, H, W, y0, x0, region_h, region_w, data_range, out_sums4, (cudaStream_t)stream);
+}
+
 int64_t mnf_token_block_weight_bytes(int32_t with_ffn) { return token_block_weight_bytes(with_ffn); }
 
 int32_t mnf_token_block_pack_weights(mnf_ctx* ctx, const float* merge_w, const float* norm1_w, const float* norm1_b, const float* mlp0_w,

@@ -185,6 +185,10 @@ int launch_token_block_pack(const float* merge_w, const float* g1, const float* 
 int launch_token_block(const float* attn, const float* source, const void* weights, int with_ffn, float eps, float* out, int64_t T,
                        cudaStream_t s);
 
+// metrics.cu: masked / cropped PSNR + SSIM sums of a rendered view (misc/metrics.py)
+int launch_image_metrics(const float* pred, const float* gt, const unsigned char* mask, int H, int W, int y0, int x0, int rh, int rw,
+                         float data_range, double* out4, cudaStream_t s);
+
 int launch_window_attn_ref(const float* q, const float* k, const float* v, float* out, int B, int h, int w, int C,
                            int num_splits, int with_shift, cudaStream_t s);
 
