@@ -177,9 +177,19 @@ instance_norm_nhwc_stats_kernel(const T* __restrict__ x, float* __restrict__ par
   if (last) {
     __threadfence();
     const float* img = partial + (size_t)n * n_chunks * 2 * C;
+    // (ncu / launch list: this tail was most of the kernel -- one thread walked the image's ~200 partial sums with ONE dependent
+    // L2 load in flight, ~250 cycles each.  Sixteen loads per step now; the additions keep the chunk order: same bits.)
     for (int j = tid; j < 2 * C; j += kNhwcThreads) {
       float a = 0.f;
-      for (int c = 0; c < n_chunks; ++c) a += __ldcg(img + (size_t)c * 2 * C + j);
+      int c = 0;
+      for (; c + 16 <= n_chunks; c += 16) {
+        float v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] = __ldcg(img + (size_t)(c + u) * 2 * C + j);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) a += v[u];
+      }
+      for (; c < n_chunks; ++c) a += __ldcg(img + (size_t)c * 2 * C + j);
       stats[(size_t)n * 2 * C + j] = a;
     }
     if (tid == 0) counters[n] = 0u;                            // ready for the next call (stream-ordered)

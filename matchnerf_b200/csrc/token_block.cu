@@ -15,11 +15,11 @@
 //     acc2     += H[j&1] (TMEM) . W2_j^T                          tcgen05.mma TS, 8 K-steps
 // with the weights streamed through an 8-stage shared-memory ring of pre-swizzled 16 KB tiles (cp.async.bulk + mbarrier tx).
 //
-// One persistent CTA per SM, 384 threads:
+// One persistent CTA per SM, 640 threads:
 //   warp 0       weight streamer (one lane)
 //   warp 1       MMA issuer (one elected lane), owns the TMEM allocation
-//   warps 4-11   8 epilogue warps: thread = token row = TMEM lane (warp % 4 = lane quarter), two warps per quarter split the
-//                128 columns of an accumulator in halves.  They also load + convert the tile's inputs (prologue), evaluate both
+//   warps 4-19   16 epilogue warps: thread = token row = TMEM lane (warp % 4 = lane quarter), four warps per quarter split the
+//                128 columns of an accumulator in 32-column quarters.  They also load + convert the tile's inputs (prologue), evaluate both
 //                LayerNorms (a thread sees its whole row in TMEM: no cross-thread reduction) and write the result.
 // TMEM (512 columns): acc1[0] [0,128)  acc1[1] [128,256)  acc2 [256,384)  H[0] [384,448)  H[1] [448,512).
 // Shared memory: X = 4 K-blocks [128 rows][64 fp16] SWIZZLE_128B (K-blocks 0,1 = source, 2,3 = LN1 output; before the merge
@@ -41,8 +41,9 @@ constexpr int kHid = 1024;                   // ffn hidden width (2 * d_model * 
 constexpr int kHidChunks = kHid / 128;       // 8
 constexpr int kTileBytes = 128 * 128;        // one [128 rows][64 fp16] SWIZZLE_128B tile
 constexpr int kStages = 8;
-constexpr int kThreads = 384;
-constexpr int kEpiThreads = 256;
+constexpr int kEpiWarps = 16;
+constexpr int kThreads = (4 + kEpiWarps) * 32;      // 640
+constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr uint32_t kColAcc1 = 0, kColAcc2 = 256, kColH = 384;
 constexpr int kTilesFfn = 2 + 32 + 16, kTilesNoFfn = 2;
 
@@ -240,7 +241,10 @@ token_block_kernel(const float* __restrict__ attn, const float* __restrict__ sou
     }
   } else if (warp >= 4) {
     // ================================================================== epilogue warps
-    const int ew = warp - 4, q = warp & 3, hf = ew >> 2;
+    // ncu of the first version (8 warps, 64 columns per thread): tensor pipe 27 %, issue slots 34 %, 3 long-scoreboard stalls per
+    // issue -- two warps per scheduler cannot hide the tcgen05.ld round trips and the MUFU / FMA chains of the GELU, the epilogue
+    // (not the MMAs) set the pace.  Now 16 warps: four per lane quarter, 32 columns each, both loads of a chunk in flight at once.
+    const int ew = warp - 4, q = warp & 3, cq = ew >> 2;       // cq: which 32 of the 128 columns
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
     uint32_t G = 0, C = 0, it = 0;
@@ -248,11 +252,11 @@ token_block_kernel(const float* __restrict__ attn, const float* __restrict__ sou
       const int64_t tok0 = tile * kTok;
       // ---- prologue: attention tile -> X K-blocks 2,3; source tile -> X K-blocks 0,1 (fp16, swizzled).  A warp reads whole rows.
 #pragma unroll
-      for (int rr = 0; rr < 16; rr += 4) {
+      for (int rr = 0; rr < kTok / kEpiWarps; rr += 4) {
         float4 a[4], s[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int64_t g = tok0 + ew * 16 + rr + u;
+          const int64_t g = tok0 + ew * (kTok / kEpiWarps) + rr + u;
           if (g < T) {
             a[u] = __ldg(reinterpret_cast<const float4*>(attn + g * kCh) + lane);
             s[u] = __ldg(reinterpret_cast<const float4*>(source + g * kCh) + lane);
@@ -263,7 +267,7 @@ token_block_kernel(const float* __restrict__ attn, const float* __restrict__ sou
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const uint32_t r = ew * 16 + rr + u;
+          const uint32_t r = ew * (kTok / kEpiWarps) + rr + u;
           const uint32_t off = (uint32_t)(lane >> 4) * kTileBytes + tc::sw128_offset(r, (lane & 15) * 4);
           *reinterpret_cast<uint2*>(sX + 2 * kTileBytes + off) = make_uint2(pack_h2(a[u].x, a[u].y), pack_h2(a[u].z, a[u].w));
           *reinterpret_cast<uint2*>(sX + off) = make_uint2(pack_h2(s[u].x, s[u].y), pack_h2(s[u].z, s[u].w));
@@ -274,8 +278,8 @@ token_block_kernel(const float* __restrict__ attn, const float* __restrict__ sou
 
       const int64_t g = tok0 + row;
       const bool valid = g < T;
-      const float* src_row = source + (valid ? g : 0) * kCh + hf * 64;
-      float* out_row = out + (valid ? g : 0) * kCh + hf * 64;
+      const float* src_row = source + (valid ? g : 0) * kCh + cq * 32;
+      float* out_row = out + (valid ? g : 0) * kCh + cq * 32;
       // ---- LayerNorm 1 on the merge product
       {
         const uint32_t b = G & 1u;
@@ -285,35 +289,32 @@ token_block_kernel(const float* __restrict__ attn, const float* __restrict__ sou
         const uint32_t acc = lane_addr + kColAcc1 + b * 128;
         float mean, rstd;
         row_stats(acc, eps, mean, rstd);
+        uint32_t r[32];
+        tc::tmem_ld32(acc + cq * 32, r);
+        tc::tmem_wait_ld(r);
+        float y[32];
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          uint32_t r[16];
-          tc::tmem_ld16(acc + hf * 64 + c4 * 16, r);
-          tc::tmem_wait_ld(r);
-          float y[16];
+        for (int i = 0; i < 32; i += 4) {
+          const int col = cq * 32 + i;
+          const float4 gm = __ldg(reinterpret_cast<const float4*>(ln + col));
+          const float4 bt = __ldg(reinterpret_cast<const float4*>(ln + 128 + col));
+          y[i + 0] = fmaf((__uint_as_float(r[i + 0]) - mean) * rstd, gm.x, bt.x);
+          y[i + 1] = fmaf((__uint_as_float(r[i + 1]) - mean) * rstd, gm.y, bt.y);
+          y[i + 2] = fmaf((__uint_as_float(r[i + 2]) - mean) * rstd, gm.z, bt.z);
+          y[i + 3] = fmaf((__uint_as_float(r[i + 3]) - mean) * rstd, gm.w, bt.w);
+        }
+        if (with_ffn) {
 #pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            const int col = hf * 64 + c4 * 16 + i;
-            const float4 gm = __ldg(reinterpret_cast<const float4*>(ln + col));
-            const float4 bt = __ldg(reinterpret_cast<const float4*>(ln + 128 + col));
-            y[i + 0] = fmaf((__uint_as_float(r[i + 0]) - mean) * rstd, gm.x, bt.x);
-            y[i + 1] = fmaf((__uint_as_float(r[i + 1]) - mean) * rstd, gm.y, bt.y);
-            y[i + 2] = fmaf((__uint_as_float(r[i + 2]) - mean) * rstd, gm.z, bt.z);
-            y[i + 3] = fmaf((__uint_as_float(r[i + 3]) - mean) * rstd, gm.w, bt.w);
+          for (int h8 = 0; h8 < 4; ++h8) {
+            const uint4 pk = make_uint4(pack_h2(y[h8 * 8 + 0], y[h8 * 8 + 1]), pack_h2(y[h8 * 8 + 2], y[h8 * 8 + 3]),
+                                        pack_h2(y[h8 * 8 + 4], y[h8 * 8 + 5]), pack_h2(y[h8 * 8 + 6], y[h8 * 8 + 7]));
+            *reinterpret_cast<uint4*>(sX + (2 + (cq >> 1)) * kTileBytes + tc::sw128_offset(row, (cq & 1) * 32 + h8 * 8)) = pk;
           }
-          if (with_ffn) {
+        } else if (valid) {
 #pragma unroll
-            for (int h8 = 0; h8 < 2; ++h8) {
-              const uint4 pk = make_uint4(pack_h2(y[h8 * 8 + 0], y[h8 * 8 + 1]), pack_h2(y[h8 * 8 + 2], y[h8 * 8 + 3]),
-                                          pack_h2(y[h8 * 8 + 4], y[h8 * 8 + 5]), pack_h2(y[h8 * 8 + 6], y[h8 * 8 + 7]));
-              *reinterpret_cast<uint4*>(sX + (2 + hf) * kTileBytes + tc::sw128_offset(row, c4 * 16 + h8 * 8)) = pk;
-            }
-          } else if (valid) {
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              const float4 s4 = __ldg(reinterpret_cast<const float4*>(src_row + c4 * 16 + i));
-              *reinterpret_cast<float4*>(out_row + c4 * 16 + i) = make_float4(s4.x + y[i], s4.y + y[i + 1], s4.z + y[i + 2], s4.w + y[i + 3]);
-            }
+          for (int i = 0; i < 32; i += 4) {
+            const float4 s4 = __ldg(reinterpret_cast<const float4*>(src_row + i));
+            *reinterpret_cast<float4*>(out_row + i) = make_float4(s4.x + y[i], s4.y + y[i + 1], s4.z + y[i + 2], s4.w + y[i + 3]);
           }
         }
         tc::tc_fence_before_sync();
@@ -324,28 +325,27 @@ token_block_kernel(const float* __restrict__ attn, const float* __restrict__ sou
         tc::mbar_arrive(&sm.acc1_empty[b]);
       }
       if (!with_ffn) continue;
-      // ---- hidden chunks: H[hb] = fp16(GELU(acc1[b])), this warp's 64 columns
+      // ---- hidden chunks: H[hb] = fp16(GELU(acc1[b])), this warp's 32 columns
       for (int j = 0; j < kHidChunks; ++j) {
         const uint32_t b = G & 1u, hb = C & 1u;
         tc::mbar_wait(&sm.acc1_full[b], (G >> 1) & 1u);
-        tc::mbar_wait(&sm.h_empty[hb], ((C >> 1) & 1u) ^ 1u);
         tc::tc_fence_after_sync();
         ++G;
+        uint32_t r0[16], r1[16];
+        const uint32_t acc = lane_addr + kColAcc1 + b * 128 + cq * 32;
+        tc::tmem_ld16(acc, r0);
+        tc::tmem_ld16(acc + 16, r1);
+        tc::mbar_wait(&sm.h_empty[hb], ((C >> 1) & 1u) ^ 1u);      // FFN2 of chunk j - 2 has read H[hb] (long done: no stall in steady state)
         ++C;
-        const uint32_t acc = lane_addr + kColAcc1 + b * 128 + hf * 64;
-        const uint32_t hdst = lane_addr + kColH + hb * 64 + hf * 32;
-        uint32_t r[2][16];
-        tc::tmem_ld16(acc, r[0]);
+        uint32_t pk[16];
+        tc::tmem_wait_ld(r0);
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          tc::tmem_wait_ld(r[c4 & 1]);
-          if (c4 < 3) tc::tmem_ld16(acc + (c4 + 1) * 16, r[(c4 + 1) & 1]);      // next chunk in flight under the math
-          uint32_t pk[8];
+        for (int i = 0; i < 8; ++i) pk[i] = pack_h2(gelu_erf(__uint_as_float(r0[2 * i])), gelu_erf(__uint_as_float(r0[2 * i + 1])));
+        tc::tmem_wait_ld(r1);
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            pk[i] = pack_h2(gelu_erf(__uint_as_float(r[c4 & 1][2 * i])), gelu_erf(__uint_as_float(r[c4 & 1][2 * i + 1])));
-          tc::tmem_st8(hdst + c4 * 8, pk);
-        }
+        for (int i = 0; i < 8; ++i) pk[8 + i] = pack_h2(gelu_erf(__uint_as_float(r1[2 * i])), gelu_erf(__uint_as_float(r1[2 * i + 1])));
+        tc::tc_fence_after_sync();
+        tc::tmem_st16(lane_addr + kColH + hb * 64 + cq * 16, pk);
         tc::tmem_wait_st();
         tc::tc_fence_before_sync();
         tc::mbar_arrive(&sm.h_ready[hb]);
@@ -358,25 +358,22 @@ token_block_kernel(const float* __restrict__ attn, const float* __restrict__ sou
         const uint32_t acc = lane_addr + kColAcc2;
         float mean, rstd;
         row_stats(acc, eps, mean, rstd);
+        uint32_t r[32];
+        tc::tmem_ld32(acc + cq * 32, r);
+        tc::tmem_wait_ld(r);
+        if (valid) {
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          uint32_t r[16];
-          tc::tmem_ld16(acc + hf * 64 + c4 * 16, r);
-          tc::tmem_wait_ld(r);
-          if (valid) {
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              const int col = hf * 64 + c4 * 16 + i;
-              const float4 s4 = __ldg(reinterpret_cast<const float4*>(src_row + c4 * 16 + i));
-              const float4 gm = __ldg(reinterpret_cast<const float4*>(ln + 256 + col));
-              const float4 bt = __ldg(reinterpret_cast<const float4*>(ln + 384 + col));
-              float4 o;
-              o.x = s4.x + fmaf((__uint_as_float(r[i + 0]) - mean) * rstd, gm.x, bt.x);
-              o.y = s4.y + fmaf((__uint_as_float(r[i + 1]) - mean) * rstd, gm.y, bt.y);
-              o.z = s4.z + fmaf((__uint_as_float(r[i + 2]) - mean) * rstd, gm.z, bt.z);
-              o.w = s4.w + fmaf((__uint_as_float(r[i + 3]) - mean) * rstd, gm.w, bt.w);
-              *reinterpret_cast<float4*>(out_row + c4 * 16 + i) = o;
-            }
+          for (int i = 0; i < 32; i += 4) {
+            const int col = cq * 32 + i;
+            const float4 s4 = __ldg(reinterpret_cast<const float4*>(src_row + i));
+            const float4 gm = __ldg(reinterpret_cast<const float4*>(ln + 256 + col));
+            const float4 bt = __ldg(reinterpret_cast<const float4*>(ln + 384 + col));
+            float4 o;
+            o.x = s4.x + fmaf((__uint_as_float(r[i + 0]) - mean) * rstd, gm.x, bt.x);
+            o.y = s4.y + fmaf((__uint_as_float(r[i + 1]) - mean) * rstd, gm.y, bt.y);
+            o.z = s4.z + fmaf((__uint_as_float(r[i + 2]) - mean) * rstd, gm.z, bt.z);
+            o.w = s4.w + fmaf((__uint_as_float(r[i + 3]) - mean) * rstd, gm.w, bt.w);
+            *reinterpret_cast<float4*>(out_row + i) = o;
           }
         }
         tc::tc_fence_before_sync();      // orders these TMEM reads before the a_ready arrival of the next tile (acc2 is rewritten after it)

@@ -230,9 +230,9 @@ class MatchNeRF(nn.Module):
 
     def launches_per_image(self, n_chunks: int = 1) -> int:
         """Kernels of THIS library launched per full-image forward (bench.py's gpu_launches): tensor-core gather + its v3 fix-up pass
-        + decoder per render chunk, 12 x (K-attn operand pre-pack + K-attn), 2 feature-map + 1 image packing kernels, 15 fused
-        instance norms."""
-        return 3 * n_chunks + 24 + 3 + 15
+        + decoder per render chunk; per transformer layer (12) the fused projection / operand-packing kernel, K-attn and K-block;
+        15 NHWC instance norms of two kernels each; 2 feature-map + 1 image packing kernels."""
+        return 3 * n_chunks + 12 * 3 + 15 * 2 + 3
 
     def _packed_scenes(self, ref_poses, ref_images, ref_feats_list):
         """Pack (once per set of feature maps) the per-batch-item scenes the kernels read."""
