@@ -517,6 +517,15 @@ def run_ours(args):
             q, k, v = (torch.randn(6, 64 * 80, 128, generator=g).to(dev) for _ in range(3))
             t_a0 = ev_time(lambda: ctx.window_attn(q, k, v, 64, 80, 2, False), 10)
             t_a1 = ev_time(lambda: ctx.window_attn(q, k, v, 64, 80, 2, True), 10)
+            # the other two kernels of a transformer layer: fused q/k/v projection + attention, and K-block (merge + LN [+ FFN + LN] + residual)
+            mk = lambda *sh: (torch.randn(*sh, generator=g) / sh[-1] ** 0.5).to(dev)
+            pblob = ctx.window_attn_pack_proj(mk(128, 128), mk(128, 128), mk(128, 128))
+            t_p1 = ev_time(lambda: ctx.window_attn_proj(q, k, pblob, 64, 80, 2, True, target_roll=3), 10)
+            ln = lambda: (1 + 0.1 * torch.randn(128, generator=g)).to(dev)
+            blob0 = ctx.token_block_pack(mk(128, 128), ln(), ln())
+            blob1 = ctx.token_block_pack(mk(128, 128), ln(), ln(), mk(1024, 256), mk(128, 1024), ln(), ln())
+            t_b0 = ev_time(lambda: ctx.token_block(q, k, blob0, False), 10)
+            t_b1 = ev_time(lambda: ctx.token_block(q, k, blob1, True), 10)
         n_samp = chunk * S_
         n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
         clk = (clocks or {}).get("sm_max_mhz") or 1965.0
@@ -533,6 +542,13 @@ def run_ours(args):
             window_attn=dict(ms_per_call_noshift=t_a0, ms_per_call_shift=t_a1, algorithmic_TFLOPs_noshift=att_tfs0,
                              algorithmic_TFLOPs_shift=att_tfs1, frac_of_tensor_peak=0.5 * (att_tfs0 + att_tfs1) / pk["tensor"],
                              calls_per_step=12),
+            window_attn_fused_projection=dict(ms_per_call_shift=t_p1, projection_and_packing_ms=t_p1 - t_a1 + 0.011,
+                                              note="q/k/v projections (tcgen05) inside the operand-packing kernel + K-attn; the unfused call above "
+                                                   "includes the 11 us pre-pack pass this replaces together with three cuBLAS GEMMs", calls_per_step=12),
+            token_block=dict(ms_per_call_no_ffn=t_b0, ms_per_call_ffn=t_b1, tokens=6 * 64 * 80,
+                             algorithmic_TFLOPs_ffn=6 * 64 * 80 * 2 * (128 * 128 + 256 * 1024 + 1024 * 128) / (t_b1 * 1e-3) / 1e12,
+                             frac_of_tensor_peak_ffn=6 * 64 * 80 * 2 * (128 * 128 + 256 * 1024 + 1024 * 128) / (t_b1 * 1e-3) / 1e12 / pk["tensor"],
+                             note="merge + LayerNorm (+ FFN + LayerNorm) + residual of a TransformerLayer, one tcgen05 kernel; 6 calls of each kind per step"),
             encoder=dict(ms_per_call=t_e, note="CUDA graph: backbone / up-sampler convolutions (cuDNN) + this repo's kernels")), pk
 
     # ---- untimed extras (rank 0): per-kernel timing, S = 128, parity of the timed workload, reference on this GPU / the host
