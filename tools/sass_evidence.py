@@ -19,7 +19,8 @@ def main():
         m = re.search(r"Function : (\S+)", line)
         if m:
             name = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
-            cur = re.sub(r"\(.*", "", name).replace("mnf::", "").replace("(anonymous namespace)::", "")
+            name = name.replace("(anonymous namespace)::", "").replace("mnf::", "")
+            cur = re.sub(r"\(.*", "", name)
             kernels[cur] = collections.Counter()
             continue
         m = re.match(r"\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
