@@ -61,7 +61,9 @@ class EvalTools:
 
     def get_psnr(self, full: bool = False, **kwargs) -> float:
         sq, n, _, _ = self._get_sums(full)
-        return -10.0 * math.log(sq / n) / math.log(10.0)
+        if n == 0:
+            raise ValueError("no unmasked pixel to evaluate")
+        return float("inf") if sq == 0 else -10.0 * math.log(sq / n) / math.log(10.0)     # identical images: numpy's -log(0) = inf
 
     def get_ssim(self, full: bool = False, **kwargs) -> float:
         _, _, s, n = self._get_sums(full)
