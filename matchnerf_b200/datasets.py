@@ -1,36 +1,87 @@
-"""Dataset loader for forward-facing captures in the LLFF / COLMAP layout (``<root>/<scene>/images/*`` + ``poses_bounds.npy``), with
-the reference's sample schema -- the ``datas_dict['colmap']`` entry of datasets/__init__.py (datasets/colmap.py:13-173 on top of
-datasets/llff.py:104-159), i.e. what ``test.py --yaml=demo_own`` / ``test_video_own`` read.  Host-side I/O: numpy + PIL, cameras of a
-scene computed for all views at once.
+"""Dataset loaders with the reference's sample schema (datasets/__init__.py ``datas_dict``): DTU (datasets/dtu.py), NeRF-synthetic
+"Blender" (datasets/blender.py), LLFF (datasets/llff.py) and forward-facing captures in the LLFF / COLMAP layout
+(datasets/colmap.py).  Host-side I/O (numpy, PIL, OpenCV for the DTU depth maps); cameras of a scene are computed for all views at
+once.  Every loader is pinned field by field -- bit for bit -- against the unmodified reference loader on the reference's demo scene
+and on synthetic dataset trees (tests/test_datasets_cpu.py).  The IBRNet and Tanks-and-Temples loaders are not built.
 
 A sample (one target view + its ``n_views`` source views, target LAST) is the batch ``MatchNeRF.forward`` consumes:
     images [V+1, 3, H, W] float32 in [0, 1]   extrinsics [V+1, 4, 4] world->camera   intrinsics [V+1, 3, 3]   near_fars [V+1, 2]
-    view_ids [V+1]   scene   img_wh   c2ws_all [N_train, 4, 4]
-The other loaders of the reference (DTU, Blender, LLFF hold-out, IBRNet, TnT) read datasets that are not available offline; they are
-not built.
+    view_ids [V+1]   scene   img_wh   (+ depth [H, W] for DTU val / test, + c2ws_all [N_train, 4, 4] for LLFF / COLMAP)
+
+The view splits of the MVSNeRF protocol live in ``configs/pairs.th`` and ``configs/dtu_meta/*.txt`` of the reference checkout
+(looked up relative to the working directory, as the reference does, or under ``meta_root``).  ``pairs.th`` is a pickled dict of
+numpy arrays: ``torch.load`` refuses it since PyTorch 2.6 (``weights_only`` default), which breaks the reference's own DTU / LLFF /
+Blender loaders on a current PyTorch -- ``load_pairs`` is the fix SURVEY 8(f) rank 4 names.
 """
 from __future__ import annotations
 
+import json
 import os
+import re
 from typing import Dict, List, Sequence, Tuple
 
 import numpy as np
 import torch
 
 IMAGE_EXTENSIONS = (".jpg", ".JPG", ".jpeg", ".JPEG", ".png", ".PNG", ".ppm", ".PPM", ".bmp", ".BMP", ".tif", ".TIF", ".tiff", ".TIFF")
-# poses_bounds.npy stores camera-to-world columns as [down, right, back]; the model's convention is OpenCV [right, down, forward]
-_FLIP_YZ = np.diag([1.0, -1.0, -1.0, 1.0])
-DEPTH_SCALE = 0.47058824          # datasets/colmap.py:104: the nearest bound lands a little above 1 / 0.47 ~ 2.1 after rescaling
+# poses_bounds.npy / transforms_*.json store camera-to-world with the OpenGL axes [right, up, back]; the model's convention is
+# OpenCV [right, down, forward]
+_FLIP_YZ_INT = np.array([[1, 0, 0, 0], [0, -1, 0, 0], [0, 0, -1, 0], [0, 0, 0, 1]])
+COLMAP_DEPTH_SCALE = 0.47058824   # datasets/colmap.py:104
+LLFF_DEPTH_SCALE = 0.75           # datasets/llff.py:178
 
 
+# ---------------------------------------------------------------------------------------------------------------- helpers
 def list_images(folder: str) -> List[str]:
     """misc/utils.py:265-275: image file names of a folder, sorted."""
     return sorted(f for f in os.listdir(folder) if f.endswith(IMAGE_EXTENSIONS))
 
 
-def split_views(cam_positions: np.ndarray, n_select: int = 20, n_interval: int = 6) -> Tuple[np.ndarray, np.ndarray]:
-    """(train_views, test_views) of a scene (datasets/colmap.py:13-46): the ``n_select`` cameras closest (L1) to the mean camera
-    position, every ``n_interval``-th of them held out for testing; scenes of at most three images test on image 0 from (2, 1, 0)."""
+def load_pairs(meta_root: str = "configs") -> Dict[str, np.ndarray]:
+    """``configs/pairs.th``: {'<scene>_train' / '_val' / '_test', 'dtu_train', 'dtu_test'} -> view ids (a pickled dict of numpy
+    arrays, hence ``weights_only=False``: a file of the user's own reference checkout)."""
+    return torch.load(os.path.join(meta_root, "pairs.th"), weights_only=False)
+
+
+def image_tensor(path: str, size_wh: Sequence[int], resample, blend_alpha: bool = False) -> torch.Tensor:
+    """PIL image -> resized [C, H, W] float32 in [0, 1] (torchvision ``ToTensor``); ``blend_alpha``: RGBA composited on white
+    (datasets/blender.py:39-40)."""
+    from PIL import Image
+    img = Image.open(path).resize(tuple(int(v) for v in size_wh), resample)
+    a = np.array(img, dtype=np.uint8)
+    if a.ndim == 2:
+        a = a[..., None]
+    t = torch.from_numpy(np.ascontiguousarray(a)).permute(2, 0, 1).float().div(255.0)
+    if blend_alpha:
+        t = t[:3] * t[-1:] + (1 - t[-1:])
+    return t
+
+
+def by_distance(train_c2w: np.ndarray, target_c2w: np.ndarray) -> np.ndarray:
+    """Order of the training cameras by L1 distance of their centres to the target camera (the 'nearest' source-view rule,
+    e.g. datasets/llff.py:146-151)."""
+    return np.argsort(np.abs(train_c2w[:, :3, 3] - target_c2w[:3, 3]).sum(-1))
+
+
+def read_pfm(path: str) -> np.ndarray:
+    """Portable float map (misc/utils.py:278-315): 'Pf' / 'PF' header, width height, scale (negative = little endian), rows stored
+    bottom to top."""
+    with open(path, "rb") as f:
+        kind = f.readline().decode("utf-8").rstrip()
+        if kind not in ("PF", "Pf"):
+            raise Exception("Not a PFM file.")
+        m = re.match(r"^(\d+)\s(\d+)\s$", f.readline().decode("utf-8"))
+        if not m:
+            raise Exception("Malformed PFM header.")
+        width, height = int(m.group(1)), int(m.group(2))
+        endian = "<" if float(f.readline().rstrip()) < 0 else ">"
+        data = np.fromfile(f, endian + "f")
+    return np.flipud(data.reshape((height, width, 3) if kind == "PF" else (height, width)))
+
+
+def _split_views_by_centre(cam_positions: np.ndarray, n_select: int = 20, n_interval: int = 6) -> Tuple[np.ndarray, np.ndarray]:
+    """(train_views, test_views) of a COLMAP scene (datasets/colmap.py:13-46): the ``n_select`` cameras closest (L1) to the mean
+    camera position, every ``n_interval``-th of them held out; scenes of at most three images test on image 0 from (2, 1, 0)."""
     n = cam_positions.shape[0]
     if n <= 3:
         return np.array([2, 1, 0]), np.array([0])
@@ -39,21 +90,32 @@ def split_views(cam_positions: np.ndarray, n_select: int = 20, n_interval: int =
     return np.delete(order, range(0, n_select, n_interval)), order[::n_interval]
 
 
+# ------------------------------------------------------------------------------------------- LLFF / COLMAP (poses_bounds.npy)
 class PosesBoundsScene:
-    """Cameras of one scene from ``poses_bounds.npy`` ([N, 17]: a 3 x 5 block [R | t | (h, w, focal)] + near / far per image),
-    datasets/colmap.py:89-131: axes re-ordered to OpenCV, translation and bounds divided by ``DEPTH_SCALE * min(near)``, intrinsics
-    rescaled to the requested image size, world-to-camera as the float32 inverse."""
+    """Cameras of one forward-facing scene from ``poses_bounds.npy`` ([N, 17]: a 3 x 5 block [R | t | (h, w, focal)] + near / far per
+    image): axes re-ordered to OpenCV, optionally re-centred on the average pose (LLFF, datasets/llff.py:17-70), translation and
+    bounds divided by ``depth_scale * min(near)``, intrinsics rescaled to the requested image size, world-to-camera as the float32
+    inverse (datasets/llff.py:161-204, datasets/colmap.py:89-131)."""
 
-    def __init__(self, scene_dir: str, img_wh: Sequence[int]):
+    def __init__(self, scene_dir: str, img_wh: Sequence[int], depth_scale: float, recentre: bool):
         pb = np.load(os.path.join(scene_dir, "poses_bounds.npy"))
         blocks = pb[:, :15].reshape(-1, 3, 5)
         self.images = list_images(os.path.join(scene_dir, "images"))
-        c2w = np.concatenate([blocks[..., 1:2], -blocks[..., :1], blocks[..., 2:4]], -1) @ _FLIP_YZ       # [N, 3, 4]
-        bounds = pb[:, -2:].copy()
-        scale = bounds.min() * DEPTH_SCALE
-        c2w[..., 3] /= scale
-        self.near_fars = bounds / scale
+        self.raw_positions = blocks[..., 3]
+        c2w = np.concatenate([blocks[..., 1:2], -blocks[..., :1], blocks[..., 2:4]], -1)       # [down, right, back] -> [right, up, back]
         n = c2w.shape[0]
+        if recentre:
+            avg = np.eye(4)
+            avg[:3] = self._average_pose(c2w)
+            homo = np.concatenate([c2w, np.tile(np.array([0, 0, 0, 1]), (n, 1, 1))], 1)
+            c2w = (np.linalg.inv(avg) @ homo @ _FLIP_YZ_INT)[:, :3]
+        else:
+            c2w = c2w @ _FLIP_YZ_INT
+        bounds = pb[:, -2:].copy()
+        scale = bounds.min() * depth_scale
+        bounds /= scale
+        c2w[..., 3] /= scale
+        self.near_fars = bounds
         self.c2w = np.tile(np.eye(4), (n, 1, 1))
         self.c2w[:, :3] = c2w
         self.w2c = np.stack([np.linalg.inv(m.astype(np.float32)) for m in self.c2w])
@@ -62,77 +124,291 @@ class PosesBoundsScene:
         self.K = np.zeros((n, 3, 3))
         self.K[:, 0, 0], self.K[:, 1, 1] = focal * w / raw_w, focal * h / raw_h
         self.K[:, 0, 2], self.K[:, 1, 2], self.K[:, 2, 2] = w / 2, h / 2, 1.0
-        # the split is taken on the poses BEFORE the OpenCV flip and the rescaling (gen_pairs, colmap.py:36-40)
-        self.train_views, self.test_views = split_views(blocks[..., 3])
+
+    @staticmethod
+    def _average_pose(c2w: np.ndarray) -> np.ndarray:
+        """[3, 4] pose whose centre is the mean camera centre, z the normalised mean viewing axis, x orthogonal to the mean up axis."""
+        unit = lambda v: v / np.linalg.norm(v)
+        z = unit(c2w[..., 2].mean(0))
+        x = unit(np.cross(c2w[..., 1].mean(0), z))
+        return np.stack([x, np.cross(z, x), z, c2w[..., 3].mean(0)], 1)
 
 
-class MVSDatasetCOLMAP(torch.utils.data.Dataset):
-    """``datas_dict['colmap']`` (datasets/colmap.py:49-173).  ``test_views_method``: 'nearest' = source views sorted by L1 camera
-    distance to the target, 'fixed' = the training views in split order and only the first test view (video rendering).
-    ``nf_mode``: 'avg' / 'minmax' = one near / far pair for all views of a sample (colmap.py:155-164)."""
+class _ForwardFacing(torch.utils.data.Dataset):
+    """Shared part of the LLFF and COLMAP loaders: metas = (scene, target view, source views in order, all training views)."""
+    name = ""
+    depth_scale = LLFF_DEPTH_SCALE
+    recentre = True
 
-    def __init__(self, root_dir, split, n_views=3, img_wh=None, downSample=1.0, max_len=-1, scene_list=None,
-                 test_views_method="nearest", nf_mode="avg", **kwargs):
+    def _setup(self, root_dir, split, n_views, img_wh, max_len, scene_list):
         if split != "test":
-            raise AssertionError('Only support "test" split for colmap dataset!')
+            raise AssertionError('Only support "test" split for blender dataset!')
         if img_wh is None:
             raise ValueError("img_wh = (width, height) is required")
-        if nf_mode not in ("avg", "minmax"):
-            raise Exception(f"Unknown near far mode {nf_mode}")
-        if test_views_method not in ("nearest", "fixed"):
-            raise Exception("Unknown evaluate method [%s]" % test_views_method)
-        self.root_dir, self.split, self.n_views, self.max_len, self.nf_mode = root_dir, split, int(n_views), int(max_len), nf_mode
-        self.img_wh = [int(v) for v in img_wh]
+        self.root_dir, self.split, self.n_views, self.max_len = root_dir, split, int(n_views), int(max_len)
+        self.img_wh = img_wh
         if scene_list is None:
             scene_list = sorted(x for x in os.listdir(root_dir) if os.path.isdir(os.path.join(root_dir, x)))
-        self.scenes: Dict[str, PosesBoundsScene] = {}
-        self.metas = []                                    # (scene, target view, source views in order, all training views)
-        for name in scene_list:
-            sc = PosesBoundsScene(os.path.join(root_dir, name), self.img_wh)
-            self.scenes[name] = sc
-            tests = sc.test_views[:1] if test_views_method == "fixed" else sc.test_views
-            for tgt in tests:
-                if test_views_method == "nearest":
-                    d = np.abs(sc.c2w[sc.train_views, :3, 3] - sc.c2w[tgt, :3, 3]).sum(-1)
-                    src = [sc.train_views[i] for i in np.argsort(d)]
-                else:
-                    src = sc.train_views
-                self.metas.append((name, tgt, src, sc.train_views))
+        self.scenes: Dict[str, PosesBoundsScene] = {
+            s: PosesBoundsScene(os.path.join(root_dir, s), img_wh, self.depth_scale, self.recentre) for s in scene_list}
+        self.metas = []
+        return scene_list
+
+    def _add_scene(self, name, train_views, test_views, method):
+        sc = self.scenes[name]
+        if method not in ("nearest", "fixed"):
+            raise Exception("Unknown evaluate method [%s]" % method)
+        for tgt in test_views:
+            src = [train_views[i] for i in by_distance(sc.c2w[np.asarray(train_views)], sc.c2w[tgt])] if method == "nearest" else train_views
+            self.metas.append((name, tgt, src, train_views))
 
     def get_name(self):
-        return "colmap"
+        return self.name
 
     def __len__(self):
         return len(self.metas) if self.max_len <= 0 else self.max_len
 
-    def _load_image(self, scene: str, view: int) -> torch.Tensor:
-        from PIL import Image
-        path = os.path.join(self.root_dir, scene, "images", self.scenes[scene].images[view])
-        img = Image.open(path).resize(tuple(self.img_wh), Image.LANCZOS)
-        a = np.array(img.convert("RGB") if img.mode not in ("RGB", "L") else img, dtype=np.uint8)
-        if a.ndim == 2:
-            a = a[..., None]
-        return torch.from_numpy(np.ascontiguousarray(a)).permute(2, 0, 1).float().div(255.0)      # ToTensor: [C, H, W] in [0, 1]
+    def _near_fars(self, nf: np.ndarray) -> np.ndarray:
+        return nf.mean(0)                                                      # one pair for all views (llff.py:232-233)
 
     def __getitem__(self, idx):
+        from PIL import Image
         scene, tgt, src, train_views = self.metas[idx]
         sc = self.scenes[scene]
-        ids = [int(src[i]) for i in range(self.n_views)] + [int(tgt)]
-        nf = sc.near_fars[ids]
-        if self.nf_mode == "minmax":
-            nf_all = np.array([nf.min() * 0.8, nf.max() * 1.2])
-        else:
-            nf_all = nf.mean(0)
+        ids = [src[i] for i in range(self.n_views)] + [tgt]
+        img_wh = np.array(self.img_wh).astype("int")
         return {
-            "images": torch.stack([self._load_image(scene, v) for v in ids]).float(),
+            "images": torch.stack([image_tensor(os.path.join(self.root_dir, scene, "images", sc.images[v]), img_wh, Image.LANCZOS)
+                                   for v in ids]).float(),
             "extrinsics": sc.w2c[ids].astype(np.float32),
             "intrinsics": sc.K[ids].astype(np.float32),
             "view_ids": np.array(ids),
             "scene": scene,
-            "img_wh": np.array(self.img_wh).astype("int"),
-            "near_fars": np.repeat(nf_all[None], len(ids), 0).astype(np.float32),
+            "img_wh": img_wh,
+            "near_fars": np.repeat(self._near_fars(sc.near_fars[ids])[None], len(ids), 0).astype(np.float32),
             "c2ws_all": sc.c2w[np.asarray(train_views)].astype(np.float32),
         }
 
 
-datas_dict = {"colmap": MVSDatasetCOLMAP}
+class MVSDatasetRealFF(_ForwardFacing):
+    """``datas_dict['llff']`` (datasets/llff.py:73-242).  ``eval_mode`` 'mvsnerf': the train / val views of ``configs/pairs.th``;
+    'gpnr': every 8th image held out."""
+    name = "llff"
+
+    def __init__(self, root_dir, split, n_views=3, img_wh=None, downSample=1.0, max_len=-1, scene_list=None,
+                 test_views_method="nearest", eval_mode="mvsnerf", meta_root="configs", **kwargs):
+        scene_list = self._setup(root_dir, split, n_views, img_wh, max_len, scene_list)
+        self.eval_mode = eval_mode
+        pairs = load_pairs(meta_root)
+        for s in scene_list:
+            if eval_mode == "mvsnerf":
+                train, test = pairs[f"{s}_train"], pairs[f"{s}_val"]
+            elif eval_mode == "gpnr":
+                n = len(self.scenes[s].images)
+                test = np.arange(0, n, 8)
+                train = np.array([x for x in range(n) if x not in test])
+            else:
+                raise Exception(f"Unknown eval_mode {eval_mode}.")
+            self._add_scene(s, train, test, test_views_method)
+
+
+class MVSDatasetCOLMAP(_ForwardFacing):
+    """``datas_dict['colmap']`` (datasets/colmap.py:49-173): own captures processed with LLFF's imgs2poses.  The split is taken on
+    the raw poses (``gen_pairs``); poses are NOT re-centred; ``test_views_method`` 'fixed' keeps only the first test view (video
+    rendering); ``nf_mode`` 'avg' / 'minmax' (colmap.py:155-164)."""
+    name = "colmap"
+    depth_scale = COLMAP_DEPTH_SCALE
+    recentre = False
+
+    def __init__(self, root_dir, split, n_views=3, img_wh=None, downSample=1.0, max_len=-1, scene_list=None,
+                 test_views_method="nearest", nf_mode="avg", **kwargs):
+        if nf_mode not in ("avg", "minmax"):
+            raise Exception(f"Unknown near far mode {nf_mode}")
+        self.nf_mode = nf_mode
+        scene_list = self._setup(root_dir, split, n_views, img_wh, max_len, scene_list)
+        for s in scene_list:
+            train, test = _split_views_by_centre(self.scenes[s].raw_positions)
+            self._add_scene(s, train, test[:1] if test_views_method == "fixed" else test, test_views_method)
+
+    def _near_fars(self, nf):
+        return np.array([nf.min() * 0.8, nf.max() * 1.2]) if self.nf_mode == "minmax" else nf.mean(0)
+
+
+# ---------------------------------------------------------------------------------------------------------------- Blender
+class MVSDatasetBlender(torch.utils.data.Dataset):
+    """``datas_dict['blender']`` (datasets/blender.py): NeRF-synthetic scenes (``transforms_{train,test}.json`` + RGBA PNGs),
+    800-pixel renders, near / far (2, 6).  'mvsnerf': train / val ids of ``configs/pairs.th`` inside the raw train split; 'gpnr':
+    the raw train split as sources, the raw test split as targets."""
+
+    def __init__(self, root_dir, split, n_views=3, img_wh=None, downSample=1.0, max_len=-1, scene_list=None,
+                 test_views_method="nearest", eval_mode="mvsnerf", meta_root="configs", **kwargs):
+        if split != "test":
+            raise AssertionError('Only support "test" split for blender dataset!')
+        if eval_mode not in ("mvsnerf", "gpnr"):
+            raise AssertionError("Only support mvsnerf and gpnr test mode.")
+        if img_wh is None or img_wh[0] % 32 or img_wh[1] % 32:
+            raise AssertionError("img_wh must both be multiples of 32!")
+        if test_views_method not in ("nearest", "fixed"):
+            raise Exception("Unknown evaluate method [%s]" % test_views_method)
+        self.root_dir, self.split, self.n_views, self.max_len, self.eval_mode, self.img_wh = root_dir, split, int(n_views), int(max_len), eval_mode, img_wh
+        if scene_list is None:
+            scene_list = sorted(x for x in os.listdir(root_dir) if os.path.isdir(os.path.join(root_dir, x)))
+        pairs = load_pairs(meta_root)
+        self.cams: Dict[Tuple[str, object], Tuple[np.ndarray, np.ndarray, np.ndarray, str]] = {}    # (scene, view) -> (K, w2c, c2w, file)
+        self.metas = []                                                                            # (scene, target, sources in order)
+        for s in scene_list:
+            if eval_mode == "mvsnerf":
+                train, test = pairs[f"{s}_train"], pairs[f"{s}_val"]
+                self._read_split(s, "train", [*train, *test], lambda v: v)
+            else:
+                train = self._numbered(s, "train")
+                test = self._numbered(s, "test")
+                self._read_split(s, "train", train, lambda v: int(v.split("_")[-1]))
+                self._read_split(s, "test", test, lambda v: int(v.split("_")[-1]))
+            train_c2w = np.stack([self.cams[(s, v)][2] for v in train])
+            for tgt in test:
+                src = [train[i] for i in by_distance(train_c2w, self.cams[(s, tgt)][2])] if test_views_method == "nearest" else train
+                self.metas.append((s, tgt, src))
+
+    def _numbered(self, scene, part):
+        names = [x for x in os.listdir(os.path.join(self.root_dir, scene, part)) if x.endswith("png")]
+        return [f"{part}_{i}" for i in sorted({int(x.split('.')[0].split('_')[-1]) for x in names})]
+
+    def _read_split(self, scene, part, views, frame_index):
+        with open(os.path.join(self.root_dir, scene, f"transforms_{part}.json")) as f:
+            meta = json.load(f)
+        w, h = self.img_wh
+        focal = 0.5 * 800.0 / np.tan(0.5 * meta["camera_angle_x"]) * w / 800.0            # the renders are 800 pixels wide
+        K = np.array([[focal, 0, w / 2], [0, focal, h / 2], [0, 0, 1]])
+        for v in views:
+            frame = meta["frames"][frame_index(v)]
+            c2w = np.array(frame["transform_matrix"]) @ _FLIP_YZ_INT
+            self.cams[(scene, v)] = (K, np.linalg.inv(c2w), c2w, f"{frame['file_path']}.png")
+
+    def get_name(self):
+        return "blender"
+
+    def __len__(self):
+        return len(self.metas) if self.max_len <= 0 else self.max_len
+
+    def __getitem__(self, idx):
+        from PIL import Image
+        scene, tgt, src = self.metas[idx]
+        ids = [src[i] for i in range(self.n_views)] + [tgt]
+        img_wh = np.array(self.img_wh).astype("int")
+        cams = [self.cams[(scene, v)] for v in ids]
+        return {
+            "images": torch.stack([image_tensor(os.path.join(self.root_dir, scene, c[3]), img_wh, Image.LANCZOS, blend_alpha=True)
+                                   for c in cams]).float(),
+            "extrinsics": np.stack([c[1] for c in cams]).astype(np.float32),
+            "intrinsics": np.stack([c[0] for c in cams]).astype(np.float32),
+            "near_fars": np.stack([[2.0, 6.0]] * len(ids)).astype(np.float32),
+            "scene": scene,
+            "img_wh": img_wh,
+            "view_ids": np.array([int(v.split("_")[-1]) if isinstance(v, str) else v for v in ids]),
+        }
+
+
+# -------------------------------------------------------------------------------------------------------------------- DTU
+class MVSDatasetDTU(torch.utils.data.Dataset):
+    """``datas_dict['dtu']`` (datasets/dtu.py): the MVSNet pre-processing of DTU (``Cameras/train/*_cam.txt``,
+    ``Rectified/<scan>_train/rect_<view+1>_<light>_r5000.png``, ``Depths/<scan>/depth_map_<view>.pfm``).  World units are scaled
+    by 1/200; intrinsics are stored for quarter resolution (x 4, x ``downSample``).  'train': all 49 reference views x 7 lights
+    with 3 of the first ``3 + n_add_train_views`` listed source views drawn per sample; 'val': view 24, light 3 of the training
+    scans; 'test': the MVSNeRF protocol (16 + 4 views of ``configs/pairs.th``, light 3, target depth for the object mask)."""
+    scale_factor = 1.0 / 200
+
+    def __init__(self, root_dir, split, n_views=3, img_wh=None, downSample=1.0, max_len=-1, test_views_method="nearest",
+                 n_add_train_views=2, meta_root="configs", **kwargs):
+        if split not in ("train", "val", "test"):
+            raise AssertionError('split must be either "train", "val" or "test"!')
+        if img_wh is not None and (img_wh[0] % 32 or img_wh[1] % 32):
+            raise AssertionError("img_wh must both be multiples of 32!")
+        self.root_dir, self.split, self.n_views, self.img_wh, self.downSample, self.max_len = root_dir, split, int(n_views), img_wh, downSample, int(max_len)
+        self.n_add_train_views, self.permute_train_src = int(n_add_train_views), True
+        read_scans = lambda name: [ln.rstrip() for ln in open(os.path.join(meta_root, "dtu_meta", name)).readlines()]
+        self.metas = []                                         # (scan, light, target view, source views in order)
+        if split == "test":
+            pairs = load_pairs(meta_root)
+            train_views, test_views = pairs["dtu_train"], pairs["dtu_test"]
+            self._read_cameras([*train_views, *test_views])
+            if test_views_method not in ("nearest", "fixed"):
+                raise Exception("Unknown evaluate method [%s]" % test_views_method)
+            train_c2w = np.stack([self.c2w[v] for v in train_views])
+            for scan in read_scans("val_all.txt"):
+                for tgt in test_views:
+                    src = [train_views[i] for i in by_distance(train_c2w, self.c2w[tgt])] if test_views_method == "nearest" else train_views
+                    self.metas.append((scan, 3, tgt, src))
+        else:
+            lights = range(7) if split == "train" else [3]
+            with open(os.path.join(meta_root, "dtu_meta", "view_pairs.txt")) as f:
+                rows = f.read().split("\n")
+            listing = []                                        # (reference view, its source views by matching score)
+            for i in range(int(rows[0])):
+                listing.append((int(rows[1 + 2 * i].rstrip()), [int(x) for x in rows[2 + 2 * i].rstrip().split()[1::2]]))
+            used = []
+            for scan in read_scans("train_all.txt"):
+                for ref, srcs in listing:
+                    if split == "val" and ref != 24:
+                        continue
+                    for light in lights:
+                        self.metas.append((scan, light, ref, srcs))
+                        used.append([ref] + srcs)
+            self._read_cameras(np.unique(used))
+
+    def _read_cameras(self, view_ids):
+        self.K, self.w2c, self.c2w, self.near_far = {}, {}, {}, {}
+        for v in view_ids:
+            with open(os.path.join(self.root_dir, f"Cameras/train/{v:08d}_cam.txt")) as f:
+                lines = [ln.rstrip() for ln in f.readlines()]
+            w2c = np.fromstring(" ".join(lines[1:5]), dtype=np.float32, sep=" ").reshape(4, 4)      # text mode: the parser the reference uses
+            K = np.fromstring(" ".join(lines[7:10]), dtype=np.float32, sep=" ").reshape(3, 3)
+            K[:2] *= 4
+            K[:2] = K[:2] * self.downSample
+            w2c[:3, 3] *= self.scale_factor
+            d0, dstep = (float(t) for t in lines[11].split()[:2])
+            near = d0 * self.scale_factor
+            self.K[v], self.w2c[v], self.c2w[v] = K, w2c, np.linalg.inv(w2c)
+            self.near_far[v] = [near, near + dstep * 192 * self.scale_factor]
+
+    def _read_depth(self, path):
+        import cv2
+        d = np.array(read_pfm(path), dtype=np.float32)                                         # 1200 x 1600
+        d = cv2.resize(d, None, fx=0.5, fy=0.5, interpolation=cv2.INTER_NEAREST)[44:556, 80:720]   # the 512 x 640 crop of the images
+        return cv2.resize(d, None, fx=self.downSample, fy=self.downSample, interpolation=cv2.INTER_NEAREST)
+
+    def get_name(self):
+        return "dtu"
+
+    def __len__(self):
+        return len(self.metas) if self.max_len <= 0 else self.max_len
+
+    def __getitem__(self, idx):
+        from PIL import Image
+        scan, light, tgt, srcs = self.metas[idx]
+        if self.permute_train_src and self.split == "train":
+            pick = torch.sort(torch.randperm(self.n_views + self.n_add_train_views)[: self.n_views])[0]
+            ids = [srcs[i] for i in pick] + [tgt]
+        else:
+            ids = [srcs[i] for i in range(self.n_views)] + [tgt]
+        img_wh = np.round(np.array(self.img_wh) * self.downSample).astype("int")
+        sample = {
+            # the image files count views from 1
+            "images": torch.stack([image_tensor(os.path.join(self.root_dir, f"Rectified/{scan}_train/rect_{v + 1:03d}_{light}_r5000.png"),
+                                                img_wh, Image.BILINEAR) for v in ids]).float(),
+            "extrinsics": np.stack([self.w2c[v] for v in ids]).astype(np.float32),
+            "intrinsics": np.stack([self.K[v] for v in ids]).astype(np.float32),
+            "near_fars": np.stack([self.near_far[v] for v in ids]).astype(np.float32),
+            "view_ids": np.array(ids),
+            "scene": scan,
+            "img_wh": img_wh,
+        }
+        if self.split in ("test", "val"):
+            path = os.path.join(self.root_dir, f"Depths/{scan}/depth_map_{tgt:04d}.pfm")
+            if not os.path.exists(path):
+                raise AssertionError("Must provide depth for evaluating purpose.")
+            sample["depth"] = (self._read_depth(path) * self.scale_factor).astype(np.float32)
+        return sample
+
+
+datas_dict = {"dtu": MVSDatasetDTU, "blender": MVSDatasetBlender, "llff": MVSDatasetRealFF, "colmap": MVSDatasetCOLMAP}
