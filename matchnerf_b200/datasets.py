@@ -1,8 +1,8 @@
 """Dataset loaders with the reference's sample schema (datasets/__init__.py ``datas_dict``): DTU (datasets/dtu.py), NeRF-synthetic
-"Blender" (datasets/blender.py), LLFF (datasets/llff.py) and forward-facing captures in the LLFF / COLMAP layout
-(datasets/colmap.py).  Host-side I/O (numpy, PIL, OpenCV for the DTU depth maps); cameras of a scene are computed for all views at
+"Blender" (datasets/blender.py), LLFF (datasets/llff.py), forward-facing captures in the LLFF / COLMAP layout
+(datasets/colmap.py), the IBRNet training collection (datasets/ibrnet.py) and Tanks and Temples (datasets/tnt.py).  Host-side I/O (numpy, PIL, OpenCV for the DTU depth maps); cameras of a scene are computed for all views at
 once.  Every loader is pinned field by field -- bit for bit -- against the unmodified reference loader on the reference's demo scene
-and on synthetic dataset trees (tests/test_datasets_cpu.py).  The IBRNet and Tanks-and-Temples loaders are not built.
+and on synthetic dataset trees (tests/test_datasets_cpu.py).
 
 A sample (one target view + its ``n_views`` source views, target LAST) is the batch ``MatchNeRF.forward`` consumes:
     images [V+1, 3, H, W] float32 in [0, 1]   extrinsics [V+1, 4, 4] world->camera   intrinsics [V+1, 3, 3]   near_fars [V+1, 2]
@@ -411,4 +411,142 @@ class MVSDatasetDTU(torch.utils.data.Dataset):
         return sample
 
 
-datas_dict = {"dtu": MVSDatasetDTU, "blender": MVSDatasetBlender, "llff": MVSDatasetRealFF, "colmap": MVSDatasetCOLMAP}
+# ------------------------------------------------------------------------------------------------------------------ IBRNet
+class MVSDatasetIBRNet(torch.utils.data.Dataset):
+    """``datas_dict['ibrnet']`` (datasets/ibrnet.py): the IBRNet training collection -- ``<root>/<subset>/<scene>/`` folders in the
+    LLFF layout.  Every image of a scene is a target once ('train'; image 0 only for 'val'), its sources are the other images by
+    camera distance; 'train' draws ``n_views`` of the nearest ``n_views + 3``."""
+
+    def __init__(self, root_dir, split, n_views=3, img_wh=None, downSample=1.0, max_len=-1, scene_list=None,
+                 test_views_method="nearest", **kwargs):
+        from glob import glob
+        if split not in ("train", "val"):
+            raise AssertionError('Only support "train" and "val" split for IBRNet dataset!')
+        if test_views_method != "nearest":
+            raise Exception("Unknown evaluate method [%s]" % test_views_method)
+        self.root_dir, self.split, self.n_views, self.max_len, self.img_wh = root_dir, split, int(n_views), int(max_len), img_wh
+        self.scenes: Dict[str, PosesBoundsScene] = {}
+        self.metas = []                                         # (scene folder, target view, the other views by distance)
+        for subset in glob(os.path.join(root_dir, "*/")):       # the reference's enumeration order
+            for folder in glob(os.path.join(subset, "*/")):
+                sc = PosesBoundsScene(folder, img_wh, LLFF_DEPTH_SCALE, recentre=True)
+                self.scenes[folder] = sc
+                n = sc.c2w.shape[0]
+                for tgt in (range(n) if split == "train" else [0]):
+                    others = [v for v in range(n) if v != tgt]
+                    self.metas.append((folder, tgt, [others[i] for i in by_distance(sc.c2w[others], sc.c2w[tgt])]))
+
+    @staticmethod
+    def scene_name(folder: str) -> str:
+        return "_".join(folder.strip("/").split("/")[-2:])
+
+    def get_name(self):
+        return "ibrnet"
+
+    def __len__(self):
+        return len(self.metas) if self.max_len <= 0 else self.max_len
+
+    def __getitem__(self, idx):
+        from PIL import Image
+        folder, tgt, src = self.metas[idx]
+        sc = self.scenes[folder]
+        if self.split == "train":
+            pick = torch.sort(torch.randperm(self.n_views + 3)[: self.n_views])[0]
+            ids = [src[i] for i in pick] + [tgt]
+        else:
+            ids = src[: self.n_views] + [tgt]
+        img_wh = np.array(self.img_wh).astype("int")
+        return {
+            "images": torch.stack([image_tensor(os.path.join(folder, "images", sc.images[v]), img_wh, Image.LANCZOS) for v in ids]).float(),
+            "extrinsics": sc.w2c[ids].astype(np.float32),
+            "intrinsics": sc.K[ids].astype(np.float32),
+            "view_ids": np.array(ids),
+            "scene": self.scene_name(folder),
+            "img_wh": img_wh,
+            "near_fars": np.repeat(sc.near_fars[ids].mean(0)[None], len(ids), 0).astype(np.float32),
+        }
+
+
+# -------------------------------------------------------------------------------------------------------- Tanks and Temples
+class MVSDatasetTNT(torch.utils.data.Dataset):
+    """``datas_dict['tnt']`` (datasets/tnt.py): Tanks and Temples in the MVSNet layout (``<scene>/cams_1/<id>_cam.txt``,
+    ``<scene>/images/<id>.jpg``), world units scaled by 500; intrinsics are rescaled per image from its native size; the splits are
+    the ``TNT_<scene>_train / _val`` entries of ``configs/pairs.th`` ('mvsnerf') or every 8th image ('gpnr')."""
+    scale_factor = 500.0
+
+    def __init__(self, root_dir, split, n_views=3, img_wh=None, downSample=1.0, max_len=-1, scene_list=None,
+                 test_views_method="nearest", eval_mode="mvsnerf", nf_mode="avg", meta_root="configs", **kwargs):
+        if split != "test":
+            raise AssertionError('Only support "test" split for TNT dataset!')
+        if test_views_method not in ("nearest", "fixed"):
+            raise Exception("Unknown evaluate method [%s]" % test_views_method)
+        self.root_dir, self.split, self.n_views, self.max_len, self.img_wh = root_dir, split, int(n_views), int(max_len), img_wh
+        self.nf_mode, self.eval_mode = nf_mode, eval_mode
+        if scene_list is None:
+            scene_list = sorted(x for x in os.listdir(root_dir) if os.path.isdir(os.path.join(root_dir, x)))
+        pairs = load_pairs(meta_root)
+        self.cams: Dict[Tuple[str, int], Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]] = {}     # (scene, view) -> (K, w2c, c2w, near_far)
+        self.metas = []                                         # (scene, target view, source views in order, all training views)
+        for s in scene_list:
+            if eval_mode == "mvsnerf":
+                train, test = pairs[f"TNT_{s}_train"], pairs[f"TNT_{s}_val"]
+            else:                                               # 'gpnr' (the reference falls through to it for any other value)
+                n = len(list_images(os.path.join(root_dir, s, "images")))
+                test = np.arange(0, n, 8)
+                train = np.array([x for x in range(n) if x not in test])
+            for v in [*train, *test]:
+                with open(os.path.join(root_dir, s, "cams_1", f"{v:08d}_cam.txt")) as f:
+                    lines = [ln.rstrip() for ln in f.readlines()]
+                w2c = np.fromstring(" ".join(lines[1:5]), dtype=np.float32, sep=" ").reshape(4, 4)
+                K = np.fromstring(" ".join(lines[7:10]), dtype=np.float32, sep=" ").reshape(3, 3)
+                w2c[:3, 3] *= self.scale_factor
+                span = lines[11].split()
+                self.cams[(s, v)] = (K, w2c, np.linalg.inv(w2c.astype(np.float32)),
+                                     np.array([float(span[0]) * self.scale_factor, float(span[-1]) * self.scale_factor]))
+            train_c2w = np.stack([self.cams[(s, v)][2] for v in train])
+            for tgt in test:
+                src = [train[i] for i in by_distance(train_c2w, self.cams[(s, tgt)][2])] if test_views_method == "nearest" else train
+                self.metas.append((s, tgt, src, train))
+
+    def get_name(self):
+        return "tnt"
+
+    def __len__(self):
+        return len(self.metas) if self.max_len <= 0 else self.max_len
+
+    def __getitem__(self, idx):
+        from PIL import Image
+        scene, tgt, src, train = self.metas[idx]
+        ids = [src[i] for i in range(self.n_views)] + [tgt]
+        img_wh = np.array(self.img_wh).astype("int")
+        imgs, Ks = [], []
+        for v in ids:
+            path = os.path.join(self.root_dir, scene, "images", f"{v:08d}.jpg")
+            with Image.open(path) as im:
+                ori_w, ori_h = im.size
+            imgs.append(image_tensor(path, img_wh, Image.LANCZOS))
+            K = self.cams[(scene, v)][0].copy()
+            K[0] *= img_wh[0] / ori_w
+            K[1] *= img_wh[1] / ori_h
+            Ks.append(K)
+        nf = np.stack([self.cams[(scene, v)][3] for v in ids])
+        if self.nf_mode == "minmax":
+            nf_all = np.array([nf.min() * 0.8, nf.max() * 1.2])
+        elif self.nf_mode == "avg":
+            nf_all = nf.mean(0)
+        else:
+            raise Exception(f"Unknown near far mode {self.nf_mode}")
+        return {
+            "images": torch.stack(imgs).float(),
+            "extrinsics": np.stack([self.cams[(scene, v)][1] for v in ids]).astype(np.float32),
+            "intrinsics": np.stack(Ks).astype(np.float32),
+            "view_ids": np.array(ids),
+            "scene": scene,
+            "img_wh": img_wh,
+            "near_fars": np.repeat(nf_all[None], len(ids), 0).astype(np.float32),
+            "c2ws_all": np.stack([self.cams[(scene, v)][2] for v in train]).astype(np.float32),
+        }
+
+
+datas_dict = {"dtu": MVSDatasetDTU, "blender": MVSDatasetBlender, "llff": MVSDatasetRealFF, "colmap": MVSDatasetCOLMAP,
+              "ibrnet": MVSDatasetIBRNet, "tnt": MVSDatasetTNT}

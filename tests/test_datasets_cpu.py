@@ -144,6 +144,57 @@ def test_blender_synthetic_scenes_match_reference_loader(tmp_path, monkeypatch, 
     assert s["images"].shape == (4, 3, 32, 32) and float(s["images"].max()) <= 1.0
 
 
+# ------------------------------------------------------------------------------------------------------------------ IBRNet
+def test_ibrnet_synthetic_collection_matches_reference_loader(tmp_path):
+    g = np.random.default_rng(13)
+    data = tmp_path / "ibrnet_collected"
+    for subset, scenes in (("ibrnet_collected_1", ("a1", "b2")), ("real_iconic_noface", ("c3",))):
+        for scene in scenes:
+            n = int(g.integers(7, 11))
+            _write_images(data / subset / scene / "images", [f"{i:03d}.png" for i in range(n)], (36, 48), g)
+            np.save(data / subset / scene / "poses_bounds.npy", _poses_bounds(n, g))
+    for split in ("val", "train"):
+        ours, ref_ds = _both("ibrnet", str(data), split=split, n_views=3, img_wh=[32, 24])
+        assert len(ours) == (3 if split == "val" else sum(sc.c2w.shape[0] for sc in ours.scenes.values()))
+        for i in range(0, len(ours), 3):
+            torch.manual_seed(100 + i)
+            a = ours[i]
+            torch.manual_seed(100 + i)
+            _same(a, ref_ds[i])
+
+
+# ------------------------------------------------------------------------------------------------------------------ Tanks and Temples
+def test_tnt_synthetic_scenes_match_reference_loader(tmp_path, monkeypatch, legacy_torch_load):
+    from PIL import Image
+    g = np.random.default_rng(17)
+    data = tmp_path / "tnt"
+    pairs = {}
+    for scene, n, size in (("Family", 19, (54, 96)), ("Horse", 17, (60, 80))):
+        (data / scene / "cams_1").mkdir(parents=True)
+        (data / scene / "images").mkdir(parents=True)
+        for v in range(n):
+            ang = v * 0.3
+            E = np.eye(4)
+            E[:3, :3] = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]])
+            E[:3, 3] = [0.01 * g.standard_normal(), 0.002 * g.standard_normal(), 0.01 + 0.001 * g.standard_normal()]
+            K = np.array([[1165.7 + g.random(), 0, 962.8], [0, 1166.1 + g.random(), 541.9], [0, 0, 1]])
+            txt = "extrinsic\n" + "\n".join(" ".join(repr(float(x)) for x in r) for r in E) + "\n\nintrinsic\n" + \
+                  "\n".join(" ".join(repr(float(x)) for x in r) for r in K) + f"\n\n{0.002 + 0.001 * g.random()} 0.00001 192 {0.02 + 0.01 * g.random()}\n"
+            (data / scene / "cams_1" / f"{v:08d}_cam.txt").write_text(txt)
+            Image.fromarray((g.random((*size, 3)) * 255).astype(np.uint8)).save(data / scene / "images" / f"{v:08d}.jpg", quality=95)
+        perm = g.permutation(n)
+        pairs[f"TNT_{scene}_train"], pairs[f"TNT_{scene}_val"] = perm[:12], perm[12:15]
+    (tmp_path / "configs").mkdir()
+    torch.save(pairs, tmp_path / "configs" / "pairs.th")
+    monkeypatch.chdir(tmp_path)
+    for kw in (dict(test_views_method="nearest", eval_mode="mvsnerf", nf_mode="avg"), dict(test_views_method="fixed", eval_mode="mvsnerf", nf_mode="minmax"),
+               dict(test_views_method="nearest", eval_mode="gpnr", nf_mode="avg")):
+        ours, ref_ds = _both("tnt", str(data), n_views=3, img_wh=[64, 32], **kw)
+        assert len(ours) >= 5
+        for i in range(len(ours)):
+            _same(ours[i], ref_ds[i])
+
+
 # ------------------------------------------------------------------------------------------------------------------ DTU
 def _write_pfm(path, a):
     with open(path, "wb") as f:
