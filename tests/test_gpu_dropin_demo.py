@@ -63,3 +63,18 @@ def test_reference_dataset_and_model_call_on_the_demo_scene():
     assert rms(rgb[~inner], r_rgb[~inner]) < 0.15
     gt = batch["images"][0, -1].permute(1, 2, 0).reshape(-1, 3)
     assert abs(psnr(rgb[inner], gt[inner]) - psnr(r_rgb[inner], gt[inner])) < 0.01      # PSNR against the real photograph (misc/metrics.py:35-41)
+    # the evaluation loop's numbers (coach.py:430-439: no depth in this dataset -> the 80 % centre crop): this repo's EvalTools on the
+    # GPU for this repo's render vs the reference's metric definitions (oracle/metrics_oracle.py) for the reference's render
+    from matchnerf_b200.metrics import EvalTools
+    from oracle import metrics_oracle as MO
+    tools = EvalTools(DEV)
+    tools.set_inputs(rgb.reshape(H, W, 3).to(DEV), gt.reshape(H, W, 3).to(DEV), None)
+    mine = tools.get_metrics(["PSNR", "SSIM"])
+    theirs = MO.eval_metrics(r_rgb.reshape(H, W, 3).numpy(), gt.reshape(H, W, 3).numpy(), None)
+    assert abs(mine["PSNR"] - theirs["PSNR"]) < 0.01 and abs(mine["SSIM"] - theirs["SSIM"]) < 1e-3, (mine, theirs)
+    # and this repo's own loader hands the model the very same batch (tests/test_datasets_cpu.py pins every field)
+    from matchnerf_b200.datasets import datas_dict as own_datas
+    own = own_datas["colmap"](os.path.join(ref, "docs/demo_data"), "test", n_views=3, img_wh=[256, 160], max_len=-1, scene_list=["printer"],
+                              test_views_method="fixed", nf_mode="minmax")
+    own_batch = next(iter(torch.utils.data.DataLoader(own, batch_size=1, shuffle=False)))
+    assert all(torch.equal(own_batch[k], batch[k]) for k in ("images", "extrinsics", "intrinsics", "near_fars", "view_ids"))
