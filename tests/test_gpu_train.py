@@ -113,3 +113,42 @@ def test_train_steps_follow_the_oracle():
         cos = float((ga * gb).sum() / (ga.norm() * gb.norm()).clamp_min(1e-30))
         assert float(gb.norm()) > 0 and cos > bar, (part, cos)
         assert abs(float(ga.norm()) / float(gb.norm()) - 1.0) < 0.05, (part, float(ga.norm()), float(gb.norm()))
+
+
+def test_train_iteration_with_gradient_bucket():
+    """sharding.train_iteration (the reference's coach.train_iteration across ranks, here one rank): gradients accumulate into the
+    flat bucket, the step equals the plain zero_grad / backward / clip / step sequence on a twin model, and the loss goes down."""
+    from matchnerf_b200.matchnerf import MatchNeRF
+    from matchnerf_b200.sharding import GradBucket, train_iteration
+    from matchnerf_b200.utils import AttrDict
+    H, W, S, R = 64, 96, 16, 256
+    opt = make_opts(**{"nerf.sample_intvs": S, "nerf.rand_rays_train": R, "nerf.sample_stratified": False})
+    opt.device = DEV
+    nets = []
+    for _ in range(2):
+        m = MatchNeRF(opt).train()
+        m.feat_enc.load_state_dict(synth.synthetic_encoder(1))
+        m.nerf_dec.load_state_dict(synth.synthetic_decoder(0))
+        nets.append(m.to(DEV))
+    g = torch.Generator().manual_seed(21)
+    images = torch.rand(1, 4, 3, H, W, generator=g)
+    extr, intr, nf = synth.synthetic_cameras(H, W)
+    batch = lambda: AttrDict(images=images.to(DEV), extrinsics=extr.to(DEV), intrinsics=intr.to(DEV), near_fars=nf.to(DEV))
+    bucket = GradBucket(nets[0].parameters())
+    optims = [torch.optim.AdamW(n.parameters(), lr=5e-4, weight_decay=1e-4) for n in nets]
+    losses = []
+    for step in range(3):
+        torch.manual_seed(100 + step)                                   # same random rays on both sides
+        losses.append(float(train_iteration(nets[0], batch(), optims[0], bucket, clip_enc=1.0)))
+        assert float(bucket.flat.abs().sum()) > 0
+        torch.manual_seed(100 + step)
+        optims[1].zero_grad()
+        out = nets[1](batch(), mode="train")
+        gt = images[0, 3].permute(1, 2, 0).reshape(-1, 3).to(DEV)[out["ray_idx"]]
+        torch.nn.functional.mse_loss(out["rgb"][0], gt).backward()
+        torch.nn.utils.clip_grad_norm_(nets[1].feat_enc.parameters(), 1.0)
+        optims[1].step()
+    a = torch.cat([p.detach().reshape(-1) for p in nets[0].parameters()])
+    b = torch.cat([p.detach().reshape(-1) for p in nets[1].parameters()])
+    assert float((a - b).abs().max()) < 1e-5 * max(1.0, float(b.abs().max())), float((a - b).abs().max())   # atomics in the gather backward: last bits
+    assert losses[-1] < losses[0]
