@@ -135,7 +135,9 @@ def test_train_iteration_with_gradient_bucket():
     extr, intr, nf = synth.synthetic_cameras(H, W)
     batch = lambda: AttrDict(images=images.to(DEV), extrinsics=extr.to(DEV), intrinsics=intr.to(DEV), near_fars=nf.to(DEV))
     bucket = GradBucket(nets[0].parameters())
-    optims = [torch.optim.AdamW(n.parameters(), lr=5e-4, weight_decay=1e-4) for n in nets]
+    # plain SGD: the parameter update is linear in the gradient, so the comparison below measures the GRADIENTS (Adam's normalisation
+    # turns last-bit noise on near-zero gradient elements -- the gather backward accumulates with atomics -- into +-lr steps)
+    optims = [torch.optim.SGD(n.parameters(), lr=1e-2) for n in nets]
     start = torch.cat([p.detach().reshape(-1) for p in nets[1].parameters()]).clone()
     losses = []
     for step in range(3):
@@ -151,7 +153,6 @@ def test_train_iteration_with_gradient_bucket():
         optims[1].step()
     a = torch.cat([p.detach().reshape(-1) for p in nets[0].parameters()])
     b = torch.cat([p.detach().reshape(-1) for p in nets[1].parameters()])
-    # the gather backward accumulates with atomics (summation order varies run to run: last bits of the encoder gradients, which
-    # Adam's normalisation can amplify on near-cancelling elements), so: the two parameter trajectories agree to 2 % of the update
-    assert float((b - start).norm()) > 0 and float((a - b).norm()) < 0.02 * float((b - start).norm()), (float((a - b).norm()), float((b - start).norm()))
+    # atomics in the gather backward: the summation order varies run to run (last bits of the encoder gradients)
+    assert float((b - start).norm()) > 0 and float((a - b).norm()) < 2e-3 * float((b - start).norm()), (float((a - b).norm()), float((b - start).norm()))
     assert losses[-1] < losses[0]
