@@ -140,10 +140,13 @@ def test_train_iteration_with_gradient_bucket():
     optims = [torch.optim.SGD(n.parameters(), lr=1e-2) for n in nets]
     start = torch.cat([p.detach().reshape(-1) for p in nets[1].parameters()]).clone()
     losses = []
+    flat = lambda n: torch.cat([p.detach().reshape(-1) for p in n.parameters()])
     for step in range(3):
         torch.manual_seed(100 + step)                                   # same random rays on both sides
         losses.append(float(train_iteration(nets[0], batch(), optims[0], bucket, clip_enc=1.0)))
         assert float(bucket.flat.abs().sum()) > 0
+        if step > 0:                                                    # the twin comparison is made on the FIRST step (identical
+            continue                                                    # parameters going in); later steps only feed the loss trend
         torch.manual_seed(100 + step)
         optims[1].zero_grad()
         out = nets[1](batch(), mode="train")
@@ -151,8 +154,8 @@ def test_train_iteration_with_gradient_bucket():
         torch.nn.functional.mse_loss(out["rgb"][0], gt).backward()
         torch.nn.utils.clip_grad_norm_(nets[1].feat_enc.parameters(), 1.0)
         optims[1].step()
-    a = torch.cat([p.detach().reshape(-1) for p in nets[0].parameters()])
-    b = torch.cat([p.detach().reshape(-1) for p in nets[1].parameters()])
-    # atomics in the gather backward: the summation order varies run to run (last bits of the encoder gradients)
-    assert float((b - start).norm()) > 0 and float((a - b).norm()) < 2e-3 * float((b - start).norm()), (float((a - b).norm()), float((b - start).norm()))
+        a, b = flat(nets[0]), flat(nets[1])
+    # run-to-run variation of the gradients (tools/r02_train_det.py: cuDNN backward + the gather's atomics, 3.5e-4 relative on the
+    # backbone, 5e-6 on the transformer, 0 on the decoder) is all that separates the two sequences
+    assert float((b - start).norm()) > 0 and float((a - b).norm()) < 1e-3 * float((b - start).norm()), (float((a - b).norm()), float((b - start).norm()))
     assert losses[-1] < losses[0]
