@@ -288,17 +288,20 @@ def train_step_times(dev, S=128, n_rays=1024, steps=5, warmup=2):
     from oracle import synth
     host = synthetic_batch(100)
 
-    def loop(net, make_batch):
+    def loop(net, make_batch, precision=None):
+        from matchnerf_b200.train_path import training_precision
+        import contextlib
         net.train()
         enc_params = list(net.feat_enc.parameters())
         optim = torch.optim.AdamW(net.parameters(), lr=5e-4, weight_decay=1e-4)
         gt_all = host["images"][0, 3].permute(1, 2, 0).reshape(-1, 3).to(dev)
 
         def step():
-            out = net(make_batch(), mode="train")
-            loss = ((out["rgb"][0] - gt_all[out["ray_idx"]]) ** 2).mean()
-            optim.zero_grad()
-            loss.backward()
+            with (training_precision(precision) if precision else contextlib.nullcontext()):
+                out = net(make_batch(), mode="train")
+                loss = ((out["rgb"][0] - gt_all[out["ray_idx"]]) ** 2).mean()
+                optim.zero_grad()
+                loss.backward()
             torch.nn.utils.clip_grad_norm_(enc_params, 1.0)
             optim.step()
             return loss
@@ -321,9 +324,14 @@ def train_step_times(dev, S=128, n_rays=1024, steps=5, warmup=2):
     m.feat_enc.load_state_dict(synth.synthetic_encoder(1))
     m.nerf_dec.load_state_dict(synth.synthetic_decoder(0))
     m.to(dev)
-    res["ours_ms_per_step"], res["ours_last_loss"] = loop(m, lambda: AttrDict({k: v.to(dev) for k, v in host.items()}))
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    res["ours_fp32_ms_per_step"], res["ours_fp32_last_loss"] = loop(m, lambda: AttrDict({k: v.to(dev) for k, v in host.items()}), "fp32")
+    m.load_state_dict(sd0)
+    res["ours_ms_per_step"], res["ours_last_loss"] = loop(m, lambda: AttrDict({k: v.to(dev) for k, v in host.items()}), "tf32")
     res["ours_path"] = ("K-gather forward + backward: this repo's CUDA kernels behind an autograd Function; decoder / ray transformer / "
-                        "compositing / encoder: library GEMMs + cuDNN under autograd (matchnerf_b200/train_path.py)")
+                        "compositing / encoder: library GEMMs + cuDNN under autograd (matchnerf_b200/train_path.py); ours_ms_per_step: "
+                        "TF32 tensor-core math for the whole step, forward and backward (train_path.training_precision, the default of "
+                        "sharding.train_iteration); ours_fp32_ms_per_step: PyTorch's default fp32 math, as the reference runs")
     del m
     torch.cuda.empty_cache()
     try:

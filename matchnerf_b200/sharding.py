@@ -187,20 +187,24 @@ class GradBucket:
         return self.flat
 
 
-def train_iteration(model, batch, optimizer, bucket: GradBucket, clip_enc: Optional[float] = 1.0, scheduler=None):
+def train_iteration(model, batch, optimizer, bucket: GradBucket, clip_enc: Optional[float] = 1.0, scheduler=None,
+                    precision: str = "tf32"):
     """One training step with the reference's semantics (coach.py:215-243, compute_loss :245-258) across ranks: forward in 'train' mode
     (random rays of this rank's sample), MSE against the target view at those rays, backward into the bucket, ONE gradient all-reduce
     (mean over ranks), ``clip_grad_norm_`` on the encoder AFTER the reduce (coach.py:225-226 clips what the optimiser sees), optimiser
-    (and per-iteration scheduler) step.  Returns the local loss."""
+    (and per-iteration scheduler) step.  ``precision``: math mode of the library GEMMs / convolutions of the step, forward and
+    backward (``train_path.training_precision``; "fp32" = the reference's arithmetic).  Returns the local loss."""
+    from .train_path import training_precision
     bucket.zero()
-    pred = model(batch, mode="train")
-    images = batch["images"]
-    b, _, c = images.shape[:3]
-    gt = images[:, -1].reshape(b, c, -1).permute(0, 2, 1)
-    if "ray_idx" in pred:
-        gt = gt[:, pred["ray_idx"]]
-    loss = torch.nn.functional.mse_loss(pred["rgb"], gt)
-    loss.backward()
+    with training_precision(precision):
+        pred = model(batch, mode="train")
+        images = batch["images"]
+        b, _, c = images.shape[:3]
+        gt = images[:, -1].reshape(b, c, -1).permute(0, 2, 1)
+        if "ray_idx" in pred:
+            gt = gt[:, pred["ray_idx"]]
+        loss = torch.nn.functional.mse_loss(pred["rgb"], gt)
+        loss.backward()
     bucket.all_reduce_mean()
     if clip_enc is not None:
         torch.nn.utils.clip_grad_norm_(model.feat_enc.parameters(), clip_enc)

@@ -17,6 +17,7 @@ parameters from ``matchnerf_b200.cond_nerf.CondNeRF`` (same state_dict keys as t
 from __future__ import annotations
 
 import math
+import os
 from typing import Tuple
 
 import torch
@@ -149,6 +150,35 @@ def render_rays_train(model, opt, tgt_pose, ray_idx, ref_poses, ref_images, ref_
     return composite_samples(rgb, sigma, depth, bool(model.nerf_setbg_opaque))
 
 
+class training_precision:
+    """Scoped cuBLAS / cuDNN math mode for a WHOLE training step -- forward AND backward: autograd launches the backward GEMMs after
+    ``forward`` has returned, so the encoder's own scope (``GMFlow.matmul_precision``) does not cover them, and the decoder / ray
+    transformer GEMMs of the training path are never inside it.  A torch.profiler pass of the step (tools/r02_train_prof.py) showed
+    57 of 124 ms per two steps in fp32 ``simt_sgemm`` kernels.  "tf32": 10-bit-mantissa operands, fp32 accumulation on the tensor
+    cores (the "bf16 / TF32 training step" of SURVEY 8f rank 2); "fp32": PyTorch's defaults (what the reference runs)."""
+
+    def __init__(self, mode: str = "tf32"):
+        if mode not in ("tf32", "fp32"):
+            raise ValueError("precision must be 'tf32' or 'fp32'")
+        self.mode = mode
+
+    def __enter__(self):
+        self.prev = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+        on = self.mode == "tf32"
+        torch.backends.cuda.matmul.allow_tf32 = on
+        torch.backends.cudnn.allow_tf32 = on
+        return self
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = self.prev
+        return False
+
+
+# training-step attention through F.scaled_dot_product_attention (library) instead of explicit GEMMs: measured SLOWER on B200 at DTU
+# size (fp32 inputs: the memory-efficient backend; 74 ms vs 66.5 ms per training step, tools/r02_train_ab.py) -- opt-in only
+USE_SDPA = os.environ.get("MNF_TRAIN_SDPA", "0") != "0"
+
+
 def window_attention_autograd(q, k, v, h: int, w: int, num_splits: int, with_shift: bool):
     """Split-window attention (models/gmflow/transformer.py:46-105, :19-43) as index-gathered batched GEMMs, for the training
     step only (inference uses the tcgen05 kernel behind mnf_window_attn_fwd).  Tokens are gathered per window through an index
@@ -169,8 +199,13 @@ def window_attention_autograd(q, k, v, h: int, w: int, num_splits: int, with_shi
     reg = reg.view(num_splits, wh, num_splits, ww).permute(0, 2, 1, 3).reshape(num_splits * num_splits, wh * ww)
     bias = torch.where(reg[:, :, None] == reg[:, None, :], 0.0, -100.0).to(q.dtype)      # [windows, Lw, Lw]
     g = lambda t: t[:, tok]                                                   # [B, windows, Lw, C]
-    att = (g(q) @ g(k).transpose(-1, -2)) * (1.0 / math.sqrt(C)) + bias[None]
-    out_w = att.softmax(-1) @ g(v)
+    if USE_SDPA and q.is_cuda:
+        # library fused attention (windows in the head dimension, the shift mask as an additive bias): no [B, windows, Lw, Lw]
+        # score / probability tensors saved for backward (157 MB each per call at DTU size)
+        out_w = F.scaled_dot_product_attention(g(q), g(k), g(v), attn_mask=bias if (sh or sw) else None)
+    else:
+        att = (g(q) @ g(k).transpose(-1, -2)) * (1.0 / math.sqrt(C)) + bias[None]
+        out_w = att.softmax(-1) @ g(v)
     flat = tok.reshape(-1)
     inv = torch.empty_like(flat)
     inv[flat] = torch.arange(flat.numel(), device=dev)                        # token id -> its row in the window-major list

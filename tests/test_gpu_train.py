@@ -159,3 +159,39 @@ def test_train_iteration_with_gradient_bucket():
     # backbone, 5e-6 on the transformer, 0 on the decoder) is all that separates the two sequences
     assert float((b - start).norm()) > 0 and float((a - b).norm()) < 1e-3 * float((b - start).norm()), (float((a - b).norm()), float((b - start).norm()))
     assert losses[-1] < losses[0]
+
+
+def test_tf32_training_precision_matches_fp32_gradients():
+    """train_path.training_precision('tf32') (the default of sharding.train_iteration: tensor-core GEMMs / convolutions for the whole
+    step, forward and backward) against the same backward in fp32: gradients aligned (cosine > 0.999 decoder, > 0.99 encoder), norms
+    within 3 %, and the scope restores the process-wide flags."""
+    from matchnerf_b200.matchnerf import MatchNeRF
+    from matchnerf_b200.train_path import training_precision
+    from matchnerf_b200.utils import AttrDict
+    H, W, S, R = 64, 96, 16, 256
+    opt = make_opts(**{"nerf.sample_intvs": S, "nerf.rand_rays_train": R, "nerf.sample_stratified": True})
+    opt.device = DEV
+    m = MatchNeRF(opt).train()
+    m.feat_enc.load_state_dict(synth.synthetic_encoder(1))
+    m.nerf_dec.load_state_dict(synth.synthetic_decoder(0))
+    m.to(DEV)
+    g = torch.Generator().manual_seed(31)
+    images = torch.rand(1, 4, 3, H, W, generator=g)
+    extr, intr, nf = synth.synthetic_cameras(H, W)
+    flags = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    grads = {}
+    for mode in ("fp32", "tf32"):
+        torch.manual_seed(7)
+        m.zero_grad(set_to_none=True)
+        with training_precision(mode):
+            out = m(AttrDict(images=images.to(DEV), extrinsics=extr.to(DEV), intrinsics=intr.to(DEV), near_fars=nf.to(DEV)), mode="train")
+            gt = images[0, 3].permute(1, 2, 0).reshape(-1, 3).to(DEV)[out["ray_idx"]]
+            torch.nn.functional.mse_loss(out["rgb"][0], gt).backward()
+        grads[mode] = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+        assert (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32) == flags
+    for part, bar in (("nerf_dec", 0.999), ("feat_enc", 0.99)):
+        ks = [k for k in grads["fp32"] if k.startswith(part)]
+        a = torch.cat([grads["tf32"][k].reshape(-1) for k in ks])
+        b = torch.cat([grads["fp32"][k].reshape(-1) for k in ks])
+        cos = float((a * b).sum() / (a.norm() * b.norm()))
+        assert cos > bar and abs(float(a.norm() / b.norm()) - 1.0) < 0.03, (part, cos, float(a.norm()), float(b.norm()))
