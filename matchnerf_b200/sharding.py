@@ -188,12 +188,13 @@ class GradBucket:
 
 
 def train_iteration(model, batch, optimizer, bucket: GradBucket, clip_enc: Optional[float] = 1.0, scheduler=None,
-                    precision: str = "tf32"):
+                    precision: Optional[str] = None):
     """One training step with the reference's semantics (coach.py:215-243, compute_loss :245-258) across ranks: forward in 'train' mode
     (random rays of this rank's sample), MSE against the target view at those rays, backward into the bucket, ONE gradient all-reduce
     (mean over ranks), ``clip_grad_norm_`` on the encoder AFTER the reduce (coach.py:225-226 clips what the optimiser sees), optimiser
     (and per-iteration scheduler) step.  ``precision``: math mode of the library GEMMs / convolutions of the step, forward and
-    backward (``train_path.training_precision``; "fp32" = the reference's arithmetic).  Returns the local loss."""
+    backward (``train_path.training_precision``: None = PyTorch's defaults, as the reference runs; "tf32" is faster but opt-in, see
+    there).  Returns the local loss."""
     from .train_path import training_precision
     bucket.zero()
     with training_precision(precision):

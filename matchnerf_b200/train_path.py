@@ -154,19 +154,25 @@ class training_precision:
     """Scoped cuBLAS / cuDNN math mode for a WHOLE training step -- forward AND backward: autograd launches the backward GEMMs after
     ``forward`` has returned, so the encoder's own scope (``GMFlow.matmul_precision``) does not cover them, and the decoder / ray
     transformer GEMMs of the training path are never inside it.  A torch.profiler pass of the step (tools/r02_train_prof.py) showed
-    57 of 124 ms per two steps in fp32 ``simt_sgemm`` kernels.  "tf32": 10-bit-mantissa operands, fp32 accumulation on the tensor
-    cores (the "bf16 / TF32 training step" of SURVEY 8f rank 2); "fp32": PyTorch's defaults (what the reference runs)."""
+    57 of 124 ms per two steps in fp32 ``simt_sgemm`` kernels.
+      None    leave the process-wide flags alone (PyTorch's defaults = what the reference runs: fp32 GEMMs, TF32 convolutions);
+      "tf32"  10-bit-mantissa operands, fp32 accumulation on the tensor cores for every GEMM / convolution of the step (the
+              "bf16 / TF32 training step" of SURVEY 8f rank 2): 47 ms instead of 67-79 ms per step on B200 -- but OPT-IN: on the
+              random-initialised test encoder the backward in TF32 moves the ENCODER gradient to cosine 0.69 against the fp32
+              backward (decoder gradient: 0.997; tests/test_gpu_train.py) -- twelve attention layers amplify the operand rounding;
+              whether trained weights behave better cannot be measured here (no checkpoint offline);
+      "fp32"  fp32 everywhere, convolutions included."""
 
-    def __init__(self, mode: str = "tf32"):
-        if mode not in ("tf32", "fp32"):
-            raise ValueError("precision must be 'tf32' or 'fp32'")
+    def __init__(self, mode=None):
+        if mode not in (None, "tf32", "fp32"):
+            raise ValueError("precision must be None, 'tf32' or 'fp32'")
         self.mode = mode
 
     def __enter__(self):
         self.prev = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
-        on = self.mode == "tf32"
-        torch.backends.cuda.matmul.allow_tf32 = on
-        torch.backends.cudnn.allow_tf32 = on
+        if self.mode is not None:
+            torch.backends.cuda.matmul.allow_tf32 = self.mode == "tf32"
+            torch.backends.cudnn.allow_tf32 = self.mode == "tf32"
         return self
 
     def __exit__(self, *exc):

@@ -161,11 +161,12 @@ def test_train_iteration_with_gradient_bucket():
     assert losses[-1] < losses[0]
 
 
-def test_tf32_training_precision_matches_fp32_gradients():
-    """train_path.training_precision('tf32') (the default of sharding.train_iteration: tensor-core GEMMs / convolutions for the whole
-    step, forward and backward) against the same backward in fp32: gradients aligned (cosine > 0.99 decoder -- measured 0.997: 10-bit
-    operand mantissas through the positional encoding's 2^9 frequencies and six layers -- > 0.97 encoder), norms within 5 %, and the scope
-    restores the process-wide flags."""
+def test_tf32_training_precision_scope():
+    """train_path.training_precision('tf32') (opt-in: tensor-core GEMMs / convolutions for the whole step, forward and backward)
+    against the same backward in fp32 on the random-initialised test model: the DECODER gradient stays aligned (cosine > 0.99,
+    measured 0.997), the ENCODER gradient does not (measured 0.69: twelve attention layers amplify the operand rounding of the
+    backward GEMMs -- the reason the mode is not the default; only reported and sanity-bounded here), and the scope restores the
+    process-wide flags."""
     from matchnerf_b200.matchnerf import MatchNeRF
     from matchnerf_b200.train_path import training_precision
     from matchnerf_b200.utils import AttrDict
@@ -181,22 +182,24 @@ def test_tf32_training_precision_matches_fp32_gradients():
     extr, intr, nf = synth.synthetic_cameras(H, W)
     flags = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
     grads = {}
-    for mode in ("fp32", "tf32"):
+    for mode in ("fp32", "tf32", None):
         torch.manual_seed(7)
         m.zero_grad(set_to_none=True)
         with training_precision(mode):
+            if mode is None:
+                assert (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32) == flags
             out = m(AttrDict(images=images.to(DEV), extrinsics=extr.to(DEV), intrinsics=intr.to(DEV), near_fars=nf.to(DEV)), mode="train")
             gt = images[0, 3].permute(1, 2, 0).reshape(-1, 3).to(DEV)[out["ray_idx"]]
             torch.nn.functional.mse_loss(out["rgb"][0], gt).backward()
         grads[mode] = {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
         assert (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32) == flags
     seen = {}
-    for part, bar in (("nerf_dec", 0.99), ("feat_enc", 0.97)):
+    for part in ("nerf_dec", "feat_enc"):
         ks = [k for k in grads["fp32"] if k.startswith(part)]
         a = torch.cat([grads["tf32"][k].reshape(-1) for k in ks])
         b = torch.cat([grads["fp32"][k].reshape(-1) for k in ks])
         seen[part] = (float((a * b).sum() / (a.norm() * b.norm())), float(a.norm()), float(b.norm()))
     print("tf32 vs fp32 gradients (cosine, norm tf32, norm fp32):", seen)
-    for part, bar in (("nerf_dec", 0.99), ("feat_enc", 0.97)):
-        cos, na, nb = seen[part]
-        assert cos > bar and abs(na / nb - 1.0) < 0.05, seen
+    cos, na, nb = seen["nerf_dec"]
+    assert cos > 0.99 and abs(na / nb - 1.0) < 0.05, seen
+    assert seen["feat_enc"][0] > 0.3 and all(torch.isfinite(v).all() for v in grads["tf32"].values()), seen
