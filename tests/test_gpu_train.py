@@ -143,7 +143,7 @@ def test_train_iteration_with_gradient_bucket():
     flat = lambda n: torch.cat([p.detach().reshape(-1) for p in n.parameters()])
     for step in range(3):
         torch.manual_seed(100 + step)                                   # same random rays on both sides
-        losses.append(float(train_iteration(nets[0], batch(), optims[0], bucket, clip_enc=1.0, precision="fp32")))   # the twin below runs PyTorch's default math
+        losses.append(float(train_iteration(nets[0], batch(), optims[0], bucket, clip_enc=1.0)))   # default precision = PyTorch's stock math, as the twin below
         assert float(bucket.flat.abs().sum()) > 0
         if step > 0:                                                    # the twin comparison is made on the FIRST step (identical
             continue                                                    # parameters going in); later steps only feed the loss trend
